@@ -1,0 +1,591 @@
+"""
+CPU ORACLE (numpy) for the per-k-point Wannier-interpolation path of cMax347/MEPinterp.
+
+*** TEST INFRASTRUCTURE ONLY ***  Nothing in the product path (mepinterp_b200/, the C-ABI library,
+the CLI driver) may import or execute this file.  Only tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py use it, and only as the checker.
+
+It restates, function by function, the Fortran of the reference (paths relative to /root/reference):
+
+    constants           src/constants.f90:6-23
+    read_hr_file        src/file_io.f90:663-746
+    parse_input_cfg     src/input_paras.f90:103-181   (syntax: thirdparty/config_fortran/m_config.f90:226-311)
+    get_linspace        src/matrix_math.f90:74-100
+    get_rel_kpt / mesh  src/k_space.f90:341-375, core.f90:165-178
+    set_recip_latt      src/k_space.f90:263-293
+    FT_R_to_k           src/wann_interp.f90:151-281   (H, dH; both FT conventions; use_cart_velo)
+    zheevd_wrapper      src/matrix_math.f90:192-226   (numpy.linalg.eigh == LAPACK zheevd, OpenBLAS build)
+    rotate_gauge        src/wann_interp.f90:502-550   (U^dagger H_a U)
+    get_velo            src/wann_interp.f90:406-444   (no position operator: V = Hbar)
+    fd_stat, N_el       src/statistics.f90:41-124
+    kubo_ahc_tens       src/kubo.f90:37-78
+    velo_ahc_tens       src/kubo.f90:86-140
+    kubo_ohc_tens       src/kubo.f90:145-198
+    photo_2nd_cond      src/photo.f90:16-86
+    mep_niu_LC / IC     src/mep_niu.f90:47-159
+    kubo_mep_LC / IC    src/kubo_mep.f90:51-149
+    core_worker         src/core.f90:79-298 (k loop + accumulation), :317-415 (fermi_selector),
+                        :419-603 (integrate_over_k_space, mep_sum_bands), k_space.f90:81-202 (normalize_k_int)
+
+The position-operator branch (A_ka, Om_kab; *_CS terms; kubo_opt_tens) is never reached by inputs that
+consist of a `_hr.dat` only (k_space.f90:229-233): CS terms and opt_s/opt_a are returned as zeros exactly as
+the reference does (mep_niu.f90:29, kubo_mep.f90:28, kubo.f90:225).
+
+Parity pin status: the reference cannot be compiled here (no Fortran compiler, no MPI).  The oracle is
+pinned by (a) the reference's own golden AHC tensors config/FeMn_TB/delta*/ahc_tens.npy and
+ahcVELO_sol*.npy to mesh-convergence level (<= 2e-3 relative, producing mesh unrecorded),
+(b) the KATs of tests/test_matrix_math.f90 and tests/test_kSpace.f90, (c) an independent C restatement
+(oracle/cpu_ref.c) agreeing to 1e-12.  MEP / ohc / photo tensors are "parity unpinned" by the reference
+(it ships neither a golden nor a test for them); for those the two restatements are the only pin.
+
+Everything is vectorised over a batch of k-points (leading axis) for speed; the per-k formulas are the
+reference's, term for term.  Array index order follows the Fortran: V[k, a, n, m] == V_ka(a,n,m).
+"""
+from __future__ import annotations
+
+import math
+import os
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+# --------------------------------------------------------------------------- constants.f90:6-23
+PI_DP = 4.0 * math.atan(1.0)
+AU_TO_ANGSTRM = 0.52917721092
+AU_TO_EV = 27.211385
+KBOLTZ_EH_K = 8.6173303 * 1e-5 / AU_TO_EV
+MIN_TEMP = 1e-2  # statistics.f90:32
+
+
+def levi_civita() -> np.ndarray:
+    """matrix_math.f90:103-139"""
+    lc = np.zeros((3, 3, 3))
+    lc[0, 1, 2] = lc[1, 2, 0] = lc[2, 0, 1] = 1.0
+    lc[2, 1, 0] = lc[0, 2, 1] = lc[1, 0, 2] = -1.0
+    return lc
+
+
+def get_linspace(lo: float, hi: float, n: int) -> np.ndarray:
+    """matrix_math.f90:74-100: n>1 -> lo + i*delta ; else the single value lo."""
+    if n > 1:
+        delta = (hi - lo) / float(n - 1)
+        return lo + np.arange(n, dtype=np.float64) * delta
+    return np.array([lo], dtype=np.float64)
+
+
+# --------------------------------------------------------------------------- inputs
+@dataclass
+class Model:
+    """What read_tb_basis + init_parameters hand to core_worker (file_io.f90:800, input_paras.f90:79)."""
+    nw: int
+    nR: int
+    R: np.ndarray            # (3, nR) fractional, as stored in R_vect
+    H: np.ndarray            # (nw, nw, nR) complex, Hartree
+    a_latt: np.ndarray       # (3,3): a_latt[i,:] = a_i * a0  (rows!)  input_paras.f90:165-168
+    wf_centers: Optional[np.ndarray] = None   # (3, nw) fractional, or None -> Wannier FT convention
+
+
+@dataclass
+class Params:
+    mp_grid: tuple = (4, 4, 4)
+    do_gauge_trafo: bool = True
+    use_cart_velo: bool = False
+    do_mep: bool = False
+    do_kubo: bool = False
+    do_ahc: bool = False
+    do_opt: bool = False
+    do_write_mep_bands: bool = True
+    valence_bands: int = 1
+    n_hw: int = 1
+    n_eF: int = 1
+    hw_min: float = 0.0      # Hartree
+    hw_max: float = 0.0
+    eF_min: float = 0.0
+    eF_max: float = 0.0
+    T_kelvin: float = 0.0
+    eta: float = 0.0         # Hartree
+    kubo_tol: float = 1e-5
+    seed_name: str = "wf1"
+    plot_bands: bool = False
+    R_vect_float: bool = False
+
+
+def read_hr_file(path: str, use_R_float: bool = False):
+    """file_io.f90:663-746.  Returns R (3,nR) and H (nw,nw,nR) in Hartree.
+    Degeneracies are read and ignored (file_io.f90:685-709); |Re|,|Im| < 1e-7 eV -> 0 (:732-733);
+    H_mat(m,n,sc) with m,n the 4th/5th columns (:734); R taken from the first line of each block (:723-724)."""
+    with open(path, "r") as fh:
+        fh.readline()
+        nw = int(fh.readline().split()[0])
+        nR = int(fh.readline().split()[0])
+        deg = []
+        while len(deg) < nR:
+            deg += [int(x) for x in fh.readline().split()]
+        if len(deg) != nR:
+            raise ValueError("[read_hr_file]: ERROR issue reading Wigner Seitz degeneracy")
+        R = np.zeros((3, nR))
+        H = np.zeros((nw, nw, nR), dtype=np.complex128)
+        for sc in range(nR):
+            for wf in range(nw * nw):
+                tok = fh.readline().split()
+                r3 = [float(t) for t in tok[0:3]]
+                m, n = int(tok[3]), int(tok[4])
+                re, im = float(tok[5]), float(tok[6])
+                if wf == 0:
+                    R[:, sc] = r3
+                if abs(re) < 1e-7:
+                    re = 0.0
+                if abs(im) < 1e-7:
+                    im = 0.0
+                H[m - 1, n - 1, sc] = complex(re, im)
+    H = H / AU_TO_EV
+    return R, H
+
+
+def _cfg_logical(tok: str) -> bool:
+    t = tok.strip().lstrip(".").upper()
+    if t.startswith("T"):
+        return True
+    if t.startswith("F"):
+        return False
+    raise ValueError(f"bad logical {tok!r}")
+
+
+def parse_input_cfg(path: str):
+    """input_paras.f90:103-181 on the m_config syntax (m_config.f90:226-311): `[section]`, `key = v1 v2 ...`,
+    comments # and ;, separators space/comma/quote/tab.  Returns (Params, a_latt(3,3), wf_centers or None)."""
+    raw = {}
+    section = ""
+    with open(path, "r") as fh:
+        for line in fh:
+            for c in "#;":
+                if c in line:
+                    line = line[: line.index(c)]
+            line = line.strip()
+            if not line:
+                continue
+            if line.startswith("["):
+                section = line[1: line.index("]")].strip()
+                continue
+            if "=" not in line:
+                continue
+            key, val = line.split("=", 1)
+            toks = val.replace(",", " ").replace("'", " ").replace('"', " ").replace("\t", " ").split()
+            raw[f"{section}%{key.strip()}"] = toks
+
+    def get(key, conv, default=None, n=None):
+        if key not in raw:
+            if default is None:
+                raise KeyError(f"input.cfg: missing {key}")
+            return default
+        vals = [conv(t) for t in raw[key]]
+        if n is None:
+            return vals[0]
+        if len(vals) < n:
+            raise ValueError(f"input.cfg: {key} needs {n} values")
+        return vals[:n]
+
+    a1 = get("unitCell%a1", float, n=3)
+    a2 = get("unitCell%a2", float, n=3)
+    a3 = get("unitCell%a3", float, n=3)
+    a0 = get("unitCell%a0", float, 1.0)
+    a_latt = a0 * np.array([a1, a2, a3], dtype=np.float64)           # rows = a_i  (input_paras.f90:165-168)
+    N_wf = get("wannBase%N_wf", int, 0)
+    wf_centers = None
+    if N_wf > 0:                                                      # input_paras.f90:127-132
+        wf_centers = np.array([get("wannBase%wf_centers_x", float, n=N_wf),
+                               get("wannBase%wf_centers_y", float, n=N_wf),
+                               get("wannBase%wf_centers_z", float, n=N_wf)], dtype=np.float64)
+    p = Params(
+        mp_grid=tuple(get("wannInterp%mp_grid", int, n=3)),
+        do_gauge_trafo=get("wannInterp%doGaugeTrafo", _cfg_logical, True),
+        use_cart_velo=get("wannInterp%use_cart_velo", _cfg_logical, False),
+        do_mep=get("jobs%do_mep", _cfg_logical, False),
+        do_kubo=get("jobs%do_kubo", _cfg_logical, False),
+        do_ahc=get("jobs%do_ahc", _cfg_logical, False),
+        do_opt=get("jobs%do_opt", _cfg_logical, False),
+        do_write_mep_bands=get("MEP%do_write_mep_bands", _cfg_logical, False),
+        valence_bands=get("MEP%valence_bands", int, 1),
+        n_hw=max(1, get("Laser%N_hw", int, 1)),                      # input_paras.f90:174
+        n_eF=get("Fermi%N_eF", int, 1),
+        hw_min=get("Laser%hw_min", float, 0.0) / AU_TO_EV,           # :171-172
+        hw_max=get("Laser%hw_max", float, 0.0) / AU_TO_EV,
+        eF_min=get("Fermi%eF_min", float, 0.0) / AU_TO_EV,           # :176-178
+        eF_max=get("Fermi%eF_max", float, 0.0) / AU_TO_EV,
+        T_kelvin=get("Fermi%Tkelvin", float, 0.0),
+        eta=get("Fermi%eta_smearing", float, 0.0) / AU_TO_EV,
+        kubo_tol=get("Fermi%kuboTol", float, 1e-5),
+        seed_name=get("wannBase%seed_name", str, "wf1"),
+        plot_bands=get("jobs%plot_bands", _cfg_logical, False),
+        R_vect_float=get("jobs%R_vect_float", _cfg_logical, False),
+    )
+    return p, a_latt, wf_centers
+
+
+def load_model(run_dir: str):
+    """input.cfg + w90files/<seed>_hr.dat -> (Model, Params)   (main.f90:24-45, core.f90:144)."""
+    p, a_latt, wfc = parse_input_cfg(os.path.join(run_dir, "input.cfg"))
+    R, H = read_hr_file(os.path.join(run_dir, "w90files", p.seed_name + "_hr.dat"), p.R_vect_float)
+    nw = H.shape[0]
+    if wfc is not None and wfc.shape[1] != nw:
+        raise ValueError("N_wf does not match num_wann of the _hr file")
+    return Model(nw=nw, nR=R.shape[1], R=R, H=H, a_latt=a_latt, wf_centers=wfc), p
+
+
+# --------------------------------------------------------------------------- k-space
+def set_recip_latt(a_latt: np.ndarray):
+    """k_space.f90:263-293: treats COLUMNS of a_latt as a_i (Q7); returns (recip_latt with b_i in columns, unit_vol)."""
+    a1, a2, a3 = a_latt[:, 0], a_latt[:, 1], a_latt[:, 2]
+    unit_vol = float(np.dot(np.cross(a1, a2), a3))
+    b1 = 2.0 * PI_DP * np.cross(a2, a3) / unit_vol
+    b2 = 2.0 * PI_DP * np.cross(a3, a1) / unit_vol
+    b3 = 2.0 * PI_DP * np.cross(a1, a2) / unit_vol
+    recip = np.stack([b1, b2, b3], axis=1)
+    return recip, unit_vol
+
+
+def get_rel_kpt(qix, qiy, qiz, mp_grid):
+    """k_space.f90:351-375 (1-based q).  Vectorised."""
+    n1, n2, n3 = (float(x) for x in mp_grid)
+    k1 = (2.0 * np.asarray(qix, dtype=np.float64) - n1 - 1.0) / (2.0 * n1)
+    k2 = (2.0 * np.asarray(qiy, dtype=np.float64) - n2 - 1.0) / (2.0 * n2)
+    k3 = (2.0 * np.asarray(qiz, dtype=np.float64) - n3 - 1.0) / (2.0 * n3)
+    return np.stack([k1, k2, k3], axis=-1)
+
+
+def mesh_kpts(mp_grid, lin_begin: int = 0, lin_end: Optional[int] = None) -> np.ndarray:
+    """k-points of the MP mesh in the loop order of core.f90:165-167 (kix fastest), for the 0-based
+    linear range [lin_begin, lin_end) with lin = (kix-1) + N1*((kiy-1) + N2*(kiz-1))."""
+    n1, n2, n3 = mp_grid
+    nk = n1 * n2 * n3
+    if lin_end is None:
+        lin_end = nk
+    lin = np.arange(lin_begin, lin_end, dtype=np.int64)
+    kix = lin % n1 + 1
+    kiy = (lin // n1) % n2 + 1
+    kiz = lin // (n1 * n2) + 1
+    return get_rel_kpt(kix, kiy, kiz, mp_grid)
+
+
+# --------------------------------------------------------------------------- Fourier sums
+def ft_R_to_k(model: Model, kpts: np.ndarray, use_cart_velo: bool = False):
+    """wann_interp.f90:151-281.  kpts (K,3) fractional -> H_k (K,nw,nw), H_ka (K,3,nw,nw)."""
+    K = kpts.shape[0]
+    nw, nR = model.nw, model.nR
+    two_pi = 2.0 * PI_DP
+    H_k = np.zeros((K, nw, nw), dtype=np.complex128)
+    H_ka = np.zeros((K, 3, nw, nw), dtype=np.complex128)
+    a_latt = model.a_latt
+    if model.wf_centers is not None:
+        # TB convention :200-241.  delta_at(:,n,m) = atom_frac(:,m) - atom_frac(:,n)   (:203)
+        tau = model.wf_centers
+        delta = tau[:, None, :] - tau[:, :, None]                    # (3, n, m)
+        recip, _ = set_recip_latt(a_latt)
+        kcart = kpts @ recip.T                                       # matmul(recip_latt, kpt)  k_space.f90:387
+        for sc in range(nR):
+            dR = model.R[:, sc][:, None, None] + delta               # (3,n,m)   :213
+            if use_cart_velo:
+                dR_cart = np.einsum("ij,jnm->inm", a_latt, dR)       # matmul(a_latt, dR)  :396
+                ang = np.einsum("ki,inm->knm", kcart, dR_cart)       # :217
+            else:
+                ang = two_pi * np.einsum("ki,inm->knm", kpts, dR)    # :219
+                dR_cart = two_pi * dR                                # :231
+            ph = np.cos(ang) + 1j * np.sin(ang)                      # :223
+            Hr = model.H[:, :, sc][None, :, :]
+            H_k += ph * Hr                                           # :225
+            H_ka += (ph * Hr)[:, None, :, :] * (1j * dR_cart)[None]  # :234
+    else:
+        # Wannier convention :254-279
+        for sc in range(nR):
+            ang = two_pi * (kpts @ model.R[:, sc])                   # :259
+            ph = np.cos(ang) + 1j * np.sin(ang)                      # :260
+            Hr = model.H[:, :, sc]
+            H_k += ph[:, None, None] * Hr[None]                      # :262
+            if use_cart_velo:
+                dR_cart = a_latt @ model.R[:, sc]                    # :268
+            else:
+                dR_cart = two_pi * model.R[:, sc]                    # :270
+            for a in range(3):
+                H_ka[:, a] += ph[:, None, None] * (1j * dR_cart[a]) * Hr[None]   # :274
+    return H_k, H_ka
+
+
+def get_wann_interp(model: Model, kpts: np.ndarray, do_gauge_trafo=True, use_cart_velo=False):
+    """wann_interp.f90:56-108 for an explicit list of k-points: returns e_k (K,nw), V_ka (K,3,nw,nw), U (K,nw,nw)."""
+    H_k, H_ka = ft_R_to_k(model, kpts, use_cart_velo)
+    # zheevd_wrapper('V','U'): only the upper triangle is referenced -> symmetrise from the upper triangle
+    iu = np.triu_indices(model.nw, 1)
+    Hh = H_k.copy()
+    Hh[:, iu[1], iu[0]] = np.conj(H_k[:, iu[0], iu[1]])
+    dg = np.arange(model.nw)
+    Hh[:, dg, dg] = Hh[:, dg, dg].real
+    e_k, U = np.linalg.eigh(Hh, UPLO="U")
+    if do_gauge_trafo:
+        Ud = np.conj(np.swapaxes(U, -1, -2))
+        V = np.einsum("knp,kapq,kqm->kanm", Ud, H_ka, U, optimize=True)     # rotate_gauge :517-528
+    else:
+        V = H_ka                                                            # get_velo :440
+    return e_k, V, U
+
+
+# --------------------------------------------------------------------------- occupations
+def fd_stat(e_k: np.ndarray, ef_lst: np.ndarray, T_kelvin: float) -> np.ndarray:
+    """statistics.f90:65-90.  e_k (K,nw), ef (n_eF) -> fd (K, n_eF, nw) == fd_distrib(ef_idx, n)."""
+    d = e_k[:, None, :] - ef_lst[None, :, None]
+    if T_kelvin > MIN_TEMP:
+        T_smear = KBOLTZ_EH_K * T_kelvin
+        with np.errstate(over="ignore"):
+            return 1.0 / (1.0 + np.exp(d / T_smear))
+    return (d < 0.0).astype(np.float64)
+
+
+# --------------------------------------------------------------------------- band sums (per k, batched)
+def _offdiag_mask(nw):
+    return ~np.eye(nw, dtype=bool)
+
+
+def kubo_ahc_tens(e, V, fd):
+    """kubo.f90:37-78 -> (K,3,3,n_eF).  No degeneracy guard (inf/NaN propagate)."""
+    nw = e.shape[1]
+    dE2 = (e[:, None, :] - e[:, :, None]) ** 2                        # [k,n,np] = (e_np - e_n)^2
+    W = np.imag(np.einsum("kinp,kjpn->kijnp", V, V))                  # Im[V(i,n,np) V(j,np,n)]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        T = -2.0 * W / dE2[:, None, None, :, :]
+    T = np.where(_offdiag_mask(nw)[None, None, None], T, 0.0)
+    curv = T.sum(axis=-1)                                             # (k,i,j,n)
+    return -np.einsum("kijn,ken->kije", curv, fd)
+
+
+def velo_ahc_tens(e, V, hw, fd, eta):
+    """kubo.f90:86-140 -> (K,3,3,n_hw,n_eF) complex."""
+    nw = e.shape[1]
+    z = hw + 1j * eta
+    dE2 = (e[:, :, None] - e[:, None, :]) ** 2                        # (e_n - e_np)^2
+    W = np.imag(np.einsum("kinp,kjpn->kijnp", V, V))
+    dfd = fd[:, :, :, None] - fd[:, :, None, :]                       # [k,ef,n,np] = f_n - f_np
+    mask = _offdiag_mask(nw)
+    out = np.zeros((e.shape[0], 3, 3, hw.size, fd.shape[1]), dtype=np.complex128)
+    for h in range(hw.size):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            g = 1.0 / (dE2 - z[h] ** 2)                               # (k,n,np)
+        g = np.where(mask[None], g, 0.0)
+        out[:, :, :, h, :] = np.einsum("kijnp,knp,kenp->kije", W, g, np.where(mask[None, None], dfd, 0.0))
+    return out
+
+
+def kubo_ohc_tens(e, V, hw, fd, eta):
+    """kubo.f90:145-198 -> (K,3,3,n_hw,n_eF) complex."""
+    nw = e.shape[1]
+    dE = e[:, :, None] - e[:, None, :]                                # [k,m,n] = e_m - e_n
+    P = np.einsum("kinm,kjmn->kijmn", V, V)                           # V(i,n,m) V(j,m,n) indexed [m,n]
+    df = fd[:, :, :, None] - fd[:, :, None, :]                        # [k,ef,m,n] = f_m - f_n
+    mask = _offdiag_mask(nw)
+    df = np.where(mask[None, None], df, 0.0)
+    out = np.zeros((e.shape[0], 3, 3, hw.size, fd.shape[1]), dtype=np.complex128)
+    for h in range(hw.size):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            g = 1.0 / (dE * (dE - hw[h] - 1j * eta))
+        g = np.where(mask[None], g, 0.0)
+        out[:, :, :, h, :] = 1j * np.einsum("kijmn,kmn,kemn->kije", P, g, df)
+    return out
+
+
+def photo_2nd_cond(e, V, hw, fd, eta):
+    """photo.f90:16-86 -> (K,3,3,3,n_hw,n_eF) complex.  m==n included, l==n skipped."""
+    K, nw = e.shape
+    i_eta = 1j * eta
+    dE_nm = (e[:, :, None] - e[:, None, :]) - i_eta                   # [k,n,m]
+    dE_nl = (e[:, :, None] - e[:, None, :]) - i_eta                   # [k,n,l]
+    df_ln = fd[:, :, None, :] - fd[:, :, :, None]                     # [k,ef,n,l] = f_l - f_n
+    mask_nl = _offdiag_mask(nw)
+    df_ln = np.where(mask_nl[None, None], df_ln, 0.0)
+    # vvv(a,b,c; n,l,m) = V(a,n,l) V(b,l,m) V(c,m,n)
+    out = np.zeros((K, 3, 3, 3, hw.size, fd.shape[1]), dtype=np.complex128)
+    for h in range(hw.size):
+        s = np.zeros((K, nw, nw, nw), dtype=np.complex128)            # [k,n,l,m]
+        for om in (-1.0, 1.0):
+            dE_nl_hw = dE_nl + om * hw[h] - i_eta                     # [k,n,l]
+            s += 1.0 / (dE_nm[:, :, None, :] * dE_nl_hw[:, :, :, None])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            s = s / hw[h] ** 2
+        # weight by df_ln (per eF) and contract
+        for ef in range(fd.shape[1]):
+            w = s * df_ln[:, ef, :, :, None]                          # [k,n,l,m]
+            out[:, :, :, :, h, ef] = np.einsum("kanl,kblm,kcmn,knlm->kabc", V, V, V, w, optimize=True)
+    return out
+
+
+def _mep_lc_terms(e, V):
+    """Common kernel of mep_niu_LC (mep_niu.f90:69-95) and kubo_mep_LC (kubo_mep.f90:67-94):
+    returns num[k,i,j,n0,n] = sum_kl eps_jkl Re[V(i,n0,n) V(k,n,n0) V(l,n0,n0)] and den[k,n0,n] = (e_n0-e_n)^3."""
+    lc = levi_civita()
+    nw = e.shape[1]
+    Vd = np.einsum("klnn->kln", V)                                    # V(l,n0,n0)
+    t = np.einsum("kion,kbno,kco->kibcon", V, V, Vd, optimize=True)   # V(i,n0,n) V(b,n,n0) V(c,n0,n0) [o=n0]
+    num = np.einsum("jbc,kibcon->kijon", lc, t.real, optimize=True)
+    den = (e[:, :, None] - e[:, None, :]) ** 3
+    return num, den
+
+
+def _mep_ic_terms(e, V):
+    """Common kernel of mep_niu_IC (mep_niu.f90:125-155) and kubo_mep_IC (kubo_mep.f90:119-146):
+    num[k,i,j,n0,n,m] = - sum_kl eps_jkl Re[V(i,n0,n) V(k,n,m) V(l,m,n0)],
+    den[k,n0,n,m] = (e_n0-e_n)^2 (e_n0-e_m)."""
+    lc = levi_civita()
+    t = np.einsum("kion,kbnm,kcmo->kibconm", V, V, V, optimize=True)
+    num = -np.einsum("jbc,kibconm->kijonm", lc, t.real, optimize=True)
+    d = e[:, :, None] - e[:, None, :]                                 # [k,n0,x] = e_n0 - e_x
+    den = (d ** 2)[:, :, :, None] * d[:, :, None, :]
+    return num, den
+
+
+def mep_niu_LC(e, V, valence_bands, kubo_tol):
+    """mep_niu.f90:47-99 -> (K,3,3,nval).  Terms with |den| <= kubo_tol skipped."""
+    nw = e.shape[1]
+    num, den = _mep_lc_terms(e, V)
+    ok = (np.abs(den) > kubo_tol) & _offdiag_mask(nw)[None]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        T = np.where(ok[:, None, None], num / den[:, None, None], 0.0)
+    return T.sum(axis=-1)[:, :, :, :valence_bands]
+
+
+def mep_niu_IC(e, V, valence_bands, kubo_tol):
+    """mep_niu.f90:102-159 -> (K,3,3,nval)."""
+    nw = e.shape[1]
+    num, den = _mep_ic_terms(e, V)
+    off = _offdiag_mask(nw)
+    ok = (np.abs(den) > kubo_tol) & off[None, :, :, None] & off[None, :, None, :]   # n/=n0 and m/=n0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        T = np.where(ok[:, None, None], num / den[:, None, None], 0.0)
+    return T.sum(axis=(-1, -2))[:, :, :, :valence_bands]
+
+
+def kubo_mep_LC(e, V, fd):
+    """kubo_mep.f90:51-97 -> (K,3,3,n_eF).  All n0, Fermi weight f_n0, no tolerance guard."""
+    nw = e.shape[1]
+    num, den = _mep_lc_terms(e, V)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        T = num / den[:, None, None]
+    T = np.where(_offdiag_mask(nw)[None, None, None], T, 0.0).sum(axis=-1)   # (k,i,j,n0)
+    return np.einsum("kijo,keo->kije", T, fd)
+
+
+def kubo_mep_IC(e, V, fd):
+    """kubo_mep.f90:100-149 -> (K,3,3,n_eF)."""
+    nw = e.shape[1]
+    num, den = _mep_ic_terms(e, V)
+    off = _offdiag_mask(nw)
+    ok = off[None, :, :, None] & off[None, :, None, :]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        T = num / den[:, None, None]
+    T = np.where(ok[:, None, None], T, 0.0).sum(axis=(-1, -2))
+    return np.einsum("kijo,keo->kije", T, fd)
+
+
+# --------------------------------------------------------------------------- core_worker
+@dataclass
+class Partials:
+    """Un-normalised k-sums (the *_loc arrays of core.f90:88-115) — what MPI_REDUCE would sum."""
+    n_k: int = 0
+    Ne: np.ndarray = None
+    arrays: dict = field(default_factory=dict)
+
+    def add(self, other: "Partials"):
+        self.n_k += other.n_k
+        self.Ne = other.Ne.copy() if self.Ne is None else self.Ne + other.Ne
+        for key, val in other.arrays.items():
+            self.arrays[key] = val.copy() if key not in self.arrays else self.arrays[key] + val
+        return self
+
+
+def accumulate(model: Model, p: Params, lin_begin: int, lin_end: int, batch: int = 2048) -> Partials:
+    """The k-loop body of core.f90:165-270 over the 0-based linear mesh range [lin_begin, lin_end)."""
+    ef_lst = get_linspace(p.eF_min, p.eF_max, p.n_eF)                # core.f90:124
+    hw_lst = get_linspace(p.hw_min, p.hw_max, p.n_hw)                # :125
+    part = Partials(n_k=0, Ne=np.zeros(p.n_eF))
+    acc = part.arrays
+
+    def add(name, val):
+        s = val.sum(axis=0)
+        acc[name] = s if name not in acc else acc[name] + s
+
+    for b0 in range(lin_begin, lin_end, batch):
+        b1 = min(lin_end, b0 + batch)
+        kpts = mesh_kpts(p.mp_grid, b0, b1)
+        e, V, _ = get_wann_interp(model, kpts, p.do_gauge_trafo, p.use_cart_velo)
+        fd = fd_stat(e, ef_lst, p.T_kelvin)                          # (K, n_eF, nw)
+        part.Ne += fd.sum(axis=(0, 2))                               # core.f90:187
+        part.n_k += (b1 - b0)
+        if p.do_mep:                                                 # :198-202
+            add("mep_bands_ic", mep_niu_IC(e, V, p.valence_bands, p.kubo_tol))
+            add("mep_bands_lc", mep_niu_LC(e, V, p.valence_bands, p.kubo_tol))
+        if p.do_kubo:                                                # :207-216
+            add("kubo_mep_ic", kubo_mep_IC(e, V, fd))
+            add("kubo_mep_lc", kubo_mep_LC(e, V, fd))
+        if p.do_ahc:                                                 # :221-230
+            add("kubo_ahc", kubo_ahc_tens(e, V, fd))
+            add("velo_ahc", velo_ahc_tens(e, V, hw_lst, fd, p.eta))
+            add("kubo_ohc", kubo_ohc_tens(e, V, hw_lst, fd, p.eta))
+        if p.do_opt:                                                 # :235-242 (kubo_opt_tens == 0 without A_ka)
+            add("photo2", photo_2nd_cond(e, V, hw_lst, fd, p.eta))
+    return part
+
+
+def fermi_selector(n_ki_glob: int, Ne_sum: np.ndarray, valence_bands: int) -> int:
+    """core.f90:317-415: 0-based index of the first minimum of |Ne/N_k - nval| (strict '<', :383)."""
+    Ne = Ne_sum / float(n_ki_glob)
+    opt_idx = 0
+    opt_err = abs(Ne[0] - float(valence_bands))
+    for i in range(Ne.size):
+        err = abs(Ne[i] - float(valence_bands))
+        if err < opt_err:
+            opt_idx, opt_err = i, err
+    return opt_idx
+
+
+def finalize(model: Model, p: Params, part: Partials) -> dict:
+    """core.f90:276-292, 419-561; k_space.f90:81-202.  Returns the tensors the reference writes to out/*.npy
+    (Fortran index order, e.g. ahc_velo[i,j,hw])."""
+    _, unit_vol = set_recip_latt(model.a_latt)
+    n_k_mesh = p.mp_grid[0] * p.mp_grid[1] * p.mp_grid[2]
+    norm = abs(unit_vol * float(n_k_mesh))                            # normalize_k_int
+    eF_idx = fermi_selector(part.n_k, part.Ne, p.valence_bands)
+    a = part.arrays
+    out = {"n_k": part.n_k, "eF_idx": eF_idx, "Ne": part.Ne / float(part.n_k),
+           "hw_lst": get_linspace(p.hw_min, p.hw_max, p.n_hw), "ef_lst": get_linspace(p.eF_min, p.eF_max, p.n_eF)}
+    if p.do_mep:                                                      # mep_sum_bands core.f90:570-603
+        ic, lc = a["mep_bands_ic"], a["mep_bands_lc"]                 # (3,3,nval)
+        out["mep_ic"] = ic.sum(axis=-1) / norm
+        out["mep_lc"] = lc.sum(axis=-1) / norm
+        out["mep_cs"] = np.zeros((3, 3))
+        out["mep_tens"] = out["mep_ic"] + out["mep_lc"] + out["mep_cs"]     # file_io.f90 write_mep_tensors
+        if p.do_write_mep_bands:
+            out["mep_bands"] = (ic + lc) / norm
+    if p.do_kubo:
+        out["kubo_mep_ic"] = a["kubo_mep_ic"][:, :, eF_idx] / norm
+        out["kubo_mep_lc"] = a["kubo_mep_lc"][:, :, eF_idx] / norm
+        out["kubo_mep_cs"] = np.zeros((3, 3))
+        out["kubo_mep_tens"] = out["kubo_mep_ic"] + out["kubo_mep_lc"] + out["kubo_mep_cs"]
+    if p.do_ahc:
+        out["ahc_tens"] = a["kubo_ahc"][:, :, eF_idx] / norm
+        out["ahcVELO"] = a["velo_ahc"][:, :, :, eF_idx] / norm
+        out["ohcVELO"] = a["kubo_ohc"][:, :, :, eF_idx] / norm
+    if p.do_opt:
+        out["opt_Ssymm"] = np.zeros((3, 3, p.n_hw), dtype=np.complex128)
+        out["opt_Asymm"] = np.zeros((3, 3, p.n_hw), dtype=np.complex128)
+        out["photoC_2nd"] = a["photo2"] / norm                        # not sliced at eF_idx (core.f90:515)
+    return out
+
+
+def core_worker(model: Model, p: Params, n_shards: int = 1, batch: int = 2048) -> dict:
+    """Whole-mesh run.  n_shards>1 splits the linear k range into contiguous slabs and sums the partials,
+    which is what the MPI ranks + MPI_REDUCE of the reference amount to (mpi_comm.f90:80-99, core.f90:467-526)."""
+    nk = p.mp_grid[0] * p.mp_grid[1] * p.mp_grid[2]
+    total = Partials(n_k=0, Ne=None)
+    per = -(-nk // n_shards)
+    for s in range(n_shards):
+        b0, b1 = s * per, min(nk, (s + 1) * per)
+        if b1 > b0:
+            total.add(accumulate(model, p, b0, b1, batch))
+    return finalize(model, p, total)
