@@ -1,0 +1,119 @@
+/*
+ * mepb.h — C ABI of the B200-native per-k-point Wannier-interpolation path (libmepb.so).
+ *
+ * The reference (cMax347/MEPinterp, Fortran 2003 + MPI) has no plugin / FFI layer; the seam this library
+ * replaces is the Fortran call site in core_worker:
+ *      src/core.f90:165-270   the k-loop body: get_wann_interp (src/wann_interp.f90:56-108) followed by the
+ *                             per-k response functions (src/kubo.f90, kubo_mep.f90, mep_niu.f90, photo.f90)
+ *                             whose results are += accumulated
+ *      src/core.f90:276-292   fermi_selector + integrate_over_k_space (reduce, normalise)
+ *      src/band_calc.f90:67-75 get_wann_interp on an explicit k list (band mode)
+ * A Fortran host binds these entry points with an `interface ... bind(C)` block (INTEGRATION.md shows it);
+ * everything is plain pointers and sizes: column-major, caller-owned, FP64, complex = interleaved (re,im), so
+ * Fortran arrays H_tb(n,m,R), R_vect(3,R), wf_centers(3,n), a_latt(3,3) pass unchanged.
+ *
+ * No CPU fallback exists: every compute entry point runs hand-written sm_100a kernels and returns
+ * MEPB_ERR_CUDA when no usable device is present.
+ */
+#ifndef MEPB_H
+#define MEPB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MEPB_OK                 0
+#define MEPB_ERR_ARG          (-1)   /* NULL / out-of-range argument                                         */
+#define MEPB_ERR_CUDA         (-2)   /* no device, or a CUDA call failed (mepb_last_error has the text)      */
+#define MEPB_ERR_NOT_HERMITIAN (-3)  /* H(R) set is not closed under R -> -R with H(-R) = H(R)^dagger        */
+#define MEPB_ERR_UNSUPPORTED  (-4)   /* position-operator branch (r != NULL), or nw/nR outside kernel limits */
+#define MEPB_ERR_EIG          (-5)   /* eigensolver did not converge for some k (reference: zheevd info/=0 -> stop,
+                                        src/matrix_math.f90:224)                                              */
+#define MEPB_ERR_STATE        (-6)   /* call order (finalize before accumulate, ...)                         */
+
+/* == what read_tb_basis (src/file_io.f90:800) + init_parameters (src/input_paras.f90:79) hand to core_worker */
+typedef struct {
+    int32_t nw;               /* num_wann                                                                     */
+    int32_t nR;               /* number of R points                                                           */
+    const double *R;          /* (3,nR)   R_vect as stored: fractional                       file_io.f90:724   */
+    const double *H;          /* (nw,nw,nR) complex, Hartree                                 file_io.f90:732-741 */
+    const double *r;          /* (3,nw,nw,nR) complex position operator or NULL; non-NULL -> MEPB_ERR_UNSUPPORTED */
+    const double *wf_centers; /* (3,nw) fractional or NULL: NULL selects the Wannier FT convention, non-NULL the
+                                 tight-binding convention                                    wann_interp.f90:192 */
+    double a_latt[9];         /* Fortran a_latt(3,3) column-major; a_latt(i,:) = a_i*a0      input_paras.f90:165-168 */
+} mepb_model;
+
+/* == the module globals of src/input_paras.f90:49-68 that the hot path reads (already in atomic units) */
+typedef struct {
+    int32_t mp_grid[3];
+    int32_t do_gauge_trafo, use_cart_velo;
+    int32_t do_mep, do_kubo, do_ahc, do_opt, do_write_mep_bands;
+    int32_t valence_bands, n_hw, n_eF;
+    double  hw_min, hw_max, eF_min, eF_max;     /* Hartree  (driver converts from eV, input_paras.f90:171-178) */
+    double  T_kelvin, eta /* Hartree */, kubo_tol;
+} mepb_params;
+
+/* Outputs of integrate_over_k_space (src/core.f90:419-561), laid out as the arrays save_npy writes
+ * (src/file_io.f90:266-398): column-major, first index fastest.  Any pointer may be NULL (skipped). */
+typedef struct {
+    int64_t n_k;              /* k-points summed                                                              */
+    int32_t eF_idx;           /* 0-based index chosen by fermi_selector                       core.f90:317-415 */
+    int64_t n_degenerate;     /* (k, n, m) band pairs with |E_n - E_m| == 0 met by an unguarded formula (Q6)   */
+    double *Ne;               /* (n_eF)      electrons per k-point for each trial E_F          core.f90:329     */
+    double *mep_ic, *mep_lc, *mep_cs;          /* (3,3)                                                         */
+    double *mep_bands;                         /* (3,3,valence_bands)  only if do_write_mep_bands               */
+    double *kubo_mep_ic, *kubo_mep_lc, *kubo_mep_cs;   /* (3,3)                                                 */
+    double *ahc;                               /* (3,3)                       ahc_tens.npy                      */
+    double *ahc_velo, *ohc_velo;               /* (3,3,n_hw) complex          ahcVELO.npy, ohcVELO.npy          */
+    double *opt_s, *opt_a;                     /* (3,3,n_hw) complex          zeros without position operator   */
+    double *photo2;                            /* (3,3,3,n_hw,n_eF) complex   photoC_2nd.npy                    */
+} mepb_result;
+
+typedef struct mepb_ctx mepb_ctx;
+
+/* Upload the model, precompute the Fourier right-hand side, allocate accumulators on CUDA device `device`.
+ * Replaces: read_tb_basis hand-over + kspace_allocator + allo_core_loc_arrays (core.f90:127-153). */
+int mepb_create(const mepb_model *model, const mepb_params *params, int device, mepb_ctx **out);
+void mepb_destroy(mepb_ctx *ctx);
+
+/* Whole Monkhorst-Pack mesh on this context's device: accumulate + finalize.  Replaces core_worker's k-loop
+ * and integrate_over_k_space for a 1-rank run (core.f90:165-292). */
+int mepb_run_mesh(mepb_ctx *ctx, mepb_result *out);
+
+/* The MPI-host / multi-GPU variant: each rank accumulates a contiguous slab [lin_begin, lin_end) of the 0-based
+ * linear mesh index lin = (kix-1) + N1*((kiy-1) + N2*(kiz-1)) (loop order of core.f90:165-167), exports its
+ * un-normalised partial sums as one packed FP64 buffer, the host sums the buffers across ranks (MPI_Allreduce /
+ * ncclAllReduce — the reference's mpi_reduce_sum calls, core.f90:467-526, fused into one), imports the sum, and
+ * finalizes (fermi_selector + normalize_k_int). */
+int     mepb_reset(mepb_ctx *ctx);
+int     mepb_accumulate(mepb_ctx *ctx, int64_t lin_begin, int64_t lin_end);
+int64_t mepb_partials_size(const mepb_ctx *ctx);                    /* number of doubles                        */
+int     mepb_get_partials(mepb_ctx *ctx, double *buf);              /* host buffer                              */
+int     mepb_set_partials(mepb_ctx *ctx, const double *buf);        /* host buffer                              */
+/* same, but the packed buffer lives in device memory of this context's device (for NCCL all-reduce in place) */
+int     mepb_partials_device_ptr(mepb_ctx *ctx, double **dptr);
+int     mepb_finalize(mepb_ctx *ctx, mepb_result *out);
+
+/* Batched get_wann_interp (wann_interp.f90:56-108) on an explicit list of fractional k-points: band mode
+ * (band_calc.f90:67-75) and the parity harness.  kpt (3,nk); e_k (nw,nk); V_ka (3,nw,nw,nk) complex or NULL.
+ * V_ka is gauge dependent (eigenvector phases); compare only gauge-invariant combinations. */
+int mepb_interp(mepb_ctx *ctx, int64_t nk, const double *kpt, double *e_k, double *V_ka);
+
+/* Fourier sums only (FT_R_to_k, wann_interp.f90:151-281): H_k (nw,nw,nk), H_ka (3,nw,nw,nk) complex, W gauge.
+ * Gauge independent, so it is compared element-wise against the oracle. */
+int mepb_fourier(mepb_ctx *ctx, int64_t nk, const double *kpt, double *H_k, double *H_ka);
+
+/* timing of the last mepb_accumulate / mepb_run_mesh on the device (CUDA events), and kernel launches issued */
+double  mepb_last_kernel_ms(const mepb_ctx *ctx);
+int64_t mepb_kernel_launches(const mepb_ctx *ctx);
+
+const char *mepb_strerror(int code);
+const char *mepb_last_error(void);
+const char *mepb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEPB_H */
