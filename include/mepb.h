@@ -27,7 +27,6 @@ extern "C" {
 #define MEPB_OK                 0
 #define MEPB_ERR_ARG          (-1)   /* NULL / out-of-range argument                                         */
 #define MEPB_ERR_CUDA         (-2)   /* no device, or a CUDA call failed (mepb_last_error has the text)      */
-#define MEPB_ERR_NOT_HERMITIAN (-3)  /* H(R) set is not closed under R -> -R with H(-R) = H(R)^dagger        */
 #define MEPB_ERR_UNSUPPORTED  (-4)   /* position-operator branch (r != NULL), or nw/nR outside kernel limits */
 #define MEPB_ERR_EIG          (-5)   /* eigensolver did not converge for some k (reference: zheevd info/=0 -> stop,
                                         src/matrix_math.f90:224)                                              */

@@ -1,0 +1,249 @@
+"""ctypes binding of libmepb.so — the C ABI declared in include/mepb.h.
+
+This is plumbing only: it marshals numpy arrays into the plain-pointer structs of the ABI.  All compute happens in
+the hand-written sm_100a kernels behind `mepb_*`; if the shared library is missing or no GPU is present the calls
+fail loudly (there is no CPU path in the product).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from types import SimpleNamespace
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmepb.so")
+_LIB = None
+
+OK = 0
+ERR_ARG, ERR_CUDA, ERR_NOT_HERMITIAN, ERR_UNSUPPORTED, ERR_EIG, ERR_STATE = -1, -2, -3, -4, -5, -6
+
+EXPORTS = ["mepb_create", "mepb_destroy", "mepb_run_mesh", "mepb_reset", "mepb_accumulate", "mepb_partials_size",
+           "mepb_get_partials", "mepb_set_partials", "mepb_partials_device_ptr", "mepb_finalize", "mepb_interp",
+           "mepb_fourier", "mepb_last_kernel_ms", "mepb_kernel_launches", "mepb_strerror", "mepb_last_error", "mepb_version"]
+
+
+class MepbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libmepb error {code}: {msg}")
+        self.code = code
+
+
+class CModel(C.Structure):
+    _fields_ = [("nw", C.c_int32), ("nR", C.c_int32), ("R", C.c_void_p), ("H", C.c_void_p), ("r", C.c_void_p),
+                ("wf_centers", C.c_void_p), ("a_latt", C.c_double * 9)]
+
+
+class CParams(C.Structure):
+    _fields_ = [("mp_grid", C.c_int32 * 3), ("do_gauge_trafo", C.c_int32), ("use_cart_velo", C.c_int32),
+                ("do_mep", C.c_int32), ("do_kubo", C.c_int32), ("do_ahc", C.c_int32), ("do_opt", C.c_int32),
+                ("do_write_mep_bands", C.c_int32), ("valence_bands", C.c_int32), ("n_hw", C.c_int32), ("n_eF", C.c_int32),
+                ("hw_min", C.c_double), ("hw_max", C.c_double), ("eF_min", C.c_double), ("eF_max", C.c_double),
+                ("T_kelvin", C.c_double), ("eta", C.c_double), ("kubo_tol", C.c_double)]
+
+
+class CResult(C.Structure):
+    _fields_ = [("n_k", C.c_int64), ("eF_idx", C.c_int32), ("n_degenerate", C.c_int64), ("Ne", C.c_void_p),
+                ("mep_ic", C.c_void_p), ("mep_lc", C.c_void_p), ("mep_cs", C.c_void_p), ("mep_bands", C.c_void_p),
+                ("kubo_mep_ic", C.c_void_p), ("kubo_mep_lc", C.c_void_p), ("kubo_mep_cs", C.c_void_p),
+                ("ahc", C.c_void_p), ("ahc_velo", C.c_void_p), ("ohc_velo", C.c_void_p),
+                ("opt_s", C.c_void_p), ("opt_a", C.c_void_p), ("photo2", C.c_void_p)]
+
+
+def lib():
+    """Load libmepb.so (built in-tree by mepinterp_b200/build.py).  Raises if it is missing — no fallback."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise MepbError(ERR_CUDA, f"{LIB_PATH} not built; run `python -m mepinterp_b200.build` (needs nvcc)")
+        L = C.CDLL(LIB_PATH)
+        vp = C.c_void_p
+        L.mepb_create.argtypes = [C.POINTER(CModel), C.POINTER(CParams), C.c_int, C.POINTER(vp)]
+        L.mepb_destroy.argtypes = [vp]
+        L.mepb_destroy.restype = None
+        L.mepb_run_mesh.argtypes = [vp, C.POINTER(CResult)]
+        L.mepb_reset.argtypes = [vp]
+        L.mepb_accumulate.argtypes = [vp, C.c_int64, C.c_int64]
+        L.mepb_partials_size.argtypes = [vp]
+        L.mepb_partials_size.restype = C.c_int64
+        L.mepb_get_partials.argtypes = [vp, vp]
+        L.mepb_set_partials.argtypes = [vp, vp]
+        L.mepb_partials_device_ptr.argtypes = [vp, C.POINTER(vp)]
+        L.mepb_finalize.argtypes = [vp, C.POINTER(CResult)]
+        L.mepb_interp.argtypes = [vp, C.c_int64, vp, vp, vp]
+        L.mepb_fourier.argtypes = [vp, C.c_int64, vp, vp, vp]
+        L.mepb_last_kernel_ms.argtypes = [vp]
+        L.mepb_last_kernel_ms.restype = C.c_double
+        L.mepb_kernel_launches.argtypes = [vp]
+        L.mepb_kernel_launches.restype = C.c_int64
+        L.mepb_strerror.argtypes = [C.c_int]
+        L.mepb_strerror.restype = C.c_char_p
+        L.mepb_last_error.restype = C.c_char_p
+        L.mepb_version.restype = C.c_char_p
+        _LIB = L
+    return _LIB
+
+
+def _check(rc):
+    if rc != OK:
+        L = lib()
+        raise MepbError(rc, f"{L.mepb_strerror(rc).decode()} — {L.mepb_last_error().decode()}")
+
+
+def _f(a, dtype):
+    return np.asfortranarray(np.asarray(a, dtype=dtype))
+
+
+def make_params(**kw) -> SimpleNamespace:
+    """Parameter bundle with the reference's names (src/input_paras.f90:49-68), energies already in Hartree."""
+    d = dict(mp_grid=(4, 4, 4), do_gauge_trafo=True, use_cart_velo=False, do_mep=False, do_kubo=False, do_ahc=False,
+             do_opt=False, do_write_mep_bands=True, valence_bands=1, n_hw=1, n_eF=1, hw_min=0.0, hw_max=0.0,
+             eF_min=0.0, eF_max=0.0, T_kelvin=0.0, eta=0.0, kubo_tol=1e-5)
+    d.update(kw)
+    return SimpleNamespace(**d)
+
+
+def make_model(R, H, a_latt, wf_centers=None) -> SimpleNamespace:
+    """R (3,nR) fractional; H (nw,nw,nR) complex Hartree; a_latt (3,3) rows = a_i; wf_centers (3,nw) or None."""
+    H = np.asarray(H)
+    return SimpleNamespace(nw=H.shape[0], nR=H.shape[2], R=np.asarray(R, dtype=np.float64), H=H,
+                           a_latt=np.asarray(a_latt, dtype=np.float64), wf_centers=wf_centers)
+
+
+class Context:
+    """One mepb_ctx: a model + parameter set resident on one B200."""
+
+    def __init__(self, model, params, device: int = 0):
+        self.nw, self.nR = int(model.nw), int(model.nR)
+        self._R = _f(model.R, np.float64)
+        self._H = _f(model.H, np.complex128)
+        self._wfc = None if model.wf_centers is None else _f(model.wf_centers, np.float64)
+        m = CModel()
+        m.nw, m.nR = self.nw, self.nR
+        m.R, m.H, m.r = self._R.ctypes.data, self._H.ctypes.data, None
+        m.wf_centers = None if self._wfc is None else self._wfc.ctypes.data
+        al = np.asarray(model.a_latt, dtype=np.float64)
+        for j in range(3):
+            for i in range(3):
+                m.a_latt[i + 3 * j] = al[i, j]
+        p = CParams()
+        for i in range(3):
+            p.mp_grid[i] = int(params.mp_grid[i])
+        for k in ("do_gauge_trafo", "use_cart_velo", "do_mep", "do_kubo", "do_ahc", "do_opt", "do_write_mep_bands"):
+            setattr(p, k, int(bool(getattr(params, k))))
+        p.valence_bands, p.n_hw, p.n_eF = int(params.valence_bands), int(params.n_hw), int(params.n_eF)
+        for k in ("hw_min", "hw_max", "eF_min", "eF_max", "T_kelvin", "eta", "kubo_tol"):
+            setattr(p, k, float(getattr(params, k)))
+        self.cm, self.cp, self.params = m, p, params
+        self._h = C.c_void_p()
+        _check(lib().mepb_create(C.byref(m), C.byref(p), int(device), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().mepb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- mesh runs
+    @property
+    def n_kpts(self) -> int:
+        g = self.params.mp_grid
+        return int(g[0]) * int(g[1]) * int(g[2])
+
+    def reset(self):
+        _check(lib().mepb_reset(self._h))
+
+    def accumulate(self, lin_begin: int, lin_end: int):
+        _check(lib().mepb_accumulate(self._h, int(lin_begin), int(lin_end)))
+
+    def partials_size(self) -> int:
+        return int(lib().mepb_partials_size(self._h))
+
+    def get_partials(self, out=None) -> np.ndarray:
+        if out is None:
+            out = np.zeros(self.partials_size())
+        _check(lib().mepb_get_partials(self._h, out.ctypes.data))
+        return out
+
+    def set_partials(self, buf: np.ndarray):
+        buf = np.ascontiguousarray(buf, dtype=np.float64)
+        assert buf.size == self.partials_size()
+        _check(lib().mepb_set_partials(self._h, buf.ctypes.data))
+
+    def partials_device_ptr(self) -> int:
+        p = C.c_void_p()
+        _check(lib().mepb_partials_device_ptr(self._h, C.byref(p)))
+        return int(p.value)
+
+    def _result(self, call) -> dict:
+        P = self.params
+        n_hw, n_eF, nval = int(P.n_hw), int(P.n_eF), int(P.valence_bands)
+        bufs = {"Ne": np.zeros(n_eF)}
+        if P.do_mep:
+            for k in ("mep_ic", "mep_lc", "mep_cs"):
+                bufs[k] = np.zeros((3, 3), order="F")
+            if P.do_write_mep_bands:
+                bufs["mep_bands"] = np.zeros((3, 3, nval), order="F")
+        if P.do_kubo:
+            for k in ("kubo_mep_ic", "kubo_mep_lc", "kubo_mep_cs"):
+                bufs[k] = np.zeros((3, 3), order="F")
+        if P.do_ahc:
+            bufs["ahc"] = np.zeros((3, 3), order="F")
+            bufs["ahc_velo"] = np.zeros((3, 3, n_hw), dtype=np.complex128, order="F")
+            bufs["ohc_velo"] = np.zeros((3, 3, n_hw), dtype=np.complex128, order="F")
+        if P.do_opt:
+            bufs["opt_s"] = np.zeros((3, 3, n_hw), dtype=np.complex128, order="F")
+            bufs["opt_a"] = np.zeros((3, 3, n_hw), dtype=np.complex128, order="F")
+            bufs["photo2"] = np.zeros((3, 3, 3, n_hw, n_eF), dtype=np.complex128, order="F")
+        res = CResult()
+        for k, v in bufs.items():
+            setattr(res, k, v.ctypes.data)
+        _check(call(res))
+        out = {"n_k": int(res.n_k), "eF_idx": int(res.eF_idx), "n_degenerate": int(res.n_degenerate), "Ne": bufs["Ne"]}
+        names = {"ahc": "ahc_tens", "ahc_velo": "ahcVELO", "ohc_velo": "ohcVELO", "opt_s": "opt_Ssymm",
+                 "opt_a": "opt_Asymm", "photo2": "photoC_2nd"}     # file names of file_io.f90:266-398
+        for k, v in bufs.items():
+            if k != "Ne":
+                out[names.get(k, k)] = v
+        if P.do_mep:
+            out["mep_tens"] = out["mep_ic"] + out["mep_lc"] + out["mep_cs"]
+        if P.do_kubo:
+            out["kubo_mep_tens"] = out["kubo_mep_ic"] + out["kubo_mep_lc"] + out["kubo_mep_cs"]
+        return out
+
+    def finalize(self) -> dict:
+        return self._result(lambda res: lib().mepb_finalize(self._h, C.byref(res)))
+
+    def run_mesh(self) -> dict:
+        return self._result(lambda res: lib().mepb_run_mesh(self._h, C.byref(res)))
+
+    # ---- explicit k lists
+    def interp(self, kpts, want_V: bool = True):
+        kp = _f(np.asarray(kpts, dtype=np.float64).T, np.float64)        # (3,nk)
+        nk, nw = kp.shape[1], self.nw
+        e = np.zeros((nw, nk), order="F")
+        V = np.zeros((3, nw, nw, nk), dtype=np.complex128, order="F") if want_V else None
+        _check(lib().mepb_interp(self._h, nk, kp.ctypes.data, e.ctypes.data, None if V is None else V.ctypes.data))
+        return e, V
+
+    def fourier(self, kpts):
+        kp = _f(np.asarray(kpts, dtype=np.float64).T, np.float64)
+        nk, nw = kp.shape[1], self.nw
+        Hk = np.zeros((nw, nw, nk), dtype=np.complex128, order="F")
+        Hka = np.zeros((3, nw, nw, nk), dtype=np.complex128, order="F")
+        _check(lib().mepb_fourier(self._h, nk, kp.ctypes.data, Hk.ctypes.data, Hka.ctypes.data))
+        return Hk, Hka
+
+    @property
+    def last_kernel_ms(self) -> float:
+        return float(lib().mepb_last_kernel_ms(self._h))
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(lib().mepb_kernel_launches(self._h))

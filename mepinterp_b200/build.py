@@ -1,0 +1,47 @@
+"""Build libmepb.so (hand-written sm_100a kernels + C ABI) in-tree with nvcc.  No torch, no JIT cache."""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+SOURCES = ["mepb_small.cu", "mepb_sweep.cu", "mepb_large.cu", "mepb_api.cu"]
+LIB = os.path.join(HERE, "libmepb.so")
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-O3"]
+
+
+def nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _stale(target: str, deps) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    hdrs = [os.path.join(CSRC, "mepb_internal.cuh"), os.path.join(HERE, "..", "include", "mepb.h")]
+    objs = []
+    srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    for s in srcs:
+        src = os.path.join(CSRC, s)
+        obj = os.path.join(CSRC, s.replace(".cu", ".o"))
+        if force or _stale(obj, [src] + hdrs):
+            cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            subprocess.check_call(cmd)
+        objs.append(obj)
+    if force or _stale(LIB, objs):
+        subprocess.check_call([nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart"])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

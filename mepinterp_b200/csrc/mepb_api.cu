@@ -1,0 +1,586 @@
+// mepb_api.cu — the C ABI of libmepb.so (include/mepb.h): context, chunked launch schedule, reduction, finalize.
+//
+// Host-side mirror of the reference's core_worker shell (src/core.f90:79-298): where the Fortran walks the mesh
+// k by k and += into *_loc arrays, this schedules the mesh in chunks of k-points over two CUDA streams
+// (interpolation kernel of chunk i+1 overlaps the frequency sweep of chunk i), keeps every accumulator on the
+// device, and only at finalize copies a few KB back.  No CPU compute path exists here.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mepb_internal.cuh"
+
+using namespace mepb;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string &msg) { g_last_error = msg; return code; }
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e_ = (expr);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(MEPB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));              \
+    } while (0)
+
+struct PackedLayout {  // identical to oracle/cpu_ref.c make_layout (documented in include/mepb.h)
+    long long total, ne, mep_ic, mep_lc, kmep_ic, kmep_lc, ahc, velo, ohc, photo;
+};
+PackedLayout make_layout(const mepb_params &p) {
+    PackedLayout L;
+    long long o = 2;
+    L.ne = o; o += p.n_eF;
+    L.mep_ic = L.mep_lc = L.kmep_ic = L.kmep_lc = L.ahc = L.velo = L.ohc = L.photo = -1;
+    if (p.do_mep) { L.mep_ic = o; o += 9LL * p.valence_bands; L.mep_lc = o; o += 9LL * p.valence_bands; }
+    if (p.do_kubo) { L.kmep_ic = o; o += 9LL * p.n_eF; L.kmep_lc = o; o += 9LL * p.n_eF; }
+    if (p.do_ahc) { L.ahc = o; o += 9LL * p.n_eF; L.velo = o; o += 18LL * p.n_hw * p.n_eF; L.ohc = o; o += 18LL * p.n_hw * p.n_eF; }
+    if (p.do_opt) { L.photo = o; o += 54LL * p.n_hw * p.n_eF; }
+    L.total = o;
+    return L;
+}
+
+// compact per-eF accumulator block on the device: [static NS | sweep n_hw*18 | photo n_hw*54]
+struct CompactShape {
+    int ns, sweep, photo, per_ef;
+};
+
+__global__ void pack_kernel(const double *__restrict__ c0, const double *__restrict__ c1, CompactShape cs, int nw, int nval,
+                            int n_hw, int n_eF, int do_mep, int do_kubo, int do_ahc, int do_opt, PackedLayout L,
+                            double *__restrict__ packed) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    auto C = [&](int ief, int i) { return c0[(size_t)ief * cs.per_ef + i] + c1[(size_t)ief * cs.per_ef + i]; };
+    if (tid == 0) { packed[0] = C(0, S_NK); packed[1] = C(0, S_NDEG); }
+    for (int i = tid; i < n_eF; i += nth) packed[L.ne + i] = C(i, S_NE);
+    if (do_mep)
+        for (int i = tid; i < 9 * nval; i += nth) {
+            packed[L.mep_ic + i] = C(0, S_NIU + i);
+            packed[L.mep_lc + i] = C(0, S_NIU + 9 * nw + i);
+        }
+    if (do_kubo)
+        for (int i = tid; i < 9 * n_eF; i += nth) {
+            const int ief = i / 9, q = i % 9;
+            packed[L.kmep_ic + i] = C(ief, S_KIC + q);
+            packed[L.kmep_lc + i] = C(ief, S_KLC + q);
+        }
+    if (do_ahc) {
+        for (int i = tid; i < 9 * n_eF; i += nth) packed[L.ahc + i] = C(i / 9, S_AHC + i % 9);
+        const long long per = 18LL * n_hw;
+        for (long long i = tid; i < per * n_eF; i += nth) {
+            const int ief = (int)(i / per);
+            const long long r = i % per;
+            const int ri = (int)(r & 1);
+            const int q = (int)((r >> 1) % 9), w = (int)((r >> 1) / 9), a = q % 3, b = q / 3;      // element (a,b)
+            const int sw = cs.ns + w * kSweepAcc;     // X1 [0..5] X2 [6..11] Y1 [12..23] Y2 [24..35]
+            // antisymmetric part  Xc = X1 + i X2   for (0,1),(0,2),(1,2)
+            double xr = 0.0, xi = 0.0, vr = 0.0, vi = 0.0;
+            if (a != b) {
+                const int lo = a < b ? a : b, hi = a < b ? b : a;
+                const int comp = (lo == 0) ? (hi - 1) : 2;
+                const double x1r = C(ief, sw + 2 * comp), x1i = C(ief, sw + 2 * comp + 1);
+                const double x2r = C(ief, sw + 6 + 2 * comp), x2i = C(ief, sw + 6 + 2 * comp + 1);
+                const double sg = a < b ? 1.0 : -1.0;
+                xr = sg * (x1r - x2i); xi = sg * (x1i + x2r);
+                vr = -sg * x2r; vi = -sg * x2i;                               // velo_ahc = - X2
+            }
+            // symmetric part  Yc = Y1 + i Y2   for (0,0),(1,1),(2,2),(0,1),(0,2),(1,2)
+            int ca;
+            if (a == b) ca = a;
+            else { const int lo = a < b ? a : b, hi = a < b ? b : a; ca = (lo == 0) ? (2 + hi) : 5; }
+            const double y1r = C(ief, sw + 12 + 2 * ca), y1i = C(ief, sw + 12 + 2 * ca + 1);
+            const double y2r = C(ief, sw + 24 + 2 * ca), y2i = C(ief, sw + 24 + 2 * ca + 1);
+            const double tr = xr + (y1r - y2i), ti = xi + (y1i + y2r);      // Xc + Yc
+            packed[L.velo + i] = ri ? vi : vr;
+            packed[L.ohc + i] = ri ? tr : -ti;                              // i (Xc + Yc)
+        }
+    }
+    if (do_opt) {
+        const long long per = 54LL * n_hw;
+        for (long long i = tid; i < per * n_eF; i += nth) {
+            const int ief = (int)(i / per);
+            const long long r = i % per;                                  // (q + 27 w)*2 + ri
+            const int ri = (int)(r & 1), q = (int)((r >> 1) % 27), w = (int)((r >> 1) / 27);
+            packed[L.photo + i] = C(ief, cs.ns + cs.sweep + w * kPhotoAcc + 2 * q + ri);
+        }
+    }
+}
+
+struct StreamBuf {
+    cudaStream_t st = nullptr;
+    cudaEvent_t done = nullptr;
+    double *items_ahc = nullptr; int *cnt_ahc = nullptr;
+    double *items_photo = nullptr; int *cnt_photo = nullptr;
+    double *block_static = nullptr, *block_sweep = nullptr, *block_photo = nullptr;
+    double *compact = nullptr;   // [n_eF][per_ef]
+};
+
+}  // namespace
+
+struct mepb_ctx {
+    int device = 0, sm_count = 0;
+    mepb_params p{};
+    int nw = 0, nR = 0;
+    bool has_tau = false;
+    bool herm = true;      // H(R) Hermitian-closed: V_a Hermitian -> compact items / 18-accumulator sweep
+    double a_latt[9];
+    // device model
+    double2 *d_H = nullptr; double *d_Rf = nullptr, *d_cR = nullptr, *d_tau = nullptr, *d_tM = nullptr, *d_hw = nullptr;
+    std::vector<double> ef_lst, hw_lst;
+    // schedule
+    long long chunk = 0;
+    int max_pairs = 0, max_photo = 0;
+    int grid_interp = 0, grid_sweep = 0, ns_sweep = 0, grid_photo = 0, ns_photo = 0;
+    CompactShape cs{};
+    PackedLayout L{};
+    StreamBuf sb[2];
+    double *d_packed = nullptr;
+    int *d_err = nullptr;
+    bool packed_from_host = false, have_data = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double last_ms = 0.0;
+    long long launches = 0;
+    // list-mode scratch
+    double *d_kpt = nullptr, *d_e = nullptr; double2 *d_V = nullptr, *d_Hk = nullptr, *d_Hka = nullptr;
+    long long list_cap = 0;
+};
+
+namespace {
+
+DevModel dev_model(const mepb_ctx *c) {
+    DevModel m;
+    m.nw = c->nw; m.nR = c->nR; m.H = c->d_H; m.Rf = c->d_Rf; m.cR = c->d_cR;
+    m.tau = c->has_tau ? c->d_tau : nullptr; m.tM = c->d_tM;
+    return m;
+}
+Jobs make_jobs(const mepb_ctx *c, int ief, bool response) {
+    Jobs j;
+    const mepb_params &p = c->p;
+    j.do_gauge = p.do_gauge_trafo;
+    j.do_mep = response && p.do_mep && ief == 0;
+    j.do_kubo = response && p.do_kubo;
+    j.do_ahc = response && p.do_ahc;
+    j.do_opt = response && p.do_opt;
+    j.nval = p.valence_bands;
+    j.herm = c->herm ? 1 : 0;
+    j.zero_T = !(p.T_kelvin > kMinTemp);
+    j.eF = c->ef_lst[ief];
+    j.inv_kT = j.zero_T ? 0.0 : 1.0 / (kBoltzEhK * p.T_kelvin);
+    j.eta = p.eta; j.kubo_tol = p.kubo_tol;
+    return j;
+}
+
+// H(-R) == H(R)^dagger for every R in the set?  (needed: the kernels use V(j,m,n) = conj V(j,n,m) when they
+// combine the (n,m) and (m,n) terms of the Kubo sums; the reference would silently diagonalise the upper triangle)
+bool hermitian_closed(const mepb_model *m, std::string *why) {
+    const int nw = m->nw, nR = m->nR;
+    double hmax = 0.0;
+    for (long long i = 0; i < 2LL * nw * nw * nR; ++i) hmax = std::max(hmax, std::fabs(m->H[i]));
+    const double tol = 1e-10 * std::max(hmax, 1e-300);
+    for (int r = 0; r < nR; ++r) {
+        int partner = -1;
+        for (int s = 0; s < nR; ++s)
+            if (std::fabs(m->R[3 * r] + m->R[3 * s]) < 1e-9 && std::fabs(m->R[3 * r + 1] + m->R[3 * s + 1]) < 1e-9 &&
+                std::fabs(m->R[3 * r + 2] + m->R[3 * s + 2]) < 1e-9) { partner = s; break; }
+        const double *Hr = m->H + 2LL * nw * nw * r;
+        if (partner < 0) {
+            for (long long i = 0; i < 2LL * nw * nw; ++i)
+                if (std::fabs(Hr[i]) > tol) { *why = "R point " + std::to_string(r) + " has no -R partner"; return false; }
+            continue;
+        }
+        const double *Hs = m->H + 2LL * nw * nw * partner;
+        for (int a = 0; a < nw; ++a)
+            for (int b = 0; b < nw; ++b) {
+                const double re1 = Hr[2 * (a + nw * b)], im1 = Hr[2 * (a + nw * b) + 1];
+                const double re2 = Hs[2 * (b + nw * a)], im2 = Hs[2 * (b + nw * a) + 1];
+                if (std::fabs(re1 - re2) > tol || std::fabs(im1 + im2) > tol) {
+                    *why = "H(-R)(m,n) != conj(H(R)(n,m)) at R index " + std::to_string(r);
+                    return false;
+                }
+            }
+    }
+    return true;
+}
+
+void free_all(mepb_ctx *c) {
+    cudaSetDevice(c->device);
+    cudaFree(c->d_H); cudaFree(c->d_Rf); cudaFree(c->d_cR); cudaFree(c->d_tau); cudaFree(c->d_tM); cudaFree(c->d_hw);
+    for (auto &s : c->sb) {
+        cudaFree(s.items_ahc); cudaFree(s.cnt_ahc); cudaFree(s.items_photo); cudaFree(s.cnt_photo);
+        cudaFree(s.block_static); cudaFree(s.block_sweep); cudaFree(s.block_photo); cudaFree(s.compact);
+        if (s.st) cudaStreamDestroy(s.st);
+        if (s.done) cudaEventDestroy(s.done);
+    }
+    cudaFree(c->d_packed); cudaFree(c->d_err);
+    cudaFree(c->d_kpt); cudaFree(c->d_e); cudaFree(c->d_V); cudaFree(c->d_Hk); cudaFree(c->d_Hka);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+}
+
+int check_err_flag(mepb_ctx *c) {
+    int h = 0;
+    CUDA_TRY(cudaMemcpy(&h, c->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (h != 0) return fail(MEPB_ERR_EIG, "Jacobi eigensolver did not converge for at least one k-point");
+    return MEPB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *mepb_version(void) { return "mepb 0.1 (sm_100a)"; }
+const char *mepb_last_error(void) { return g_last_error.c_str(); }
+const char *mepb_strerror(int code) {
+    switch (code) {
+        case MEPB_OK: return "ok";
+        case MEPB_ERR_ARG: return "invalid argument";
+        case MEPB_ERR_CUDA: return "CUDA error or no device";
+        case MEPB_ERR_UNSUPPORTED: return "unsupported input (position operator / size limits)";
+        case MEPB_ERR_EIG: return "eigensolver did not converge";
+        case MEPB_ERR_STATE: return "invalid call order";
+        default: return "unknown error";
+    }
+}
+
+int mepb_create(const mepb_model *model, const mepb_params *params, int device, mepb_ctx **out) {
+    if (!model || !params || !out) return fail(MEPB_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (model->nw < 1 || model->nR < 1 || !model->R || !model->H) return fail(MEPB_ERR_ARG, "bad model");
+    if (model->r) return fail(MEPB_ERR_UNSUPPORTED, "position operator (r_tb) branch is not implemented");
+    const mepb_params &p = *params;
+    if (p.mp_grid[0] < 1 || p.mp_grid[1] < 1 || p.mp_grid[2] < 1 || p.n_hw < 1 || p.n_eF < 1)
+        return fail(MEPB_ERR_ARG, "bad mp_grid / n_hw / n_eF");
+    if ((p.do_mep || p.do_kubo) && (p.valence_bands < 0 || p.valence_bands > model->nw))
+        return fail(MEPB_ERR_ARG, "valence_bands out of range");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return fail(MEPB_ERR_CUDA, "no CUDA device (libmepb has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(MEPB_ERR_ARG, "device index out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(MEPB_ERR_CUDA, "libmepb is built for sm_100a only");
+    if (!small_supported(model->nw, model->nR))
+        return fail(MEPB_ERR_UNSUPPORTED, "num_wann/nR outside the limits of the compiled kernels");
+
+    mepb_ctx *c = new mepb_ctx();
+    c->device = device; c->sm_count = prop.multiProcessorCount;
+    c->p = p; c->nw = model->nw; c->nR = model->nR; c->has_tau = (model->wf_centers != nullptr);
+    { std::string why; c->herm = hermitian_closed(model, &why); }
+    std::memcpy(c->a_latt, model->a_latt, sizeof(c->a_latt));
+    const int nw = c->nw, nR = c->nR;
+    // linspaces (matrix_math.f90:74-100, core.f90:124-125)
+    auto linspace = [](double lo, double hi, int n) {
+        std::vector<double> v(n);
+        if (n > 1) { const double d = (hi - lo) / (double)(n - 1); for (int i = 0; i < n; ++i) v[i] = lo + (double)i * d; }
+        else v[0] = lo;
+        return v;
+    };
+    c->ef_lst = linspace(p.eF_min, p.eF_max, p.n_eF);
+    c->hw_lst = linspace(p.hw_min, p.hw_max, p.n_hw);
+    // weights c_a(R) = M.R and t = M.tau ; M = 2 pi or a_latt (matmul, wann_interp.f90:387-399)
+    const double two_pi = 2.0 * (4.0 * std::atan(1.0));
+    std::vector<double> Rf(3 * nR), cR(3 * nR), tau(3 * nw, 0.0), tM(3 * nw, 0.0);
+    auto applyM = [&](const double *x, double *y) {
+        if (p.use_cart_velo)
+            for (int i = 0; i < 3; ++i) y[i] = model->a_latt[i] * x[0] + model->a_latt[i + 3] * x[1] + model->a_latt[i + 6] * x[2];
+        else
+            for (int i = 0; i < 3; ++i) y[i] = two_pi * x[i];
+    };
+    for (int r = 0; r < nR; ++r) { for (int i = 0; i < 3; ++i) Rf[3 * r + i] = model->R[3 * r + i]; applyM(&model->R[3 * r], &cR[3 * r]); }
+    if (c->has_tau)
+        for (int n = 0; n < nw; ++n) { for (int i = 0; i < 3; ++i) tau[3 * n + i] = model->wf_centers[3 * n + i]; applyM(&tau[3 * n], &tM[3 * n]); }
+    auto up = [&](void **dst, const void *src, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc(dst, bytes);
+        if (e != cudaSuccess) return e;
+        return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+    };
+#define CT(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { std::string m_ = cudaGetErrorString(e_); free_all(c); delete c; return fail(MEPB_ERR_CUDA, std::string(#expr) + ": " + m_); } } while (0)
+    CT(up((void **)&c->d_H, model->H, sizeof(double) * 2 * (size_t)nw * nw * nR));
+    CT(up((void **)&c->d_Rf, Rf.data(), sizeof(double) * 3 * nR));
+    CT(up((void **)&c->d_cR, cR.data(), sizeof(double) * 3 * nR));
+    CT(up((void **)&c->d_tau, tau.data(), sizeof(double) * 3 * nw));
+    CT(up((void **)&c->d_tM, tM.data(), sizeof(double) * 3 * nw));
+    CT(up((void **)&c->d_hw, c->hw_lst.data(), sizeof(double) * p.n_hw));
+    CT(cudaMalloc((void **)&c->d_err, sizeof(int)));
+    CT(cudaMemset(c->d_err, 0, sizeof(int)));
+    // schedule: chunk sized so the item buffers stay below ~768 MB per stream
+    c->max_pairs = nw * (nw - 1) / 2;
+    c->max_photo = nw * (nw - 1);
+    const long long nk_mesh = (long long)p.mp_grid[0] * p.mp_grid[1] * p.mp_grid[2];
+    size_t per_k = 0;
+    const int istr = c->herm ? kAhcItemH : kAhcItemG;
+    if (p.do_ahc) per_k += sizeof(double) * istr * c->max_pairs + sizeof(int);
+    if (p.do_opt) per_k += sizeof(double) * kPhotoItem * c->max_photo + sizeof(int);
+    long long chunk = 1 << 18;
+    if (per_k) chunk = std::min<long long>(chunk, (long long)((768ull << 20) / per_k));
+    chunk = std::max<long long>(1024, std::min(chunk, std::max<long long>(nk_mesh, 1024)));
+    c->chunk = chunk;
+    c->grid_interp = interp_small_grid(nw, nR, c->sm_count, chunk);
+    c->grid_sweep = sweep_ahc_grid(c->sm_count, chunk, p.n_hw, &c->ns_sweep);
+    c->grid_photo = sweep_photo_grid(c->sm_count, chunk, p.n_hw, &c->ns_photo);
+    c->cs.ns = static_size(nw); c->cs.sweep = p.n_hw * kSweepAcc; c->cs.photo = p.n_hw * kPhotoAcc;
+    c->cs.per_ef = c->cs.ns + c->cs.sweep + c->cs.photo;
+    c->L = make_layout(p);
+    for (auto &s : c->sb) {
+        CT(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+        CT(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        if (p.do_ahc) {
+            CT(cudaMalloc((void **)&s.items_ahc, sizeof(double) * istr * c->max_pairs * (size_t)chunk));
+            CT(cudaMalloc((void **)&s.cnt_ahc, sizeof(int) * (size_t)chunk));
+            CT(cudaMalloc((void **)&s.block_sweep, sizeof(double) * kSweepAcc * (size_t)c->ns_sweep * c->grid_sweep));
+        }
+        if (p.do_opt) {
+            CT(cudaMalloc((void **)&s.items_photo, sizeof(double) * kPhotoItem * c->max_photo * (size_t)chunk));
+            CT(cudaMalloc((void **)&s.cnt_photo, sizeof(int) * (size_t)chunk));
+            CT(cudaMalloc((void **)&s.block_photo, sizeof(double) * kPhotoAcc * (size_t)c->ns_photo * c->grid_photo));
+        }
+        CT(cudaMalloc((void **)&s.block_static, sizeof(double) * (size_t)c->cs.ns * c->grid_interp));
+        CT(cudaMalloc((void **)&s.compact, sizeof(double) * (size_t)c->cs.per_ef * p.n_eF));
+        CT(cudaMemset(s.compact, 0, sizeof(double) * (size_t)c->cs.per_ef * p.n_eF));
+    }
+    CT(cudaMalloc((void **)&c->d_packed, sizeof(double) * (size_t)c->L.total));
+    CT(cudaMemset(c->d_packed, 0, sizeof(double) * (size_t)c->L.total));
+    CT(cudaEventCreate(&c->ev0));
+    CT(cudaEventCreate(&c->ev1));
+#undef CT
+    *out = c;
+    return MEPB_OK;
+}
+
+void mepb_destroy(mepb_ctx *c) {
+    if (!c) return;
+    free_all(c);
+    delete c;
+}
+
+int mepb_reset(mepb_ctx *c) {
+    if (!c) return fail(MEPB_ERR_ARG, "null ctx");
+    CUDA_TRY(cudaSetDevice(c->device));
+    for (auto &s : c->sb) CUDA_TRY(cudaMemsetAsync(s.compact, 0, sizeof(double) * (size_t)c->cs.per_ef * c->p.n_eF, s.st));
+    CUDA_TRY(cudaMemsetAsync(c->d_packed, 0, sizeof(double) * (size_t)c->L.total, c->sb[0].st));
+    CUDA_TRY(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->sb[0].st));
+    for (auto &s : c->sb) CUDA_TRY(cudaStreamSynchronize(s.st));
+    c->packed_from_host = false; c->have_data = false;
+    return MEPB_OK;
+}
+
+int mepb_accumulate(mepb_ctx *c, int64_t lin_begin, int64_t lin_end) {
+    if (!c) return fail(MEPB_ERR_ARG, "null ctx");
+    const mepb_params &p = c->p;
+    const long long nk_mesh = (long long)p.mp_grid[0] * p.mp_grid[1] * p.mp_grid[2];
+    if (lin_begin < 0 || lin_end > nk_mesh || lin_begin > lin_end) return fail(MEPB_ERR_ARG, "k range outside the mesh");
+    if (c->packed_from_host) return fail(MEPB_ERR_STATE, "accumulate after set_partials; call mepb_reset first");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const DevModel m = dev_model(c);
+    const int ns = c->cs.ns;
+    CUDA_TRY(cudaEventRecord(c->ev0, c->sb[0].st));
+    CUDA_TRY(cudaStreamWaitEvent(c->sb[1].st, c->ev0, 0));
+    int which = 0;
+    for (int ief = 0; ief < p.n_eF; ++ief) {
+        const Jobs jb = make_jobs(c, ief, true);
+        for (long long k0 = lin_begin; k0 < lin_end; k0 += c->chunk) {
+            const long long nk = std::min<long long>(c->chunk, lin_end - k0);
+            StreamBuf &s = c->sb[which];
+            which ^= 1;
+            KSource ks; ks.list = nullptr; ks.lin_begin = k0; ks.nk = nk; ks.N1 = p.mp_grid[0]; ks.N2 = p.mp_grid[1]; ks.N3 = p.mp_grid[2];
+            InterpOut o; std::memset(&o, 0, sizeof(o));
+            o.items_ahc = jb.do_ahc ? s.items_ahc : nullptr; o.cnt_ahc = s.cnt_ahc;
+            o.items_photo = jb.do_opt ? s.items_photo : nullptr; o.cnt_photo = s.cnt_photo;
+            o.block_static = s.block_static; o.err_flag = c->d_err;
+            const int gi = interp_small_grid(c->nw, c->nR, c->sm_count, nk);
+            CUDA_TRY(launch_interp_small(m, ks, jb, o, c->max_pairs, gi, s.st));
+            CUDA_TRY(launch_reduce_rows(s.block_static, gi, ns, s.compact + (size_t)ief * c->cs.per_ef, ns, 0, 0, s.st));
+            c->launches += 2;
+            if (jb.do_ahc) {
+                int nsl; const int gs = sweep_ahc_grid(c->sm_count, nk, p.n_hw, &nsl);
+                CUDA_TRY(launch_sweep_ahc(c->herm, s.items_ahc, s.cnt_ahc, c->max_pairs, nk, p.n_hw, c->d_hw, p.eta, s.block_sweep, gs, s.st));
+                const int nacc = c->herm ? kSweepAccH : kSweepAcc;          // Hermitian kernel fills X2,Y1 = slots [6,24)
+                CUDA_TRY(launch_reduce_rows(s.block_sweep, gs * (nsl / p.n_hw), p.n_hw * nacc,
+                                            s.compact + (size_t)ief * c->cs.per_ef + ns, nacc, kSweepAcc, c->herm ? 6 : 0, s.st));
+                c->launches += 2;
+            }
+            if (jb.do_opt) {
+                int nsl; const int gs = sweep_photo_grid(c->sm_count, nk, p.n_hw, &nsl);
+                CUDA_TRY(launch_sweep_photo(s.items_photo, s.cnt_photo, c->max_photo, nk, p.n_hw, c->d_hw, p.eta, s.block_photo, gs, s.st));
+                CUDA_TRY(launch_reduce_rows(s.block_photo, gs * (nsl / p.n_hw), p.n_hw * kPhotoAcc,
+                                            s.compact + (size_t)ief * c->cs.per_ef + ns + c->cs.sweep, kPhotoAcc, kPhotoAcc, 0, s.st));
+                c->launches += 2;
+            }
+        }
+    }
+    CUDA_TRY(cudaEventRecord(c->sb[1].done, c->sb[1].st));
+    CUDA_TRY(cudaStreamWaitEvent(c->sb[0].st, c->sb[1].done, 0));
+    CUDA_TRY(cudaEventRecord(c->ev1, c->sb[0].st));
+    CUDA_TRY(cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->last_ms = ms;
+    c->have_data = true;
+    return check_err_flag(c);
+}
+
+static int pack_now(mepb_ctx *c) {
+    const mepb_params &p = c->p;
+    pack_kernel<<<32, 256, 0, c->sb[0].st>>>(c->sb[0].compact, c->sb[1].compact, c->cs, c->nw, p.valence_bands, p.n_hw, p.n_eF,
+                                              p.do_mep, p.do_kubo, p.do_ahc, p.do_opt, c->L, c->d_packed);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(c->sb[0].st));
+    c->launches += 1;
+    return MEPB_OK;
+}
+
+int64_t mepb_partials_size(const mepb_ctx *c) { return c ? c->L.total : 0; }
+
+int mepb_get_partials(mepb_ctx *c, double *buf) {
+    if (!c || !buf) return fail(MEPB_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (!c->packed_from_host) { int rc = pack_now(c); if (rc) return rc; }
+    CUDA_TRY(cudaMemcpy(buf, c->d_packed, sizeof(double) * (size_t)c->L.total, cudaMemcpyDeviceToHost));
+    return MEPB_OK;
+}
+int mepb_set_partials(mepb_ctx *c, const double *buf) {
+    if (!c || !buf) return fail(MEPB_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpy(c->d_packed, buf, sizeof(double) * (size_t)c->L.total, cudaMemcpyHostToDevice));
+    c->packed_from_host = true; c->have_data = true;
+    return MEPB_OK;
+}
+int mepb_partials_device_ptr(mepb_ctx *c, double **dptr) {
+    if (!c || !dptr) return fail(MEPB_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (!c->packed_from_host) { int rc = pack_now(c); if (rc) return rc; }
+    c->packed_from_host = true;    // the caller may all-reduce in place; finalize reads d_packed as is
+    *dptr = c->d_packed;
+    return MEPB_OK;
+}
+
+int mepb_finalize(mepb_ctx *c, mepb_result *out) {
+    if (!c || !out) return fail(MEPB_ERR_ARG, "null argument");
+    if (!c->have_data) return fail(MEPB_ERR_STATE, "finalize before accumulate / set_partials");
+    const mepb_params &p = c->p;
+    std::vector<double> h((size_t)c->L.total);
+    {
+        CUDA_TRY(cudaSetDevice(c->device));
+        if (!c->packed_from_host) { int rc = pack_now(c); if (rc) return rc; }
+        CUDA_TRY(cudaMemcpy(h.data(), c->d_packed, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
+    }
+    const PackedLayout &L = c->L;
+    const int n_ef = p.n_eF, n_hw = p.n_hw, nval = p.valence_bands;
+    // unit cell volume: columns of a_latt as a_i (k_space.f90:274-278); |det| is transpose invariant
+    const double *a1 = c->a_latt, *a2 = c->a_latt + 3, *a3 = c->a_latt + 6;
+    const double vol = (a1[1] * a2[2] - a1[2] * a2[1]) * a3[0] + (a1[2] * a2[0] - a1[0] * a2[2]) * a3[1] + (a1[0] * a2[1] - a1[1] * a2[0]) * a3[2];
+    const double nk_mesh = (double)p.mp_grid[0] * (double)p.mp_grid[1] * (double)p.mp_grid[2];
+    const double norm = std::fabs(vol * nk_mesh);                       // normalize_k_int, k_space.f90:81-202
+    const double n_k = h[0];
+    if (!(n_k > 0.0)) return fail(MEPB_ERR_STATE, "no k-points accumulated");
+    // fermi_selector (core.f90:352-393): first minimum of |Ne/N_k - nval|, strict <
+    int opt = 0;
+    double opt_err = std::fabs(h[L.ne] / n_k - (double)nval);
+    for (int ef = 0; ef < n_ef; ++ef) {
+        const double e = std::fabs(h[L.ne + ef] / n_k - (double)nval);
+        if (e < opt_err) { opt = ef; opt_err = e; }
+    }
+    out->n_k = (int64_t)n_k; out->eF_idx = opt; out->n_degenerate = (int64_t)h[1];
+    if (out->Ne) for (int ef = 0; ef < n_ef; ++ef) out->Ne[ef] = h[L.ne + ef] / n_k;
+    if (p.do_mep) {                                                     // mep_sum_bands, core.f90:570-603
+        for (int q = 0; q < 9; ++q) {
+            double ic = 0, lc = 0;
+            for (int n0 = 0; n0 < nval; ++n0) { ic += h[L.mep_ic + q + 9 * n0]; lc += h[L.mep_lc + q + 9 * n0]; }
+            if (out->mep_ic) out->mep_ic[q] = ic / norm;
+            if (out->mep_lc) out->mep_lc[q] = lc / norm;
+            if (out->mep_cs) out->mep_cs[q] = 0.0;                      // no position operator: mep_niu.f90:29
+        }
+        if (out->mep_bands && p.do_write_mep_bands)
+            for (int q = 0; q < 9 * nval; ++q) out->mep_bands[q] = (h[L.mep_ic + q] + h[L.mep_lc + q]) / norm;
+    }
+    if (p.do_kubo)
+        for (int q = 0; q < 9; ++q) {
+            if (out->kubo_mep_ic) out->kubo_mep_ic[q] = h[L.kmep_ic + q + 9 * opt] / norm;
+            if (out->kubo_mep_lc) out->kubo_mep_lc[q] = h[L.kmep_lc + q + 9 * opt] / norm;
+            if (out->kubo_mep_cs) out->kubo_mep_cs[q] = 0.0;            // kubo_mep.f90:28
+        }
+    if (p.do_ahc) {
+        if (out->ahc) for (int q = 0; q < 9; ++q) out->ahc[q] = h[L.ahc + q + 9 * opt] / norm;
+        const long long sl = 18LL * n_hw;
+        if (out->ahc_velo) for (long long q = 0; q < sl; ++q) out->ahc_velo[q] = h[L.velo + q + sl * opt] / norm;
+        if (out->ohc_velo) for (long long q = 0; q < sl; ++q) out->ohc_velo[q] = h[L.ohc + q + sl * opt] / norm;
+    }
+    if (p.do_opt) {
+        const long long sl = 18LL * n_hw;
+        if (out->opt_s) for (long long q = 0; q < sl; ++q) out->opt_s[q] = 0.0;    // kubo.f90:225 (A_ka not allocated)
+        if (out->opt_a) for (long long q = 0; q < sl; ++q) out->opt_a[q] = 0.0;
+        if (out->photo2) for (long long q = 0; q < 54LL * n_hw * n_ef; ++q) out->photo2[q] = h[L.photo + q] / norm;   // core.f90:515
+    }
+    return MEPB_OK;
+}
+
+int mepb_run_mesh(mepb_ctx *c, mepb_result *out) {
+    if (!c || !out) return fail(MEPB_ERR_ARG, "null argument");
+    int rc = mepb_reset(c);
+    if (rc) return rc;
+    const long long nk = (long long)c->p.mp_grid[0] * c->p.mp_grid[1] * c->p.mp_grid[2];
+    rc = mepb_accumulate(c, 0, nk);
+    if (rc) return rc;
+    return mepb_finalize(c, out);
+}
+
+static int ensure_list(mepb_ctx *c, long long cap) {
+    if (cap <= c->list_cap) return MEPB_OK;
+    cudaFree(c->d_kpt); cudaFree(c->d_e); cudaFree(c->d_V); cudaFree(c->d_Hk); cudaFree(c->d_Hka);
+    c->d_kpt = c->d_e = nullptr; c->d_V = c->d_Hk = c->d_Hka = nullptr; c->list_cap = 0;
+    const size_t nw = c->nw;
+    CUDA_TRY(cudaMalloc((void **)&c->d_kpt, sizeof(double) * 3 * cap));
+    CUDA_TRY(cudaMalloc((void **)&c->d_e, sizeof(double) * nw * cap));
+    CUDA_TRY(cudaMalloc((void **)&c->d_V, sizeof(double2) * 3 * nw * nw * cap));
+    CUDA_TRY(cudaMalloc((void **)&c->d_Hk, sizeof(double2) * nw * nw * cap));
+    CUDA_TRY(cudaMalloc((void **)&c->d_Hka, sizeof(double2) * 3 * nw * nw * cap));
+    c->list_cap = cap;
+    return MEPB_OK;
+}
+
+static int list_run(mepb_ctx *c, int64_t nk, const double *kpt, double *e_k, double *V_ka, double *H_k, double *H_ka) {
+    if (!c || !kpt || nk < 0) return fail(MEPB_ERR_ARG, "bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const long long cap = std::min<long long>(std::max<long long>(nk, 1), 1 << 16);
+    int rc = ensure_list(c, cap);
+    if (rc) return rc;
+    const DevModel m = dev_model(c);
+    const Jobs jb = make_jobs(c, 0, false);
+    const size_t nw = c->nw;
+    cudaStream_t st = c->sb[0].st;
+    for (long long k0 = 0; k0 < nk; k0 += cap) {
+        const long long n = std::min<long long>(cap, nk - k0);
+        CUDA_TRY(cudaMemcpyAsync(c->d_kpt, kpt + 3 * k0, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, st));
+        KSource ks; ks.list = c->d_kpt; ks.lin_begin = 0; ks.nk = n; ks.N1 = ks.N2 = ks.N3 = 1;
+        InterpOut o; std::memset(&o, 0, sizeof(o));
+        o.e_out = e_k ? c->d_e : nullptr; o.V_out = V_ka ? c->d_V : nullptr;
+        o.Hk_out = H_k ? c->d_Hk : nullptr; o.Hka_out = H_ka ? c->d_Hka : nullptr;
+        if (V_ka && !e_k) o.e_out = c->d_e;
+        o.err_flag = c->d_err;
+        CUDA_TRY(launch_interp_small(m, ks, jb, o, c->max_pairs, interp_small_grid(c->nw, c->nR, c->sm_count, n), st));
+        c->launches += 1;
+        if (e_k) CUDA_TRY(cudaMemcpyAsync(e_k + nw * k0, c->d_e, sizeof(double) * nw * n, cudaMemcpyDeviceToHost, st));
+        if (V_ka) CUDA_TRY(cudaMemcpyAsync(V_ka + 2 * 3 * nw * nw * k0, c->d_V, sizeof(double2) * 3 * nw * nw * n, cudaMemcpyDeviceToHost, st));
+        if (H_k) CUDA_TRY(cudaMemcpyAsync(H_k + 2 * nw * nw * k0, c->d_Hk, sizeof(double2) * nw * nw * n, cudaMemcpyDeviceToHost, st));
+        if (H_ka) CUDA_TRY(cudaMemcpyAsync(H_ka + 2 * 3 * nw * nw * k0, c->d_Hka, sizeof(double2) * 3 * nw * nw * n, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    return check_err_flag(c);
+}
+
+int mepb_interp(mepb_ctx *c, int64_t nk, const double *kpt, double *e_k, double *V_ka) {
+    if (!e_k && !V_ka) return fail(MEPB_ERR_ARG, "nothing requested");
+    return list_run(c, nk, kpt, e_k, V_ka, nullptr, nullptr);
+}
+int mepb_fourier(mepb_ctx *c, int64_t nk, const double *kpt, double *H_k, double *H_ka) {
+    if (!H_k && !H_ka) return fail(MEPB_ERR_ARG, "nothing requested");
+    return list_run(c, nk, kpt, nullptr, nullptr, H_k, H_ka);
+}
+
+double mepb_last_kernel_ms(const mepb_ctx *c) { return c ? c->last_ms : 0.0; }
+int64_t mepb_kernel_launches(const mepb_ctx *c) { return c ? c->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,150 @@
+// mepb_internal.cuh — shared between the kernels and the C-ABI host code of libmepb.so.
+// sm_100a only.  All arithmetic FP64.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/mepb.h"
+
+namespace mepb {
+
+// ---------------------------------------------------------------------------------------------------------
+// constants (reference: src/constants.f90:6-23, src/statistics.f90:32) — must be the same literals
+// ---------------------------------------------------------------------------------------------------------
+constexpr double kAuToEv = 27.211385;
+constexpr double kBoltzEhK = 8.6173303 * 1e-5 / kAuToEv;
+constexpr double kMinTemp = 1e-2;
+
+// ---------------------------------------------------------------------------------------------------------
+// "pair items": what the interpolation kernels hand to the frequency-sweep kernels through HBM.
+//   For a band pair n<m (dE = E_m - E_n, fdm = f_m - f_n) let P(i,j) = V(i,n,m) V(j,m,n),
+//   Asym(i,j) = P(i,j) - P(j,i), Sym(i,j) = P(i,j) + P(j,i).  Combining the (n,m) and (m,n) terms of
+//   kubo.f90:111-135 and :172-194 (no hermiticity of V assumed; g(w) = 1/(dE^2 - z^2), z = w + i eta):
+//       velo_ahc(i,j,w) = - sum fdm Im Asym(i,j) g(w)
+//       kubo_ohc(i,j,w) = i sum fdm g(w) [ Asym(i,j) + (z/dE) Sym(i,j) ]
+//   GENERAL item (20 doubles): [0] c = dE^2 + eta^2, [1..3] fdm Re Asym (01,02,12), [4..6] fdm Im Asym,
+//       [7..12] (fdm/dE) Re Sym (00,11,22,01,02,12), [13..18] (fdm/dE) Im Sym, [19] pad
+//   HERMITIAN item (10 doubles), used when H(R) is Hermitian-closed so that V_a is Hermitian and
+//       Re Asym = Im Sym = 0:  [0] c, [1..3] fdm Im Asym, [4..9] (fdm/dE) Re Sym
+//   Sweep accumulators per frequency (36 doubles): X1 = sum fdm ReAsym g (3 complex), X2 = sum fdm ImAsym g (3 complex),
+//       Y1 = sum (fdm/dE) ReSym z g (6 complex), Y2 = sum (fdm/dE) ImSym z g (6 complex); the Hermitian kernel fills X2, Y1.
+//   PHOTO item (56 doubles) for an ordered pair (n,l), l != n, df = f_l - f_n:
+//     [0..53] T(a,b,c) = df V(a,n,l) sum_m V(b,l,m) V(c,m,n) / (E_n - E_m - i eta)   complex, index a+3b+9c
+//     [54] xr = E_n - E_l     [55] pad
+//   photo2(a,b,c,w) = sum T(abc) (1/w^2) sum_{s=+-1} 1/(xr + s w - 2 i eta)          (photo.f90:44-81)
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kAhcItemH = 10;   // Hermitian item
+constexpr int kAhcItemG = 20;   // general item
+constexpr int kPhotoItem = 56;
+constexpr int kSweepAcc = 36;   // per frequency: X1(3c) X2(3c) Y1(6c) Y2(6c)
+constexpr int kSweepAccH = 18;  // Hermitian kernel: X2, Y1 (contiguous at offset 6 of the 36)
+constexpr int kPhotoAcc = 54;   // per frequency: 27 complex
+
+// static (frequency independent) per-block partial sums written by the interpolation kernels
+//   [0] n_k  [1] n_degenerate  [2] Ne  [3..11] ahc(3,3)  [12..20] kubo_mep_ic  [21..29] kubo_mep_lc
+//   [30 .. 30+9*nw) mep_niu_ic(3,3,n0)   [30+9*nw .. 30+18*nw) mep_niu_lc(3,3,n0)
+constexpr int S_NK = 0, S_NDEG = 1, S_NE = 2, S_AHC = 3, S_KIC = 12, S_KLC = 21, S_NIU = 30;
+__host__ __device__ inline int static_size(int nw) { return S_NIU + 18 * nw; }
+
+struct DevModel {
+    int nw, nR;
+    const double2 *H;    // [nR][nw*nw], element n + nw*m (Fortran H_tb(n,m,R))
+    const double *Rf;    // [nR][3] fractional R
+    const double *cR;    // [nR][3] M.R  with M = 2 pi (use_cart_velo=F) or a_latt (T)       wann_interp.f90:268-271
+    const double *tau;   // [nw][3] fractional centres or nullptr (Wannier convention)        wann_interp.f90:192
+    const double *tM;    // [nw][3] M.tau (zeros when tau == nullptr)
+};
+
+struct KSource {          // where the k-points of a launch come from
+    const double *list;   // [nk][3] explicit fractional k (band mode / parity) or nullptr -> MP mesh
+    long long lin_begin;  // first 0-based linear mesh index of this launch
+    long long nk;         // k-points in this launch
+    int N1, N2, N3;       // mp_grid
+};
+
+struct Jobs {
+    int do_gauge, do_mep, do_kubo, do_ahc, do_opt;
+    int nval;
+    int herm;             // H(R) Hermitian-closed -> Hermitian items (10 doubles) else general items (20)
+    int zero_T;           // T_kelvin <= min_temp -> step function                            statistics.f90:74-87
+    double eF, inv_kT, eta, kubo_tol;
+};
+
+struct InterpOut {
+    // list-mode outputs (any may be nullptr)
+    double *e_out;        // (nw, nk)
+    double2 *V_out;       // (3, nw, nw, nk)
+    double2 *Hk_out;      // (nw, nw, nk)      W gauge
+    double2 *Hka_out;     // (3, nw, nw, nk)   W gauge
+    // response-mode outputs
+    double *items_ahc;    // [nk][max_pairs][10 or 20]
+    int *cnt_ahc;         // [nk]
+    double *items_photo;  // [nk][nw*(nw-1)][56]
+    int *cnt_photo;       // [nk]
+    double *block_static; // [gridDim.x][static_size(nw)]
+    int *err_flag;        // set to 1 when the eigensolver fails to converge
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// complex helpers on double2
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ double2 cmulc(double2 a, double2 b) {  // a * conj(b)
+    return make_double2(fma(a.x, b.x, a.y * b.y), fma(a.y, b.x, -a.x * b.y));
+}
+__device__ __forceinline__ double2 cconj(double2 a) { return make_double2(a.x, -a.y); }
+__device__ __forceinline__ void cfma(double2 &acc, double2 a, double2 b) {  // acc += a*b
+    acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
+}
+__device__ __forceinline__ void cfmac(double2 &acc, double2 a, double2 b) {  // acc += conj(a)*b
+    acc.x = fma(a.x, b.x, acc.x); acc.x = fma(a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y); acc.y = fma(-a.y, b.x, acc.y);
+}
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 cscale(double s, double2 a) { return make_double2(s * a.x, s * a.y); }
+__device__ __forceinline__ double2 crcp(double2 a) {  // 1/a  (IEEE division: inf/NaN propagate like the reference)
+    double d = 1.0 / fma(a.x, a.x, a.y * a.y);
+    return make_double2(a.x * d, -a.y * d);
+}
+// reciprocal for the sweep inner loops: MUFU.RCP64H seed + 2 Newton steps (7.4 DFMA-equivalents measured vs 11 for '/')
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double fermi(double e, const Jobs &j) {  // statistics.f90:41-61
+    if (j.zero_T) return (e < j.eF) ? 1.0 : 0.0;
+    return 1.0 / (1.0 + exp((e - j.eF) * j.inv_kT));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// launchers (defined in the .cu files)
+// ---------------------------------------------------------------------------------------------------------
+bool small_supported(int nw, int nR);
+cudaError_t launch_interp_small(const DevModel &m, const KSource &ks, const Jobs &jobs, const InterpOut &out, int max_pairs,
+                                int grid, cudaStream_t st);
+int interp_small_grid(int nw, int nR, int sm_count, long long nk);
+
+cudaError_t launch_sweep_ahc(bool herm, const double *items, const int *cnt, int max_pairs, long long nk, int n_hw,
+                             const double *hw, double eta, double *block_out, int grid, cudaStream_t st);
+int sweep_ahc_grid(int sm_count, long long nk, int n_hw, int *slots_out);
+cudaError_t launch_sweep_photo(const double *items, const int *cnt, int max_items, long long nk, int n_hw, const double *hw,
+                               double eta, double *block_out, int grid, cudaStream_t st);
+int sweep_photo_grid(int sm_count, long long nk, int n_hw, int *slots_out);
+// out[(c / group) * out_stride + out_off + c % group] += sum_r in[r*cols + c]
+cudaError_t launch_reduce_rows(const double *in, int rows, int cols, double *out_accum, int group, int out_stride, int out_off,
+                               cudaStream_t st);
+
+}  // namespace mepb
