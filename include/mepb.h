@@ -104,6 +104,28 @@ int mepb_interp(mepb_ctx *ctx, int64_t nk, const double *kpt, double *e_k, doubl
  * Gauge independent, so it is compared element-wise against the oracle. */
 int mepb_fourier(mepb_ctx *ctx, int64_t nk, const double *kpt, double *H_k, double *H_ka);
 
+/* Re-upload H(R) from a host buffer into an existing context (same nw, nR, R set, FT convention): the per-call input
+ * of a parameter sweep — the reference re-reads w90files/<seed>_hr.dat in a fresh process per parameter value
+ * (scripts/mep_worker.py:133-150, scripts/probe_phi.py). */
+int mepb_update_model(mepb_ctx *ctx, const mepb_model *model);
+
+/* CUDA-event stopwatch on the context's launch stream (brackets any sequence of mepb_* calls; ms on the device). */
+int mepb_timer_start(mepb_ctx *ctx);
+int mepb_timer_stop(mepb_ctx *ctx, double *ms);
+
+/* Per-kernel-class device timing: when on, mepb_accumulate serialises its schedule onto one stream and brackets every
+ * launch with CUDA events (slower; used for the roofline figures, never for throughput numbers). */
+#define MEPB_PROF_INTERP       0   /* fused Fourier + eigensolve + rotation + static band sums kernel */
+#define MEPB_PROF_SWEEP_AHC    1   /* velo_ahc / kubo_ohc frequency sweep                             */
+#define MEPB_PROF_SWEEP_PHOTO  2   /* photo_2nd_cond frequency sweep                                  */
+#define MEPB_PROF_REDUCE       3   /* block-partial reductions                                        */
+#define MEPB_PROF_KINDS        4
+int mepb_set_profiling(mepb_ctx *ctx, int on);
+int mepb_get_profile(const mepb_ctx *ctx, int kind, double *ms_total, int64_t *launches);
+/* (k, band pair) items the last packed run handed to the frequency sweep `kind` (MEPB_PROF_SWEEP_AHC / _PHOTO): the
+ * unit count behind the sweeps' algorithmic flop figures (valid after mepb_get_partials / mepb_finalize). */
+int64_t mepb_work_items(const mepb_ctx *ctx, int kind);
+
 /* timing of the last mepb_accumulate / mepb_run_mesh on the device (CUDA events), and kernel launches issued */
 double  mepb_last_kernel_ms(const mepb_ctx *ctx);
 int64_t mepb_kernel_launches(const mepb_ctx *ctx);

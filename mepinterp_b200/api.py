@@ -21,7 +21,8 @@ ERR_ARG, ERR_CUDA, ERR_NOT_HERMITIAN, ERR_UNSUPPORTED, ERR_EIG, ERR_STATE = -1, 
 
 EXPORTS = ["mepb_create", "mepb_destroy", "mepb_run_mesh", "mepb_reset", "mepb_accumulate", "mepb_partials_size",
            "mepb_get_partials", "mepb_set_partials", "mepb_partials_device_ptr", "mepb_finalize", "mepb_interp",
-           "mepb_fourier", "mepb_last_kernel_ms", "mepb_kernel_launches", "mepb_strerror", "mepb_last_error", "mepb_version"]
+           "mepb_fourier", "mepb_update_model", "mepb_timer_start", "mepb_timer_stop", "mepb_set_profiling",
+           "mepb_get_profile", "mepb_work_items", "mepb_last_kernel_ms", "mepb_kernel_launches", "mepb_strerror", "mepb_last_error", "mepb_version"]
 
 
 class MepbError(RuntimeError):
@@ -73,6 +74,13 @@ def lib():
         L.mepb_finalize.argtypes = [vp, C.POINTER(CResult)]
         L.mepb_interp.argtypes = [vp, C.c_int64, vp, vp, vp]
         L.mepb_fourier.argtypes = [vp, C.c_int64, vp, vp, vp]
+        L.mepb_update_model.argtypes = [vp, C.POINTER(CModel)]
+        L.mepb_timer_start.argtypes = [vp]
+        L.mepb_timer_stop.argtypes = [vp, C.POINTER(C.c_double)]
+        L.mepb_set_profiling.argtypes = [vp, C.c_int]
+        L.mepb_get_profile.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+        L.mepb_work_items.argtypes = [vp, C.c_int]
+        L.mepb_work_items.restype = C.c_int64
         L.mepb_last_kernel_ms.argtypes = [vp]
         L.mepb_last_kernel_ms.restype = C.c_double
         L.mepb_kernel_launches.argtypes = [vp]
@@ -239,6 +247,37 @@ class Context:
         Hka = np.zeros((3, nw, nw, nk), dtype=np.complex128, order="F")
         _check(lib().mepb_fourier(self._h, nk, kp.ctypes.data, Hk.ctypes.data, Hka.ctypes.data))
         return Hk, Hka
+
+    def update_model(self, H):
+        """Re-upload H(R) (nw,nw,nR complex, Hartree) from host memory; same R set and FT convention."""
+        self._H = _f(H, np.complex128)
+        assert self._H.shape == (self.nw, self.nw, self.nR)
+        self.cm.H = self._H.ctypes.data
+        _check(lib().mepb_update_model(self._h, C.byref(self.cm)))
+
+    def timer_start(self):
+        _check(lib().mepb_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_double()
+        _check(lib().mepb_timer_stop(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    PROF_KINDS = ("interp", "sweep_ahc", "sweep_photo", "reduce")
+
+    def set_profiling(self, on: bool):
+        _check(lib().mepb_set_profiling(self._h, int(bool(on))))
+
+    def get_profile(self) -> dict:
+        out = {}
+        for i, name in enumerate(self.PROF_KINDS):
+            ms, n = C.c_double(), C.c_int64()
+            _check(lib().mepb_get_profile(self._h, i, C.byref(ms), C.byref(n)))
+            out[name] = {"ms": float(ms.value), "launches": int(n.value)}
+        return out
+
+    def work_items(self) -> dict:
+        return {"sweep_ahc": int(lib().mepb_work_items(self._h, 1)), "sweep_photo": int(lib().mepb_work_items(self._h, 2))}
 
     @property
     def last_kernel_ms(self) -> float:

@@ -39,7 +39,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             subprocess.check_call(cmd)
         objs.append(obj)
     if force or _stale(LIB, objs):
-        subprocess.check_call([nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart"])
+        subprocess.check_call([nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart"])
     return LIB
 
 

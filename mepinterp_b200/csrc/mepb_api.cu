@@ -143,6 +143,14 @@ struct mepb_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_ms = 0.0;
     long long launches = 0;
+    long long n_items_ahc = 0, n_items_photo = 0;
+    // optional per-kernel-class timing (serialises the schedule onto one stream; used by bench.py for the roofline)
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_ev;          // pairs (start, stop)
+    std::vector<int> prof_kind;
+    double prof_ms[MEPB_PROF_KINDS] = {0, 0, 0, 0};
+    long long prof_n[MEPB_PROF_KINDS] = {0, 0, 0, 0};
+    cudaEvent_t tm0 = nullptr, tm1 = nullptr;  // mepb_timer_start / stop
     // list-mode scratch
     double *d_kpt = nullptr, *d_e = nullptr; double2 *d_V = nullptr, *d_Hk = nullptr, *d_Hka = nullptr;
     long long list_cap = 0;
@@ -218,6 +226,32 @@ void free_all(mepb_ctx *c) {
     cudaFree(c->d_kpt); cudaFree(c->d_e); cudaFree(c->d_V); cudaFree(c->d_Hk); cudaFree(c->d_Hka);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->tm0) cudaEventDestroy(c->tm0);
+    if (c->tm1) cudaEventDestroy(c->tm1);
+    for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
+}
+
+// profiling helpers: bracket one launch on stream st with an event pair
+struct ProfScope {
+    mepb_ctx *c; cudaStream_t st; int kind; bool on;
+    ProfScope(mepb_ctx *c_, cudaStream_t st_, int kind_) : c(c_), st(st_), kind(kind_), on(c_->profiling) {
+        if (!on) return;
+        cudaEvent_t a, b;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        c->prof_ev.push_back(a); c->prof_ev.push_back(b); c->prof_kind.push_back(kind);
+        cudaEventRecord(a, st);
+    }
+    ~ProfScope() { if (on) cudaEventRecord(c->prof_ev.back(), st); }
+};
+void prof_collect(mepb_ctx *c) {
+    for (size_t i = 0; i < c->prof_kind.size(); ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->prof_ev[2 * i], c->prof_ev[2 * i + 1]) == cudaSuccess) {
+            c->prof_ms[c->prof_kind[i]] += ms; c->prof_n[c->prof_kind[i]] += 1;
+        }
+    }
+    for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
+    c->prof_ev.clear(); c->prof_kind.clear();
 }
 
 int check_err_flag(mepb_ctx *c) {
@@ -345,6 +379,8 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
     CT(cudaMemset(c->d_packed, 0, sizeof(double) * (size_t)c->L.total));
     CT(cudaEventCreate(&c->ev0));
     CT(cudaEventCreate(&c->ev1));
+    CT(cudaEventCreate(&c->tm0));
+    CT(cudaEventCreate(&c->tm1));
 #undef CT
     *out = c;
     return MEPB_OK;
@@ -384,29 +420,34 @@ int mepb_accumulate(mepb_ctx *c, int64_t lin_begin, int64_t lin_end) {
         for (long long k0 = lin_begin; k0 < lin_end; k0 += c->chunk) {
             const long long nk = std::min<long long>(c->chunk, lin_end - k0);
             StreamBuf &s = c->sb[which];
-            which ^= 1;
+            if (!c->profiling) which ^= 1;
             KSource ks; ks.list = nullptr; ks.lin_begin = k0; ks.nk = nk; ks.N1 = p.mp_grid[0]; ks.N2 = p.mp_grid[1]; ks.N3 = p.mp_grid[2];
             InterpOut o; std::memset(&o, 0, sizeof(o));
             o.items_ahc = jb.do_ahc ? s.items_ahc : nullptr; o.cnt_ahc = s.cnt_ahc;
             o.items_photo = jb.do_opt ? s.items_photo : nullptr; o.cnt_photo = s.cnt_photo;
             o.block_static = s.block_static; o.err_flag = c->d_err;
             const int gi = interp_small_grid(c->nw, c->nR, c->sm_count, nk);
-            CUDA_TRY(launch_interp_small(m, ks, jb, o, c->max_pairs, gi, s.st));
-            CUDA_TRY(launch_reduce_rows(s.block_static, gi, ns, s.compact + (size_t)ief * c->cs.per_ef, ns, 0, 0, s.st));
+            { ProfScope ps(c, s.st, MEPB_PROF_INTERP); CUDA_TRY(launch_interp_small(m, ks, jb, o, c->max_pairs, gi, s.st)); }
+            { ProfScope ps(c, s.st, MEPB_PROF_REDUCE);
+              CUDA_TRY(launch_reduce_rows(s.block_static, gi, ns, s.compact + (size_t)ief * c->cs.per_ef, ns, 0, 0, s.st)); }
             c->launches += 2;
             if (jb.do_ahc) {
                 int nsl; const int gs = sweep_ahc_grid(c->sm_count, nk, p.n_hw, &nsl);
-                CUDA_TRY(launch_sweep_ahc(c->herm, s.items_ahc, s.cnt_ahc, c->max_pairs, nk, p.n_hw, c->d_hw, p.eta, s.block_sweep, gs, s.st));
+                { ProfScope ps(c, s.st, MEPB_PROF_SWEEP_AHC);
+                  CUDA_TRY(launch_sweep_ahc(c->herm, s.items_ahc, s.cnt_ahc, c->max_pairs, nk, p.n_hw, c->d_hw, p.eta, s.block_sweep, gs, s.st)); }
                 const int nacc = c->herm ? kSweepAccH : kSweepAcc;          // Hermitian kernel fills X2,Y1 = slots [6,24)
-                CUDA_TRY(launch_reduce_rows(s.block_sweep, gs * (nsl / p.n_hw), p.n_hw * nacc,
-                                            s.compact + (size_t)ief * c->cs.per_ef + ns, nacc, kSweepAcc, c->herm ? 6 : 0, s.st));
+                { ProfScope ps(c, s.st, MEPB_PROF_REDUCE);
+                  CUDA_TRY(launch_reduce_rows(s.block_sweep, gs * (nsl / p.n_hw), p.n_hw * nacc,
+                                              s.compact + (size_t)ief * c->cs.per_ef + ns, nacc, kSweepAcc, c->herm ? 6 : 0, s.st)); }
                 c->launches += 2;
             }
             if (jb.do_opt) {
                 int nsl; const int gs = sweep_photo_grid(c->sm_count, nk, p.n_hw, &nsl);
-                CUDA_TRY(launch_sweep_photo(s.items_photo, s.cnt_photo, c->max_photo, nk, p.n_hw, c->d_hw, p.eta, s.block_photo, gs, s.st));
-                CUDA_TRY(launch_reduce_rows(s.block_photo, gs * (nsl / p.n_hw), p.n_hw * kPhotoAcc,
-                                            s.compact + (size_t)ief * c->cs.per_ef + ns + c->cs.sweep, kPhotoAcc, kPhotoAcc, 0, s.st));
+                { ProfScope ps(c, s.st, MEPB_PROF_SWEEP_PHOTO);
+                  CUDA_TRY(launch_sweep_photo(s.items_photo, s.cnt_photo, c->max_photo, nk, p.n_hw, c->d_hw, p.eta, s.block_photo, gs, s.st)); }
+                { ProfScope ps(c, s.st, MEPB_PROF_REDUCE);
+                  CUDA_TRY(launch_reduce_rows(s.block_photo, gs * (nsl / p.n_hw), p.n_hw * kPhotoAcc,
+                                              s.compact + (size_t)ief * c->cs.per_ef + ns + c->cs.sweep, kPhotoAcc, kPhotoAcc, 0, s.st)); }
                 c->launches += 2;
             }
         }
@@ -419,11 +460,22 @@ int mepb_accumulate(mepb_ctx *c, int64_t lin_begin, int64_t lin_end) {
     CUDA_TRY(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     c->last_ms = ms;
     c->have_data = true;
+    if (c->profiling) prof_collect(c);
     return check_err_flag(c);
 }
 
 static int pack_now(mepb_ctx *c) {
     const mepb_params &p = c->p;
+    {   // work counters (items emitted to the frequency sweeps), summed over both stream buffers and all eF
+        c->n_items_ahc = c->n_items_photo = 0;
+        for (auto &s : c->sb)
+            for (int ief = 0; ief < p.n_eF; ++ief) {
+                double h2[2];
+                CUDA_TRY(cudaMemcpyAsync(h2, s.compact + (size_t)ief * c->cs.per_ef + S_NIT, sizeof(h2), cudaMemcpyDeviceToHost, c->sb[0].st));
+                CUDA_TRY(cudaStreamSynchronize(c->sb[0].st));
+                c->n_items_ahc += (long long)h2[0]; c->n_items_photo += (long long)h2[1];
+            }
+    }
     pack_kernel<<<32, 256, 0, c->sb[0].st>>>(c->sb[0].compact, c->sb[1].compact, c->cs, c->nw, p.valence_bands, p.n_hw, p.n_eF,
                                               p.do_mep, p.do_kubo, p.do_ahc, p.do_opt, c->L, c->d_packed);
     CUDA_TRY(cudaGetLastError());
@@ -578,6 +630,53 @@ int mepb_interp(mepb_ctx *c, int64_t nk, const double *kpt, double *e_k, double 
 int mepb_fourier(mepb_ctx *c, int64_t nk, const double *kpt, double *H_k, double *H_ka) {
     if (!H_k && !H_ka) return fail(MEPB_ERR_ARG, "nothing requested");
     return list_run(c, nk, kpt, nullptr, nullptr, H_k, H_ka);
+}
+
+int mepb_update_model(mepb_ctx *c, const mepb_model *model) {
+    if (!c || !model || !model->H || !model->R) return fail(MEPB_ERR_ARG, "null argument");
+    if (model->nw != c->nw || model->nR != c->nR) return fail(MEPB_ERR_ARG, "update_model: nw / nR differ from the context's");
+    if ((model->wf_centers != nullptr) != c->has_tau) return fail(MEPB_ERR_ARG, "update_model: FT convention differs");
+    if (model->r) return fail(MEPB_ERR_UNSUPPORTED, "position operator (r_tb) branch is not implemented");
+    CUDA_TRY(cudaSetDevice(c->device));
+    { std::string why; c->herm = hermitian_closed(model, &why); }
+    cudaStream_t st = c->sb[0].st;
+    CUDA_TRY(cudaMemcpyAsync(c->d_H, model->H, sizeof(double) * 2 * (size_t)c->nw * c->nw * c->nR, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return MEPB_OK;
+}
+
+int mepb_timer_start(mepb_ctx *c) {
+    if (!c) return fail(MEPB_ERR_ARG, "null ctx");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaEventRecord(c->tm0, c->sb[0].st));
+    return MEPB_OK;
+}
+int mepb_timer_stop(mepb_ctx *c, double *ms_out) {
+    if (!c || !ms_out) return fail(MEPB_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaEventRecord(c->tm1, c->sb[0].st));
+    CUDA_TRY(cudaEventSynchronize(c->tm1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, c->tm0, c->tm1));
+    *ms_out = ms;
+    return MEPB_OK;
+}
+int mepb_set_profiling(mepb_ctx *c, int on) {
+    if (!c) return fail(MEPB_ERR_ARG, "null ctx");
+    c->profiling = (on != 0);
+    for (int i = 0; i < MEPB_PROF_KINDS; ++i) { c->prof_ms[i] = 0.0; c->prof_n[i] = 0; }
+    return MEPB_OK;
+}
+int mepb_get_profile(const mepb_ctx *c, int kind, double *ms_total, int64_t *launches) {
+    if (!c || kind < 0 || kind >= MEPB_PROF_KINDS) return fail(MEPB_ERR_ARG, "bad argument");
+    if (ms_total) *ms_total = c->prof_ms[kind];
+    if (launches) *launches = c->prof_n[kind];
+    return MEPB_OK;
+}
+
+int64_t mepb_work_items(const mepb_ctx *c, int kind) {
+    if (!c) return 0;
+    return kind == MEPB_PROF_SWEEP_AHC ? c->n_items_ahc : kind == MEPB_PROF_SWEEP_PHOTO ? c->n_items_photo : 0;
 }
 
 double mepb_last_kernel_ms(const mepb_ctx *c) { return c ? c->last_ms : 0.0; }

@@ -40,9 +40,10 @@ constexpr int kSweepAccH = 18;  // Hermitian kernel: X2, Y1 (contiguous at offse
 constexpr int kPhotoAcc = 54;   // per frequency: 27 complex
 
 // static (frequency independent) per-block partial sums written by the interpolation kernels
-//   [0] n_k  [1] n_degenerate  [2] Ne  [3..11] ahc(3,3)  [12..20] kubo_mep_ic  [21..29] kubo_mep_lc
-//   [30 .. 30+9*nw) mep_niu_ic(3,3,n0)   [30+9*nw .. 30+18*nw) mep_niu_lc(3,3,n0)
-constexpr int S_NK = 0, S_NDEG = 1, S_NE = 2, S_AHC = 3, S_KIC = 12, S_KLC = 21, S_NIU = 30;
+//   [0] n_k  [1] n_degenerate  [2] Ne  [3] # AHC pair items emitted  [4] # photo items emitted (work counters for the
+//   roofline)  [5..13] ahc(3,3)  [14..22] kubo_mep_ic  [23..31] kubo_mep_lc
+//   [32 .. 32+9*nw) mep_niu_ic(3,3,n0)   [32+9*nw .. 32+18*nw) mep_niu_lc(3,3,n0)
+constexpr int S_NK = 0, S_NDEG = 1, S_NE = 2, S_NIT = 3, S_NPH = 4, S_AHC = 5, S_KIC = 14, S_KLC = 23, S_NIU = 32;
 __host__ __device__ inline int static_size(int nw) { return S_NIU + 18 * nw; }
 
 struct DevModel {

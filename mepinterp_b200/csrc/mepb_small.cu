@@ -210,7 +210,7 @@ interp_small_kernel(const DevModel m, const KSource ks, const Jobs jb, const Int
     const bool need_eig = (out.e_out != nullptr) || (out.block_static != nullptr);
 
     for (int i = lane; i < 18 + 18 * NW; i += 32) mep[i] = 0.0;
-    double acc_nk = 0.0, acc_ndeg = 0.0, acc_ne = 0.0, acc_ahc[9];
+    double acc_nk = 0.0, acc_ndeg = 0.0, acc_ne = 0.0, acc_nit = 0.0, acc_nph = 0.0, acc_ahc[9];
 #pragma unroll
     for (int q = 0; q < 9; ++q) acc_ahc[q] = 0.0;
     __syncwarp();
@@ -441,7 +441,7 @@ interp_small_kernel(const DevModel m, const KSource ks, const Jobs jb, const Int
                 }
                 n_items_before += __popc(bal);
             }
-            if (out.cnt_ahc && lane == 0) out.cnt_ahc[ik] = n_items_before;
+            if (out.cnt_ahc && lane == 0) { out.cnt_ahc[ik] = n_items_before; acc_nit += (double)n_items_before; }
         }
         // ------------------------------------------------------------------ MEP sums (mep_niu.f90, kubo_mep.f90)
         if (jb.do_mep || jb.do_kubo) {
@@ -588,7 +588,7 @@ interp_small_kernel(const DevModel m, const KSource ks, const Jobs jb, const Int
                 }
                 n_before += __popc(bal);
             }
-            if (lane == 0) out.cnt_photo[ik] = n_before;
+            if (lane == 0) { out.cnt_photo[ik] = n_before; acc_nph += (double)n_before; }
         }
         __syncwarp();
     }
@@ -597,15 +597,16 @@ interp_small_kernel(const DevModel m, const KSource ks, const Jobs jb, const Int
     __syncthreads();
     constexpr int NS = S_NIU + 18 * NW;
     // each warp reduces its lane registers and stages its NS-vector at the start of its own region (A, U, Ha are dead
-    // now and contiguous: 10*NW*LD doubles >= NS = 24+18*NW for NW >= 4)
+    // now and contiguous: 10*NW*LD doubles >= NS = 32+18*NW for NW >= 4)
     double *wv = reinterpret_cast<double *>(As);
     {
         const double nk = warp_sum(acc_nk), nd = warp_sum(acc_ndeg), ne = warp_sum(acc_ne);
+        const double nit = warp_sum(acc_nit), nph = warp_sum(acc_nph);
 #pragma unroll
         for (int q = 0; q < 9; ++q) acc_ahc[q] = warp_sum(acc_ahc[q]);
         __syncwarp();
         if (lane == 0) {
-            wv[S_NK] = nk; wv[S_NDEG] = nd; wv[S_NE] = ne;
+            wv[S_NK] = nk; wv[S_NDEG] = nd; wv[S_NE] = ne; wv[S_NIT] = nit; wv[S_NPH] = nph;
 #pragma unroll
             for (int q = 0; q < 9; ++q) wv[S_AHC + q] = acc_ahc[q];
         }

@@ -404,6 +404,32 @@ int cpu_ref_accumulate_mt(const mepb_model *mo, const mepb_params *p, int64_t li
     return rc;
 }
 
+/* Test helper (not a reference function): partials_abs[i] += sum_k |X_i(k)|, the un-cancelled magnitude of every
+ * k-sum, so that parity tests can measure errors relative to sum |term| instead of |sum| (entries 0,1 and Ne are
+ * plain sums, so cpu_ref_finalize of this buffer gives the per-tensor magnitudes with the same eF_idx). */
+int cpu_ref_accumulate_abs(const mepb_model *mo, const mepb_params *p, int64_t lin_begin, int64_t lin_end, int nthreads,
+                           double *partials_abs) {
+    int64_t n = make_layout(p).total;
+    if (nthreads < 1) nthreads = 1;
+    double *priv = (double *)calloc((size_t)n * nthreads * 2, sizeof(double));
+    int rc = 0;
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(nthreads) schedule(static, 1)
+#endif
+    for (int r = 0; r < nthreads; ++r) {
+        double *acc = priv + (size_t)n * (2 * r), *one = priv + (size_t)n * (2 * r + 1);
+        for (int64_t lin = lin_begin + r; lin < lin_end; lin += nthreads) {
+            memset(one, 0, sizeof(double) * n);
+            int e = cpu_ref_accumulate(mo, p, lin, lin + 1, 0, 1, one);
+            if (e != 0) rc = e;
+            for (int64_t i = 0; i < n; ++i) acc[i] += fabs(one[i]);
+        }
+    }
+    for (int r = 0; r < nthreads; ++r) for (int64_t i = 0; i < n; ++i) partials_abs[i] += priv[(size_t)n * (2 * r) + i];
+    free(priv);
+    return rc;
+}
+
 /* core.f90:317-415 (first minimum, strict <), :419-603, k_space.f90:81-202 */
 int cpu_ref_finalize(const mepb_model *mo, const mepb_params *p, const double *partials, mepb_result *out) {
     layout_t L = make_layout(p);

@@ -62,6 +62,7 @@ def lib():
         L.cpu_ref_partials_size.argtypes = [C.POINTER(CParams)]
         L.cpu_ref_accumulate.argtypes = [C.POINTER(CModel), C.POINTER(CParams), C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p]
         L.cpu_ref_accumulate_mt.argtypes = [C.POINTER(CModel), C.POINTER(CParams), C.c_int64, C.c_int64, C.c_int, C.c_void_p]
+        L.cpu_ref_accumulate_abs.argtypes = [C.POINTER(CModel), C.POINTER(CParams), C.c_int64, C.c_int64, C.c_int, C.c_void_p]
         L.cpu_ref_finalize.argtypes = [C.POINTER(CModel), C.POINTER(CParams), C.c_void_p, C.POINTER(CResult)]
         L.cpu_ref_interp.argtypes = [C.POINTER(CModel), C.POINTER(CParams), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         rc = L.cpu_ref_init(openblas_path().encode())
@@ -116,6 +117,14 @@ class Handle:
         if rc != 0:
             raise RuntimeError(f"cpu_ref_accumulate rc={rc}")
         return partials
+
+    def accumulate_abs(self, lin_begin, lin_end, nthreads=1):
+        """sum_k |X(k)| for every packed entry (test helper: the scale reassociation errors are measured against)."""
+        buf = np.zeros(self.partials_size())
+        rc = lib().cpu_ref_accumulate_abs(C.byref(self.cm), C.byref(self.cp), lin_begin, lin_end, nthreads, buf.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f"cpu_ref_accumulate_abs rc={rc}")
+        return buf
 
     def finalize(self, partials) -> dict:
         return finalize_with(lambda res: lib().cpu_ref_finalize(C.byref(self.cm), C.byref(self.cp), partials.ctypes.data, C.byref(res)),

@@ -1,0 +1,272 @@
+"""GPU parity tests (`-m gpu`): libmepb's hand-written sm_100a path, called through the C ABI (ctypes, include/mepb.h),
+against the CPU oracle on identical inputs.
+
+Bars (BASELINE.json north_star): eigenvalues 1e-10 relative, response tensors 1e-8 relative in FP64, gauge-invariant
+quantities only.  "Relative" is measured against the un-cancelled magnitude of each k-sum, plus the oracle's own
+movement under a 2-ulp perturbation of H(R) for the tensors the reference leaves unguarded at near-degenerate bands
+(tests/cases.py::oracle_reference explains both yardsticks).  Fourier sums are gauge independent and are compared
+element-wise at 1e-13.  Nothing here reads /root/reference.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import cpu_ref
+from oracle import mep_oracle as mo
+from tests.cases import GOLDEN, assert_parity, ev, load_case, oracle_reference, rel_err, synthetic_model
+
+pytestmark = pytest.mark.gpu
+
+EIG_TOL = 1e-10
+TENS_TOL = 1e-8
+
+
+def _cases_small():
+    all_jobs = dict(do_mep=True, do_kubo=True, do_ahc=True, do_opt=True, n_hw=7, hw_min=ev(0.03), hw_max=ev(6.0), eta=ev(0.1))
+    yield "C1_souza_ahc_mep_32^3_full", load_case("souza_phi0", mp_grid=(32, 32, 32))
+    yield "C1_souza_kubo_16^3", load_case("souza_phi0", mp_grid=(16, 16, 16), do_kubo=True)
+    yield "C2_femn_ahc_nhw121_16^3", load_case("femn_d0.900", mp_grid=(16, 16, 16))
+    yield "C2_femn_d1.1_ahc_12^3", load_case("femn_d1.100", mp_grid=(12, 12, 12))
+    yield "C3_femn_mep_kubo_16^3", load_case("femn_d0.900", mp_grid=(16, 16, 16), do_ahc=False, do_mep=True, do_kubo=True, n_hw=1, hw_max=0.0)
+    yield "C4_rashba_opt_ahc_nhw200_8^3", load_case("femn_rashba", mp_grid=(8, 8, 8))
+    yield "femn_all_jobs_T300_neF3_ragged", load_case("femn_d0.900", mp_grid=(11, 12, 13), n_eF=3, eF_min=ev(-0.5), eF_max=ev(0.5),
+                                                       T_kelvin=300.0, **all_jobs)
+    yield "rashba_all_jobs_T0", load_case("femn_rashba", mp_grid=(7, 6, 5), **dict(all_jobs, n_hw=9))
+    sm = synthetic_model(8, 5, tb_centers=True)
+    yield "syn_nw8_tb_cart_velo", (sm, mo.Params(mp_grid=(10, 11, 12), valence_bands=3, use_cart_velo=True, **all_jobs))
+    yield "syn_nw8_no_gauge_trafo", (sm, mo.Params(mp_grid=(6, 6, 6), valence_bands=3, do_gauge_trafo=False, T_kelvin=120.0, **all_jobs))
+    for nw in (4, 16):
+        yield f"syn_nw{nw}_wannier_T200", (synthetic_model(nw, 3), mo.Params(mp_grid=(8, 8, 8), valence_bands=nw // 2, T_kelvin=200.0,
+                                                                              **dict(all_jobs, n_hw=5)))
+    yield "syn_nw16_tb_neF2", (synthetic_model(16, 2, tb_centers=True),
+                               mo.Params(mp_grid=(5, 5, 5), valence_bands=7, n_eF=2, eF_min=ev(-0.3), eF_max=ev(0.2), **all_jobs))
+
+
+CASES = dict(_cases_small())
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_fourier_sums_elementwise(libmepb, name):
+    """FT_R_to_k (wann_interp.f90:151-281): H(k), dH/dk_a(k) are gauge independent -> element-wise."""
+    model, params = CASES[name]
+    kp = np.random.default_rng(5).uniform(-0.5, 0.5, size=(301, 3))
+    kp[0] = 0.0                                         # Gamma
+    kp[1] = (0.5, -0.5, 0.25)                           # zone boundary
+    _, _, Hk_r, Hka_r = cpu_ref.Handle(model, params).interp(kp, want_V=False, want_H=True)
+    ctx = libmepb.Context(model, params)
+    Hk, Hka = ctx.fourier(kp)
+    ctx.close()
+    assert rel_err(Hk, Hk_r) < 1e-13
+    assert rel_err(Hka, Hka_r) < 1e-13
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_eigenvalues_and_gauge_invariants(libmepb, name):
+    """zheevd + rotate_gauge (matrix_math.f90:192-226, wann_interp.f90:502-550): eigenvalues ascending, 1e-10 relative;
+    sum rules tr H = sum E, ||H_upper-Hermitian||_F^2 = sum E^2; V diagonal (band velocities) and the gauge-invariant
+    Frobenius norms sum_nm |V_a(n,m)|^2 = ||dH_a||_F^2."""
+    model, params = CASES[name]
+    kp = np.random.default_rng(6).uniform(-0.5, 0.5, size=(257, 3))
+    h = cpu_ref.Handle(model, params)
+    e_r, V_r, Hk_r, Hka_r = h.interp(kp, want_V=True, want_H=True)
+    ctx = libmepb.Context(model, params)
+    e, V = ctx.interp(kp)
+    ctx.close()
+    hnorm = np.abs(e_r).max()
+    assert np.all(np.diff(e, axis=0) >= 0.0)
+    assert np.abs(e - e_r).max() <= EIG_TOL * hnorm
+    assert np.abs(e.sum(axis=0) - np.einsum("nnk->k", Hk_r).real).max() <= 1e-12 * hnorm * model.nw
+    if params.do_gauge_trafo:
+        fro_V = (np.abs(V) ** 2).sum(axis=(1, 2))
+        fro_H = (np.abs(Hka_r) ** 2).sum(axis=(1, 2))
+        assert np.abs(fro_V - fro_H).max() <= 1e-11 * fro_H.max()
+        # band velocities: invariant wherever the band is isolated
+        gap = np.minimum(np.diff(e_r, axis=0, prepend=-np.inf), np.diff(e_r, axis=0, append=np.inf)[..., :])
+        iso = np.abs(gap) > 1e-4
+        dV = np.einsum("annk->ank", V) - np.einsum("annk->ank", V_r)
+        assert np.abs(dV[:, iso]).max() <= 1e-9 * np.abs(V_r).max()
+    else:
+        assert rel_err(V, V_r) < 1e-13                  # W gauge: V = dH
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_run_mesh_parity(libmepb, name):
+    """core_worker (core.f90:79-298) end to end: every tensor the reference writes to out/*.npy."""
+    model, params = CASES[name]
+    ref, scale, sens = oracle_reference(model, params)
+    ctx = libmepb.Context(model, params)
+    out = ctx.run_mesh()
+    launches = ctx.kernel_launches
+    ctx.close()
+    assert launches > 0
+    assert_parity(out, ref, scale, sens, tol=TENS_TOL, label=name)
+    if params.do_ahc:
+        a = out["ahc_tens"]
+        assert np.abs(a + a.T).max() <= 1e-12 * scale["ahc_tens"]
+
+
+def test_golden_ahc_anchor_on_gpu(libmepb):
+    """The reference's golden FeMn sigma_xy (config/FeMn_TB/delta0.900 via tests/golden) at the test's own 64^3 mesh and at
+    BASELINE config 2's 128^3: mesh-convergence-level pin (1.1e-3 and 7.4e-4 from the golden)."""
+    gold = np.load(os.path.join(GOLDEN, "femn_d0.900", "ahc_tens.npy"))
+    gold_w = np.load(os.path.join(GOLDEN, "femn_d0.900", "ahcVELO.npy"))
+    for mesh, tol, tol_w in ((64, 2e-3, 2.5e-4), (128, 1.5e-3, 5e-5)):
+        m, p = load_case("femn_d0.900", mp_grid=(mesh,) * 3)
+        ctx = libmepb.Context(m, p)
+        out = ctx.run_mesh()
+        ctx.close()
+        assert out["n_k"] == mesh ** 3
+        assert rel_err(out["ahc_tens"], gold) < tol
+        assert np.abs(out["ahcVELO"] - gold_w).max() < tol_w
+        assert np.abs(out["ahc_tens"] + out["ahc_tens"].T).max() < 1e-15
+    m, p = load_case("femn_d1.000", mp_grid=(32, 32, 32))
+    ctx = libmepb.Context(m, p)
+    out = ctx.run_mesh()
+    ctx.close()
+    assert np.abs(out["ahc_tens"]).max() < 1e-10         # zero by symmetry, like the golden
+
+
+def test_full_size_c2_shard_linearity(libmepb):
+    """BASELINE config 2 at full size (128^3, n_hw=121): size-independent properties — the sum of ragged slab partials
+    equals the whole-mesh partials (linearity / 'sum over ranks'), and a second context fed the summed buffer through
+    mepb_set_partials finalizes to the same tensors."""
+    m, p = load_case("femn_d0.900", mp_grid=(128, 128, 128))
+    nk = 128 ** 3
+    ctx = libmepb.Context(m, p)
+    ctx.reset(); ctx.accumulate(0, nk)
+    whole = ctx.get_partials().copy()
+    res_whole = ctx.finalize()
+    cuts = [0, 1, 777_777, 777_777, 1_500_001, nk]          # ragged, one empty slab
+    tot = np.zeros_like(whole)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        ctx.reset(); ctx.accumulate(a, b)
+        tot += ctx.get_partials()
+    assert tot[0] == whole[0] == nk
+    mag = np.abs(whole).max()
+    assert np.abs(tot - whole).max() <= 1e-11 * mag
+    ctx2 = libmepb.Context(m, p)
+    ctx2.set_partials(tot)
+    res2 = ctx2.finalize()
+    ctx2.close(); ctx.close()
+    for k in ("ahc_tens", "ahcVELO", "ohcVELO"):
+        assert rel_err(res2[k], res_whole[k]) < 1e-10
+
+
+def test_sharded_two_contexts_equal_oracle(libmepb):
+    """The MPI-host variant of the ABI (accumulate / get_partials / set_partials / finalize) with 3 'ranks'."""
+    from mepinterp_b200 import dist as mdist
+    m, p = load_case("souza_phi0", mp_grid=(9, 8, 7), do_kubo=True)
+    nk = 9 * 8 * 7
+    ref, scale, sens = oracle_reference(m, p)
+    bufs = []
+    for r in range(3):
+        c = libmepb.Context(m, p)
+        c.reset()
+        c.accumulate(*mdist.slab(r, 3, nk))
+        bufs.append(c.get_partials().copy())
+        c.close()
+    c = libmepb.Context(m, p)
+    c.set_partials(mdist.sum_partials_host(bufs))
+    out = c.finalize()
+    c.close()
+    assert_parity(out, ref, scale, sens, tol=TENS_TOL)
+    # raw packed layout is the oracle's layout (include/mepb.h): compare un-normalised sums entry by entry
+    raw = cpu_ref.Handle(m, p).accumulate(0, nk)
+    tot = mdist.sum_partials_host(bufs)
+    assert tot.shape == raw.shape and tot[0] == raw[0]
+
+
+def test_edge_meshes_and_ranges(libmepb):
+    m, p = load_case("souza_phi0", mp_grid=(1, 1, 1), do_kubo=True)
+    ref, scale, sens = oracle_reference(m, p)
+    ctx = libmepb.Context(m, p)
+    assert_parity(ctx.run_mesh(), ref, scale, sens, tol=TENS_TOL)
+    # empty range is legal and adds nothing; finalize with nothing accumulated is a state error
+    ctx.reset(); ctx.accumulate(0, 0)
+    with pytest.raises(libmepb.MepbError) as ei:
+        ctx.finalize()
+    assert ei.value.code == libmepb.api.ERR_STATE
+    with pytest.raises(libmepb.MepbError) as ei:
+        ctx.accumulate(0, 2)                             # outside the 1-point mesh
+    assert ei.value.code == libmepb.api.ERR_ARG
+    ctx.close()
+    for grid in ((1, 1, 37), (3, 1, 2), (2, 5, 1)):
+        m, p = load_case("femn_d0.900", mp_grid=grid, n_hw=3)
+        ref, scale, sens = oracle_reference(m, p)
+        ctx = libmepb.Context(m, p)
+        assert_parity(ctx.run_mesh(), ref, scale, sens, tol=TENS_TOL, label=str(grid))
+        ctx.close()
+
+
+def test_call_order_and_argument_errors(libmepb):
+    m, p = load_case("souza_phi0", mp_grid=(2, 2, 2))
+    ctx = libmepb.Context(m, p)
+    with pytest.raises(libmepb.MepbError) as ei:
+        ctx.finalize()
+    assert ei.value.code == libmepb.api.ERR_STATE
+    ctx.set_partials(np.zeros(ctx.partials_size()))
+    with pytest.raises(libmepb.MepbError) as ei:
+        ctx.accumulate(0, 8)                             # accumulate after set_partials needs a reset
+    assert ei.value.code == libmepb.api.ERR_STATE
+    ctx.reset(); ctx.accumulate(0, 8)
+    assert ctx.finalize()["n_k"] == 8
+    ctx.close()
+    # position operator branch is not implemented: loud error, not silent zeros
+    cm = ctx.cm
+    dummy = np.zeros(8)
+    cm.r = dummy.ctypes.data
+    h = C.c_void_p()
+    assert libmepb.lib().mepb_create(C.byref(cm), C.byref(ctx.cp), 0, C.byref(h)) == libmepb.api.ERR_UNSUPPORTED
+    cm.r = None
+    assert libmepb.lib().mepb_create(C.byref(cm), C.byref(ctx.cp), 99, C.byref(h)) == libmepb.api.ERR_ARG
+    bad = mo.Params(mp_grid=(2, 2, 0))
+    with pytest.raises(libmepb.MepbError):
+        libmepb.Context(m, bad)
+
+
+def test_exact_degeneracy_matches_reference_semantics(libmepb):
+    """Q6: no guard in kubo_ahc_tens / kubo_ohc_tens / kubo_mep (kubo.f90:65,186; kubo_mep.f90:73,126) -> inf/NaN propagate,
+    guarded mep_niu (mep_niu.f90:73,132) and the eta-regularised velo_ahc stay finite; offending pairs are counted."""
+    nw = 4
+    H = np.zeros((nw, nw, 1), dtype=np.complex128)
+    H[:, :, 0] = np.diag([-1.0, -1.0, 1.0, 1.0])
+    m = mo.Model(nw=nw, nR=1, R=np.zeros((3, 1)), H=H, a_latt=np.eye(3) * 3.0)
+    p = mo.Params(mp_grid=(2, 2, 2), do_ahc=True, do_mep=True, do_kubo=True, valence_bands=2, n_hw=2, hw_max=ev(1.0), eta=ev(0.1))
+    with np.errstate(all="ignore"):
+        ref = cpu_ref.Handle(m, p).run_mesh()
+    ctx = libmepb.Context(m, p)
+    out = ctx.run_mesh()
+    ctx.close()
+    assert out["n_degenerate"] == ref["n_degenerate"] == 16
+    for k in ("ahc_tens", "kubo_mep_lc"):
+        assert np.array_equal(np.isfinite(out[k]), np.isfinite(ref[k])), k
+    for k in ("ahcVELO", "mep_ic", "mep_lc"):
+        assert np.all(np.isfinite(out[k])) and np.all(np.isfinite(ref[k])), k
+        assert np.abs(out[k] - ref[k]).max() < 1e-12
+
+
+def test_repeatability_bitwise(libmepb):
+    """Fixed launch shapes + fixed-order tree reductions: two runs of the same mesh give bit-identical tensors."""
+    m, p = load_case("femn_d0.900", mp_grid=(24, 24, 24), n_hw=11)
+    ctx = libmepb.Context(m, p)
+    a = ctx.run_mesh()
+    b = ctx.run_mesh()
+    ctx.close()
+    for k in ("ahc_tens", "ahcVELO", "ohcVELO"):
+        assert np.array_equal(a[k], b[k]), k
+
+
+def test_nccl_sharded_if_multi_gpu(libmepb):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "tests", "nccl_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "NCCL_SHARDED_OK" in r.stdout
