@@ -65,7 +65,9 @@ def make_workload(name: str, n_gpus: int):
 def flops_model(model, params):
     """Algorithmic FP64 flops per unit for each kernel class (DESIGN.md 'Kernels and rooflines')."""
     nw, nR = model.nw, model.nR
-    interp = 8.0 * nR * nw * nw * 4 + 36.0 * nw ** 3                 # Fourier sums (H, 3 dH) + LAPACK-convention eigensolve
+    split = nw in (4, 8)                                              # thread-per-k eigensolver kernel (mepb_eig.cu)
+    eig = 8.0 * nR * (nw * (nw + 1) // 2) + 36.0 * nw ** 3            # Fourier sum of H (upper triangle) + LAPACK-convention eigensolve
+    interp = 8.0 * nR * nw * nw * 4 + (0.0 if split else 36.0 * nw ** 3)   # Fourier sums (H, 3 dH)
     if params.do_gauge_trafo:
         interp += 48.0 * nw ** 3                                      # U^dagger (d_a H) U, a = 1..3
     if params.do_ahc:
@@ -73,7 +75,7 @@ def flops_model(model, params):
     if params.do_mep or params.do_kubo:
         interp += 130.0 * nw * (nw - 1) ** 2
     herm = True
-    return {"interp_per_k": interp,
+    return {"interp_per_k": interp, "eig_per_k": eig if split else 0.0,
             "sweep_ahc_per_item_hw": 56.0 if herm else 92.0,          # 1 complex reciprocal + 18 (36) accumulate FMAs
             "sweep_photo_per_item_hw": 246.0}                          # 27 complex MACs + the two-pole factor
 
@@ -263,11 +265,11 @@ def main():
     ctx.set_profiling(False)
     fm = flops_model(model, params)
     nk_loc = b1 - b0
-    work = {"interp": fm["interp_per_k"] * nk_loc,
+    work = {"interp": fm["interp_per_k"] * nk_loc, "eig": fm["eig_per_k"] * nk_loc,
             "sweep_ahc": fm["sweep_ahc_per_item_hw"] * items["sweep_ahc"] * params.n_hw,
             "sweep_photo": fm["sweep_photo_per_item_hw"] * items["sweep_photo"] * params.n_hw}
     kernels = {}
-    for k in ("interp", "sweep_ahc", "sweep_photo", "reduce"):
+    for k in ("eig", "interp", "sweep_ahc", "sweep_photo", "reduce"):
         if prof[k]["launches"]:
             ms = prof[k]["ms"]
             kernels[k] = {"ms_per_pass": ms, "launches": prof[k]["launches"], "share": None,

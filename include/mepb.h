@@ -115,11 +115,12 @@ int mepb_timer_stop(mepb_ctx *ctx, double *ms);
 
 /* Per-kernel-class device timing: when on, mepb_accumulate serialises its schedule onto one stream and brackets every
  * launch with CUDA events (slower; used for the roofline figures, never for throughput numbers). */
-#define MEPB_PROF_INTERP       0   /* fused Fourier + eigensolve + rotation + static band sums kernel */
+#define MEPB_PROF_INTERP       0   /* fused Fourier(dH) + rotation + static band sums + pair items     */
 #define MEPB_PROF_SWEEP_AHC    1   /* velo_ahc / kubo_ohc frequency sweep                             */
 #define MEPB_PROF_SWEEP_PHOTO  2   /* photo_2nd_cond frequency sweep                                  */
 #define MEPB_PROF_REDUCE       3   /* block-partial reductions                                        */
-#define MEPB_PROF_KINDS        4
+#define MEPB_PROF_EIG          4   /* thread-per-k Fourier(H) + Jacobi eigensolver (num_wann 4, 8)     */
+#define MEPB_PROF_KINDS        5
 int mepb_set_profiling(mepb_ctx *ctx, int on);
 int mepb_get_profile(const mepb_ctx *ctx, int kind, double *ms_total, int64_t *launches);
 /* (k, band pair) items the last packed run handed to the frequency sweep `kind` (MEPB_PROF_SWEEP_AHC / _PHOTO): the

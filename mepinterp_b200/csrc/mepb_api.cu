@@ -116,6 +116,7 @@ struct StreamBuf {
     double *items_photo = nullptr; int *cnt_photo = nullptr;
     double *block_static = nullptr, *block_sweep = nullptr, *block_photo = nullptr;
     double *compact = nullptr;   // [n_eF][per_ef]
+    double *eig_E = nullptr; double2 *eig_U = nullptr;   // [chunk][nw], [chunk][nw*nw] from the thread-per-k eigensolver
 };
 
 }  // namespace
@@ -126,6 +127,7 @@ struct mepb_ctx {
     int nw = 0, nR = 0;
     bool has_tau = false;
     bool herm = true;      // H(R) Hermitian-closed: V_a Hermitian -> compact items / 18-accumulator sweep
+    bool eig_thread = false;   // eigenpairs from the thread-per-k kernel (nw 4, 8)
     double a_latt[9];
     // device model
     double2 *d_H = nullptr; double *d_Rf = nullptr, *d_cR = nullptr, *d_tau = nullptr, *d_tM = nullptr, *d_hw = nullptr;
@@ -148,8 +150,8 @@ struct mepb_ctx {
     bool profiling = false;
     std::vector<cudaEvent_t> prof_ev;          // pairs (start, stop)
     std::vector<int> prof_kind;
-    double prof_ms[MEPB_PROF_KINDS] = {0, 0, 0, 0};
-    long long prof_n[MEPB_PROF_KINDS] = {0, 0, 0, 0};
+    double prof_ms[MEPB_PROF_KINDS] = {0, 0, 0, 0, 0};
+    long long prof_n[MEPB_PROF_KINDS] = {0, 0, 0, 0, 0};
     cudaEvent_t tm0 = nullptr, tm1 = nullptr;  // mepb_timer_start / stop
     // list-mode scratch
     double *d_kpt = nullptr, *d_e = nullptr; double2 *d_V = nullptr, *d_Hk = nullptr, *d_Hka = nullptr;
@@ -219,6 +221,7 @@ void free_all(mepb_ctx *c) {
     for (auto &s : c->sb) {
         cudaFree(s.items_ahc); cudaFree(s.cnt_ahc); cudaFree(s.items_photo); cudaFree(s.cnt_photo);
         cudaFree(s.block_static); cudaFree(s.block_sweep); cudaFree(s.block_photo); cudaFree(s.compact);
+        cudaFree(s.eig_E); cudaFree(s.eig_U);
         if (s.st) cudaStreamDestroy(s.st);
         if (s.done) cudaEventDestroy(s.done);
     }
@@ -303,6 +306,7 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
     c->device = device; c->sm_count = prop.multiProcessorCount;
     c->p = p; c->nw = model->nw; c->nR = model->nR; c->has_tau = (model->wf_centers != nullptr);
     { std::string why; c->herm = hermitian_closed(model, &why); }
+    c->eig_thread = eig_thread_supported(model->nw) && !getenv("MEPB_WARP_JACOBI");
     std::memcpy(c->a_latt, model->a_latt, sizeof(c->a_latt));
     const int nw = c->nw, nR = c->nR;
     // linspaces (matrix_math.f90:74-100, core.f90:124-125)
@@ -371,6 +375,10 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
             CT(cudaMalloc((void **)&s.cnt_photo, sizeof(int) * (size_t)chunk));
             CT(cudaMalloc((void **)&s.block_photo, sizeof(double) * kPhotoAcc * (size_t)c->ns_photo * c->grid_photo));
         }
+        if (c->eig_thread) {
+            CT(cudaMalloc((void **)&s.eig_E, sizeof(double) * nw * (size_t)chunk));
+            CT(cudaMalloc((void **)&s.eig_U, sizeof(double2) * nw * nw * (size_t)chunk));
+        }
         CT(cudaMalloc((void **)&s.block_static, sizeof(double) * (size_t)c->cs.ns * c->grid_interp));
         CT(cudaMalloc((void **)&s.compact, sizeof(double) * (size_t)c->cs.per_ef * p.n_eF));
         CT(cudaMemset(s.compact, 0, sizeof(double) * (size_t)c->cs.per_ef * p.n_eF));
@@ -427,6 +435,12 @@ int mepb_accumulate(mepb_ctx *c, int64_t lin_begin, int64_t lin_end) {
             o.items_photo = jb.do_opt ? s.items_photo : nullptr; o.cnt_photo = s.cnt_photo;
             o.block_static = s.block_static; o.err_flag = c->d_err;
             const int gi = interp_small_grid(c->nw, c->nR, c->sm_count, nk);
+            if (c->eig_thread) {
+                ProfScope ps(c, s.st, MEPB_PROF_EIG);
+                CUDA_TRY(launch_eig_small(m, ks, s.eig_E, s.eig_U, c->d_err, c->sm_count, s.st));
+                o.e_in = s.eig_E; o.U_in = s.eig_U;
+                c->launches += 1;
+            }
             { ProfScope ps(c, s.st, MEPB_PROF_INTERP); CUDA_TRY(launch_interp_small(m, ks, jb, o, c->max_pairs, gi, s.st)); }
             { ProfScope ps(c, s.st, MEPB_PROF_REDUCE);
               CUDA_TRY(launch_reduce_rows(s.block_static, gi, ns, s.compact + (size_t)ief * c->cs.per_ef, ns, 0, 0, s.st)); }
@@ -596,7 +610,7 @@ static int ensure_list(mepb_ctx *c, long long cap) {
 static int list_run(mepb_ctx *c, int64_t nk, const double *kpt, double *e_k, double *V_ka, double *H_k, double *H_ka) {
     if (!c || !kpt || nk < 0) return fail(MEPB_ERR_ARG, "bad argument");
     CUDA_TRY(cudaSetDevice(c->device));
-    const long long cap = std::min<long long>(std::max<long long>(nk, 1), 1 << 16);
+    const long long cap = std::min<long long>(std::min<long long>(std::max<long long>(nk, 1), 1 << 16), c->chunk);
     int rc = ensure_list(c, cap);
     if (rc) return rc;
     const DevModel m = dev_model(c);
@@ -612,6 +626,11 @@ static int list_run(mepb_ctx *c, int64_t nk, const double *kpt, double *e_k, dou
         o.Hk_out = H_k ? c->d_Hk : nullptr; o.Hka_out = H_ka ? c->d_Hka : nullptr;
         if (V_ka && !e_k) o.e_out = c->d_e;
         o.err_flag = c->d_err;
+        if (c->eig_thread && o.e_out) {
+            CUDA_TRY(launch_eig_small(m, ks, c->sb[0].eig_E, c->sb[0].eig_U, c->d_err, c->sm_count, st));
+            o.e_in = c->sb[0].eig_E; o.U_in = c->sb[0].eig_U;
+            c->launches += 1;
+        }
         CUDA_TRY(launch_interp_small(m, ks, jb, o, c->max_pairs, interp_small_grid(c->nw, c->nR, c->sm_count, n), st));
         c->launches += 1;
         if (e_k) CUDA_TRY(cudaMemcpyAsync(e_k + nw * k0, c->d_e, sizeof(double) * nw * n, cudaMemcpyDeviceToHost, st));

@@ -1,0 +1,236 @@
+// mepb_eig.cu — batched Hermitian eigensolver for small num_wann: ONE THREAD PER k-POINT.
+//
+// Replaces the per-k LAPACK zheevd('V','U') of the reference (src/matrix_math.f90:192-226, called from
+// src/wann_interp.f90:95) for nw in {4, 8}.  Each thread
+//   1. builds the upper triangle of H(k) = sum_R e^{2 pi i k.R} H(R) in registers           (wann_interp.f90:206-279)
+//   2. diagonalises it by cyclic two-sided Jacobi: the matrix lives in registers in "tournament order" — the pairs of a
+//      round are always the positions (0,1),(2,3),.. and the Brent-Luk permutation is applied to rows and columns after
+//      every round, so every register index is a compile-time constant (no shuffles, no barriers, no divergence inside
+//      a round); the eigenvector matrix U lives in shared memory, one 16-byte column of lanes per matrix element
+//      (conflict-free LDS.128/STS.128)
+//   3. writes the ascending eigenvalues and the matching eigenvector columns to HBM for the band-sum kernel.
+// The rotation formulas are those of the warp-per-k solver in mepb_small.cu (validated against zheevd to 1e-15).
+#include "mepb_internal.cuh"
+
+namespace mepb {
+
+namespace {
+
+template <int NW> struct EigCfg;
+template <> struct EigCfg<4> { static constexpr int TPB = 256; };
+template <> struct EigCfg<8> { static constexpr int TPB = 224; };   // 224 threads x 1 KB of U = 224 KB of shared memory
+
+// Brent-Luk tournament: new position i takes the row/column that sat at position sigma(i)
+template <int NW> __host__ __device__ constexpr int sigma(int i) {
+    constexpr int NP = NW / 2;
+    if (NP == 1) return i;
+    if (i == 0) return 0;
+    if (i == 2) return 1;
+    if (i == 2 * NP - 1) return 2 * (NP - 1);
+    if (i % 2 == 0) return i - 2;      // top row shifts right
+    return i + 2;                       // bottom row shifts left
+}
+
+template <int NW>
+__global__ void __launch_bounds__(EigCfg<NW>::TPB, 1)
+eig_small_kernel(const DevModel m, const KSource ks, double *__restrict__ E_out, double2 *__restrict__ U_out,
+                 int *__restrict__ err_flag) {
+    constexpr int TPB = EigCfg<NW>::TPB, NP = NW / 2, NW2 = NW * NW;
+    extern __shared__ __align__(16) double2 Us[];            // [NW2][TPB], element (row + NW*col)
+    const int tid = threadIdx.x;
+    const int nR = m.nR;
+    const bool has_tau = (m.tau != nullptr);
+
+    for (long long ik = (long long)blockIdx.x * TPB + tid; ik < ks.nk; ik += (long long)gridDim.x * TPB) {
+        // ------------------------------------------------------------------ k-point (k_space.f90:351-375)
+        double k1, k2, k3;
+        if (ks.list) { k1 = ks.list[3 * ik]; k2 = ks.list[3 * ik + 1]; k3 = ks.list[3 * ik + 2]; }
+        else {
+            const long long lin = ks.lin_begin + ik;
+            const long long q1 = lin % ks.N1 + 1, q2 = (lin / ks.N1) % ks.N2 + 1, q3 = lin / ((long long)ks.N1 * ks.N2) + 1;
+            k1 = (2.0 * (double)q1 - (double)ks.N1 - 1.0) / (2.0 * (double)ks.N1);
+            k2 = (2.0 * (double)q2 - (double)ks.N2 - 1.0) / (2.0 * (double)ks.N2);
+            k3 = (2.0 * (double)q3 - (double)ks.N3 - 1.0) / (2.0 * (double)ks.N3);
+        }
+        // ------------------------------------------------------------------ Fourier sum, upper triangle (zheevd 'U')
+        double ar[NW][NW], ai[NW][NW];                         // [p][q], p <= q used
+#pragma unroll
+        for (int p = 0; p < NW; ++p)
+#pragma unroll
+            for (int q = 0; q < NW; ++q) { ar[p][q] = 0.0; ai[p][q] = 0.0; }
+        for (int R = 0; R < nR; ++R) {
+            const double x = 2.0 * (k1 * __ldg(&m.Rf[3 * R]) + k2 * __ldg(&m.Rf[3 * R + 1]) + k3 * __ldg(&m.Rf[3 * R + 2]));
+            double s, c; sincospi(x, &s, &c);
+            const double2 *HR = m.H + (size_t)R * NW2;
+#pragma unroll
+            for (int q = 0; q < NW; ++q)
+#pragma unroll
+                for (int p = 0; p <= q; ++p) {
+                    const double2 h = __ldg(&HR[p + NW * q]);
+                    ar[p][q] = fma(c, h.x, ar[p][q]); ar[p][q] = fma(-s, h.y, ar[p][q]);
+                    if (p != q) { ai[p][q] = fma(c, h.y, ai[p][q]); ai[p][q] = fma(s, h.x, ai[p][q]); }
+                }
+        }
+        if (has_tau) {   // tight-binding convention: H(n,m) <- conj(d_n) H(n,m) d_m, d_n = e^{2 pi i k.tau_n}
+            double dr[NW], di[NW];
+#pragma unroll
+            for (int n = 0; n < NW; ++n) {
+                const double x = 2.0 * (k1 * __ldg(&m.tau[3 * n]) + k2 * __ldg(&m.tau[3 * n + 1]) + k3 * __ldg(&m.tau[3 * n + 2]));
+                sincospi(x, &di[n], &dr[n]);
+            }
+#pragma unroll
+            for (int q = 0; q < NW; ++q)
+#pragma unroll
+                for (int p = 0; p < q; ++p) {
+                    const double wr = dr[q] * dr[p] + di[q] * di[p], wi = di[q] * dr[p] - dr[q] * di[p];   // d_q conj(d_p)
+                    const double hr = ar[p][q], hi = ai[p][q];
+                    ar[p][q] = hr * wr - hi * wi; ai[p][q] = hr * wi + hi * wr;
+                }
+        }
+        // ------------------------------------------------------------------ Jacobi
+        double nrm = 0.0;
+#pragma unroll
+        for (int q = 0; q < NW; ++q)
+#pragma unroll
+            for (int p = 0; p <= q; ++p)
+                nrm += (p == q) ? ar[p][q] * ar[p][q] : 2.0 * (ar[p][q] * ar[p][q] + ai[p][q] * ai[p][q]);
+#pragma unroll
+        for (int e = 0; e < NW2; ++e) Us[e * TPB + tid] = make_double2((e % NW) == (e / NW) ? 1.0 : 0.0, 0.0);
+        int perm[NW];                                          // position -> storage column of U
+#pragma unroll
+        for (int i = 0; i < NW; ++i) perm[i] = i;
+        bool ok = (nrm >= 0.0);                                // NaN -> fail
+        if (nrm > 0.0) {
+            const double tol = 1e-26 * nrm;
+            ok = false;
+            for (int sweep = 0; sweep < 30 && !ok; ++sweep) {
+                double off2 = 0.0;
+                for (int r = 0; r < NW - 1; ++r) {
+                    double rc[NP], rsx[NP], rsy[NP];
+                    // ---- rotation parameters of the NP pairs (2i, 2i+1)
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) {
+                        const int p = 2 * i, q = 2 * i + 1;
+                        const double a = ar[p][p], d = ar[q][q], bx = ar[p][q], by = ai[p][q];
+                        const double bb = fma(bx, bx, by * by);
+                        const bool rot = bb > 1e-300;
+                        const double zeta = 0.5 * (d - a), az = fabs(zeta);
+                        const double h = sqrt(fma(zeta, zeta, bb));
+                        const double y = 2.0 * h * (az + h);
+                        const double ry = rot ? rsqrt(y) : 0.0;
+                        const double sg = zeta < 0.0 ? -1.0 : 1.0;
+                        rc[i] = rot ? (az + h) * ry : 1.0;
+                        const double sr = sg * ry;
+                        rsx[i] = sr * bx; rsy[i] = sr * by;
+                        const double tb = sg * bb * (2.0 * h) * ry * ry;
+                        ar[p][p] = a - tb; ar[q][q] = d + tb; ar[p][q] = 0.0; ai[p][q] = 0.0;
+                        off2 += rot ? bb : 0.0;
+                    }
+                    // ---- off-diagonal 2x2 blocks (pair i rows, pair k columns), i < k:  B <- J_i^dagger B J_k
+#pragma unroll
+                    for (int i = 0; i < NP; ++i)
+#pragma unroll
+                        for (int k = i + 1; k < NP; ++k) {
+                            const int p = 2 * i, q = 2 * i + 1, pp = 2 * k, qq = 2 * k + 1;
+                            const double ci = rc[i], six = rsx[i], siy = rsy[i], cj = rc[k], sjx = rsx[k], sjy = rsy[k];
+                            const double bppx = ar[p][pp], bppy = ai[p][pp], bpqx = ar[p][qq], bpqy = ai[p][qq];
+                            const double bqpx = ar[q][pp], bqpy = ai[q][pp], bqqx = ar[q][qq], bqqy = ai[q][qq];
+                            // columns: t(.,pp) = c x - conj(s) y ; t(.,qq) = s x + c y
+                            const double tppx = cj * bppx - (sjx * bpqx + sjy * bpqy), tppy = cj * bppy - (sjx * bpqy - sjy * bpqx);
+                            const double tqpx = cj * bqpx - (sjx * bqqx + sjy * bqqy), tqpy = cj * bqpy - (sjx * bqqy - sjy * bqqx);
+                            const double tpqx = sjx * bppx - sjy * bppy + cj * bpqx, tpqy = sjx * bppy + sjy * bppx + cj * bpqy;
+                            const double tqqx = sjx * bqpx - sjy * bqpy + cj * bqqx, tqqy = sjx * bqpy + sjy * bqpx + cj * bqqy;
+                            // rows: out_p = c t_p - s t_q ; out_q = conj(s) t_p + c t_q
+                            ar[p][pp] = ci * tppx - (six * tqpx - siy * tqpy); ai[p][pp] = ci * tppy - (six * tqpy + siy * tqpx);
+                            ar[q][pp] = six * tppx + siy * tppy + ci * tqpx;   ai[q][pp] = six * tppy - siy * tppx + ci * tqpy;
+                            ar[p][qq] = ci * tpqx - (six * tqqx - siy * tqqy); ai[p][qq] = ci * tpqy - (six * tqqy + siy * tqqx);
+                            ar[q][qq] = six * tpqx + siy * tpqy + ci * tqqx;   ai[q][qq] = six * tpqy - siy * tpqx + ci * tqqy;
+                        }
+                    // ---- U <- U J  (columns perm[2i], perm[2i+1])
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) {
+                        const double c = rc[i], sx = rsx[i], sy = rsy[i];
+                        double2 *up = Us + (size_t)(NW * perm[2 * i]) * TPB + tid, *uq = Us + (size_t)(NW * perm[2 * i + 1]) * TPB + tid;
+#pragma unroll
+                        for (int row = 0; row < NW; ++row) {
+                            const double2 x = up[row * TPB], y = uq[row * TPB];
+                            up[row * TPB] = make_double2(c * x.x - (sx * y.x + sy * y.y), c * x.y - (sx * y.y - sy * y.x));
+                            uq[row * TPB] = make_double2(sx * x.x - sy * x.y + c * y.x, sx * x.y + sy * x.x + c * y.y);
+                        }
+                    }
+                    // ---- tournament permutation of rows and columns (compile-time indices: register moves only)
+                    {
+                        double br[NW][NW], bi[NW][NW];
+#pragma unroll
+                        for (int j = 0; j < NW; ++j)
+#pragma unroll
+                            for (int i = 0; i <= j; ++i) {
+                                const int si = sigma<NW>(i), sj = sigma<NW>(j);
+                                if (si <= sj) { br[i][j] = ar[si][sj]; bi[i][j] = ai[si][sj]; }
+                                else { br[i][j] = ar[sj][si]; bi[i][j] = -ai[sj][si]; }
+                            }
+                        int pn[NW];
+#pragma unroll
+                        for (int i = 0; i < NW; ++i) pn[i] = perm[sigma<NW>(i)];
+#pragma unroll
+                        for (int j = 0; j < NW; ++j) {
+                            perm[j] = pn[j];
+#pragma unroll
+                            for (int i = 0; i <= j; ++i) { ar[i][j] = br[i][j]; ai[i][j] = (i == j) ? 0.0 : bi[i][j]; }
+                        }
+                    }
+                }
+                ok = (off2 <= tol);
+            }
+        }
+        if (!ok) atomicExch(err_flag, 1);
+        // ------------------------------------------------------------------ ascending order (zheevd), ties by original index
+        double *Eo = E_out + (size_t)ik * NW;
+        double2 *Uo = U_out + (size_t)ik * NW2;
+#pragma unroll
+        for (int j = 0; j < NW; ++j) {
+            const double ej = ar[j][j];
+            int rank = 0;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) {
+                const double ei = ar[i][i];
+                rank += (ei < ej || (ei == ej && perm[i] < perm[j])) ? 1 : 0;
+            }
+            Eo[rank] = ej;
+            const double2 *uc = Us + (size_t)(NW * perm[j]) * TPB + tid;
+#pragma unroll
+            for (int row = 0; row < NW; ++row) Uo[row + NW * rank] = uc[row * TPB];
+        }
+    }
+}
+
+template <int NW>
+cudaError_t launch_eig_t(const DevModel &m, const KSource &ks, double *E_out, double2 *U_out, int *err_flag, int sm_count,
+                         cudaStream_t st) {
+    constexpr int TPB = EigCfg<NW>::TPB;
+    const size_t smem = sizeof(double2) * NW * NW * TPB;
+    cudaError_t e = cudaFuncSetAttribute(eig_small_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int per_sm = (int)((227 * 1024) / (smem + 1024)) < 1 ? 1 : (int)((227 * 1024) / (smem + 1024));
+    long long grid = (ks.nk + TPB - 1) / TPB;
+    const long long cap = (long long)sm_count * per_sm;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    eig_small_kernel<NW><<<(int)grid, TPB, smem, st>>>(m, ks, E_out, U_out, err_flag);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+bool eig_thread_supported(int nw) { return nw == 4 || nw == 8; }
+
+cudaError_t launch_eig_small(const DevModel &m, const KSource &ks, double *E_out, double2 *U_out, int *err_flag, int sm_count,
+                             cudaStream_t st) {
+    switch (m.nw) {
+        case 4: return launch_eig_t<4>(m, ks, E_out, U_out, err_flag, sm_count, st);
+        case 8: return launch_eig_t<8>(m, ks, E_out, U_out, err_flag, sm_count, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace mepb

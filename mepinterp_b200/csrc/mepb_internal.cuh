@@ -83,6 +83,9 @@ struct InterpOut {
     int *cnt_photo;       // [nk]
     double *block_static; // [gridDim.x][static_size(nw)]
     int *err_flag;        // set to 1 when the eigensolver fails to converge
+    // inputs from the thread-per-k eigensolver (mepb_eig.cu); nullptr -> the kernel runs its own warp-level Jacobi
+    const double *e_in;   // (nw, nk) ascending
+    const double2 *U_in;  // (nw, nw, nk) eigenvectors in columns, same order
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -137,6 +140,9 @@ bool small_supported(int nw, int nR);
 cudaError_t launch_interp_small(const DevModel &m, const KSource &ks, const Jobs &jobs, const InterpOut &out, int max_pairs,
                                 int grid, cudaStream_t st);
 int interp_small_grid(int nw, int nR, int sm_count, long long nk);
+bool eig_thread_supported(int nw);
+cudaError_t launch_eig_small(const DevModel &m, const KSource &ks, double *E_out, double2 *U_out, int *err_flag, int sm_count,
+                             cudaStream_t st);
 
 cudaError_t launch_sweep_ahc(bool herm, const double *items, const int *cnt, int max_pairs, long long nk, int n_hw,
                              const double *hw, double eta, double *block_out, int grid, cudaStream_t st);

@@ -301,18 +301,23 @@ interp_small_kernel(const DevModel m, const KSource ks, const Jobs jb, const Int
         __syncwarp();
         if (!need_eig) continue;
         // ------------------------------------------------------------------ 3. eigensolve
-        const bool ok = jacobi_warp<NW>(As, Us, rot, lane);
-        if (!ok && lane == 0) atomicExch(out.err_flag, 1);
-        __syncwarp();
-        // sort ascending (zheevd order); rank by (value, index)
-        if (lane < NW) {
-            const double ej = As[lane * LD + lane].x;
-            int rank = 0;
-            for (int i = 0; i < NW; ++i) {
-                const double ei = As[i * LD + i].x;
-                rank += (ei < ej || (ei == ej && i < lane)) ? 1 : 0;
+        if (out.U_in) {   // eigenpairs come from the thread-per-k solver (mepb_eig.cu), already in ascending order
+            for (int idx = lane; idx < NW2; idx += 32) Us[(idx % NW) * LD + idx / NW] = out.U_in[(size_t)ik * NW2 + idx];
+            if (lane < NW) { es[lane] = out.e_in[(size_t)ik * NW + lane]; perm[lane] = lane; }
+        } else {
+            const bool ok = jacobi_warp<NW>(As, Us, rot, lane);
+            if (!ok && lane == 0) atomicExch(out.err_flag, 1);
+            __syncwarp();
+            // sort ascending (zheevd order); rank by (value, index)
+            if (lane < NW) {
+                const double ej = As[lane * LD + lane].x;
+                int rank = 0;
+                for (int i = 0; i < NW; ++i) {
+                    const double ei = As[i * LD + i].x;
+                    rank += (ei < ej || (ei == ej && i < lane)) ? 1 : 0;
+                }
+                es[rank] = ej; perm[rank] = lane;
             }
-            es[rank] = ej; perm[rank] = lane;
         }
         __syncwarp();
         if (lane < NW) {
