@@ -117,6 +117,7 @@ struct StreamBuf {
     double *block_static = nullptr, *block_sweep = nullptr, *block_photo = nullptr;
     double *compact = nullptr;   // [n_eF][per_ef]
     double *eig_E = nullptr; double2 *eig_U = nullptr;   // [chunk][nw], [chunk][nw*nw] from the thread-per-k eigensolver
+    double2 *Hk = nullptr, *Hka = nullptr, *Vscr = nullptr;   // general path: [chunk][nw^2], [chunk][3][nw^2], [grid][3][nw^2]
 };
 
 }  // namespace
@@ -128,6 +129,10 @@ struct mepb_ctx {
     bool has_tau = false;
     bool herm = true;      // H(R) Hermitian-closed: V_a Hermitian -> compact items / 18-accumulator sweep
     bool eig_thread = false;   // eigenpairs from the thread-per-k kernel (nw 4, 8)
+    bool large = false;        // general path (mepb_large.cu)
+    FourierPlan fp{};
+    int *d_ridx = nullptr, *d_elem = nullptr; double2 *d_Hp = nullptr; double *d_Rfp = nullptr, *d_cRp = nullptr;
+    double2 *d_Hka_int = nullptr;
     double a_latt[9];
     // device model
     double2 *d_H = nullptr; double *d_Rf = nullptr, *d_cR = nullptr, *d_tau = nullptr, *d_tM = nullptr, *d_hw = nullptr;
@@ -150,8 +155,8 @@ struct mepb_ctx {
     bool profiling = false;
     std::vector<cudaEvent_t> prof_ev;          // pairs (start, stop)
     std::vector<int> prof_kind;
-    double prof_ms[MEPB_PROF_KINDS] = {0, 0, 0, 0, 0};
-    long long prof_n[MEPB_PROF_KINDS] = {0, 0, 0, 0, 0};
+    double prof_ms[MEPB_PROF_KINDS] = {};
+    long long prof_n[MEPB_PROF_KINDS] = {};
     cudaEvent_t tm0 = nullptr, tm1 = nullptr;  // mepb_timer_start / stop
     // list-mode scratch
     double *d_kpt = nullptr, *d_e = nullptr; double2 *d_V = nullptr, *d_Hk = nullptr, *d_Hka = nullptr;
@@ -189,7 +194,7 @@ bool hermitian_closed(const mepb_model *m, std::string *why) {
     const int nw = m->nw, nR = m->nR;
     double hmax = 0.0;
     for (long long i = 0; i < 2LL * nw * nw * nR; ++i) hmax = std::max(hmax, std::fabs(m->H[i]));
-    const double tol = 1e-10 * std::max(hmax, 1e-300);
+    const double tol = 4e-16 * std::max(hmax, 1e-300);     // exact closure up to the last bit of the eV -> Hartree division
     for (int r = 0; r < nR; ++r) {
         int partner = -1;
         for (int s = 0; s < nR; ++s)
@@ -215,17 +220,81 @@ bool hermitian_closed(const mepb_model *m, std::string *why) {
     return true;
 }
 
+// Host-side plan of the dense Fourier contraction: packed element tiles of H(R), per-axis phase tables.
+cudaError_t build_fourier_plan(mepb_ctx *c, const mepb_model *model, const std::vector<double> &cR) {
+    const int nw = c->nw, nR = c->nR, nw2 = nw * nw, TN = kFourierTN, RC = kFourierRC;
+    FourierPlan &fp = c->fp;
+    std::vector<int> elem;
+    if (c->herm) { for (int m = 0; m < nw; ++m) for (int n = 0; n <= m; ++n) elem.push_back(n | (m << 16)); }
+    else { for (int m = 0; m < nw; ++m) for (int n = 0; n < nw; ++n) elem.push_back(n | (m << 16)); }
+    fp.nel = (int)elem.size();
+    fp.ntiles = (fp.nel + TN - 1) / TN;
+    fp.nRp = (nR + RC - 1) / RC * RC;
+    fp.herm = c->herm ? 1 : 0;
+    elem.resize((size_t)fp.ntiles * TN, elem[0]);
+    std::vector<double2> Hp((size_t)fp.ntiles * fp.nRp * TN, make_double2(0.0, 0.0));
+    for (int t = 0; t < fp.ntiles; ++t)
+        for (int R = 0; R < nR; ++R)
+            for (int j = 0; j < TN; ++j) {
+                const int el = t * TN + j;
+                if (el >= fp.nel) continue;
+                const int n = elem[el] & 0xffff, m = elem[el] >> 16;
+                const double *h = model->H + 2 * ((size_t)n + (size_t)nw * m + (size_t)nw2 * R);
+                Hp[((size_t)t * fp.nRp + R) * TN + j] = make_double2(h[0], h[1]);
+            }
+    // distinct lattice coordinates per axis
+    std::vector<double> uv[3];
+    for (int a = 0; a < 3; ++a) {
+        for (int R = 0; R < nR; ++R) uv[a].push_back(model->R[3 * R + a]);
+        std::sort(uv[a].begin(), uv[a].end());
+        uv[a].erase(std::unique(uv[a].begin(), uv[a].end()), uv[a].end());
+    }
+    fp.u1 = (int)uv[0].size(); fp.u2 = (int)uv[1].size(); fp.u3 = (int)uv[2].size();
+    fp.utot = fp.u1 + fp.u2 + fp.u3;
+    fp.direct = (fp.utot > kFourierMaxU) ? 1 : 0;
+    std::vector<int> ridx(fp.nRp, 0);
+    if (!fp.direct) {
+        int o = 0;
+        for (int a = 0; a < 3; ++a) for (double v : uv[a]) fp.uval[o++] = v;
+        const int off[3] = {0, fp.u1, fp.u1 + fp.u2};
+        for (int R = 0; R < fp.nRp; ++R) {
+            int packed = 0;
+            for (int a = 0; a < 3; ++a) {
+                int i = 0;
+                if (R < nR) i = (int)(std::lower_bound(uv[a].begin(), uv[a].end(), model->R[3 * R + a]) - uv[a].begin());
+                packed |= (off[a] + i) << (8 * a);
+            }
+            ridx[R] = packed;
+        }
+    }
+    std::vector<double> Rfp(3 * (size_t)fp.nRp, 0.0), cRp(3 * (size_t)fp.nRp, 0.0);
+    for (int i = 0; i < 3 * nR; ++i) { Rfp[i] = model->R[i]; cRp[i] = cR[i]; }
+    auto up = [&](void **dst, const void *src, size_t bytes) -> cudaError_t {
+        if (!*dst) { cudaError_t e = cudaMalloc(dst, bytes); if (e != cudaSuccess) return e; }
+        return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+    };
+    cudaError_t e;
+    if ((e = up((void **)&c->d_ridx, ridx.data(), sizeof(int) * ridx.size())) != cudaSuccess) return e;
+    if ((e = up((void **)&c->d_elem, elem.data(), sizeof(int) * elem.size())) != cudaSuccess) return e;
+    if ((e = up((void **)&c->d_Hp, Hp.data(), sizeof(double2) * Hp.size())) != cudaSuccess) return e;
+    if ((e = up((void **)&c->d_Rfp, Rfp.data(), sizeof(double) * Rfp.size())) != cudaSuccess) return e;
+    if ((e = up((void **)&c->d_cRp, cRp.data(), sizeof(double) * cRp.size())) != cudaSuccess) return e;
+    fp.ridx = c->d_ridx; fp.elem = c->d_elem; fp.Hp = c->d_Hp; fp.Rf = c->d_Rfp; fp.cR = c->d_cRp;
+    return cudaSuccess;
+}
+
 void free_all(mepb_ctx *c) {
     cudaSetDevice(c->device);
     cudaFree(c->d_H); cudaFree(c->d_Rf); cudaFree(c->d_cR); cudaFree(c->d_tau); cudaFree(c->d_tM); cudaFree(c->d_hw);
     for (auto &s : c->sb) {
         cudaFree(s.items_ahc); cudaFree(s.cnt_ahc); cudaFree(s.items_photo); cudaFree(s.cnt_photo);
         cudaFree(s.block_static); cudaFree(s.block_sweep); cudaFree(s.block_photo); cudaFree(s.compact);
-        cudaFree(s.eig_E); cudaFree(s.eig_U);
+        cudaFree(s.eig_E); cudaFree(s.eig_U); cudaFree(s.Hk); cudaFree(s.Hka); cudaFree(s.Vscr);
         if (s.st) cudaStreamDestroy(s.st);
         if (s.done) cudaEventDestroy(s.done);
     }
     cudaFree(c->d_packed); cudaFree(c->d_err);
+    cudaFree(c->d_ridx); cudaFree(c->d_elem); cudaFree(c->d_Hp); cudaFree(c->d_Rfp); cudaFree(c->d_cRp); cudaFree(c->d_Hka_int);
     cudaFree(c->d_kpt); cudaFree(c->d_e); cudaFree(c->d_V); cudaFree(c->d_Hk); cudaFree(c->d_Hka);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -299,14 +368,17 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail(MEPB_ERR_CUDA, "libmepb is built for sm_100a only");
-    if (!small_supported(model->nw, model->nR))
-        return fail(MEPB_ERR_UNSUPPORTED, "num_wann/nR outside the limits of the compiled kernels");
+    const char *force = getenv("MEPB_PATH");                  // testing knob: "large" forces the general path
+    const bool want_large = (force && std::string(force) == "large") || !small_supported(model->nw, model->nR);
+    if (want_large && !large_supported(model->nw))
+        return fail(MEPB_ERR_UNSUPPORTED, "num_wann outside the limits of the compiled kernels (2..64)");
 
     mepb_ctx *c = new mepb_ctx();
     c->device = device; c->sm_count = prop.multiProcessorCount;
     c->p = p; c->nw = model->nw; c->nR = model->nR; c->has_tau = (model->wf_centers != nullptr);
     { std::string why; c->herm = hermitian_closed(model, &why); }
-    c->eig_thread = eig_thread_supported(model->nw) && !getenv("MEPB_WARP_JACOBI");
+    c->large = want_large;
+    c->eig_thread = !c->large && eig_thread_supported(model->nw) && !getenv("MEPB_WARP_JACOBI");
     std::memcpy(c->a_latt, model->a_latt, sizeof(c->a_latt));
     const int nw = c->nw, nR = c->nR;
     // linspaces (matrix_math.f90:74-100, core.f90:124-125)
@@ -352,11 +424,13 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
     const int istr = c->herm ? kAhcItemH : kAhcItemG;
     if (p.do_ahc) per_k += sizeof(double) * istr * c->max_pairs + sizeof(int);
     if (p.do_opt) per_k += sizeof(double) * kPhotoItem * c->max_photo + sizeof(int);
+    if (c->large) per_k += sizeof(double2) * 4 * (size_t)nw * nw;
     long long chunk = 1 << 18;
-    if (per_k) chunk = std::min<long long>(chunk, (long long)((768ull << 20) / per_k));
-    chunk = std::max<long long>(1024, std::min(chunk, std::max<long long>(nk_mesh, 1024)));
+    if (per_k) chunk = std::min<long long>(chunk, (long long)(((c->large ? 2048ull : 768ull) << 20) / per_k));
+    chunk = std::max<long long>(c->large ? 296 : 1024, std::min(chunk, std::max<long long>(nk_mesh, 1024)));
     c->chunk = chunk;
-    c->grid_interp = interp_small_grid(nw, nR, c->sm_count, chunk);
+    if (c->large) CT(build_fourier_plan(c, model, cR));
+    c->grid_interp = c->large ? eig_large_grid(c->sm_count, chunk) : interp_small_grid(nw, nR, c->sm_count, chunk);
     c->grid_sweep = sweep_ahc_grid(c->sm_count, chunk, p.n_hw, &c->ns_sweep);
     c->grid_photo = sweep_photo_grid(c->sm_count, chunk, p.n_hw, &c->ns_photo);
     c->cs.ns = static_size(nw); c->cs.sweep = p.n_hw * kSweepAcc; c->cs.photo = p.n_hw * kPhotoAcc;
@@ -374,6 +448,11 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
             CT(cudaMalloc((void **)&s.items_photo, sizeof(double) * kPhotoItem * c->max_photo * (size_t)chunk));
             CT(cudaMalloc((void **)&s.cnt_photo, sizeof(int) * (size_t)chunk));
             CT(cudaMalloc((void **)&s.block_photo, sizeof(double) * kPhotoAcc * (size_t)c->ns_photo * c->grid_photo));
+        }
+        if (c->large) {
+            CT(cudaMalloc((void **)&s.Hk, sizeof(double2) * nw * nw * (size_t)chunk));
+            CT(cudaMalloc((void **)&s.Hka, sizeof(double2) * 3 * nw * nw * (size_t)chunk));
+            CT(cudaMalloc((void **)&s.Vscr, sizeof(double2) * 3 * nw * nw * (size_t)c->grid_interp));
         }
         if (c->eig_thread) {
             CT(cudaMalloc((void **)&s.eig_E, sizeof(double) * nw * (size_t)chunk));
@@ -434,17 +513,23 @@ int mepb_accumulate(mepb_ctx *c, int64_t lin_begin, int64_t lin_end) {
             o.items_ahc = jb.do_ahc ? s.items_ahc : nullptr; o.cnt_ahc = s.cnt_ahc;
             o.items_photo = jb.do_opt ? s.items_photo : nullptr; o.cnt_photo = s.cnt_photo;
             o.block_static = s.block_static; o.err_flag = c->d_err;
-            const int gi = interp_small_grid(c->nw, c->nR, c->sm_count, nk);
+            const int gi = c->large ? eig_large_grid(c->sm_count, nk) : interp_small_grid(c->nw, c->nR, c->sm_count, nk);
+            if (c->large) {
+                { ProfScope ps(c, s.st, MEPB_PROF_FOURIER); CUDA_TRY(launch_fourier_dense(c->fp, m, ks, s.Hk, s.Hka, s.st)); }
+                { ProfScope ps(c, s.st, MEPB_PROF_EIGROT);
+                  CUDA_TRY(launch_eig_rot_large(m, ks, jb, o, c->max_pairs, s.Hk, s.Hka, s.Vscr, gi, s.st)); }
+                c->launches += 2;
+            }
             if (c->eig_thread) {
                 ProfScope ps(c, s.st, MEPB_PROF_EIG);
                 CUDA_TRY(launch_eig_small(m, ks, s.eig_E, s.eig_U, c->d_err, c->sm_count, s.st));
                 o.e_in = s.eig_E; o.U_in = s.eig_U;
                 c->launches += 1;
             }
-            { ProfScope ps(c, s.st, MEPB_PROF_INTERP); CUDA_TRY(launch_interp_small(m, ks, jb, o, c->max_pairs, gi, s.st)); }
+            if (!c->large) { ProfScope ps(c, s.st, MEPB_PROF_INTERP); CUDA_TRY(launch_interp_small(m, ks, jb, o, c->max_pairs, gi, s.st)); c->launches += 1; }
             { ProfScope ps(c, s.st, MEPB_PROF_REDUCE);
               CUDA_TRY(launch_reduce_rows(s.block_static, gi, ns, s.compact + (size_t)ief * c->cs.per_ef, ns, 0, 0, s.st)); }
-            c->launches += 2;
+            c->launches += 1;
             if (jb.do_ahc) {
                 int nsl; const int gs = sweep_ahc_grid(c->sm_count, nk, p.n_hw, &nsl);
                 { ProfScope ps(c, s.st, MEPB_PROF_SWEEP_AHC);
@@ -603,6 +688,7 @@ static int ensure_list(mepb_ctx *c, long long cap) {
     CUDA_TRY(cudaMalloc((void **)&c->d_V, sizeof(double2) * 3 * nw * nw * cap));
     CUDA_TRY(cudaMalloc((void **)&c->d_Hk, sizeof(double2) * nw * nw * cap));
     CUDA_TRY(cudaMalloc((void **)&c->d_Hka, sizeof(double2) * 3 * nw * nw * cap));
+    if (c->large) { cudaFree(c->d_Hka_int); c->d_Hka_int = nullptr; CUDA_TRY(cudaMalloc((void **)&c->d_Hka_int, sizeof(double2) * 3 * nw * nw * cap)); }
     c->list_cap = cap;
     return MEPB_OK;
 }
@@ -631,8 +717,17 @@ static int list_run(mepb_ctx *c, int64_t nk, const double *kpt, double *e_k, dou
             o.e_in = c->sb[0].eig_E; o.U_in = c->sb[0].eig_U;
             c->launches += 1;
         }
-        CUDA_TRY(launch_interp_small(m, ks, jb, o, c->max_pairs, interp_small_grid(c->nw, c->nR, c->sm_count, n), st));
-        c->launches += 1;
+        if (c->large) {
+            CUDA_TRY(launch_fourier_dense(c->fp, m, ks, c->d_Hk, c->d_Hka_int, st));
+            if (H_ka) CUDA_TRY(launch_hka_to_user(c->d_Hka_int, c->d_Hka, c->nw * c->nw, n, st));
+            InterpOut o2 = o; o2.Hk_out = nullptr; o2.Hka_out = nullptr;
+            if (o2.e_out) CUDA_TRY(launch_eig_rot_large(m, ks, jb, o2, c->max_pairs, c->d_Hk, c->d_Hka_int, c->sb[0].Vscr,
+                                                        eig_large_grid(c->sm_count, n), st));
+            c->launches += 2;
+        } else {
+            CUDA_TRY(launch_interp_small(m, ks, jb, o, c->max_pairs, interp_small_grid(c->nw, c->nR, c->sm_count, n), st));
+            c->launches += 1;
+        }
         if (e_k) CUDA_TRY(cudaMemcpyAsync(e_k + nw * k0, c->d_e, sizeof(double) * nw * n, cudaMemcpyDeviceToHost, st));
         if (V_ka) CUDA_TRY(cudaMemcpyAsync(V_ka + 2 * 3 * nw * nw * k0, c->d_V, sizeof(double2) * 3 * nw * nw * n, cudaMemcpyDeviceToHost, st));
         if (H_k) CUDA_TRY(cudaMemcpyAsync(H_k + 2 * nw * nw * k0, c->d_Hk, sizeof(double2) * nw * nw * n, cudaMemcpyDeviceToHost, st));
@@ -661,6 +756,11 @@ int mepb_update_model(mepb_ctx *c, const mepb_model *model) {
     cudaStream_t st = c->sb[0].st;
     CUDA_TRY(cudaMemcpyAsync(c->d_H, model->H, sizeof(double) * 2 * (size_t)c->nw * c->nw * c->nR, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    if (c->large) {
+        std::vector<double> cR(3 * (size_t)c->nR);
+        CUDA_TRY(cudaMemcpy(cR.data(), c->d_cR, sizeof(double) * cR.size(), cudaMemcpyDeviceToHost));
+        CUDA_TRY(build_fourier_plan(c, model, cR));
+    }
     return MEPB_OK;
 }
 

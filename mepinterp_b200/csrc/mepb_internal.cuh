@@ -89,6 +89,27 @@ struct InterpOut {
 };
 
 // ---------------------------------------------------------------------------------------------------------
+// dense Fourier contraction (mepb_large.cu): host-built plan
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kFourierTK = 64;    // k-points per CTA
+constexpr int kFourierTN = 32;    // matrix elements per CTA
+constexpr int kFourierRC = 16;    // R points per pipeline stage
+constexpr int kFourierMaxU = 96;  // distinct lattice coordinates over the three axes (else: one sincospi per (k,R))
+
+struct FourierPlan {
+    int nel, ntiles, nRp;         // computed elements (upper triangle if herm, else nw^2), tiles of kFourierTN, nR padded to kFourierRC
+    int herm;                     // mirror (m,n) = conj(n,m)
+    int direct;                   // 1: phases by sincospi per (k,R); 0: product of three per-axis table entries
+    int u1, u2, u3, utot;         // distinct coordinates per axis
+    double uval[kFourierMaxU];    // the distinct coordinates, axis 1 first
+    const int *ridx;              // [nRp] packed table rows i1 | i2 << 8 | i3 << 16
+    const int *elem;              // [ntiles*kFourierTN] packed n | m << 16
+    const double2 *Hp;            // [ntiles][nRp][kFourierTN]  H(R) elements of each tile, zero padded
+    const double *Rf;             // [nRp][3] fractional R (zero padded)
+    const double *cR;             // [nRp][3] M.R (zero padded)
+};
+
+// ---------------------------------------------------------------------------------------------------------
 // complex helpers on double2
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
@@ -153,5 +174,15 @@ int sweep_photo_grid(int sm_count, long long nk, int n_hw, int *slots_out);
 // out[(c / group) * out_stride + out_off + c % group] += sum_r in[r*cols + c]
 cudaError_t launch_reduce_rows(const double *in, int rows, int cols, double *out_accum, int group, int out_stride, int out_off,
                                cudaStream_t st);
+
+// general path, num_wann <= 64 (mepb_large.cu)
+bool large_supported(int nw);
+size_t fourier_dense_smem(const FourierPlan &fp, int nw, bool has_tau);
+cudaError_t launch_fourier_dense(const FourierPlan &fp, const DevModel &m, const KSource &ks, double2 *Hk, double2 *Hka,
+                                 cudaStream_t st);
+cudaError_t launch_hka_to_user(const double2 *in, double2 *out, int nw2, long long nk, cudaStream_t st);
+int eig_large_grid(int sm_count, long long nk);
+cudaError_t launch_eig_rot_large(const DevModel &m, const KSource &ks, const Jobs &jobs, const InterpOut &out, int max_pairs,
+                                 const double2 *Hk, const double2 *Hka, double2 *Vscr, int grid, cudaStream_t st);
 
 }  // namespace mepb

@@ -47,6 +47,40 @@ def _cases_small():
 CASES = dict(_cases_small())
 
 
+def _cases_large():
+    """General path (mepb_large.cu): num_wann up to 64.  C5 = synthetic nw=64, nR=2007 on a reduced mesh."""
+    all_jobs = dict(do_mep=True, do_kubo=True, do_ahc=True, do_opt=True, n_hw=5, hw_min=ev(0.05), hw_max=ev(4.0), eta=ev(0.1))
+    yield "C5_syn_nw64_nR2007_ahc_T300_4x3x5", (synthetic_model(64, 61), mo.Params(mp_grid=(4, 3, 5), do_ahc=True, T_kelvin=300.0))
+    yield "syn_nw64_nR123_all_jobs", (synthetic_model(64, 9), mo.Params(mp_grid=(3, 3, 3), valence_bands=30, T_kelvin=300.0, **all_jobs))
+    yield "syn_nw32_tb_centers_T0", (synthetic_model(32, 4, tb_centers=True), mo.Params(mp_grid=(4, 4, 3), valence_bands=11, **all_jobs))
+    yield "syn_nw13_odd_cart_velo", (synthetic_model(13, 5, tb_centers=True),
+                                     mo.Params(mp_grid=(5, 4, 3), valence_bands=6, use_cart_velo=True, T_kelvin=150.0, **all_jobs))
+    yield "syn_nw24_no_gauge_neF2", (synthetic_model(24, 3), mo.Params(mp_grid=(3, 4, 5), valence_bands=9, do_gauge_trafo=False, n_eF=2,
+                                                                      eF_min=ev(-0.2), eF_max=ev(0.3), T_kelvin=200.0, **all_jobs))
+
+
+CASES_LARGE = dict(_cases_large())
+FORCED_LARGE = ["C1_souza_kubo_16^3", "C2_femn_ahc_nhw121_16^3", "C4_rashba_opt_ahc_nhw200_8^3", "femn_all_jobs_T300_neF3_ragged",
+                "syn_nw8_tb_cart_velo", "syn_nw4_wannier_T200", "syn_nw16_tb_neF2"]
+
+
+class force_path:
+    """MEPB_PATH=large routes a small-num_wann model through the general kernels (testing knob of mepb_create)."""
+
+    def __init__(self, which):
+        self.which = which
+
+    def __enter__(self):
+        self.old = os.environ.get("MEPB_PATH")
+        if self.which:
+            os.environ["MEPB_PATH"] = self.which
+
+    def __exit__(self, *a):
+        os.environ.pop("MEPB_PATH", None)
+        if self.old is not None:
+            os.environ["MEPB_PATH"] = self.old
+
+
 @pytest.mark.parametrize("name", list(CASES))
 def test_fourier_sums_elementwise(libmepb, name):
     """FT_R_to_k (wann_interp.f90:151-281): H(k), dH/dk_a(k) are gauge independent -> element-wise."""
@@ -107,6 +141,51 @@ def test_run_mesh_parity(libmepb, name):
         a = out["ahc_tens"]
         # sigma_ij = -sigma_ji up to the same yardsticks (pairs of occupied near-degenerate bands cancel only to rounding x 1/dE^2)
         assert np.abs(a + a.T).max() <= TENS_TOL * scale["ahc_tens"] + 20.0 * sens["ahc_tens"]
+
+
+def _case(name):
+    if name in CASES_LARGE:
+        return CASES_LARGE[name], None
+    return CASES[name], "large"
+
+
+@pytest.mark.parametrize("name", list(CASES_LARGE) + FORCED_LARGE)
+def test_general_path_fourier_and_eigen(libmepb, name):
+    """Dense Fourier contraction (TMA-staged H(R), phase tables) element-wise at 1e-13; CTA-per-k Jacobi eigenvalues 1e-10."""
+    (model, params), force = _case(name)
+    kp = np.random.default_rng(11).uniform(-0.5, 0.5, size=(70, 3))
+    kp[0] = 0.0
+    e_r, V_r, Hk_r, Hka_r = cpu_ref.Handle(model, params).interp(kp, want_V=True, want_H=True)
+    with force_path(force):
+        ctx = libmepb.Context(model, params)
+    Hk, Hka = ctx.fourier(kp)
+    e, V = ctx.interp(kp)
+    ctx.close()
+    assert rel_err(Hk, Hk_r) < 1e-13
+    assert rel_err(Hka, Hka_r) < 1e-13
+    hnorm = np.abs(e_r).max()
+    assert np.all(np.diff(e, axis=0) >= 0.0)
+    assert np.abs(e - e_r).max() <= EIG_TOL * hnorm
+    assert np.abs((e ** 2).sum(axis=0) - (e_r ** 2).sum(axis=0)).max() <= 1e-11 * hnorm ** 2 * model.nw
+    if params.do_gauge_trafo:
+        fro_V = (np.abs(V) ** 2).sum(axis=(1, 2))
+        fro_H = (np.abs(Hka_r) ** 2).sum(axis=(1, 2))
+        assert np.abs(fro_V - fro_H).max() <= 1e-11 * fro_H.max()
+    else:
+        assert rel_err(V, V_r) < 1e-13
+
+
+@pytest.mark.parametrize("name", list(CASES_LARGE) + FORCED_LARGE)
+def test_general_path_run_mesh_parity(libmepb, name):
+    (model, params), force = _case(name)
+    ref, scale, sens = oracle_reference(model, params)
+    with force_path(force):
+        ctx = libmepb.Context(model, params)
+    out = ctx.run_mesh()
+    prof_launches = ctx.kernel_launches
+    ctx.close()
+    assert prof_launches > 0
+    assert_parity(out, ref, scale, sens, tol=TENS_TOL, label=name)
 
 
 def test_golden_ahc_anchor_on_gpu(libmepb):
