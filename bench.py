@@ -36,7 +36,7 @@ UNIT = "k-points/s"
 
 
 # ------------------------------------------------------------------------------------------------ workloads
-def make_workload(name: str, n_gpus: int):
+def make_workload(name: str, n_gpus: int, mesh: int = 0):
     """(model, params, description) — inputs in the reference's own formats, parsed by the product's host reader."""
     from mepinterp_b200 import host
     golden = os.path.join(ROOT, "tests", "golden")
@@ -57,8 +57,16 @@ def make_workload(name: str, n_gpus: int):
         model, params, _ = host.load_run_dir(os.path.join(golden, "souza_phi0"))
         params.mp_grid = (32, 32, 32 * n_gpus)
         desc = "Souza toy TB (nw=8, nR=7) AHC + MEP, k-mesh 32x32x%d" % (32 * n_gpus)
+    elif name == "C5":    # synthetic nw=64, nR=2007, AHC, T=300 K; BASELINE mesh is 200^3 (8e6 k-points, ~minutes): default 32^3 here
+        from mepinterp_b200 import api, models
+        model = models.synthetic_tb(64, 61)
+        params = api.make_params(mp_grid=(32, 32, 32 * n_gpus), do_ahc=True, T_kelvin=300.0)
+        desc = "synthetic TB (nw=64, nR=2007) AHC, k-mesh 32x32x%d (BASELINE mesh 200^3)" % (32 * n_gpus)
     else:
         raise SystemExit(f"unknown workload {name}")
+    if mesh:
+        params.mp_grid = (mesh, mesh, mesh * n_gpus)
+        desc = desc.split(", k-mesh")[0] + ", k-mesh %dx%dx%d" % params.mp_grid
     return model, params, desc
 
 
@@ -75,7 +83,14 @@ def flops_model(model, params):
     if params.do_mep or params.do_kubo:
         interp += 130.0 * nw * (nw - 1) ** 2
     herm = True
+    large = nw not in (4, 8, 16)
+    nel = nw * (nw + 1) // 2
     return {"interp_per_k": interp, "eig_per_k": eig if split else 0.0,
+            # dense Fourier contraction, Hermitian-closed input: per (k, upper-triangle element, R) one complex multiply (6),
+            # one complex add (2) and three real x complex multiply-adds (12) = 20 flops (SURVEY 8(d)'s 8*nR*nw^2*4 counts the
+            # full matrix with four independent complex MACs: 32 per (k, element, R) on nw^2 elements)
+            "fourier_per_k": 20.0 * nR * nel if large else 0.0,
+            "eig_rot_per_k": (36.0 + 48.0) * nw ** 3 + 60.0 * nw * nw if large else 0.0,
             "sweep_ahc_per_item_hw": 56.0 if herm else 92.0,          # 1 complex reciprocal + 18 (36) accumulate FMAs
             "sweep_photo_per_item_hw": 246.0}                          # 27 complex MACs + the two-pole factor
 
@@ -145,7 +160,7 @@ def cpu_port_rate(model, params, budget_s: float, threads: int):
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    model, params, desc = make_workload(args.workload, args.gpus)
+    model, params, desc = make_workload(args.workload, args.gpus, args.mesh)
     threads = os.cpu_count() or 1
     total = args.steps + args.warmup
     budget = max(2.0, min(15.0, 150.0 / max(total, 1)))
@@ -174,7 +189,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4"])
+    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4", "C5"])
+    ap.add_argument("--mesh", type=int, default=0, help="override the k-mesh: N x N x (N * gpus)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -200,7 +216,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    model, params, desc = make_workload(args.workload, world)
+    model, params, desc = make_workload(args.workload, world, args.mesh)
     nk_total = int(params.mp_grid[0]) * int(params.mp_grid[1]) * int(params.mp_grid[2])
     ctx = mb.Context(model, params, device=local)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)           # > 126 MB L2
@@ -266,10 +282,11 @@ def main():
     fm = flops_model(model, params)
     nk_loc = b1 - b0
     work = {"interp": fm["interp_per_k"] * nk_loc, "eig": fm["eig_per_k"] * nk_loc,
+            "fourier": fm["fourier_per_k"] * nk_loc, "eig_rot": fm["eig_rot_per_k"] * nk_loc,
             "sweep_ahc": fm["sweep_ahc_per_item_hw"] * items["sweep_ahc"] * params.n_hw,
             "sweep_photo": fm["sweep_photo_per_item_hw"] * items["sweep_photo"] * params.n_hw}
     kernels = {}
-    for k in ("eig", "interp", "sweep_ahc", "sweep_photo", "reduce"):
+    for k in ("fourier", "eig_rot", "eig", "interp", "sweep_ahc", "sweep_photo", "reduce"):
         if prof[k]["launches"]:
             ms = prof[k]["ms"]
             kernels[k] = {"ms_per_pass": ms, "launches": prof[k]["launches"], "share": None,

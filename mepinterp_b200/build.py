@@ -43,5 +43,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+DRIVER = os.path.join(HERE, "mepInterp")
+
+
+def build_driver(force: bool = False) -> str:
+    """g++ host driver (no CUDA code in it): links libmepb.so, rpath = its own directory."""
+    src = os.path.join(CSRC, "driver", "mepinterp_main.cpp")
+    build()
+    if force or _stale(DRIVER, [src, LIB, os.path.join(HERE, "..", "include", "mepb.h")]):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", src, "-o", DRIVER, "-L" + HERE, "-lmepb",
+                               "-Wl,-rpath,$ORIGIN", "-Wl,-rpath," + "/usr/local/cuda/lib64"])
+    return DRIVER
+
+
 if __name__ == "__main__":
+    build_driver(force="--force" in sys.argv)
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

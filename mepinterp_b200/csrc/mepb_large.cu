@@ -342,30 +342,33 @@ eig_rot_large_kernel(const DevModel m, const KSource ks, const Jobs jb, const In
                         reinterpret_cast<int *>(ro + 6)[0] = p; reinterpret_cast<int *>(ro + 6)[1] = q;
                     }
                     __syncthreads();
-                    // ---- columns: M <- M J for M = A (all rows) and M = U
-                    for (int t = tid; t < 2 * NE * NP; t += E_THREADS) {
-                        const int which = t / (NE * NP), rem = t % (NE * NP), row = rem / NP, i = rem % NP;
+                    // ---- columns: M <- M J for M = A (all rows) and M = U; one warp per row, lanes over the pairs
+                    for (int i = lane; i < NP; i += 32) {
                         const double *ro = rot + 8 * i;
                         const double c = ro[0], sx = ro[1], sy = ro[2];
                         const int p = reinterpret_cast<const int *>(ro + 6)[0], q = reinterpret_cast<const int *>(ro + 6)[1];
-                        double2 *M = which ? U : A;
-                        const double2 x = M[row * LD + p], y = M[row * LD + q];
-                        M[row * LD + p] = make_double2(c * x.x - (sx * y.x + sy * y.y), c * x.y - (sx * y.y - sy * y.x));
-                        M[row * LD + q] = make_double2(sx * x.x - sy * x.y + c * y.x, sx * x.y + sy * x.x + c * y.y);
+                        for (int row = warp; row < NE; row += E_WARPS) {
+                            const double2 x = A[row * LD + p], y = A[row * LD + q], ux = U[row * LD + p], uy = U[row * LD + q];
+                            A[row * LD + p] = make_double2(c * x.x - (sx * y.x + sy * y.y), c * x.y - (sx * y.y - sy * y.x));
+                            A[row * LD + q] = make_double2(sx * x.x - sy * x.y + c * y.x, sx * x.y + sy * x.x + c * y.y);
+                            U[row * LD + p] = make_double2(c * ux.x - (sx * uy.x + sy * uy.y), c * ux.y - (sx * uy.y - sy * uy.x));
+                            U[row * LD + q] = make_double2(sx * ux.x - sy * ux.y + c * uy.x, sx * ux.y + sy * ux.x + c * uy.y);
+                        }
                     }
                     __syncthreads();
-                    // ---- rows: A <- J^dagger A ; exact values on the rotated 2x2 block
-                    for (int t = tid; t < NP * NE; t += E_THREADS) {
-                        const int i = t / NE, col = t % NE;
+                    // ---- rows: A <- J^dagger A ; exact values on the rotated 2x2 block; one warp per pair, lanes over columns
+                    for (int i = warp; i < NP; i += E_WARPS) {
                         const double *ro = rot + 8 * i;
                         const double c = ro[0], sx = ro[1], sy = ro[2];
                         const int p = reinterpret_cast<const int *>(ro + 6)[0], q = reinterpret_cast<const int *>(ro + 6)[1];
-                        const double2 x = A[p * LD + col], y = A[q * LD + col];
-                        double2 op = make_double2(c * x.x - (sx * y.x - sy * y.y), c * x.y - (sx * y.y + sy * y.x));
-                        double2 oq = make_double2(sx * x.x + sy * x.y + c * y.x, sx * x.y - sy * x.x + c * y.y);
-                        if (col == p) { op = make_double2(ro[3], 0.0); oq = make_double2(0.0, 0.0); }
-                        else if (col == q) { op = make_double2(0.0, 0.0); oq = make_double2(ro[4], 0.0); }
-                        A[p * LD + col] = op; A[q * LD + col] = oq;
+                        for (int col = lane; col < NE; col += 32) {
+                            const double2 x = A[p * LD + col], y = A[q * LD + col];
+                            double2 op = make_double2(c * x.x - (sx * y.x - sy * y.y), c * x.y - (sx * y.y + sy * y.x));
+                            double2 oq = make_double2(sx * x.x + sy * x.y + c * y.x, sx * x.y - sy * x.x + c * y.y);
+                            if (col == p) { op = make_double2(ro[3], 0.0); oq = make_double2(0.0, 0.0); }
+                            else if (col == q) { op = make_double2(0.0, 0.0); oq = make_double2(ro[4], 0.0); }
+                            A[p * LD + col] = op; A[q * LD + col] = oq;
+                        }
                     }
                     __syncthreads();
                 }
@@ -411,8 +414,8 @@ eig_rot_large_kernel(const DevModel m, const KSource ks, const Jobs jb, const In
                     // U(buffer) <- Ha * Us     two rows x two columns per thread
                     const int njb = (nw + 1) / 2;
                     for (int t = tid; t < njb * njb; t += E_THREADS) {
-                        const int p0 = 2 * (t / njb), j0 = 2 * (t % njb);
-                        const int p1 = min(p0 + 1, nw - 1), j1 = min(j0 + 1, nw - 1);
+                        const int p0 = 2 * (t / njb), j0 = t % njb;
+                        const int p1 = min(p0 + 1, nw - 1), j1 = min(j0 + njb, nw - 1);
                         double2 s00 = make_double2(0, 0), s01 = s00, s10 = s00, s11 = s00;
                         for (int q = 0; q < nw; ++q) {
                             const double2 h0 = A[p0 * LD + q], h1 = A[p1 * LD + q], u0 = T[q * LD + j0], u1 = T[q * LD + j1];
@@ -423,8 +426,8 @@ eig_rot_large_kernel(const DevModel m, const KSource ks, const Jobs jb, const In
                     __syncthreads();
                     // V(n, j) = sum_p conj(Us(p, n)) (Ha Us)(p, j)
                     for (int t = tid; t < njb * njb; t += E_THREADS) {
-                        const int n0 = 2 * (t / njb), j0 = 2 * (t % njb);
-                        const int n1 = min(n0 + 1, nw - 1), j1 = min(j0 + 1, nw - 1);
+                        const int n0 = 2 * (t / njb), j0 = t % njb;
+                        const int n1 = min(n0 + 1, nw - 1), j1 = min(j0 + njb, nw - 1);
                         double2 s00 = make_double2(0, 0), s01 = s00, s10 = s00, s11 = s00;
                         for (int p = 0; p < nw; ++p) {
                             const double2 c0 = T[p * LD + n0], c1 = T[p * LD + n1], w0 = U[p * LD + j0], w1 = U[p * LD + j1];

@@ -1,0 +1,97 @@
+"""The C++ `mepInterp` driver (mepinterp_b200/csrc/driver): input parsing checked on CPU against the oracle's readers;
+the full run (GPU) against the oracle's tensors, through the files the reference would write."""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import cpu_ref
+from oracle import mep_oracle as mo
+from tests.cases import GOLDEN, assert_parity, oracle_reference
+
+RUNS = ["femn_d0.900", "femn_d1.100", "femn_rashba", "souza_phi0"]
+
+
+@pytest.fixture(scope="module")
+def driver():
+    from mepinterp_b200 import build as mb_build
+    return mb_build.build_driver()
+
+
+def _parse_echo(txt):
+    d = {}
+    for ln in txt.splitlines():
+        k, *v = ln.split()
+        d[k] = v
+    return d
+
+
+@pytest.mark.parametrize("name", RUNS)
+def test_driver_parses_inputs_like_the_reference_readers(driver, name):
+    d = os.path.join(GOLDEN, name)
+    r = subprocess.run([driver, "--dir", d, "--check-input"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    e = _parse_echo(r.stdout)
+    m, p = mo.load_model(d)
+    assert [int(e["nw"][0]), int(e["nw"][2])] == [m.nw, m.nR] and e["nw"][4] == p.seed_name
+    g = [int(x) for x in e["mp_grid"][:3]]
+    assert tuple(g) == tuple(p.mp_grid)
+    flags = [int(x) for x in (e["mp_grid"][4:8] + [e["mp_grid"][9], e["mp_grid"][11], e["mp_grid"][13], e["mp_grid"][15], e["mp_grid"][17], e["mp_grid"][19]])]
+    assert flags == [int(p.do_mep), int(p.do_kubo), int(p.do_ahc), int(p.do_opt), int(p.do_gauge_trafo), int(p.use_cart_velo),
+                     p.valence_bands, p.n_hw, p.n_eF, int(p.do_write_mep_bands)]
+    sc = [float(x) for x in e["scalars"]]
+    assert sc == [p.hw_min, p.hw_max, p.eF_min, p.eF_max, p.T_kelvin, p.eta, p.kubo_tol]          # bit-identical unit conversion
+    al = np.array([float(x) for x in e["a_latt"]]).reshape(3, 3, order="F")
+    np.testing.assert_array_equal(al, m.a_latt)
+    wf = [float(x) for x in e["wf_centers"][1:]]
+    if m.wf_centers is None:
+        assert wf == []
+    else:
+        np.testing.assert_array_equal(np.array(wf).reshape(-1, 3).T, m.wf_centers)
+    Rf = np.asfortranarray(m.R).ravel(order="F")
+    Hf = np.asfortranarray(m.H).ravel(order="F").view(np.float64)
+    cs = [float(x) for x in e["checksums"]]
+    assert abs(cs[0] - float((Rf * (np.arange(Rf.size) % 7 + 1)).sum())) <= 1e-12 * max(1.0, np.abs(Rf).sum())
+    assert abs(cs[1] - float((Hf * (np.arange(Hf.size) % 13 + 1)).sum())) <= 1e-12 * np.abs(Hf).sum() * 13
+    assert abs(cs[2] - float(np.abs(Hf).sum())) <= 1e-12 * np.abs(Hf).sum()
+
+
+def test_driver_errors_are_loud(driver, tmp_path):
+    r = subprocess.run([driver, "--dir", str(tmp_path), "--check-input"], capture_output=True, text=True)
+    assert r.returncode == 1 and "input.cfg" in r.stderr
+    shutil.copytree(os.path.join(GOLDEN, "souza_phi0"), tmp_path / "run")
+    hr = tmp_path / "run" / "w90files" / "wf1_hr.dat"
+    lines = hr.read_text().splitlines()
+    hr.write_text("\n".join(lines[:-5]) + "\n")
+    r = subprocess.run([driver, "--dir", str(tmp_path / "run"), "--check-input"], capture_output=True, text=True)
+    assert r.returncode == 1 and "read_hr_file" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,mesh", [("femn_d0.900", 12), ("souza_phi0", 10), ("femn_rashba", 6)])
+def test_driver_end_to_end_files(driver, tmp_path, name, mesh):
+    run = tmp_path / "run"
+    shutil.copytree(os.path.join(GOLDEN, name), run)
+    cfg = (run / "input.cfg").read_text().splitlines()
+    cfg = [("    mp_grid= %d %d %d" % (mesh, mesh, mesh)) if ln.strip().startswith("mp_grid") else ln for ln in cfg]
+    cfg = [("    N_hw= 9") if ln.strip().startswith("N_hw") else ln for ln in cfg]
+    (run / "input.cfg").write_text("\n".join(cfg) + "\n")
+    r = subprocess.run([driver, "--dir", str(run)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    m, p = mo.load_model(str(run))
+    ref, scale, sens = oracle_reference(m, p)
+    out = {"n_k": ref["n_k"], "eF_idx": ref["eF_idx"], "n_degenerate": ref["n_degenerate"], "Ne": ref["Ne"]}
+    for k, v in ref.items():
+        if isinstance(v, np.ndarray) and k != "Ne":
+            f = run / "out" / (k + ".npy")
+            assert f.exists(), k
+            arr = np.load(f)
+            assert arr.shape == v.shape and arr.flags["F_CONTIGUOUS"]
+            out[k] = arr
+    assert_parity(out, ref, scale, sens, tol=1e-8, label=name)
+    hw = np.load(run / "out" / "hw_lst.npy")
+    assert hw.shape == (9,) and abs(hw[-1] - p.hw_max * mo.AU_TO_EV) < 1e-12
+    occ = (run / "out" / "occ.dat").read_text().split()
+    assert abs(float(occ[1]) - ref["Ne"][0]) < 1e-7

@@ -58,6 +58,7 @@ def raw(rep, pat=None):
 
 
 def lines(rep, sass, func, src, top=40):
+    top = int(top)
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
