@@ -133,6 +133,8 @@ struct mepb_ctx {
     FourierPlan fp{};
     int *d_ridx = nullptr, *d_elem = nullptr; double2 *d_Hp = nullptr; double *d_Rfp = nullptr, *d_cRp = nullptr;
     double2 *d_Hka_int = nullptr;
+    int *d_sp_ptr = nullptr, *d_sp_R = nullptr; double2 *d_sp_val = nullptr;   // sparse H(R) (warp-per-k Fourier sums)
+    bool sparse = false;
     double a_latt[9];
     // device model
     double2 *d_H = nullptr; double *d_Rf = nullptr, *d_cR = nullptr, *d_tau = nullptr, *d_tM = nullptr, *d_hw = nullptr;
@@ -169,6 +171,7 @@ DevModel dev_model(const mepb_ctx *c) {
     DevModel m;
     m.nw = c->nw; m.nR = c->nR; m.H = c->d_H; m.Rf = c->d_Rf; m.cR = c->d_cR;
     m.tau = c->has_tau ? c->d_tau : nullptr; m.tM = c->d_tM;
+    m.sp_ptr = c->sparse ? c->d_sp_ptr : nullptr; m.sp_R = c->d_sp_R; m.sp_val = c->d_sp_val;
     return m;
 }
 Jobs make_jobs(const mepb_ctx *c, int ief, bool response) {
@@ -283,8 +286,36 @@ cudaError_t build_fourier_plan(mepb_ctx *c, const mepb_model *model, const std::
     return cudaSuccess;
 }
 
+// CSR (by matrix element) of the non-zero entries of H(R); used when fewer than half of the entries are non-zero
+cudaError_t build_sparse(mepb_ctx *c, const mepb_model *model) {
+    const int nw2 = c->nw * c->nw, nR = c->nR;
+    std::vector<int> ptr(nw2 + 1, 0), col;
+    std::vector<double2> val;
+    for (int idx = 0; idx < nw2; ++idx) {
+        for (int R = 0; R < nR; ++R) {
+            const double *h = model->H + 2 * ((size_t)idx + (size_t)nw2 * R);
+            if (h[0] != 0.0 || h[1] != 0.0) { col.push_back(R); val.push_back(make_double2(h[0], h[1])); }
+        }
+        ptr[idx + 1] = (int)col.size();
+    }
+    c->sparse = !getenv("MEPB_DENSE_FOURIER") && (2 * col.size() < (size_t)nw2 * nR);
+    if (!c->sparse) return cudaSuccess;
+    cudaFree(c->d_sp_ptr); cudaFree(c->d_sp_R); cudaFree(c->d_sp_val);
+    c->d_sp_ptr = c->d_sp_R = nullptr; c->d_sp_val = nullptr;
+    cudaError_t e;
+    const size_t n = std::max<size_t>(col.size(), 1);
+    col.resize(n, 0); val.resize(n, make_double2(0.0, 0.0));
+    if ((e = cudaMalloc((void **)&c->d_sp_ptr, sizeof(int) * ptr.size())) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void **)&c->d_sp_R, sizeof(int) * n)) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void **)&c->d_sp_val, sizeof(double2) * n)) != cudaSuccess) return e;
+    if ((e = cudaMemcpy(c->d_sp_ptr, ptr.data(), sizeof(int) * ptr.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+    if ((e = cudaMemcpy(c->d_sp_R, col.data(), sizeof(int) * n, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+    return cudaMemcpy(c->d_sp_val, val.data(), sizeof(double2) * n, cudaMemcpyHostToDevice);
+}
+
 void free_all(mepb_ctx *c) {
     cudaSetDevice(c->device);
+    cudaFree(c->d_sp_ptr); cudaFree(c->d_sp_R); cudaFree(c->d_sp_val);
     cudaFree(c->d_H); cudaFree(c->d_Rf); cudaFree(c->d_cR); cudaFree(c->d_tau); cudaFree(c->d_tM); cudaFree(c->d_hw);
     for (auto &s : c->sb) {
         cudaFree(s.items_ahc); cudaFree(s.cnt_ahc); cudaFree(s.items_photo); cudaFree(s.cnt_photo);
@@ -430,6 +461,7 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
     chunk = std::max<long long>(c->large ? 296 : 1024, std::min(chunk, std::max<long long>(nk_mesh, 1024)));
     c->chunk = chunk;
     if (c->large) CT(build_fourier_plan(c, model, cR));
+    else CT(build_sparse(c, model));
     c->grid_interp = c->large ? eig_large_grid(c->sm_count, chunk) : interp_small_grid(nw, nR, c->sm_count, chunk);
     c->grid_sweep = sweep_ahc_grid(c->sm_count, chunk, p.n_hw, &c->ns_sweep);
     c->grid_photo = sweep_photo_grid(c->sm_count, chunk, p.n_hw, &c->ns_photo);
@@ -440,13 +472,15 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
         CT(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
         CT(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
         if (p.do_ahc) {
-            CT(cudaMalloc((void **)&s.items_ahc, sizeof(double) * istr * c->max_pairs * (size_t)chunk));
-            CT(cudaMalloc((void **)&s.cnt_ahc, sizeof(int) * (size_t)chunk));
+            CT(cudaMalloc((void **)&s.items_ahc, sizeof(double) * istr * c->max_pairs * (size_t)(chunk + 16)));   // + one TMA stage of slack
+            CT(cudaMalloc((void **)&s.cnt_ahc, sizeof(int) * (size_t)(chunk + 16)));
+            CT(cudaMemset(s.cnt_ahc, 0, sizeof(int) * (size_t)(chunk + 16)));
             CT(cudaMalloc((void **)&s.block_sweep, sizeof(double) * kSweepAcc * (size_t)c->ns_sweep * c->grid_sweep));
         }
         if (p.do_opt) {
             CT(cudaMalloc((void **)&s.items_photo, sizeof(double) * kPhotoItem * c->max_photo * (size_t)chunk));
-            CT(cudaMalloc((void **)&s.cnt_photo, sizeof(int) * (size_t)chunk));
+            CT(cudaMalloc((void **)&s.cnt_photo, sizeof(int) * (size_t)(chunk + 16)));
+            CT(cudaMemset(s.cnt_photo, 0, sizeof(int) * (size_t)(chunk + 16)));
             CT(cudaMalloc((void **)&s.block_photo, sizeof(double) * kPhotoAcc * (size_t)c->ns_photo * c->grid_photo));
         }
         if (c->large) {
@@ -760,6 +794,8 @@ int mepb_update_model(mepb_ctx *c, const mepb_model *model) {
         std::vector<double> cR(3 * (size_t)c->nR);
         CUDA_TRY(cudaMemcpy(cR.data(), c->d_cR, sizeof(double) * cR.size(), cudaMemcpyDeviceToHost));
         CUDA_TRY(build_fourier_plan(c, model, cR));
+    } else {
+        CUDA_TRY(build_sparse(c, model));
     }
     return MEPB_OK;
 }

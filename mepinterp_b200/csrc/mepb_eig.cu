@@ -115,9 +115,12 @@ eig_small_kernel(const DevModel m, const KSource ks, double *__restrict__ E_out,
                         const double bb = fma(bx, bx, by * by);
                         const bool rot = bb > 1e-300;
                         const double zeta = 0.5 * (d - a), az = fabs(zeta);
-                        const double h = sqrt(fma(zeta, zeta, bb));
+                        const double hh = rot ? fma(zeta, zeta, bb) : 1.0;
+                        const double rh = fast_rsqrt3(hh);
+                        double h = hh * rh;                                    // sqrt(zeta^2 + |b|^2) ...
+                        h = fma(fma(-h, h, hh), 0.5 * rh, h);                  // ... plus one Heron step (no division)
                         const double y = 2.0 * h * (az + h);
-                        const double ry = rot ? rsqrt(y) : 0.0;
+                        const double ry = rot ? fast_rsqrt3(y) : 0.0;
                         const double sg = zeta < 0.0 ? -1.0 : 1.0;
                         rc[i] = rot ? (az + h) * ry : 1.0;
                         const double sr = sg * ry;
@@ -180,7 +183,13 @@ eig_small_kernel(const DevModel m, const KSource ks, double *__restrict__ E_out,
                         }
                     }
                 }
-                ok = (off2 <= tol);
+                // off-diagonal norm of what is left AFTER this sweep (saves the verification sweep of the classic test)
+                double left = 0.0;
+#pragma unroll
+                for (int q = 0; q < NW; ++q)
+#pragma unroll
+                    for (int p = 0; p < q; ++p) left += 2.0 * (ar[p][q] * ar[p][q] + ai[p][q] * ai[p][q]);
+                ok = (left <= tol) || (off2 <= tol);
             }
         }
         if (!ok) atomicExch(err_flag, 1);

@@ -53,6 +53,11 @@ struct DevModel {
     const double *cR;    // [nR][3] M.R  with M = 2 pi (use_cart_velo=F) or a_latt (T)       wann_interp.f90:268-271
     const double *tau;   // [nw][3] fractional centres or nullptr (Wannier convention)        wann_interp.f90:192
     const double *tM;    // [nw][3] M.tau (zeros when tau == nullptr)
+    // sparse form of H(R) (CSR by matrix element n + nw*m), used by the warp-per-k Fourier sums when most entries are zero
+    // (FeMn: 110 of 1728; the reference adds the zeros, file_io.f90:732-741 keeps them in H_tb) — nullptr -> dense loops
+    const int *sp_ptr;   // [nw*nw + 1]
+    const int *sp_R;     // [nnz] R index
+    const double2 *sp_val;   // [nnz]
 };
 
 struct KSource {          // where the k-points of a launch come from
@@ -152,6 +157,54 @@ __device__ __forceinline__ double warp_sum(double v) {
 __device__ __forceinline__ double fermi(double e, const Jobs &j) {  // statistics.f90:41-61
     if (j.zero_T) return (e < j.eF) ? 1.0 : 0.0;
     return 1.0 / (1.0 + exp((e - j.eF) * j.inv_kT));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX helpers (TMA bulk copy)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// 1/sqrt(x) for normal x > 0: MUFU.RSQ64H seed + one cubic step  y' = y + y e (1/2 + 3/8 e), e = 1 - x y^2
+__device__ __forceinline__ double fast_rsqrt3(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double t = x * y;
+    const double e = fma(-t, y, 1.0);
+    const double u = fma(0.375, e, 0.5);
+    const double v = y * e;
+    return fma(v, u, y);
+}
+// reciprocal with a cubic (Halley) correction of the MUFU.RCP64H seed: r' = r + r (e + e^2), e = 1 - x r
+__device__ __forceinline__ double fast_rcp3(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double e = fma(-x, r, 1.0);
+    const double t = fma(e, e, e);
+    return fma(r, t, r);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -247,6 +247,27 @@ interp_small_kernel(const DevModel m, const KSource ks, const Jobs jb, const Int
             double2 g0[3], g1[3];
 #pragma unroll
             for (int a = 0; a < 3; ++a) { g0[a] = make_double2(0, 0); g1[a] = make_double2(0, 0); }
+            if (m.sp_ptr) {
+                // sparse H(R): each lane walks the non-zero (R, value) list of its two matrix elements
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int idx = e ? idx1 : idx0;
+                    if (!(e ? v1 : v0)) continue;
+                    double2 hk = make_double2(0, 0), g[3] = {make_double2(0, 0), make_double2(0, 0), make_double2(0, 0)};
+                    const int t1 = __ldg(&m.sp_ptr[idx + 1]);
+                    for (int t = __ldg(&m.sp_ptr[idx]); t < t1; ++t) {
+                        const int R = __ldg(&m.sp_R[t]);
+                        const double2 tt = cmul(ph[R], __ldg(&m.sp_val[t]));
+                        const double c0 = __ldg(&m.cR[3 * R]), c1 = __ldg(&m.cR[3 * R + 1]), c2 = __ldg(&m.cR[3 * R + 2]);
+                        hk.x += tt.x; hk.y += tt.y;
+                        g[0].x = fma(c0, tt.x, g[0].x); g[0].y = fma(c0, tt.y, g[0].y);
+                        g[1].x = fma(c1, tt.x, g[1].x); g[1].y = fma(c1, tt.y, g[1].y);
+                        g[2].x = fma(c2, tt.x, g[2].x); g[2].y = fma(c2, tt.y, g[2].y);
+                    }
+                    if (e) { hk1 = hk; g1[0] = g[0]; g1[1] = g[1]; g1[2] = g[2]; }
+                    else { hk0 = hk; g0[0] = g[0]; g0[1] = g[1]; g0[2] = g[2]; }
+                }
+            } else {
             const double2 *Hp = m.H;
 #pragma unroll 3
             for (int R = 0; R < nR; ++R) {
@@ -268,6 +289,7 @@ interp_small_kernel(const DevModel m, const KSource ks, const Jobs jb, const Int
                     g1[1].x = fma(c1, t.x, g1[1].x); g1[1].y = fma(c1, t.y, g1[1].y);
                     g1[2].x = fma(c2, t.x, g1[2].x); g1[2].y = fma(c2, t.y, g1[2].y);
                 }
+            }
             }
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
