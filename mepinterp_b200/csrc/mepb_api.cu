@@ -130,11 +130,12 @@ struct mepb_ctx {
     bool herm = true;      // H(R) Hermitian-closed: V_a Hermitian -> compact items / 18-accumulator sweep
     bool eig_thread = false;   // eigenpairs from the thread-per-k kernel (nw 4, 8)
     bool large = false;        // general path (mepb_large.cu)
+    bool use_sub = false;      // NW-lanes-per-k band-sum kernel (mepb_sub.cu) in mesh mode
     FourierPlan fp{};
     int *d_ridx = nullptr, *d_elem = nullptr; double2 *d_Hp = nullptr; double *d_Rfp = nullptr, *d_cRp = nullptr;
     double2 *d_Hka_int = nullptr;
     int *d_sp_ptr = nullptr, *d_sp_R = nullptr; double2 *d_sp_val = nullptr;   // sparse H(R) (warp-per-k Fourier sums)
-    bool sparse = false;
+    bool sparse = false; int sp_nnz = 0;
     double a_latt[9];
     // device model
     double2 *d_H = nullptr; double *d_Rf = nullptr, *d_cR = nullptr, *d_tau = nullptr, *d_tM = nullptr, *d_hw = nullptr;
@@ -171,7 +172,7 @@ DevModel dev_model(const mepb_ctx *c) {
     DevModel m;
     m.nw = c->nw; m.nR = c->nR; m.H = c->d_H; m.Rf = c->d_Rf; m.cR = c->d_cR;
     m.tau = c->has_tau ? c->d_tau : nullptr; m.tM = c->d_tM;
-    m.sp_ptr = c->sparse ? c->d_sp_ptr : nullptr; m.sp_R = c->d_sp_R; m.sp_val = c->d_sp_val;
+    m.sp_ptr = c->sparse ? c->d_sp_ptr : nullptr; m.sp_R = c->d_sp_R; m.sp_val = c->d_sp_val; m.sp_nnz = c->sp_nnz;
     return m;
 }
 Jobs make_jobs(const mepb_ctx *c, int ief, bool response) {
@@ -299,6 +300,7 @@ cudaError_t build_sparse(mepb_ctx *c, const mepb_model *model) {
         ptr[idx + 1] = (int)col.size();
     }
     c->sparse = !getenv("MEPB_DENSE_FOURIER") && (2 * col.size() < (size_t)nw2 * nR);
+    c->sp_nnz = (int)col.size();
     if (!c->sparse) return cudaSuccess;
     cudaFree(c->d_sp_ptr); cudaFree(c->d_sp_R); cudaFree(c->d_sp_val);
     c->d_sp_ptr = c->d_sp_R = nullptr; c->d_sp_val = nullptr;
@@ -410,6 +412,7 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
     { std::string why; c->herm = hermitian_closed(model, &why); }
     c->large = want_large;
     c->eig_thread = !c->large && eig_thread_supported(model->nw) && !getenv("MEPB_WARP_JACOBI");
+    c->use_sub = c->eig_thread && sub_supported(model->nw, model->nR) && !getenv("MEPB_WARP_BANDS");
     std::memcpy(c->a_latt, model->a_latt, sizeof(c->a_latt));
     const int nw = c->nw, nR = c->nR;
     // linspaces (matrix_math.f90:74-100, core.f90:124-125)
@@ -463,6 +466,7 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
     if (c->large) CT(build_fourier_plan(c, model, cR));
     else CT(build_sparse(c, model));
     c->grid_interp = c->large ? eig_large_grid(c->sm_count, chunk) : interp_small_grid(nw, nR, c->sm_count, chunk);
+    if (c->use_sub) c->grid_interp = std::max(c->grid_interp, bands_sub_grid(nw, nR, c->sm_count, chunk));
     c->grid_sweep = sweep_ahc_grid(c->sm_count, chunk, p.n_hw, &c->ns_sweep);
     c->grid_photo = sweep_photo_grid(c->sm_count, chunk, p.n_hw, &c->ns_photo);
     c->cs.ns = static_size(nw); c->cs.sweep = p.n_hw * kSweepAcc; c->cs.photo = p.n_hw * kPhotoAcc;
@@ -547,7 +551,8 @@ int mepb_accumulate(mepb_ctx *c, int64_t lin_begin, int64_t lin_end) {
             o.items_ahc = jb.do_ahc ? s.items_ahc : nullptr; o.cnt_ahc = s.cnt_ahc;
             o.items_photo = jb.do_opt ? s.items_photo : nullptr; o.cnt_photo = s.cnt_photo;
             o.block_static = s.block_static; o.err_flag = c->d_err;
-            const int gi = c->large ? eig_large_grid(c->sm_count, nk) : interp_small_grid(c->nw, c->nR, c->sm_count, nk);
+            const int gi = c->large ? eig_large_grid(c->sm_count, nk)
+                           : c->use_sub ? bands_sub_grid(c->nw, c->nR, c->sm_count, nk) : interp_small_grid(c->nw, c->nR, c->sm_count, nk);
             if (c->large) {
                 { ProfScope ps(c, s.st, MEPB_PROF_FOURIER); CUDA_TRY(launch_fourier_dense(c->fp, m, ks, s.Hk, s.Hka, s.st)); }
                 { ProfScope ps(c, s.st, MEPB_PROF_EIGROT);
@@ -560,7 +565,12 @@ int mepb_accumulate(mepb_ctx *c, int64_t lin_begin, int64_t lin_end) {
                 o.e_in = s.eig_E; o.U_in = s.eig_U;
                 c->launches += 1;
             }
-            if (!c->large) { ProfScope ps(c, s.st, MEPB_PROF_INTERP); CUDA_TRY(launch_interp_small(m, ks, jb, o, c->max_pairs, gi, s.st)); c->launches += 1; }
+            if (!c->large) {
+                ProfScope ps(c, s.st, MEPB_PROF_INTERP);
+                if (c->use_sub) CUDA_TRY(launch_bands_sub(m, ks, jb, o, c->max_pairs, gi, s.st));
+                else CUDA_TRY(launch_interp_small(m, ks, jb, o, c->max_pairs, gi, s.st));
+                c->launches += 1;
+            }
             { ProfScope ps(c, s.st, MEPB_PROF_REDUCE);
               CUDA_TRY(launch_reduce_rows(s.block_static, gi, ns, s.compact + (size_t)ief * c->cs.per_ef, ns, 0, 0, s.st)); }
             c->launches += 1;

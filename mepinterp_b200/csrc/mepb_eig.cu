@@ -47,7 +47,12 @@ eig_small_kernel(const DevModel m, const KSource ks, double *__restrict__ E_out,
         if (ks.list) { k1 = ks.list[3 * ik]; k2 = ks.list[3 * ik + 1]; k3 = ks.list[3 * ik + 2]; }
         else {
             const long long lin = ks.lin_begin + ik;
-            const long long q1 = lin % ks.N1 + 1, q2 = (lin / ks.N1) % ks.N2 + 1, q3 = lin / ((long long)ks.N1 * ks.N2) + 1;
+            long long q1, q2, q3;
+            if (lin < 0x7fffffffLL) {     // 32-bit divisions (a 64-bit one is ~60 instructions)
+                const unsigned l32 = (unsigned)lin, n1 = (unsigned)ks.N1, n2 = (unsigned)ks.N2;
+                const unsigned t = l32 / n1;
+                q1 = l32 - t * n1 + 1; const unsigned t2 = t / n2; q2 = t - t2 * n2 + 1; q3 = t2 + 1;
+            } else { q1 = lin % ks.N1 + 1; q2 = (lin / ks.N1) % ks.N2 + 1; q3 = lin / ((long long)ks.N1 * ks.N2) + 1; }
             k1 = (2.0 * (double)q1 - (double)ks.N1 - 1.0) / (2.0 * (double)ks.N1);
             k2 = (2.0 * (double)q2 - (double)ks.N2 - 1.0) / (2.0 * (double)ks.N2);
             k3 = (2.0 * (double)q3 - (double)ks.N3 - 1.0) / (2.0 * (double)ks.N3);

@@ -58,6 +58,7 @@ struct DevModel {
     const int *sp_ptr;   // [nw*nw + 1]
     const int *sp_R;     // [nnz] R index
     const double2 *sp_val;   // [nnz]
+    int sp_nnz;
 };
 
 struct KSource {          // where the k-points of a launch come from
@@ -215,6 +216,11 @@ cudaError_t launch_interp_small(const DevModel &m, const KSource &ks, const Jobs
                                 int grid, cudaStream_t st);
 int interp_small_grid(int nw, int nR, int sm_count, long long nk);
 bool eig_thread_supported(int nw);
+// NW-lanes-per-k band-sum kernel (mepb_sub.cu): response mode, num_wann 4 / 8, eigenpairs from launch_eig_small
+bool sub_supported(int nw, int nR);
+int bands_sub_grid(int nw, int nR, int sm_count, long long nk);
+cudaError_t launch_bands_sub(const DevModel &m, const KSource &ks, const Jobs &jobs, const InterpOut &out, int max_pairs, int grid,
+                             cudaStream_t st);
 cudaError_t launch_eig_small(const DevModel &m, const KSource &ks, double *E_out, double2 *U_out, int *err_flag, int sm_count,
                              cudaStream_t st);
 

@@ -186,8 +186,10 @@ __device__ bool jacobi_warp(double2 *As, double2 *Us, double *rot, int lane) {
     return false;
 }
 
+template <int NW> constexpr int kMinBlocks = (NW <= 8) ? 3 : 2;   // resident CTAs per SM the register budget is set for
+
 template <int NW>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 2)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocks<NW>)
 interp_small_kernel(const DevModel m, const KSource ks, const Jobs jb, const InterpOut out, const int max_pairs,
                     const size_t warp_bytes) {
     using L = SL<NW>;
@@ -222,7 +224,12 @@ interp_small_kernel(const DevModel m, const KSource ks, const Jobs jb, const Int
         if (ks.list) { k1 = ks.list[3 * ik]; k2 = ks.list[3 * ik + 1]; k3 = ks.list[3 * ik + 2]; }
         else {
             const long long lin = ks.lin_begin + ik;
-            const long long q1 = lin % ks.N1 + 1, q2 = (lin / ks.N1) % ks.N2 + 1, q3 = lin / ((long long)ks.N1 * ks.N2) + 1;
+            long long q1, q2, q3;
+            if (lin < 0x7fffffffLL) {     // 32-bit divisions (a 64-bit one is ~60 instructions)
+                const unsigned l32 = (unsigned)lin, n1 = (unsigned)ks.N1, n2 = (unsigned)ks.N2;
+                const unsigned t = l32 / n1;
+                q1 = l32 - t * n1 + 1; const unsigned t2 = t / n2; q2 = t - t2 * n2 + 1; q3 = t2 + 1;
+            } else { q1 = lin % ks.N1 + 1; q2 = (lin / ks.N1) % ks.N2 + 1; q3 = lin / ((long long)ks.N1 * ks.N2) + 1; }
             k1 = (2.0 * (double)q1 - (double)ks.N1 - 1.0) / (2.0 * (double)ks.N1);
             k2 = (2.0 * (double)q2 - (double)ks.N2 - 1.0) / (2.0 * (double)ks.N2);
             k3 = (2.0 * (double)q3 - (double)ks.N3 - 1.0) / (2.0 * (double)ks.N3);
@@ -670,7 +677,8 @@ int interp_small_grid(int nw, int nR, int sm_count, long long nk) {
     size_t wb = (nw == 4) ? SL<4>::bytes(nR) : (nw == 8) ? SL<8>::bytes(nR) : SL<16>::bytes(nR);
     size_t smem = wb * kWarpsPerBlock + 1024;
     int per_sm = (int)((227 * 1024) / smem);
-    if (per_sm > 2) per_sm = 2;     // __launch_bounds__(256, 2)
+    const int cap = (nw <= 8) ? 3 : 2;   // kMinBlocks<NW>
+    if (per_sm > cap) per_sm = cap;
     if (per_sm < 1) per_sm = 1;
     long long need = (nk + kWarpsPerBlock - 1) / kWarpsPerBlock;
     long long g = (long long)sm_count * per_sm;

@@ -1,0 +1,519 @@
+// mepb_sub.cu — band-sum kernel for num_wann 4 and 8 in the response (mesh) mode: NW LANES PER k-POINT.
+//
+// Successor of the warp-per-k kernel of mepb_small.cu for the hot configurations (that one stays for num_wann = 16, for
+// explicit k lists and as the fallback).  A warp carries 32/NW k-points at once; lane g of a group owns row g in the
+// Fourier sums, column g in the gauge rotation, band n0 = g in the MEP sums, and a strided share of the band pairs.
+// Everything the groups do is the same instruction stream, so the per-k instruction count drops ~3x against one warp
+// per k (profiles/r01c: 2.1 k warp instructions per k, 20 % of the FP64 roofline).  Per k-point:
+//   1. phases e^{2 pi i k.R} (sincospi) and tight-binding diagonal phases                (wann_interp.f90:215-223,259-260)
+//   2. Fourier sums of d_a H(k) from the sparse or dense H(R)                             (wann_interp.f90:206-279)
+//   3. eigenpairs from the thread-per-k solver (mepb_eig.cu)                              (matrix_math.f90:192-226)
+//   4. V_a = U^dagger (d_a H) U                                                          (wann_interp.f90:517-528)
+//   5. occupations, static AHC, pair items, MEP (Niu + Kubo) sums, photo items           (kubo.f90, mep_niu.f90, kubo_mep.f90,
+//                                                                                         photo.f90:44-81)
+// Output formats (block_static rows, item buffers) are those of mepb_small.cu, so the sweeps and the packing are shared.
+#include "mepb_internal.cuh"
+
+namespace mepb {
+
+namespace {
+
+constexpr int kSubWarps = 4;                      // warps per CTA
+constexpr int kSubMaxNnz = 256;                   // sparse H(R) entries staged in shared memory (else read through L1)
+
+struct SpRec { double2 val; double c0, c1, c2; int R; int pad; };   // 48 bytes: one non-zero H(R)(n,m) with its weights
+
+template <int NW>
+struct SubL {  // shared-memory layout per GROUP (one k-point), bytes
+    static constexpr int LD = NW + 1;             // padded rows: row-strided stores of a group (U load, Fourier) hit distinct banks
+    static constexpr size_t oU = 0;
+    static constexpr size_t oHa = oU + sizeof(double2) * NW * LD;
+    static constexpr size_t oEs = oHa + sizeof(double2) * 3 * NW * LD;
+    static constexpr size_t oFn = oEs + sizeof(double) * NW;
+    static constexpr size_t oDn = oFn + sizeof(double) * NW;
+    static constexpr size_t oPh = oDn + sizeof(double2) * NW;
+    // group stride = 16 mod 128 bytes, so that the same element of the 32/NW groups of a warp falls into different banks
+    static size_t bytes(int nR) { size_t b = oPh + sizeof(double2) * nR; return (b + 127) / 128 * 128 + 16; }
+};
+
+template <int NW, bool MEP>
+__global__ void __launch_bounds__(kSubWarps * 32, 2)
+bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const InterpOut out, const int max_pairs, const size_t grp_bytes) {
+    using L = SubL<NW>;
+    constexpr int LD = L::LD, NW2 = NW * NW, NPAIR = NW * (NW - 1) / 2, NGRP = 32 / NW;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane % NW, grp = lane / NW;
+    const unsigned gshift = (unsigned)(grp * NW);
+    const unsigned gbits = (NW == 32) ? 0xffffffffu : ((1u << NW) - 1u);
+    unsigned char *base = smem_raw + ((size_t)warp * NGRP + grp) * grp_bytes;
+    double2 *Us = reinterpret_cast<double2 *>(base + L::oU);
+    double2 *Ha = reinterpret_cast<double2 *>(base + L::oHa);      // [a][n*LD + m]; V_a after the rotation
+    double *es = reinterpret_cast<double *>(base + L::oEs);
+    double *fn = reinterpret_cast<double *>(base + L::oFn);
+    double2 *dn = reinterpret_cast<double2 *>(base + L::oDn);
+    double2 *ph = reinterpret_cast<double2 *>(base + L::oPh);
+    const int nR = m.nR;
+    const bool has_tau = (m.tau != nullptr);
+    // CTA-wide copy of the sparse H(R) list (after the group buffers)
+    SpRec *rec = reinterpret_cast<SpRec *>(smem_raw + (size_t)kSubWarps * NGRP * grp_bytes);
+    int *sptr = reinterpret_cast<int *>(rec + kSubMaxNnz);
+    const bool sp_smem = (m.sp_ptr != nullptr) && (m.sp_nnz <= kSubMaxNnz);
+    if (sp_smem) {
+        for (int t = threadIdx.x; t < m.sp_nnz; t += blockDim.x) {
+            const int R = m.sp_R[t];
+            SpRec r; r.val = m.sp_val[t]; r.c0 = m.cR[3 * R]; r.c1 = m.cR[3 * R + 1]; r.c2 = m.cR[3 * R + 2]; r.R = R; r.pad = 0;
+            rec[t] = r;
+        }
+        for (int i = threadIdx.x; i <= NW2; i += blockDim.x) sptr[i] = m.sp_ptr[i];
+    }
+    __syncthreads();
+
+    // per-lane accumulators over all k-points of this thread's groups
+    double acc_nk = 0.0, acc_ndeg = 0.0, acc_ne = 0.0, acc_nit = 0.0, acc_nph = 0.0, acc_ahc[9];
+    constexpr int NM = MEP ? 9 : 1;
+    double niu_ic[NM], niu_lc[NM], kub_ic[NM], kub_lc[NM];        // band n0 = g (only with the MEP jobs)
+#pragma unroll
+    for (int q = 0; q < 9; ++q) acc_ahc[q] = 0.0;
+#pragma unroll
+    for (int q = 0; q < NM; ++q) { niu_ic[q] = 0.0; niu_lc[q] = 0.0; kub_ic[q] = 0.0; kub_lc[q] = 0.0; }
+
+    const long long gstride = (long long)gridDim.x * kSubWarps * NGRP;
+    const long long first = ((long long)blockIdx.x * kSubWarps + warp) * NGRP + grp;
+    const long long n_iter = (ks.nk + gstride - 1) / gstride;     // same trip count for every warp: __syncwarp stays uniform
+    for (long long it = 0; it < n_iter; ++it) {
+        const long long ik_raw = first + it * gstride;
+        const bool valid = ik_raw < ks.nk;
+        const long long ik = valid ? ik_raw : ks.nk - 1;          // idle groups recompute the last k-point and discard it
+        // ------------------------------------------------------------------ k-point (k_space.f90:351-375)
+        double k1, k2, k3;
+        {
+            const long long lin = ks.lin_begin + ik;
+            long long q1, q2, q3;
+            if (lin < 0x7fffffffLL) {
+                const unsigned l32 = (unsigned)lin, n1 = (unsigned)ks.N1, n2 = (unsigned)ks.N2;
+                const unsigned t = l32 / n1;
+                q1 = l32 - t * n1 + 1; const unsigned t2 = t / n2; q2 = t - t2 * n2 + 1; q3 = t2 + 1;
+            } else { q1 = lin % ks.N1 + 1; q2 = (lin / ks.N1) % ks.N2 + 1; q3 = lin / ((long long)ks.N1 * ks.N2) + 1; }
+            k1 = (2.0 * (double)q1 - (double)ks.N1 - 1.0) / (2.0 * (double)ks.N1);
+            k2 = (2.0 * (double)q2 - (double)ks.N2 - 1.0) / (2.0 * (double)ks.N2);
+            k3 = (2.0 * (double)q3 - (double)ks.N3 - 1.0) / (2.0 * (double)ks.N3);
+        }
+        // ------------------------------------------------------------------ 1. phases; 3. eigenpairs (loads issued early)
+        for (int R = g; R < nR; R += NW) {
+            const double x = 2.0 * (k1 * __ldg(&m.Rf[3 * R]) + k2 * __ldg(&m.Rf[3 * R + 1]) + k3 * __ldg(&m.Rf[3 * R + 2]));
+            double s, c; sincospi(x, &s, &c);
+            ph[R] = make_double2(c, s);
+        }
+        if (has_tau) {
+            const double x = 2.0 * (k1 * __ldg(&m.tau[3 * g]) + k2 * __ldg(&m.tau[3 * g + 1]) + k3 * __ldg(&m.tau[3 * g + 2]));
+            double s, c; sincospi(x, &s, &c);
+            dn[g] = make_double2(c, s);
+        }
+        {
+            const double2 *Uk = out.U_in + (size_t)ik * NW2;       // element r + NW*c ; lane g takes row g
+#pragma unroll
+            for (int c = 0; c < NW; ++c) Us[g * LD + c] = Uk[g + NW * c];
+            const double e = out.e_in[(size_t)ik * NW + g];
+            const double f = fermi(e, jb);
+            es[g] = e; fn[g] = f;
+            if (valid) acc_ne += f;
+        }
+        __syncwarp();
+        // ------------------------------------------------------------------ 2. Fourier sums of d_a H, row n = g
+        {
+            const int n = g;
+#pragma unroll 1
+            for (int mm = 0; mm < NW; ++mm) {
+                const int idx = n + NW * mm;
+                double2 hk = make_double2(0, 0), gs[3] = {make_double2(0, 0), make_double2(0, 0), make_double2(0, 0)};
+                if (sp_smem) {
+                    const int t1 = sptr[idx + 1];
+                    for (int t = sptr[idx]; t < t1; ++t) {
+                        const SpRec r = rec[t];
+                        const double2 tt = cmul(ph[r.R], r.val);
+                        hk.x += tt.x; hk.y += tt.y;
+                        gs[0].x = fma(r.c0, tt.x, gs[0].x); gs[0].y = fma(r.c0, tt.y, gs[0].y);
+                        gs[1].x = fma(r.c1, tt.x, gs[1].x); gs[1].y = fma(r.c1, tt.y, gs[1].y);
+                        gs[2].x = fma(r.c2, tt.x, gs[2].x); gs[2].y = fma(r.c2, tt.y, gs[2].y);
+                    }
+                } else if (m.sp_ptr) {
+                    const int t1 = __ldg(&m.sp_ptr[idx + 1]);
+                    for (int t = __ldg(&m.sp_ptr[idx]); t < t1; ++t) {
+                        const int R = __ldg(&m.sp_R[t]);
+                        const double2 tt = cmul(ph[R], __ldg(&m.sp_val[t]));
+                        const double c0 = __ldg(&m.cR[3 * R]), c1 = __ldg(&m.cR[3 * R + 1]), c2 = __ldg(&m.cR[3 * R + 2]);
+                        hk.x += tt.x; hk.y += tt.y;
+                        gs[0].x = fma(c0, tt.x, gs[0].x); gs[0].y = fma(c0, tt.y, gs[0].y);
+                        gs[1].x = fma(c1, tt.x, gs[1].x); gs[1].y = fma(c1, tt.y, gs[1].y);
+                        gs[2].x = fma(c2, tt.x, gs[2].x); gs[2].y = fma(c2, tt.y, gs[2].y);
+                    }
+                } else {
+#pragma unroll 3
+                    for (int R = 0; R < nR; ++R) {
+                        const double2 tt = cmul(ph[R], __ldg(&m.H[(size_t)R * NW2 + idx]));
+                        const double c0 = __ldg(&m.cR[3 * R]), c1 = __ldg(&m.cR[3 * R + 1]), c2 = __ldg(&m.cR[3 * R + 2]);
+                        hk.x += tt.x; hk.y += tt.y;
+                        gs[0].x = fma(c0, tt.x, gs[0].x); gs[0].y = fma(c0, tt.y, gs[0].y);
+                        gs[1].x = fma(c1, tt.x, gs[1].x); gs[1].y = fma(c1, tt.y, gs[1].y);
+                        gs[2].x = fma(c2, tt.x, gs[2].x); gs[2].y = fma(c2, tt.y, gs[2].y);
+                    }
+                }
+                double2 ga[3];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) ga[a] = make_double2(-gs[a].y, gs[a].x);                  // * i
+                if (has_tau) {
+                    const double2 w = cmulc(dn[mm], dn[n]);                                          // d_m conj(d_n)
+                    hk = cmul(hk, w);
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        ga[a] = cmul(ga[a], w);
+                        const double dt = __ldg(&m.tM[3 * mm + a]) - __ldg(&m.tM[3 * n + a]);
+                        ga[a].x = fma(-dt, hk.y, ga[a].x); ga[a].y = fma(dt, hk.x, ga[a].y);         // + i dt H
+                    }
+                }
+#pragma unroll
+                for (int a = 0; a < 3; ++a) Ha[a * NW * LD + n * LD + mm] = ga[a];
+            }
+        }
+        __syncwarp();
+        // ------------------------------------------------------------------ 4. gauge rotation, column mc = g
+        if (jb.do_gauge) {
+            const int mc = g;
+            double2 u[NW];
+#pragma unroll
+            for (int q = 0; q < NW; ++q) u[q] = Us[q * LD + mc];
+#pragma unroll 1
+            for (int a = 0; a < 3; ++a) {
+                double2 *Hrow = Ha + a * NW * LD;
+                double2 tmp[NW];
+#pragma unroll
+                for (int p = 0; p < NW; ++p) {
+                    double2 s = make_double2(0, 0);
+#pragma unroll
+                    for (int q = 0; q < NW; ++q) cfma(s, Hrow[p * LD + q], u[q]);
+                    tmp[p] = s;
+                }
+                __syncwarp();                                       // every lane has read Ha[a]: column mc can be overwritten
+#pragma unroll
+                for (int n = 0; n < NW; ++n) {
+                    double2 s = make_double2(0, 0);
+#pragma unroll
+                    for (int p = 0; p < NW; ++p) cfmac(s, Us[p * LD + n], tmp[p]);
+                    Hrow[n * LD + mc] = s;
+                }
+            }
+            __syncwarp();
+        }
+        const double2 *Vs = Ha;                                     // Vs[a*NW*LD + n*LD + m] = V_ka(a,n,m)
+        if (valid && g == 0) acc_nk += 1.0;
+        // ------------------------------------------------------------------ 5. pair sums + AHC items
+        {
+            const int istride = jb.herm ? kAhcItemH : kAhcItemG;
+            int n_items_before = 0;
+#pragma unroll 1
+            for (int p0 = 0; p0 < NPAIR; p0 += NW) {
+                const int pidx = p0 + g;
+                bool emit = false;
+                double item[kAhcItemG];
+                if (pidx < NPAIR) {
+                    int mm = 1, rem = pidx;
+                    while (rem >= mm) { rem -= mm; ++mm; }
+                    const int n = rem;
+                    const double dE = es[mm] - es[n];
+                    const double f_n = fn[n], f_m = fn[mm], fdm = f_m - f_n;
+                    if (dE == 0.0 && valid) acc_ndeg += 1.0;
+                    if (jb.do_ahc) {
+                        double2 vnm[3], vmn[3];
+#pragma unroll
+                        for (int a = 0; a < 3; ++a) { vnm[a] = Vs[a * NW * LD + n * LD + mm]; vmn[a] = Vs[a * NW * LD + mm * LD + n]; }
+                        double2 P[9];   // P(i,j) = V(i,n,m) V(j,m,n) at i + 3j
+#pragma unroll
+                        for (int j = 0; j < 3; ++j)
+#pragma unroll
+                            for (int i = 0; i < 3; ++i) P[i + 3 * j] = cmul(vnm[i], vmn[j]);
+                        if (valid && (f_n != 0.0 || f_m != 0.0 || dE == 0.0)) {          // kubo.f90:58-73, unguarded
+                            const double inv2 = 2.0 / (dE * dE);
+#pragma unroll
+                            for (int j = 0; j < 3; ++j)
+#pragma unroll
+                                for (int i = 0; i < 3; ++i) acc_ahc[i + 3 * j] += inv2 * (f_n * P[i + 3 * j].y + f_m * P[j + 3 * i].y);
+                        }
+                        if (fdm != 0.0 || dE == 0.0) {
+                            const double wa = fdm / dE;                                   // unguarded like kubo.f90:186
+                            item[0] = fma(dE, dE, jb.eta * jb.eta);
+                            const int ai[3] = {0, 0, 1}, aj[3] = {1, 2, 2};
+                            const int si[6] = {0, 1, 2, 0, 0, 1}, sj[6] = {0, 1, 2, 1, 2, 2};
+                            if (jb.herm) {
+#pragma unroll
+                                for (int q = 0; q < 3; ++q) item[1 + q] = fdm * (P[ai[q] + 3 * aj[q]].y - P[aj[q] + 3 * ai[q]].y);
+#pragma unroll
+                                for (int q = 0; q < 6; ++q) item[4 + q] = wa * (P[si[q] + 3 * sj[q]].x + P[sj[q] + 3 * si[q]].x);
+                            } else {
+#pragma unroll
+                                for (int q = 0; q < 3; ++q) {
+                                    item[1 + q] = fdm * (P[ai[q] + 3 * aj[q]].x - P[aj[q] + 3 * ai[q]].x);
+                                    item[4 + q] = fdm * (P[ai[q] + 3 * aj[q]].y - P[aj[q] + 3 * ai[q]].y);
+                                }
+#pragma unroll
+                                for (int q = 0; q < 6; ++q) {
+                                    item[7 + q] = wa * (P[si[q] + 3 * sj[q]].x + P[sj[q] + 3 * si[q]].x);
+                                    item[13 + q] = wa * (P[si[q] + 3 * sj[q]].y + P[sj[q] + 3 * si[q]].y);
+                                }
+                                item[19] = 0.0;
+                            }
+                            emit = valid && (out.items_ahc != nullptr);
+                        }
+                    }
+                }
+                const unsigned bal = (__ballot_sync(0xffffffffu, emit) >> gshift) & gbits;      // this group's lanes
+                if (emit) {
+                    const int slot = n_items_before + __popc(bal & ((1u << g) - 1u));
+                    double2 *dst = reinterpret_cast<double2 *>(out.items_ahc + ((size_t)ik * max_pairs + slot) * istride);
+                    if (jb.herm) {
+#pragma unroll
+                        for (int j = 0; j < kAhcItemH / 2; ++j) dst[j] = make_double2(item[2 * j], item[2 * j + 1]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < kAhcItemG / 2; ++j) dst[j] = make_double2(item[2 * j], item[2 * j + 1]);
+                    }
+                }
+                n_items_before += __popc(bal);
+            }
+            if (valid && out.cnt_ahc && g == 0) { out.cnt_ahc[ik] = n_items_before; acc_nit += (double)n_items_before; }
+        }
+        // ------------------------------------------------------------------ MEP sums, band n0 = g (mep_niu.f90, kubo_mep.f90)
+        if (MEP && (jb.do_mep || jb.do_kubo)) {
+            const int n0 = g;
+            const double e0 = es[n0];
+            double lc_g[9], lc_u[9], ic_g[9], ic_u[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) { lc_g[q] = 0; lc_u[q] = 0; ic_g[q] = 0; ic_u[q] = 0; }
+            double2 v00[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) v00[a] = Vs[a * NW * LD + n0 * LD + n0];
+#pragma unroll 1
+            for (int n = 0; n < NW; ++n) {
+                if (n == n0) continue;
+                const double d0n = e0 - es[n];
+                double2 v0n[3], vn0[3];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) { v0n[a] = Vs[a * NW * LD + n0 * LD + n]; vn0[a] = Vs[a * NW * LD + n * LD + n0]; }
+                {   // local term: sum_kl eps_jkl Re[V(i,n0,n) V(k,n,n0) V(l,n0,n0)] / (E_n0-E_n)^3
+                    const double den = d0n * d0n * d0n;
+                    const bool pass = fabs(den) > jb.kubo_tol;
+                    const double inv = 1.0 / den;
+                    auto re = [](double2 x, double2 y) { return x.x * y.x - x.y * y.y; };
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        double2 Q[3];
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) Q[k] = cmul(v0n[i], vn0[k]);
+                        const double c0 = re(Q[1], v00[2]) - re(Q[2], v00[1]);
+                        const double c1 = re(Q[2], v00[0]) - re(Q[0], v00[2]);
+                        const double c2 = re(Q[0], v00[1]) - re(Q[1], v00[0]);
+                        lc_u[i] += c0 * inv; lc_u[i + 3] += c1 * inv; lc_u[i + 6] += c2 * inv;
+                        if (pass) { lc_g[i] += c0 * inv; lc_g[i + 3] += c1 * inv; lc_g[i + 6] += c2 * inv; }
+                    }
+                }
+                {   // itinerant term: - sum_{m != n0} eps_jkl Re[V(i,n0,n) V(k,n,m) V(l,m,n0)] / ((E_n0-E_n)^2 (E_n0-E_m))
+                    double2 Zg[3], Zu[3];
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) { Zg[j] = make_double2(0, 0); Zu[j] = make_double2(0, 0); }
+                    const double d2 = d0n * d0n;
+#pragma unroll 1
+                    for (int mm = 0; mm < NW; ++mm) {
+                        if (mm == n0) continue;
+                        const double den = d2 * (e0 - es[mm]);
+                        const double inv = 1.0 / den;
+                        const bool pass = fabs(den) > jb.kubo_tol;
+                        double2 a_[3], b_[3];
+#pragma unroll
+                        for (int a = 0; a < 3; ++a) { a_[a] = Vs[a * NW * LD + n * LD + mm]; b_[a] = Vs[a * NW * LD + mm * LD + n0]; }
+                        double2 X[3];
+                        X[0] = csub(cmul(a_[1], b_[2]), cmul(a_[2], b_[1]));
+                        X[1] = csub(cmul(a_[2], b_[0]), cmul(a_[0], b_[2]));
+                        X[2] = csub(cmul(a_[0], b_[1]), cmul(a_[1], b_[0]));
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            Zu[j].x = fma(X[j].x, inv, Zu[j].x); Zu[j].y = fma(X[j].y, inv, Zu[j].y);
+                            if (pass) { Zg[j].x = fma(X[j].x, inv, Zg[j].x); Zg[j].y = fma(X[j].y, inv, Zg[j].y); }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 3; ++j)
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            ic_u[i + 3 * j] -= (v0n[i].x * Zu[j].x - v0n[i].y * Zu[j].y);
+                            ic_g[i + 3 * j] -= (v0n[i].x * Zg[j].x - v0n[i].y * Zg[j].y);
+                        }
+                }
+            }
+            if (valid) {
+                const double f0 = fn[n0];
+                if (jb.do_mep && n0 < jb.nval) {
+#pragma unroll
+                    for (int q = 0; q < NM; ++q) { niu_ic[q] += ic_g[q]; niu_lc[q] += lc_g[q]; }
+                }
+                if (jb.do_kubo) {
+#pragma unroll
+                    for (int q = 0; q < NM; ++q) { kub_ic[q] += f0 * ic_u[q]; kub_lc[q] += f0 * lc_u[q]; }
+                }
+            }
+        }
+        // ------------------------------------------------------------------ photo items (photo.f90:44-81)
+        if (jb.do_opt && out.items_photo) {
+            constexpr int NORD = NW * (NW - 1);
+            int n_before = 0;
+#pragma unroll 1
+            for (int p0 = 0; p0 < NORD; p0 += NW) {
+                const int pidx = p0 + g;
+                bool emit = false;
+                int n = 0, l = 0;
+                double df = 0.0;
+                if (pidx < NORD) {
+                    n = pidx / (NW - 1); l = pidx % (NW - 1); if (l >= n) ++l;
+                    df = fn[l] - fn[n];
+                    emit = valid && (df != 0.0);
+                }
+                const unsigned bal = (__ballot_sync(0xffffffffu, emit) >> gshift) & gbits;
+                if (emit) {
+                    double2 W[9];
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) W[q] = make_double2(0, 0);
+#pragma unroll 1
+                    for (int mm = 0; mm < NW; ++mm) {
+                        const double2 rec = crcp(make_double2(es[n] - es[mm], -jb.eta));
+                        double2 qc[3];
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) qc[c] = cmul(Vs[c * NW * LD + mm * LD + n], rec);
+#pragma unroll
+                        for (int b = 0; b < 3; ++b) {
+                            const double2 vb = Vs[b * NW * LD + l * LD + mm];
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) cfma(W[b + 3 * c], vb, qc[c]);
+                        }
+                    }
+                    const int slot = n_before + __popc(bal & ((1u << g) - 1u));
+                    double2 *dst = reinterpret_cast<double2 *>(out.items_photo + ((size_t)ik * NORD + slot) * kPhotoItem);
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        const double2 va = cscale(df, Vs[a * NW * LD + n * LD + l]);
+#pragma unroll
+                        for (int q = 0; q < 9; ++q) dst[a + 3 * q] = cmul(va, W[q]);
+                    }
+                    dst[27] = make_double2(es[n] - es[l], 0.0);
+                }
+                n_before += __popc(bal);
+            }
+            if (valid && g == 0) { out.cnt_photo[ik] = n_before; acc_nph += (double)n_before; }
+        }
+        __syncwarp();                                                   // the group's buffers are reused by the next k
+    }
+    // ---------------------------------------------------------------------- block reduction of the static sums
+    __syncthreads();
+    constexpr int NS = S_NIU + 18 * NW;
+    double *stage = reinterpret_cast<double *>(smem_raw);               // [kSubWarps][NS]  (group buffers are dead now)
+    {
+        const double nk = warp_sum(acc_nk), nd = warp_sum(acc_ndeg), ne = warp_sum(acc_ne);
+        const double nit = warp_sum(acc_nit), nph = warp_sum(acc_nph);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) acc_ahc[q] = warp_sum(acc_ahc[q]);
+        // band-resolved sums: add the lanes with the same g across the groups of the warp
+#pragma unroll
+        for (int q = 0; q < NM; ++q) {
+#pragma unroll
+            for (int o = NW; o < 32; o <<= 1) {
+                niu_ic[q] += __shfl_xor_sync(0xffffffffu, niu_ic[q], o);
+                niu_lc[q] += __shfl_xor_sync(0xffffffffu, niu_lc[q], o);
+                kub_ic[q] += __shfl_xor_sync(0xffffffffu, kub_ic[q], o);
+                kub_lc[q] += __shfl_xor_sync(0xffffffffu, kub_lc[q], o);
+            }
+        }
+        // kubo sums run over all bands: reduce over g as well
+        double kic[9], klc[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+            kic[q] = MEP ? kub_ic[q % NM] : 0.0; klc[q] = MEP ? kub_lc[q % NM] : 0.0;
+#pragma unroll
+            for (int o = NW / 2; o > 0; o >>= 1) {
+                kic[q] += __shfl_xor_sync(0xffffffffu, kic[q], o);
+                klc[q] += __shfl_xor_sync(0xffffffffu, klc[q], o);
+            }
+        }
+        double *wv = stage + (size_t)warp * NS;
+        if (lane == 0) {
+            wv[S_NK] = nk; wv[S_NDEG] = nd; wv[S_NE] = ne; wv[S_NIT] = nit; wv[S_NPH] = nph;
+#pragma unroll
+            for (int q = 0; q < 9; ++q) { wv[S_AHC + q] = acc_ahc[q]; wv[S_KIC + q] = kic[q]; wv[S_KLC + q] = klc[q]; }
+        }
+        if (lane < NW) {
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+                wv[S_NIU + 9 * lane + q] = MEP ? niu_ic[q % NM] : 0.0; wv[S_NIU + 9 * NW + 9 * lane + q] = MEP ? niu_lc[q % NM] : 0.0;
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NS; i += blockDim.x) {
+        double s = 0.0;
+        for (int w = 0; w < kSubWarps; ++w) s += stage[(size_t)w * NS + i];
+        out.block_static[(size_t)blockIdx.x * NS + i] = s;
+    }
+}
+
+template <int NW>
+size_t sub_smem(int nR) {
+    const size_t groups = (size_t)kSubWarps * (32 / NW) * SubL<NW>::bytes(nR) + sizeof(SpRec) * kSubMaxNnz + sizeof(int) * (NW * NW + 4);
+    const size_t stage = sizeof(double) * kSubWarps * (S_NIU + 18 * NW);
+    return groups > stage ? groups : stage;
+}
+
+template <int NW>
+cudaError_t launch_sub_t(const DevModel &m, const KSource &ks, const Jobs &jobs, const InterpOut &out, int max_pairs, int grid,
+                         cudaStream_t st) {
+    const size_t smem = sub_smem<NW>(m.nR);
+    cudaError_t e;
+    if (jobs.do_mep || jobs.do_kubo) {
+        e = cudaFuncSetAttribute(bands_sub_kernel<NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        bands_sub_kernel<NW, true><<<grid, kSubWarps * 32, smem, st>>>(m, ks, jobs, out, max_pairs, SubL<NW>::bytes(m.nR));
+    } else {
+        e = cudaFuncSetAttribute(bands_sub_kernel<NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        bands_sub_kernel<NW, false><<<grid, kSubWarps * 32, smem, st>>>(m, ks, jobs, out, max_pairs, SubL<NW>::bytes(m.nR));
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+bool sub_supported(int nw, int nR) {
+    if (nw == 4) return sub_smem<4>(nR) <= 100 * 1024;
+    if (nw == 8) return sub_smem<8>(nR) <= 100 * 1024;
+    return false;
+}
+
+int bands_sub_grid(int nw, int nR, int sm_count, long long nk) {
+    const size_t smem = (nw == 4 ? sub_smem<4>(nR) : sub_smem<8>(nR)) + 1024;
+    int per_sm = (int)((227 * 1024) / smem);
+    if (per_sm > 2) per_sm = 2;                        // __launch_bounds__(128, 2)
+    if (per_sm < 1) per_sm = 1;
+    const int kpb = kSubWarps * (32 / nw);
+    long long need = (nk + kpb - 1) / kpb;
+    long long g = (long long)sm_count * per_sm;
+    if (g > need) g = need;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+cudaError_t launch_bands_sub(const DevModel &m, const KSource &ks, const Jobs &jobs, const InterpOut &out, int max_pairs, int grid,
+                             cudaStream_t st) {
+    switch (m.nw) {
+        case 4: return launch_sub_t<4>(m, ks, jobs, out, max_pairs, grid, st);
+        case 8: return launch_sub_t<8>(m, ks, jobs, out, max_pairs, grid, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace mepb
