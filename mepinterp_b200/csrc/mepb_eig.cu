@@ -31,6 +31,78 @@ template <int NW> __host__ __device__ constexpr int sigma(int i) {
     return i + 2;                       // bottom row shifts left
 }
 
+// One Jacobi round on the register-resident matrix: rotation parameters of the pairs (2i, 2i+1), two-sided update of the
+// off-diagonal 2x2 blocks (rotation formulas of jacobi_warp in mepb_small.cu).
+template <int NW>
+__device__ __forceinline__ void jacobi_round_A(double (&ar)[NW][NW], double (&ai)[NW][NW], double (&rc)[NW / 2],
+                                               double (&rsx)[NW / 2], double (&rsy)[NW / 2], double &off2) {
+    constexpr int NP = NW / 2;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        const int p = 2 * i, q = 2 * i + 1;
+        const double a = ar[p][p], d = ar[q][q], bx = ar[p][q], by = ai[p][q];
+        const double bb = fma(bx, bx, by * by);
+        const bool rot = bb > 1e-300;
+        const double zeta = 0.5 * (d - a), az = fabs(zeta);
+        const double hh = rot ? fma(zeta, zeta, bb) : 1.0;
+        const double rh = fast_rsqrt3(hh);
+        double h = hh * rh;                                    // sqrt(zeta^2 + |b|^2) ...
+        h = fma(fma(-h, h, hh), 0.5 * rh, h);                  // ... plus one Heron step (no division)
+        const double y = 2.0 * h * (az + h);
+        const double ry = rot ? fast_rsqrt3(y) : 0.0;
+        const double sg = zeta < 0.0 ? -1.0 : 1.0;
+        rc[i] = rot ? (az + h) * ry : 1.0;
+        const double sr = sg * ry;
+        rsx[i] = sr * bx; rsy[i] = sr * by;
+        const double tb = sg * bb * (2.0 * h) * ry * ry;
+        ar[p][p] = a - tb; ar[q][q] = d + tb; ar[p][q] = 0.0; ai[p][q] = 0.0;
+        off2 += rot ? bb : 0.0;
+    }
+    // off-diagonal 2x2 blocks (pair i rows, pair k columns), i < k:  B <- J_i^dagger B J_k
+#pragma unroll
+    for (int i = 0; i < NP; ++i)
+#pragma unroll
+        for (int k = i + 1; k < NP; ++k) {
+            const int p = 2 * i, q = 2 * i + 1, pp = 2 * k, qq = 2 * k + 1;
+            const double ci = rc[i], six = rsx[i], siy = rsy[i], cj = rc[k], sjx = rsx[k], sjy = rsy[k];
+            const double bppx = ar[p][pp], bppy = ai[p][pp], bpqx = ar[p][qq], bpqy = ai[p][qq];
+            const double bqpx = ar[q][pp], bqpy = ai[q][pp], bqqx = ar[q][qq], bqqy = ai[q][qq];
+            // columns: t(.,pp) = c x - conj(s) y ; t(.,qq) = s x + c y
+            const double tppx = cj * bppx - (sjx * bpqx + sjy * bpqy), tppy = cj * bppy - (sjx * bpqy - sjy * bpqx);
+            const double tqpx = cj * bqpx - (sjx * bqqx + sjy * bqqy), tqpy = cj * bqpy - (sjx * bqqy - sjy * bqqx);
+            const double tpqx = sjx * bppx - sjy * bppy + cj * bpqx, tpqy = sjx * bppy + sjy * bppx + cj * bpqy;
+            const double tqqx = sjx * bqpx - sjy * bqpy + cj * bqqx, tqqy = sjx * bqpy + sjy * bqpx + cj * bqqy;
+            // rows: out_p = c t_p - s t_q ; out_q = conj(s) t_p + c t_q
+            ar[p][pp] = ci * tppx - (six * tqpx - siy * tqpy); ai[p][pp] = ci * tppy - (six * tqpy + siy * tqpx);
+            ar[q][pp] = six * tppx + siy * tppy + ci * tqpx;   ai[q][pp] = six * tppy - siy * tppx + ci * tqpy;
+            ar[p][qq] = ci * tpqx - (six * tqqx - siy * tqqy); ai[p][qq] = ci * tpqy - (six * tqqy + siy * tqqx);
+            ar[q][qq] = six * tpqx + siy * tpqy + ci * tqqx;   ai[q][qq] = six * tpqy - siy * tpqx + ci * tqqy;
+        }
+}
+
+// Tournament permutation of rows and columns (compile-time indices: register moves only)
+template <int NW>
+__device__ __forceinline__ void tournament_permute(double (&ar)[NW][NW], double (&ai)[NW][NW], int (&perm)[NW]) {
+    double br[NW][NW], bi[NW][NW];
+#pragma unroll
+    for (int j = 0; j < NW; ++j)
+#pragma unroll
+        for (int i = 0; i <= j; ++i) {
+            const int si = sigma<NW>(i), sj = sigma<NW>(j);
+            if (si <= sj) { br[i][j] = ar[si][sj]; bi[i][j] = ai[si][sj]; }
+            else { br[i][j] = ar[sj][si]; bi[i][j] = -ai[sj][si]; }
+        }
+    int pn[NW];
+#pragma unroll
+    for (int i = 0; i < NW; ++i) pn[i] = perm[sigma<NW>(i)];
+#pragma unroll
+    for (int j = 0; j < NW; ++j) {
+        perm[j] = pn[j];
+#pragma unroll
+        for (int i = 0; i <= j; ++i) { ar[i][j] = br[i][j]; ai[i][j] = (i == j) ? 0.0 : bi[i][j]; }
+    }
+}
+
 template <int NW>
 __global__ void __launch_bounds__(EigCfg<NW>::TPB, 1)
 eig_small_kernel(const DevModel m, const KSource ks, double *__restrict__ E_out, double2 *__restrict__ U_out,
@@ -110,82 +182,43 @@ eig_small_kernel(const DevModel m, const KSource ks, double *__restrict__ E_out,
             ok = false;
             for (int sweep = 0; sweep < 30 && !ok; ++sweep) {
                 double off2 = 0.0;
-                for (int r = 0; r < NW - 1; ++r) {
-                    double rc[NP], rsx[NP], rsy[NP];
-                    // ---- rotation parameters of the NP pairs (2i, 2i+1)
+                // rounds are taken two at a time: the matrix work of both happens in registers, then every row of U is read
+                // once, rotated by both rounds' rotations and written once (halves the shared-memory traffic of U <- U J)
+                for (int r = 0; r < NW - 1; r += 2) {
+                    const bool two = (r + 2 <= NW - 1);
+                    double c0[NP], x0[NP], y0[NP], c1[NP], x1[NP], y1[NP];
+                    unsigned colofs[NW];                                   // U column (in double2 units) of position pos at round r
 #pragma unroll
-                    for (int i = 0; i < NP; ++i) {
-                        const int p = 2 * i, q = 2 * i + 1;
-                        const double a = ar[p][p], d = ar[q][q], bx = ar[p][q], by = ai[p][q];
-                        const double bb = fma(bx, bx, by * by);
-                        const bool rot = bb > 1e-300;
-                        const double zeta = 0.5 * (d - a), az = fabs(zeta);
-                        const double hh = rot ? fma(zeta, zeta, bb) : 1.0;
-                        const double rh = fast_rsqrt3(hh);
-                        double h = hh * rh;                                    // sqrt(zeta^2 + |b|^2) ...
-                        h = fma(fma(-h, h, hh), 0.5 * rh, h);                  // ... plus one Heron step (no division)
-                        const double y = 2.0 * h * (az + h);
-                        const double ry = rot ? fast_rsqrt3(y) : 0.0;
-                        const double sg = zeta < 0.0 ? -1.0 : 1.0;
-                        rc[i] = rot ? (az + h) * ry : 1.0;
-                        const double sr = sg * ry;
-                        rsx[i] = sr * bx; rsy[i] = sr * by;
-                        const double tb = sg * bb * (2.0 * h) * ry * ry;
-                        ar[p][p] = a - tb; ar[q][q] = d + tb; ar[p][q] = 0.0; ai[p][q] = 0.0;
-                        off2 += rot ? bb : 0.0;
+                    for (int i = 0; i < NW; ++i) colofs[i] = (unsigned)(NW * perm[i]) * TPB + tid;
+                    jacobi_round_A<NW>(ar, ai, c0, x0, y0, off2);
+                    tournament_permute<NW>(ar, ai, perm);
+                    if (two) {
+                        jacobi_round_A<NW>(ar, ai, c1, x1, y1, off2);
+                        tournament_permute<NW>(ar, ai, perm);
                     }
-                    // ---- off-diagonal 2x2 blocks (pair i rows, pair k columns), i < k:  B <- J_i^dagger B J_k
+#pragma unroll 2
+                    for (int row = 0; row < NW; ++row) {
+                        double2 x[NW];
 #pragma unroll
-                    for (int i = 0; i < NP; ++i)
+                        for (int i = 0; i < NW; ++i) x[i] = Us[colofs[i] + row * TPB];
 #pragma unroll
-                        for (int k = i + 1; k < NP; ++k) {
-                            const int p = 2 * i, q = 2 * i + 1, pp = 2 * k, qq = 2 * k + 1;
-                            const double ci = rc[i], six = rsx[i], siy = rsy[i], cj = rc[k], sjx = rsx[k], sjy = rsy[k];
-                            const double bppx = ar[p][pp], bppy = ai[p][pp], bpqx = ar[p][qq], bpqy = ai[p][qq];
-                            const double bqpx = ar[q][pp], bqpy = ai[q][pp], bqqx = ar[q][qq], bqqy = ai[q][qq];
-                            // columns: t(.,pp) = c x - conj(s) y ; t(.,qq) = s x + c y
-                            const double tppx = cj * bppx - (sjx * bpqx + sjy * bpqy), tppy = cj * bppy - (sjx * bpqy - sjy * bpqx);
-                            const double tqpx = cj * bqpx - (sjx * bqqx + sjy * bqqy), tqpy = cj * bqpy - (sjx * bqqy - sjy * bqqx);
-                            const double tpqx = sjx * bppx - sjy * bppy + cj * bpqx, tpqy = sjx * bppy + sjy * bppx + cj * bpqy;
-                            const double tqqx = sjx * bqpx - sjy * bqpy + cj * bqqx, tqqy = sjx * bqpy + sjy * bqpx + cj * bqqy;
-                            // rows: out_p = c t_p - s t_q ; out_q = conj(s) t_p + c t_q
-                            ar[p][pp] = ci * tppx - (six * tqpx - siy * tqpy); ai[p][pp] = ci * tppy - (six * tqpy + siy * tqpx);
-                            ar[q][pp] = six * tppx + siy * tppy + ci * tqpx;   ai[q][pp] = six * tppy - siy * tppx + ci * tqpy;
-                            ar[p][qq] = ci * tpqx - (six * tqqx - siy * tqqy); ai[p][qq] = ci * tpqy - (six * tqqy + siy * tqqx);
-                            ar[q][qq] = six * tpqx + siy * tpqy + ci * tqqx;   ai[q][qq] = six * tpqy - siy * tpqx + ci * tqqy;
+                        for (int i = 0; i < NP; ++i) {                      // round r: positions (2i, 2i+1)
+                            const double2 a = x[2 * i], b = x[2 * i + 1];
+                            x[2 * i] = make_double2(c0[i] * a.x - (x0[i] * b.x + y0[i] * b.y), c0[i] * a.y - (x0[i] * b.y - y0[i] * b.x));
+                            x[2 * i + 1] = make_double2(x0[i] * a.x - y0[i] * a.y + c0[i] * b.x, x0[i] * a.y + y0[i] * a.x + c0[i] * b.y);
                         }
-                    // ---- U <- U J  (columns perm[2i], perm[2i+1])
+                        if (two) {
 #pragma unroll
-                    for (int i = 0; i < NP; ++i) {
-                        const double c = rc[i], sx = rsx[i], sy = rsy[i];
-                        double2 *up = Us + (size_t)(NW * perm[2 * i]) * TPB + tid, *uq = Us + (size_t)(NW * perm[2 * i + 1]) * TPB + tid;
-#pragma unroll
-                        for (int row = 0; row < NW; ++row) {
-                            const double2 x = up[row * TPB], y = uq[row * TPB];
-                            up[row * TPB] = make_double2(c * x.x - (sx * y.x + sy * y.y), c * x.y - (sx * y.y - sy * y.x));
-                            uq[row * TPB] = make_double2(sx * x.x - sy * x.y + c * y.x, sx * x.y + sy * x.x + c * y.y);
-                        }
-                    }
-                    // ---- tournament permutation of rows and columns (compile-time indices: register moves only)
-                    {
-                        double br[NW][NW], bi[NW][NW];
-#pragma unroll
-                        for (int j = 0; j < NW; ++j)
-#pragma unroll
-                            for (int i = 0; i <= j; ++i) {
-                                const int si = sigma<NW>(i), sj = sigma<NW>(j);
-                                if (si <= sj) { br[i][j] = ar[si][sj]; bi[i][j] = ai[si][sj]; }
-                                else { br[i][j] = ar[sj][si]; bi[i][j] = -ai[sj][si]; }
+                            for (int i = 0; i < NP; ++i) {                  // round r+1: new positions (2i, 2i+1) = old (sigma(2i), sigma(2i+1))
+                                constexpr int dummy = 0; (void)dummy;
+                                const int pa = sigma<NW>(2 * i), pb = sigma<NW>(2 * i + 1);
+                                const double2 a = x[pa], b = x[pb];
+                                x[pa] = make_double2(c1[i] * a.x - (x1[i] * b.x + y1[i] * b.y), c1[i] * a.y - (x1[i] * b.y - y1[i] * b.x));
+                                x[pb] = make_double2(x1[i] * a.x - y1[i] * a.y + c1[i] * b.x, x1[i] * a.y + y1[i] * a.x + c1[i] * b.y);
                             }
-                        int pn[NW];
-#pragma unroll
-                        for (int i = 0; i < NW; ++i) pn[i] = perm[sigma<NW>(i)];
-#pragma unroll
-                        for (int j = 0; j < NW; ++j) {
-                            perm[j] = pn[j];
-#pragma unroll
-                            for (int i = 0; i <= j; ++i) { ar[i][j] = br[i][j]; ai[i][j] = (i == j) ? 0.0 : bi[i][j]; }
                         }
+#pragma unroll
+                        for (int i = 0; i < NW; ++i) Us[colofs[i] + row * TPB] = x[i];
                     }
                 }
                 // off-diagonal norm of what is left AFTER this sweep (saves the verification sweep of the classic test)
