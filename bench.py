@@ -286,7 +286,7 @@ def main():
             "sweep_ahc": fm["sweep_ahc_per_item_hw"] * items["sweep_ahc"] * params.n_hw,
             "sweep_photo": fm["sweep_photo_per_item_hw"] * items["sweep_photo"] * params.n_hw}
     kernels = {}
-    for k in ("fourier", "eig_rot", "eig", "interp", "sweep_ahc", "sweep_photo", "reduce"):
+    for k in ("fourier", "tridiag", "tql", "zrot", "eig_rot", "eig", "interp", "sweep_ahc", "sweep_photo", "reduce"):
         if prof[k]["launches"]:
             ms = prof[k]["ms"]
             kernels[k] = {"ms_per_pass": ms, "launches": prof[k]["launches"], "share": None,

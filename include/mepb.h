@@ -121,8 +121,11 @@ int mepb_timer_stop(mepb_ctx *ctx, double *ms);
 #define MEPB_PROF_REDUCE       3   /* block-partial reductions                                        */
 #define MEPB_PROF_EIG          4   /* thread-per-k Fourier(H) + Jacobi eigensolver (num_wann 4, 8)     */
 #define MEPB_PROF_FOURIER      5   /* dense Fourier contraction, general path (num_wann <= 64)         */
-#define MEPB_PROF_EIGROT       6   /* CTA-per-k Jacobi + rotation + band sums, general path            */
-#define MEPB_PROF_KINDS        7
+#define MEPB_PROF_EIGROT       6   /* CTA-per-k back-transform + rotation + band sums, general path   */
+#define MEPB_PROF_TRIDIAG      7   /* Householder tridiagonalisation, general path                     */
+#define MEPB_PROF_TQL          8   /* thread-per-k implicit QL on the tridiagonal (rotation log)       */
+#define MEPB_PROF_ZROT         9   /* replay of the rotation log -> eigenvectors of the tridiagonal    */
+#define MEPB_PROF_KINDS        10
 int mepb_set_profiling(mepb_ctx *ctx, int on);
 int mepb_get_profile(const mepb_ctx *ctx, int kind, double *ms_total, int64_t *launches);
 /* (k, band pair) items the last packed run handed to the frequency sweep `kind` (MEPB_PROF_SWEEP_AHC / _PHOTO): the

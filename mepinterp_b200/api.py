@@ -263,7 +263,7 @@ class Context:
         _check(lib().mepb_timer_stop(self._h, C.byref(ms)))
         return float(ms.value)
 
-    PROF_KINDS = ("interp", "sweep_ahc", "sweep_photo", "reduce", "eig", "fourier", "eig_rot")
+    PROF_KINDS = ("interp", "sweep_ahc", "sweep_photo", "reduce", "eig", "fourier", "eig_rot", "tridiag", "tql", "zrot")
 
     def set_profiling(self, on: bool):
         _check(lib().mepb_set_profiling(self._h, int(bool(on))))

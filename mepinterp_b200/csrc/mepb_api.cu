@@ -118,6 +118,7 @@ struct StreamBuf {
     double *compact = nullptr;   // [n_eF][per_ef]
     double *eig_E = nullptr; double2 *eig_U = nullptr;   // [chunk][nw], [chunk][nw*nw] from the thread-per-k eigensolver
     double2 *Hk = nullptr, *Hka = nullptr, *Vscr = nullptr;   // general path: [chunk][nw^2], [chunk][3][nw^2], [grid][3][nw^2]
+    TriBuf tb{};                                                // general path: Householder + QL intermediates (mepb_tri.cu)
 };
 
 }  // namespace
@@ -131,6 +132,7 @@ struct mepb_ctx {
     bool eig_thread = false;   // eigenpairs from the thread-per-k kernel (nw 4, 8)
     bool large = false;        // general path (mepb_large.cu)
     bool use_sub = false;      // NW-lanes-per-k band-sum kernel (mepb_sub.cu) in mesh mode
+    bool tri = false;          // general path: Householder + QL eigensolver (default) instead of the in-kernel Jacobi
     FourierPlan fp{};
     int *d_ridx = nullptr, *d_elem = nullptr; double2 *d_Hp = nullptr; double *d_Rfp = nullptr, *d_cRp = nullptr;
     double2 *d_Hka_int = nullptr;
@@ -323,6 +325,8 @@ void free_all(mepb_ctx *c) {
         cudaFree(s.items_ahc); cudaFree(s.cnt_ahc); cudaFree(s.items_photo); cudaFree(s.cnt_photo);
         cudaFree(s.block_static); cudaFree(s.block_sweep); cudaFree(s.block_photo); cudaFree(s.compact);
         cudaFree(s.eig_E); cudaFree(s.eig_U); cudaFree(s.Hk); cudaFree(s.Hka); cudaFree(s.Vscr);
+        cudaFree(s.tb.Vr); cudaFree(s.tb.tau); cudaFree(s.tb.d); cudaFree(s.tb.e); cudaFree(s.tb.E); cudaFree(s.tb.rank);
+        cudaFree(s.tb.hdr); cudaFree(s.tb.nhdr); cudaFree(s.tb.log); cudaFree(s.tb.Z);
         if (s.st) cudaStreamDestroy(s.st);
         if (s.done) cudaEventDestroy(s.done);
     }
@@ -362,7 +366,7 @@ void prof_collect(mepb_ctx *c) {
 int check_err_flag(mepb_ctx *c) {
     int h = 0;
     CUDA_TRY(cudaMemcpy(&h, c->d_err, sizeof(int), cudaMemcpyDeviceToHost));
-    if (h != 0) return fail(MEPB_ERR_EIG, "Jacobi eigensolver did not converge for at least one k-point");
+    if (h != 0) return fail(MEPB_ERR_EIG, "eigensolver did not converge for at least one k-point");
     return MEPB_OK;
 }
 
@@ -411,6 +415,7 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
     c->p = p; c->nw = model->nw; c->nR = model->nR; c->has_tau = (model->wf_centers != nullptr);
     { std::string why; c->herm = hermitian_closed(model, &why); }
     c->large = want_large;
+    { const char *es = getenv("MEPB_LARGE_EIG"); c->tri = c->large && !(es && std::string(es) == "jacobi"); }
     c->eig_thread = !c->large && eig_thread_supported(model->nw) && !getenv("MEPB_WARP_JACOBI");
     c->use_sub = c->eig_thread && sub_supported(model->nw, model->nR) && !getenv("MEPB_WARP_BANDS");
     std::memcpy(c->a_latt, model->a_latt, sizeof(c->a_latt));
@@ -459,8 +464,11 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
     if (p.do_ahc) per_k += sizeof(double) * istr * c->max_pairs + sizeof(int);
     if (p.do_opt) per_k += sizeof(double) * kPhotoItem * c->max_photo + sizeof(int);
     if (c->large) per_k += sizeof(double2) * 4 * (size_t)nw * nw;
+    const int tne = tri_padded_size(nw);
+    if (c->tri) per_k += (size_t)tne * tne * (sizeof(double2) + sizeof(double)) + sizeof(double2) * tri_log_cap(tne) +
+                         sizeof(unsigned int) * kTriHdrCap + (size_t)tne * 48;
     long long chunk = 1 << 18;
-    if (per_k) chunk = std::min<long long>(chunk, (long long)(((c->large ? 2048ull : 768ull) << 20) / per_k));
+    if (per_k) chunk = std::min<long long>(chunk, (long long)(((c->large ? 6144ull : 768ull) << 20) / per_k));
     chunk = std::max<long long>(c->large ? 296 : 1024, std::min(chunk, std::max<long long>(nk_mesh, 1024)));
     c->chunk = chunk;
     if (c->large) CT(build_fourier_plan(c, model, cR));
@@ -491,6 +499,22 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
             CT(cudaMalloc((void **)&s.Hk, sizeof(double2) * nw * nw * (size_t)chunk));
             CT(cudaMalloc((void **)&s.Hka, sizeof(double2) * 3 * nw * nw * (size_t)chunk));
             CT(cudaMalloc((void **)&s.Vscr, sizeof(double2) * 3 * nw * nw * (size_t)c->grid_interp));
+        }
+        if (c->tri) {
+            TriBuf &t = s.tb;
+            t.ne = tne; t.hdr_cap = kTriHdrCap; t.log_cap = (int)tri_log_cap(tne);
+            const size_t ck = (size_t)chunk;
+            CT(cudaMalloc((void **)&t.Vr, sizeof(double2) * tne * tne * ck));
+            CT(cudaMemset(t.Vr, 0, sizeof(double2) * tne * tne * ck));
+            CT(cudaMalloc((void **)&t.tau, sizeof(double2) * tne * ck));
+            CT(cudaMalloc((void **)&t.d, sizeof(double) * tne * ck));
+            CT(cudaMalloc((void **)&t.e, sizeof(double) * tne * ck));
+            CT(cudaMalloc((void **)&t.E, sizeof(double) * tne * ck));
+            CT(cudaMalloc((void **)&t.rank, (size_t)tne * ck));
+            CT(cudaMalloc((void **)&t.hdr, sizeof(unsigned int) * kTriHdrCap * ck));
+            CT(cudaMalloc((void **)&t.nhdr, sizeof(int) * ck));
+            CT(cudaMalloc((void **)&t.log, sizeof(double2) * t.log_cap * ck));
+            CT(cudaMalloc((void **)&t.Z, sizeof(double) * tne * tne * ck));
         }
         if (c->eig_thread) {
             CT(cudaMalloc((void **)&s.eig_E, sizeof(double) * nw * (size_t)chunk));
@@ -555,8 +579,14 @@ int mepb_accumulate(mepb_ctx *c, int64_t lin_begin, int64_t lin_end) {
                            : c->use_sub ? bands_sub_grid(c->nw, c->nR, c->sm_count, nk) : interp_small_grid(c->nw, c->nR, c->sm_count, nk);
             if (c->large) {
                 { ProfScope ps(c, s.st, MEPB_PROF_FOURIER); CUDA_TRY(launch_fourier_dense(c->fp, m, ks, s.Hk, s.Hka, s.st)); }
+                if (c->tri) {
+                    { ProfScope ps(c, s.st, MEPB_PROF_TRIDIAG); CUDA_TRY(launch_tridiag(c->nw, nk, s.Hk, s.tb, c->sm_count, s.st)); }
+                    { ProfScope ps(c, s.st, MEPB_PROF_TQL); CUDA_TRY(launch_tql(c->nw, nk, s.tb, c->d_err, s.st)); }
+                    { ProfScope ps(c, s.st, MEPB_PROF_ZROT); CUDA_TRY(launch_zrot(c->nw, nk, s.tb, c->sm_count, s.st)); }
+                    c->launches += 3;
+                }
                 { ProfScope ps(c, s.st, MEPB_PROF_EIGROT);
-                  CUDA_TRY(launch_eig_rot_large(m, ks, jb, o, c->max_pairs, s.Hk, s.Hka, s.Vscr, gi, s.st)); }
+                  CUDA_TRY(launch_eig_rot_large(m, ks, jb, o, c->max_pairs, s.Hk, s.Hka, s.Vscr, s.tb, gi, s.st)); }
                 c->launches += 2;
             }
             if (c->eig_thread) {
@@ -765,8 +795,16 @@ static int list_run(mepb_ctx *c, int64_t nk, const double *kpt, double *e_k, dou
             CUDA_TRY(launch_fourier_dense(c->fp, m, ks, c->d_Hk, c->d_Hka_int, st));
             if (H_ka) CUDA_TRY(launch_hka_to_user(c->d_Hka_int, c->d_Hka, c->nw * c->nw, n, st));
             InterpOut o2 = o; o2.Hk_out = nullptr; o2.Hka_out = nullptr;
-            if (o2.e_out) CUDA_TRY(launch_eig_rot_large(m, ks, jb, o2, c->max_pairs, c->d_Hk, c->d_Hka_int, c->sb[0].Vscr,
-                                                        eig_large_grid(c->sm_count, n), st));
+            if (o2.e_out) {
+                if (c->tri) {
+                    CUDA_TRY(launch_tridiag(c->nw, n, c->d_Hk, c->sb[0].tb, c->sm_count, st));
+                    CUDA_TRY(launch_tql(c->nw, n, c->sb[0].tb, c->d_err, st));
+                    CUDA_TRY(launch_zrot(c->nw, n, c->sb[0].tb, c->sm_count, st));
+                    c->launches += 3;
+                }
+                CUDA_TRY(launch_eig_rot_large(m, ks, jb, o2, c->max_pairs, c->d_Hk, c->d_Hka_int, c->sb[0].Vscr, c->sb[0].tb,
+                                              eig_large_grid(c->sm_count, n), st));
+            }
             c->launches += 2;
         } else {
             CUDA_TRY(launch_interp_small(m, ks, jb, o, c->max_pairs, interp_small_grid(c->nw, c->nR, c->sm_count, n), st));

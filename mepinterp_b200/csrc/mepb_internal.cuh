@@ -116,6 +116,28 @@ struct FourierPlan {
 };
 
 // ---------------------------------------------------------------------------------------------------------
+// Householder + implicit-QL eigensolver of the general path (mepb_tri.cu): per-k intermediates in HBM
+//   tridiag_kernel   H(k) -> reflectors v_s, tau_s, real tridiagonal (d, e)           (LAPACK zhetd2 'L' arithmetic)
+//   tql_kernel       thread per k: implicit QL on (d, e); eigenvalues, sort ranks, and the LOG of plane rotations
+//   zrot_kernel      replays the log on Z = 1 (one thread per row of Z, rows in registers) -> real eigenvectors of T
+//   the consumer (eig_rot_large_kernel) applies the reflectors to Z: U = H_0 H_1 ... H_{n-2} Z
+// ---------------------------------------------------------------------------------------------------------
+struct TriBuf {
+    int ne;                 // padded matrix size (32 or 64); 0 -> the Jacobi solver inside eig_rot_large_kernel is used
+    int hdr_cap, log_cap;   // per-k capacity of the chase headers / rotation log
+    double2 *Vr;            // [k][ne*ne]   Vr[s*ne + i] = v_s(i)  (0 for i <= s, 1 at i = s+1)
+    double2 *tau;           // [k][ne]
+    double *d, *e;          // [k][ne]      T(i,i), T(i+1,i)
+    double *E;              // [k][ne]      ascending eigenvalues
+    unsigned char *rank;    // [k][ne]      position of tql's eigenvalue j in the ascending order
+    unsigned int *hdr;      // [k][hdr_cap] one word per QL chase: l | m << 8  (rotations in planes m-1 ... l)
+    int *nhdr;              // [k]
+    double2 *log;           // [k][log_cap] (c, s) per rotation, in execution order
+    double *Z;              // [k][ne*ne]   Z[col*ne + row], eigenvectors of T in tql's (unsorted) column order
+};
+constexpr int kTriHdrCap = 512;
+
+// ---------------------------------------------------------------------------------------------------------
 // complex helpers on double2
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
@@ -242,6 +264,12 @@ cudaError_t launch_fourier_dense(const FourierPlan &fp, const DevModel &m, const
 cudaError_t launch_hka_to_user(const double2 *in, double2 *out, int nw2, long long nk, cudaStream_t st);
 int eig_large_grid(int sm_count, long long nk);
 cudaError_t launch_eig_rot_large(const DevModel &m, const KSource &ks, const Jobs &jobs, const InterpOut &out, int max_pairs,
-                                 const double2 *Hk, const double2 *Hka, double2 *Vscr, int grid, cudaStream_t st);
+                                 const double2 *Hk, const double2 *Hka, double2 *Vscr, const TriBuf &tb, int grid, cudaStream_t st);
+// Householder + QL eigensolver stages (mepb_tri.cu); tb.ne must be tri_padded_size(nw)
+int tri_padded_size(int nw);
+size_t tri_log_cap(int ne);
+cudaError_t launch_tridiag(int nw, long long nk, const double2 *Hk, const TriBuf &tb, int sm_count, cudaStream_t st);
+cudaError_t launch_tql(int nw, long long nk, const TriBuf &tb, int *err_flag, cudaStream_t st);
+cudaError_t launch_zrot(int nw, long long nk, const TriBuf &tb, int sm_count, cudaStream_t st);
 
 }  // namespace mepb

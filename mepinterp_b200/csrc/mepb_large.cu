@@ -232,7 +232,8 @@ struct LargeSmemLayout {
 
 __global__ void __launch_bounds__(E_THREADS, 1)
 eig_rot_large_kernel(const DevModel m, const KSource ks, const Jobs jb, const InterpOut out, const int max_pairs,
-                     const double2 *__restrict__ Hk_in, const double2 *__restrict__ Hka_in, double2 *__restrict__ Vscr) {
+                     const double2 *__restrict__ Hk_in, const double2 *__restrict__ Hka_in, double2 *__restrict__ Vscr,
+                     const TriBuf tb) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int nw = m.nw, nw2 = nw * nw;
     const LargeSmemLayout L(nw);
@@ -261,6 +262,56 @@ eig_rot_large_kernel(const DevModel m, const KSource ks, const Jobs jb, const In
     __syncthreads();
 
     for (long long ik = blockIdx.x; ik < ks.nk && need_eig; ik += gridDim.x) {
+      if (tb.ne) {
+        // ------------------------------------------------------------------ U = H_0 H_1 ... H_{n-2} Z  (zunmtr 'L','N')
+        // eigenpairs of the tridiagonal matrix come from mepb_tri.cu; thread (col, part) owns rows part + 8 rr of one
+        // column of Z in registers, reflectors are broadcast from shared memory, no barrier inside the loop
+        const int NEt = tb.ne;
+        const double2 *Vr = tb.Vr + (size_t)ik * NEt * NEt;
+        double2 *taus = reinterpret_cast<double2 *>(rot);
+        for (int idx = tid; idx < (nw - 1) * nw; idx += E_THREADS) {
+            const int s = idx / nw, i = idx % nw;
+            A[s * LD + i] = Vr[(size_t)s * NEt + i];
+        }
+        if (tid < nw) {
+            es[tid] = tb.E[(size_t)ik * NEt + tid];
+            perm[tid] = (int)tb.rank[(size_t)ik * NEt + tid];
+            taus[tid] = tb.tau[(size_t)ik * NEt + tid];
+        }
+        __syncthreads();
+        {
+            const int col = min(tid >> 3, nw - 1), part = tid & 7;
+            const double *Zc = tb.Z + (size_t)ik * NEt * NEt + (size_t)col * NEt;
+            double2 z[8];
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr) { const int r = part + 8 * rr; z[rr] = make_double2(r < nw ? Zc[r] : 0.0, 0.0); }
+            for (int j = nw - 2; j >= 0; --j) {
+                const double2 tj = taus[j];
+                if (tj.x == 0.0 && tj.y == 0.0) continue;
+                double2 v[8];
+                double2 w = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr) {
+                    const int r = part + 8 * rr;
+                    v[rr] = make_double2(0.0, 0.0);
+                    if (8 * rr + 7 > j && r < nw) { v[rr] = A[j * LD + r]; cfmac(w, v[rr], z[rr]); }
+                }
+                w.x += __shfl_xor_sync(0xffffffffu, w.x, 1); w.y += __shfl_xor_sync(0xffffffffu, w.y, 1);
+                w.x += __shfl_xor_sync(0xffffffffu, w.x, 2); w.y += __shfl_xor_sync(0xffffffffu, w.y, 2);
+                w.x += __shfl_xor_sync(0xffffffffu, w.x, 4); w.y += __shfl_xor_sync(0xffffffffu, w.y, 4);
+                const double2 t = cmul(tj, w);
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr)
+                    if (8 * rr + 7 > j) { z[rr].x -= t.x * v[rr].x - t.y * v[rr].y; z[rr].y -= t.x * v[rr].y + t.y * v[rr].x; }
+            }
+            if ((tid >> 3) < nw) {
+                const int dst = perm[col];
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr) { const int r = part + 8 * rr; if (r < nw) T[r * LD + dst] = z[rr]; }
+            }
+        }
+        __syncthreads();
+      } else {
         // ------------------------------------------------------------------ load H(k), U = 1
         const double2 *Hk = Hk_in + (size_t)ik * nw2;
         double nrm_l = 0.0;
@@ -365,6 +416,9 @@ eig_rot_large_kernel(const DevModel m, const KSource ks, const Jobs jb, const In
             es[rank] = ej; perm[rank] = tid;
         }
         __syncthreads();
+        // sorted eigenvectors: T <- U[:, perm]
+        for (int idx = tid; idx < nw * nw; idx += E_THREADS) { const int r = idx / nw, j = idx % nw; T[r * LD + j] = U[r * LD + perm[j]]; }
+      }
         double f_loc = 0.0;
         if (tid < nw) {
             const double f = fermi(es[tid], jb);
@@ -372,8 +426,6 @@ eig_rot_large_kernel(const DevModel m, const KSource ks, const Jobs jb, const In
             if (out.e_out) out.e_out[(size_t)ik * nw + tid] = es[tid];
         }
         if (warp < 2) { f_loc = warp_sum(f_loc); if (lane == 0) acc_ne += f_loc; }     // nw <= 64: warps 0, 1
-        // sorted eigenvectors: T <- U[:, perm]
-        for (int idx = tid; idx < nw * nw; idx += E_THREADS) { const int r = idx / nw, j = idx % nw; T[r * LD + j] = U[r * LD + perm[j]]; }
         __syncthreads();
         const bool want_V = response || (out.V_out != nullptr);
         if (want_V) {
@@ -686,11 +738,11 @@ bool large_supported(int nw) {
 int eig_large_grid(int sm_count, long long nk) { return (int)(nk < sm_count ? (nk < 1 ? 1 : nk) : sm_count); }
 
 cudaError_t launch_eig_rot_large(const DevModel &m, const KSource &ks, const Jobs &jobs, const InterpOut &out, int max_pairs,
-                                 const double2 *Hk, const double2 *Hka, double2 *Vscr, int grid, cudaStream_t st) {
+                                 const double2 *Hk, const double2 *Hka, double2 *Vscr, const TriBuf &tb, int grid, cudaStream_t st) {
     const size_t smem = LargeSmemLayout(m.nw).total;
     cudaError_t e = cudaFuncSetAttribute(eig_rot_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    eig_rot_large_kernel<<<grid, E_THREADS, smem, st>>>(m, ks, jobs, out, max_pairs, Hk, Hka, Vscr);
+    eig_rot_large_kernel<<<grid, E_THREADS, smem, st>>>(m, ks, jobs, out, max_pairs, Hk, Hka, Vscr, tb);
     return cudaGetLastError();
 }
 

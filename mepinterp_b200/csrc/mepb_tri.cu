@@ -1,0 +1,279 @@
+// mepb_tri.cu — Hermitian eigensolver of the general path (num_wann 17..64): Householder tridiagonalisation + implicit QL.
+//
+// Replaces the reference's zheevd call (matrix_math.f90:192-226) for the CTA-per-k path.  A cyclic Jacobi solver needs
+// ~9 sweeps x 7.7 MFLOP at num_wann = 64 and three block barriers per rotation round; the classical dense route needs
+// ~25 n^3 = 6.6 MFLOP, and its only serial part (the QL recurrence on the tridiagonal) is O(n^2) scalar work that is
+// peeled off into a thread-per-k kernel where millions of k-points hide its latency:
+//
+//   tridiag_kernel<NE>  one CTA (8 NE threads) per k.  The trailing matrix lives in REGISTERS: thread (i, part) owns
+//       A(i, part + 8 jj), jj < NE/8 — every register index is a compile-time constant (the step loop is unrolled over
+//       the 8-column blocks).  Per column: zlarfg reflector, p = tau A v (8 complex FMAs + 3 shuffle stages),
+//       w = p - tau/2 (p^H v) v, rank-2 update A -= v w^H + w v^H.  Three block barriers per column.
+//       Same arithmetic as LAPACK zhetd2('L'): T = Q^H A Q real symmetric tridiagonal, Q = H_0 H_1 ... H_{n-2}.
+//   tql_kernel          one THREAD per k: implicit-shift QL (EISPACK tql2 recurrence) on (d, e) held in shared memory
+//       ([index][thread], conflict free).  Writes the eigenvalues (sorted, plus the sort ranks) and a LOG of the plane
+//       rotations (c, s) with one header word per chase instead of touching any eigenvector.
+//   zrot_kernel<NE>     replays the log on Z = 1.  One thread per ROW of Z, the whole row in registers (plane indices are
+//       compile-time: the chase is unrolled over all planes and skipped in warp-uniform blocks of 8), so a rotation is
+//       one uniform 16-byte load and four FP64 instructions, no shared memory, no barriers.
+//   The reflectors are applied to Z (U = Q Z) at the head of eig_rot_large_kernel (mepb_large.cu).
+#include "mepb_internal.cuh"
+
+namespace mepb {
+
+namespace {
+
+constexpr int kTqlThreads = 32;
+
+__device__ __forceinline__ double2 shfl_xor2(double2 v, int o) {
+    return make_double2(__shfl_xor_sync(0xffffffffu, v.x, o), __shfl_xor_sync(0xffffffffu, v.y, o));
+}
+
+// ================================================================================================ tridiagonalisation
+template <int NE>
+__global__ void __launch_bounds__(NE * 8, 1)
+tridiag_kernel(const int nw, const long long nk, const double2 *__restrict__ Hk_in, const TriBuf tb) {
+    constexpr int JJ = NE / 8, NT = NE * 8, NWARP = NT / 32;
+    __shared__ double2 xs[2][NE];
+    __shared__ double2 ws[NE];
+    __shared__ double2 red[NWARP];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i = tid >> 3, part = tid & 7;
+    const int nw2 = nw * nw;
+
+    for (long long ik = blockIdx.x; ik < nk; ik += gridDim.x) {
+        const double2 *Hk = Hk_in + (size_t)ik * nw2;
+        double2 *Vr = tb.Vr + (size_t)ik * NE * NE;
+        double2 *tau_o = tb.tau + (size_t)ik * NE;
+        double *d_o = tb.d + (size_t)ik * NE, *e_o = tb.e + (size_t)ik * NE;
+        // zheevd 'U' semantics: only the upper triangle of H(k) is referenced, Im of the diagonal ignored
+        double2 a[JJ];
+#pragma unroll
+        for (int jj = 0; jj < JJ; ++jj) {
+            const int j = part + 8 * jj;
+            double2 v = make_double2(0.0, 0.0);
+            if (i < nw && j < nw) {
+                if (i < j) v = Hk[i + nw * j];
+                else if (i > j) v = cconj(Hk[j + nw * i]);
+                else v = make_double2(Hk[i + nw * i].x, 0.0);
+            }
+            a[jj] = v;
+        }
+        if (tid < NE) { tau_o[tid] = make_double2(0.0, 0.0); e_o[tid] = 0.0; }
+        __syncthreads();     // previous matrix is done with xs / ws / red
+
+#pragma unroll
+        for (int sb = 0; sb < JJ; ++sb) {
+            for (int sl = 0; sl < 8; ++sl) {
+                const int s = 8 * sb + sl;
+                if (s > nw - 1) break;
+                const int buf = s & 1;
+                if (part == sl) {
+                    xs[buf][i] = (i > s) ? a[sb] : make_double2(0.0, 0.0);
+                    if (i == s) d_o[s] = a[sb].x;
+                }
+                if (s == nw - 1) break;
+                __syncthreads();                                                            // (1) x visible
+                const double2 alpha = xs[buf][s + 1];
+                double pn = 0.0;
+#pragma unroll
+                for (int r = lane; r < NE; r += 32)
+                    if (r > s + 1) { const double2 x = xs[buf][r]; pn = fma(x.x, x.x, fma(x.y, x.y, pn)); }
+                const double xnorm2 = warp_sum(pn);
+                double2 tau, scale;
+                double beta;
+                if (xnorm2 == 0.0 && alpha.y == 0.0) {                                      // zlarfg: H = 1
+                    tau = make_double2(0.0, 0.0); scale = make_double2(0.0, 0.0); beta = alpha.x;
+                } else {
+                    beta = -copysign(sqrt(fma(alpha.x, alpha.x, fma(alpha.y, alpha.y, xnorm2))), alpha.x);
+                    const double rb = 1.0 / beta;
+                    tau = make_double2((beta - alpha.x) * rb, -alpha.y * rb);
+                    scale = crcp(make_double2(alpha.x - beta, alpha.y));
+                }
+                auto vget = [&](int r) -> double2 {
+                    if (r <= s) return make_double2(0.0, 0.0);
+                    if (r == s + 1) return make_double2(1.0, 0.0);
+                    return cmul(xs[buf][r], scale);
+                };
+                const double2 vi = vget(i);
+                double2 vj[JJ];
+#pragma unroll
+                for (int jj = 0; jj < JJ; ++jj) vj[jj] = vget(part + 8 * jj);
+                // p = tau A v  (rows <= s are finished: p = 0 there)
+                double2 p = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int jj = 0; jj < JJ; ++jj) cfma(p, a[jj], vj[jj]);
+                p = cadd(p, shfl_xor2(p, 1)); p = cadd(p, shfl_xor2(p, 2)); p = cadd(p, shfl_xor2(p, 4));
+                p = cmul(tau, p);
+                if (i <= s) p = make_double2(0.0, 0.0);
+                // p^H v
+                double2 dt = (part == 0) ? cmulc(vi, p) : make_double2(0.0, 0.0);
+                dt = cadd(dt, shfl_xor2(dt, 8)); dt = cadd(dt, shfl_xor2(dt, 16));
+                if (lane == 0) red[warp] = dt;
+                if (part == 0) Vr[(size_t)s * NE + i] = vi;
+                if (tid == 0) { tau_o[s] = tau; e_o[s] = beta; }
+                __syncthreads();                                                            // (2)
+                double2 dot = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int w = 0; w < NWARP; ++w) dot = cadd(dot, red[w]);
+                const double2 alc = cscale(-0.5, cmul(tau, dot));
+                double2 wi = p;
+                cfma(wi, alc, vi);
+                if (part == 0) ws[i] = wi;
+                __syncthreads();                                                            // (3)
+#pragma unroll
+                for (int jj = 0; jj < JJ; ++jj) {
+                    const double2 wj = ws[part + 8 * jj];
+                    const double2 u1 = cmulc(vi, wj), u2 = cmulc(wi, vj[jj]);
+                    a[jj].x -= u1.x + u2.x; a[jj].y -= u1.y + u2.y;
+                }
+            }
+        }
+    }
+}
+
+// ================================================================================================ implicit QL, thread per k
+__global__ void __launch_bounds__(kTqlThreads)
+tql_kernel(const int n, const long long nk, const TriBuf tb, int *__restrict__ err_flag) {
+    extern __shared__ double sm[];
+    const int ne = tb.ne, t = threadIdx.x;
+    const long long ik = (long long)blockIdx.x * kTqlThreads + t;
+    if (ik >= nk) return;
+    double *dd = sm + t, *ee = sm + (size_t)ne * kTqlThreads + t;
+#define D(i) dd[(i) * kTqlThreads]
+#define E(i) ee[(i) * kTqlThreads]
+    {
+        const double *dg = tb.d + (size_t)ik * ne, *eg = tb.e + (size_t)ik * ne;
+        for (int i = 0; i < n; ++i) { D(i) = dg[i]; E(i) = (i < n - 1) ? eg[i] : 0.0; }
+    }
+    unsigned int *hdr = tb.hdr + (size_t)ik * tb.hdr_cap;
+    double2 *lg = tb.log + (size_t)ik * tb.log_cap;
+    const double eps = 1.1102230246251565e-16;
+    int nh = 0, pos = 0;
+    bool failed = false;
+    for (int l = 0; l < n && !failed; ++l) {
+        int iter = 0;
+        while (true) {
+            int m = l;
+            for (; m < n - 1; ++m) {
+                const double tst = fabs(D(m)) + fabs(D(m + 1));
+                if (fabs(E(m)) <= eps * tst) break;
+            }
+            if (m == l) break;
+            if (++iter > 60 || nh >= tb.hdr_cap || pos + (m - l) > tb.log_cap) { failed = true; break; }
+            double g = (D(l + 1) - D(l)) / (2.0 * E(l));
+            double r = sqrt(fma(g, g, 1.0));
+            g = D(m) - D(l) + E(l) / (g + copysign(r, g));
+            double s = 1.0, c = 1.0, p = 0.0;
+            int i = m - 1;
+            for (; i >= l; --i) {
+                const double ei = E(i);
+                const double f = s * ei, b = c * ei;
+                r = sqrt(fma(f, f, g * g));
+                E(i + 1) = r;
+                if (r == 0.0) { D(i + 1) -= p; E(m) = 0.0; break; }
+                const double rr = 1.0 / r;
+                s = f * rr; c = g * rr;
+                g = D(i + 1) - p;
+                r = (D(i) - g) * s + 2.0 * c * b;
+                p = s * r;
+                D(i + 1) = g + p;
+                g = c * r - b;
+                lg[pos++] = make_double2(c, s);
+            }
+            hdr[nh++] = (unsigned int)(i + 1) | ((unsigned int)m << 8);
+            if (r == 0.0 && i >= l) continue;
+            D(l) -= p; E(l) = g; E(m) = 0.0;
+        }
+    }
+    if (failed) { atomicExch(err_flag, 1); nh = 0; }
+    tb.nhdr[ik] = nh;
+    // ascending order (stable): rank of eigenvalue j, sorted copy
+    double *Eo = tb.E + (size_t)ik * ne;
+    unsigned char *rk = tb.rank + (size_t)ik * ne;
+    for (int j = 0; j < n; ++j) {
+        const double ej = D(j);
+        int rnk = 0;
+        for (int i = 0; i < n; ++i) { const double ei = D(i); rnk += (ei < ej || (ei == ej && i < j)) ? 1 : 0; }
+        Eo[rnk] = ej; rk[j] = (unsigned char)rnk;
+    }
+#undef D
+#undef E
+}
+
+// ================================================================================================ replay of the rotation log
+template <int NE>
+__global__ void __launch_bounds__(128)
+zrot_kernel(const int n, const long long nk, const TriBuf tb) {
+    constexpr int GROUPS = 128 / NE;                 // matrices per CTA
+    const int tid = threadIdx.x;
+    const int grp = tid / NE, row = tid % NE;
+    for (long long ik = (long long)blockIdx.x * GROUPS + grp; ik < nk; ik += (long long)gridDim.x * GROUPS) {
+        double z[NE];
+#pragma unroll
+        for (int j = 0; j < NE; ++j) z[j] = (j == row) ? 1.0 : 0.0;
+        const unsigned int *hdr = tb.hdr + (size_t)ik * tb.hdr_cap;
+        const double2 *lg = tb.log + (size_t)ik * tb.log_cap;
+        const int nh = tb.nhdr[ik];
+        int pos0 = 0;
+        for (int h = 0; h < nh; ++h) {
+            const unsigned int w = __ldg(hdr + h);
+            const int l = (int)(w & 0xffu), m = (int)(w >> 8);
+            const double2 *src = lg + pos0 + (m - 1);          // rotation of plane i sits at src[-i]
+#pragma unroll
+            for (int blk = NE / 8 - 1; blk >= 0; --blk) {
+                if (8 * blk < m && 8 * blk + 7 >= l) {
+#pragma unroll
+                    for (int ii = 7; ii >= 0; --ii) {
+                        const int i = 8 * blk + ii;
+                        if (i <= NE - 2) {
+                            if (i < m && i >= l) {
+                                const double2 cs = __ldg(src - i);
+                                const double f = z[i + 1 <= NE - 1 ? i + 1 : NE - 1];
+                                const double zi = z[i];
+                                z[i + 1 <= NE - 1 ? i + 1 : NE - 1] = fma(cs.y, zi, cs.x * f);
+                                z[i] = fma(cs.x, zi, -(cs.y * f));
+                            }
+                        }
+                    }
+                }
+            }
+            pos0 += m - l;
+        }
+        double *Zo = tb.Z + (size_t)ik * NE * NE;
+#pragma unroll
+        for (int j = 0; j < NE; ++j) Zo[j * NE + row] = z[j];
+    }
+    (void)n;
+}
+
+}  // namespace
+
+// ================================================================================================= launchers
+int tri_padded_size(int nw) { return nw <= 32 ? 32 : 64; }
+size_t tri_log_cap(int ne) { return (size_t)2 * ne * ne; }
+
+cudaError_t launch_tridiag(int nw, long long nk, const double2 *Hk, const TriBuf &tb, int sm_count, cudaStream_t st) {
+    const int grid = (int)std::min<long long>(nk < 1 ? 1 : nk, (long long)sm_count * (tb.ne == 32 ? 4 : 1));
+    if (tb.ne == 32) tridiag_kernel<32><<<grid, 256, 0, st>>>(nw, nk, Hk, tb);
+    else tridiag_kernel<64><<<grid, 512, 0, st>>>(nw, nk, Hk, tb);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tql(int nw, long long nk, const TriBuf &tb, int *err_flag, cudaStream_t st) {
+    const int grid = (int)((nk + kTqlThreads - 1) / kTqlThreads);
+    const size_t smem = sizeof(double) * 2 * (size_t)tb.ne * kTqlThreads;
+    tql_kernel<<<grid < 1 ? 1 : grid, kTqlThreads, smem, st>>>(nw, nk, tb, err_flag);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_zrot(int nw, long long nk, const TriBuf &tb, int sm_count, cudaStream_t st) {
+    const int groups = 128 / tb.ne;
+    long long grid = (nk + groups - 1) / groups;
+    grid = std::max<long long>(1, std::min<long long>(grid, (long long)sm_count * 8));
+    if (tb.ne == 32) zrot_kernel<32><<<(int)grid, 128, 0, st>>>(nw, nk, tb);
+    else zrot_kernel<64><<<(int)grid, 128, 0, st>>>(nw, nk, tb);
+    return cudaGetLastError();
+}
+
+}  // namespace mepb
