@@ -104,6 +104,11 @@ int mepb_interp(mepb_ctx *ctx, int64_t nk, const double *kpt, double *e_k, doubl
  * Gauge independent, so it is compared element-wise against the oracle. */
 int mepb_fourier(mepb_ctx *ctx, int64_t nk, const double *kpt, double *H_k, double *H_ka);
 
+/* Same sums on mesh points: the k-points with 0-based linear mesh index [lin_begin, lin_begin + nk) of the context's
+ * mp_grid, through the code path mepb_accumulate uses for them (general path: the mesh-separable transform).  Parity
+ * harness for that path; MEPB_ERR_UNSUPPORTED on the small-num_wann path, whose kernels never materialise H(k). */
+int mepb_fourier_mesh(mepb_ctx *ctx, int64_t lin_begin, int64_t nk, double *H_k, double *H_ka);
+
 /* Re-upload H(R) from a host buffer into an existing context (same nw, nR, R set, FT convention): the per-call input
  * of a parameter sweep — the reference re-reads w90files/<seed>_hr.dat in a fresh process per parameter value
  * (scripts/mep_worker.py:133-150, scripts/probe_phi.py). */

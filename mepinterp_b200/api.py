@@ -21,7 +21,7 @@ ERR_ARG, ERR_CUDA, ERR_NOT_HERMITIAN, ERR_UNSUPPORTED, ERR_EIG, ERR_STATE = -1, 
 
 EXPORTS = ["mepb_create", "mepb_destroy", "mepb_run_mesh", "mepb_reset", "mepb_accumulate", "mepb_partials_size",
            "mepb_get_partials", "mepb_set_partials", "mepb_partials_device_ptr", "mepb_finalize", "mepb_interp",
-           "mepb_fourier", "mepb_update_model", "mepb_timer_start", "mepb_timer_stop", "mepb_set_profiling",
+           "mepb_fourier", "mepb_fourier_mesh", "mepb_update_model", "mepb_timer_start", "mepb_timer_stop", "mepb_set_profiling",
            "mepb_get_profile", "mepb_work_items", "mepb_last_kernel_ms", "mepb_kernel_launches", "mepb_strerror", "mepb_last_error", "mepb_version"]
 
 
@@ -74,6 +74,7 @@ def lib():
         L.mepb_finalize.argtypes = [vp, C.POINTER(CResult)]
         L.mepb_interp.argtypes = [vp, C.c_int64, vp, vp, vp]
         L.mepb_fourier.argtypes = [vp, C.c_int64, vp, vp, vp]
+        L.mepb_fourier_mesh.argtypes = [vp, C.c_int64, C.c_int64, vp, vp]
         L.mepb_update_model.argtypes = [vp, C.POINTER(CModel)]
         L.mepb_timer_start.argtypes = [vp]
         L.mepb_timer_stop.argtypes = [vp, C.POINTER(C.c_double)]
@@ -246,6 +247,14 @@ class Context:
         Hk = np.zeros((nw, nw, nk), dtype=np.complex128, order="F")
         Hka = np.zeros((3, nw, nw, nk), dtype=np.complex128, order="F")
         _check(lib().mepb_fourier(self._h, nk, kp.ctypes.data, Hk.ctypes.data, Hka.ctypes.data))
+        return Hk, Hka
+
+    def fourier_mesh(self, lin_begin: int, nk: int):
+        """Fourier sums on the mesh points [lin_begin, lin_begin + nk) through the mesh code path (general path only)."""
+        nw = self.nw
+        Hk = np.zeros((nw, nw, nk), dtype=np.complex128, order="F")
+        Hka = np.zeros((3, nw, nw, nk), dtype=np.complex128, order="F")
+        _check(lib().mepb_fourier_mesh(self._h, lin_begin, nk, Hk.ctypes.data, Hka.ctypes.data))
         return Hk, Hka
 
     def update_model(self, H):

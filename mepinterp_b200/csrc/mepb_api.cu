@@ -119,6 +119,7 @@ struct StreamBuf {
     double *eig_E = nullptr; double2 *eig_U = nullptr;   // [chunk][nw], [chunk][nw*nw] from the thread-per-k eigensolver
     double2 *Hk = nullptr, *Hka = nullptr, *Vscr = nullptr;   // general path: [chunk][nw^2], [chunk][3][nw^2], [grid][3][nw^2]
     TriBuf tb{};                                                // general path: Householder + QL intermediates (mepb_tri.cu)
+    double2 *G1 = nullptr, *G2 = nullptr;                       // general path, mesh mode: separable-transform tables
 };
 
 }  // namespace
@@ -136,6 +137,9 @@ struct mepb_ctx {
     FourierPlan fp{};
     int *d_ridx = nullptr, *d_elem = nullptr; double2 *d_Hp = nullptr; double *d_Rfp = nullptr, *d_cRp = nullptr;
     double2 *d_Hka_int = nullptr;
+    SepPlan sp{};              // mesh-separable Fourier transform (general path, mesh mode)
+    int *d_map3 = nullptr, *d_ra = nullptr; double2 *d_P1 = nullptr, *d_P2 = nullptr, *d_P3 = nullptr; double *d_cw4 = nullptr;
+    double Mmat[9];            // c_a(R) = sum_j Mmat[a + 3 j] R_j
     int *d_sp_ptr = nullptr, *d_sp_R = nullptr; double2 *d_sp_val = nullptr;   // sparse H(R) (warp-per-k Fourier sums)
     bool sparse = false; int sp_nnz = 0;
     double a_latt[9];
@@ -289,6 +293,64 @@ cudaError_t build_fourier_plan(mepb_ctx *c, const mepb_model *model, const std::
     return cudaSuccess;
 }
 
+// Mesh-separable transform (SepPlan): index map of the R set on the product grid of its distinct coordinates, per-axis
+// phase tables of the Monkhorst-Pack mesh, weights of the line-table rows.  Depends on the R set and mp_grid only.
+cudaError_t build_sep_plan(mepb_ctx *c, const mepb_model *model) {
+    SepPlan &sp = c->sp;
+    const FourierPlan &fp = c->fp;
+    sp.on = 0;
+    if (fp.direct || getenv("MEPB_FOURIER_DENSE")) return cudaSuccess;
+    const int n1 = fp.u1, n2 = fp.u2, n3 = fp.u3;
+    if (n2 > 32 || n3 > 32 || (long long)n1 * n2 * n3 > (1 << 20)) return cudaSuccess;
+    sp.n1 = n1; sp.n2 = n2; sp.n3 = n3;
+    sp.nrp = (3 * n1 + kFourierRC - 1) / kFourierRC * kFourierRC;
+    sp.nelp = fp.ntiles * kFourierTN;
+    for (int b = 0; b < n2; ++b) sp.u2[b] = fp.uval[n1 + b];
+    for (int q = 0; q < n3; ++q) sp.u3[q] = fp.uval[n1 + n2 + q];
+    std::vector<int> map3((size_t)n1 * n2 * n3, -1);
+    auto find = [&](int off, int n, double v) { return (int)(std::lower_bound(fp.uval + off, fp.uval + off + n, v) - (fp.uval + off)); };
+    for (int R = 0; R < c->nR; ++R) {
+        const int a = find(0, n1, model->R[3 * R]), b = find(n1, n2, model->R[3 * R + 1]), q = find(n1 + n2, n3, model->R[3 * R + 2]);
+        int &slot = map3[((size_t)a * n2 + b) * n3 + q];
+        if (slot >= 0) return cudaSuccess;                 // duplicate R vector in the list: keep the dense kernel
+        slot = R;
+    }
+    std::vector<double> cw4(4 * (size_t)sp.nrp, 0.0);
+    std::vector<int> ra(sp.nrp, 0);
+    for (int t = 0; t < 3; ++t)
+        for (int a = 0; a < n1; ++a) {
+            const int r = t * n1 + a;
+            ra[r] = a;
+            const double f = (t == 0) ? fp.uval[a] : 1.0;
+            cw4[4 * r + 3] = (t == 0) ? 1.0 : 0.0;
+            for (int i = 0; i < 3; ++i) cw4[4 * r + i] = c->Mmat[i + 3 * t] * f;
+        }
+    auto up = [&](void **dst, const void *src, size_t bytes) -> cudaError_t {
+        if (!*dst) { cudaError_t e = cudaMalloc(dst, bytes); if (e != cudaSuccess) return e; }
+        return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+    };
+    cudaError_t e;
+    if ((e = up((void **)&c->d_map3, map3.data(), sizeof(int) * map3.size())) != cudaSuccess) return e;
+    if ((e = up((void **)&c->d_ra, ra.data(), sizeof(int) * ra.size())) != cudaSuccess) return e;
+    if ((e = up((void **)&c->d_cw4, cw4.data(), sizeof(double) * cw4.size())) != cudaSuccess) return e;
+    const int N[3] = {c->p.mp_grid[0], c->p.mp_grid[1], c->p.mp_grid[2]};
+    const int nn[3] = {n1, n2, n3}, off[3] = {0, n1, n1 + n2};
+    double2 **P[3] = {&c->d_P1, &c->d_P2, &c->d_P3};
+    double *d_u = nullptr;
+    if ((e = cudaMalloc((void **)&d_u, sizeof(double) * kFourierMaxU)) != cudaSuccess) return e;
+    if ((e = cudaMemcpy(d_u, fp.uval, sizeof(double) * fp.utot, cudaMemcpyHostToDevice)) != cudaSuccess) { cudaFree(d_u); return e; }
+    for (int a = 0; a < 3; ++a) {
+        if (!*P[a] && (e = cudaMalloc((void **)P[a], sizeof(double2) * (size_t)nn[a] * N[a])) != cudaSuccess) { cudaFree(d_u); return e; }
+        if ((e = launch_phase_table(*P[a], d_u + off[a], nn[a], N[a], 0)) != cudaSuccess) { cudaFree(d_u); return e; }
+    }
+    e = cudaDeviceSynchronize();
+    cudaFree(d_u);
+    if (e != cudaSuccess) return e;
+    sp.map3 = c->d_map3; sp.ra = c->d_ra; sp.cw4 = c->d_cw4; sp.P1 = c->d_P1; sp.P2 = c->d_P2; sp.P3 = c->d_P3;
+    sp.on = 1;
+    return cudaSuccess;
+}
+
 // CSR (by matrix element) of the non-zero entries of H(R); used when fewer than half of the entries are non-zero
 cudaError_t build_sparse(mepb_ctx *c, const mepb_model *model) {
     const int nw2 = c->nw * c->nw, nR = c->nR;
@@ -327,10 +389,12 @@ void free_all(mepb_ctx *c) {
         cudaFree(s.eig_E); cudaFree(s.eig_U); cudaFree(s.Hk); cudaFree(s.Hka); cudaFree(s.Vscr);
         cudaFree(s.tb.Vr); cudaFree(s.tb.tau); cudaFree(s.tb.d); cudaFree(s.tb.e); cudaFree(s.tb.E); cudaFree(s.tb.rank);
         cudaFree(s.tb.hdr); cudaFree(s.tb.nhdr); cudaFree(s.tb.log); cudaFree(s.tb.Z);
+        cudaFree(s.G1); cudaFree(s.G2);
         if (s.st) cudaStreamDestroy(s.st);
         if (s.done) cudaEventDestroy(s.done);
     }
     cudaFree(c->d_packed); cudaFree(c->d_err);
+    cudaFree(c->d_map3); cudaFree(c->d_ra); cudaFree(c->d_P1); cudaFree(c->d_P2); cudaFree(c->d_P3); cudaFree(c->d_cw4);
     cudaFree(c->d_ridx); cudaFree(c->d_elem); cudaFree(c->d_Hp); cudaFree(c->d_Rfp); cudaFree(c->d_cRp); cudaFree(c->d_Hka_int);
     cudaFree(c->d_kpt); cudaFree(c->d_e); cudaFree(c->d_V); cudaFree(c->d_Hk); cudaFree(c->d_Hka);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -432,6 +496,8 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
     // weights c_a(R) = M.R and t = M.tau ; M = 2 pi or a_latt (matmul, wann_interp.f90:387-399)
     const double two_pi = 2.0 * (4.0 * std::atan(1.0));
     std::vector<double> Rf(3 * nR), cR(3 * nR), tau(3 * nw, 0.0), tM(3 * nw, 0.0);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) c->Mmat[i + 3 * j] = p.use_cart_velo ? model->a_latt[i + 3 * j] : (i == j ? two_pi : 0.0);
     auto applyM = [&](const double *x, double *y) {
         if (p.use_cart_velo)
             for (int i = 0; i < 3; ++i) y[i] = model->a_latt[i] * x[0] + model->a_latt[i + 3] * x[1] + model->a_latt[i + 6] * x[2];
@@ -464,6 +530,9 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
     if (p.do_ahc) per_k += sizeof(double) * istr * c->max_pairs + sizeof(int);
     if (p.do_opt) per_k += sizeof(double) * kPhotoItem * c->max_photo + sizeof(int);
     if (c->large) per_k += sizeof(double2) * 4 * (size_t)nw * nw;
+    if (c->large) { CT(build_fourier_plan(c, model, cR)); CT(build_sep_plan(c, model)); }
+    if (c->sp.on) per_k += sizeof(double2) * (size_t)c->fp.ntiles * c->sp.nrp * kFourierTN / p.mp_grid[0] +
+                           sizeof(double2) * 2 * (size_t)c->sp.n1 * c->sp.n2 * c->sp.nelp / ((size_t)p.mp_grid[0] * p.mp_grid[1]);
     const int tne = tri_padded_size(nw);
     if (c->tri) per_k += (size_t)tne * tne * (sizeof(double2) + sizeof(double)) + sizeof(double2) * tri_log_cap(tne) +
                          sizeof(unsigned int) * kTriHdrCap + (size_t)tne * 48;
@@ -471,8 +540,7 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
     if (per_k) chunk = std::min<long long>(chunk, (long long)(((c->large ? 6144ull : 768ull) << 20) / per_k));
     chunk = std::max<long long>(c->large ? 296 : 1024, std::min(chunk, std::max<long long>(nk_mesh, 1024)));
     c->chunk = chunk;
-    if (c->large) CT(build_fourier_plan(c, model, cR));
-    else CT(build_sparse(c, model));
+    if (!c->large) CT(build_sparse(c, model));
     c->grid_interp = c->large ? eig_large_grid(c->sm_count, chunk) : interp_small_grid(nw, nR, c->sm_count, chunk);
     if (c->use_sub) c->grid_interp = std::max(c->grid_interp, bands_sub_grid(nw, nR, c->sm_count, chunk));
     c->grid_sweep = sweep_ahc_grid(c->sm_count, chunk, p.n_hw, &c->ns_sweep);
@@ -499,6 +567,12 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
             CT(cudaMalloc((void **)&s.Hk, sizeof(double2) * nw * nw * (size_t)chunk));
             CT(cudaMalloc((void **)&s.Hka, sizeof(double2) * 3 * nw * nw * (size_t)chunk));
             CT(cudaMalloc((void **)&s.Vscr, sizeof(double2) * 3 * nw * nw * (size_t)c->grid_interp));
+        }
+        if (c->sp.on) {
+            const long long nlines = chunk / p.mp_grid[0] + 2;
+            const long long nq3 = std::min<long long>(p.mp_grid[2], (nlines + p.mp_grid[1] - 2) / p.mp_grid[1] + 1);
+            CT(cudaMalloc((void **)&s.G1, sizeof(double2) * 2 * (size_t)c->sp.n1 * c->sp.n2 * c->sp.nelp * (size_t)nq3));
+            CT(cudaMalloc((void **)&s.G2, sizeof(double2) * (size_t)c->fp.ntiles * c->sp.nrp * kFourierTN * (size_t)nlines));
         }
         if (c->tri) {
             TriBuf &t = s.tb;
@@ -578,7 +652,14 @@ int mepb_accumulate(mepb_ctx *c, int64_t lin_begin, int64_t lin_end) {
             const int gi = c->large ? eig_large_grid(c->sm_count, nk)
                            : c->use_sub ? bands_sub_grid(c->nw, c->nR, c->sm_count, nk) : interp_small_grid(c->nw, c->nR, c->sm_count, nk);
             if (c->large) {
-                { ProfScope ps(c, s.st, MEPB_PROF_FOURIER); CUDA_TRY(launch_fourier_dense(c->fp, m, ks, s.Hk, s.Hka, s.st)); }
+                if (c->sp.on) {
+                    SepPlan sp = c->sp; sp.G1 = s.G1; sp.G2 = s.G2;
+                    ProfScope ps(c, s.st, MEPB_PROF_FOURIER);
+                    CUDA_TRY(launch_fourier_mesh(c->fp, sp, m, ks, s.Hk, s.Hka, s.st));
+                    c->launches += 2;
+                } else {
+                    ProfScope ps(c, s.st, MEPB_PROF_FOURIER); CUDA_TRY(launch_fourier_dense(c->fp, m, ks, s.Hk, s.Hka, s.st));
+                }
                 if (c->tri) {
                     { ProfScope ps(c, s.st, MEPB_PROF_TRIDIAG); CUDA_TRY(launch_tridiag(c->nw, nk, s.Hk, s.tb, c->sm_count, s.st)); }
                     { ProfScope ps(c, s.st, MEPB_PROF_TQL); CUDA_TRY(launch_tql(c->nw, nk, s.tb, c->d_err, s.st)); }
@@ -826,6 +907,33 @@ int mepb_interp(mepb_ctx *c, int64_t nk, const double *kpt, double *e_k, double 
 int mepb_fourier(mepb_ctx *c, int64_t nk, const double *kpt, double *H_k, double *H_ka) {
     if (!H_k && !H_ka) return fail(MEPB_ERR_ARG, "nothing requested");
     return list_run(c, nk, kpt, nullptr, nullptr, H_k, H_ka);
+}
+
+int mepb_fourier_mesh(mepb_ctx *c, int64_t lin_begin, int64_t nk, double *H_k, double *H_ka) {
+    if (!c || (!H_k && !H_ka) || nk < 0) return fail(MEPB_ERR_ARG, "bad argument");
+    if (!c->large) return fail(MEPB_ERR_UNSUPPORTED, "mepb_fourier_mesh: general path (num_wann > 16 or MEPB_PATH=large) only");
+    const mepb_params &p = c->p;
+    const long long nk_mesh = (long long)p.mp_grid[0] * p.mp_grid[1] * p.mp_grid[2];
+    if (lin_begin < 0 || lin_begin + nk > nk_mesh) return fail(MEPB_ERR_ARG, "k range outside the mesh");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const DevModel m = dev_model(c);
+    const size_t nw2 = (size_t)c->nw * c->nw;
+    StreamBuf &s = c->sb[0];
+    for (long long k0 = 0; k0 < nk; k0 += c->chunk) {
+        const long long n = std::min<long long>(c->chunk, nk - k0);
+        int rc = ensure_list(c, std::min<long long>(n, c->chunk));
+        if (rc) return rc;
+        KSource ks; ks.list = nullptr; ks.lin_begin = lin_begin + k0; ks.nk = n; ks.N1 = p.mp_grid[0]; ks.N2 = p.mp_grid[1]; ks.N3 = p.mp_grid[2];
+        if (c->sp.on) { SepPlan sp = c->sp; sp.G1 = s.G1; sp.G2 = s.G2; CUDA_TRY(launch_fourier_mesh(c->fp, sp, m, ks, s.Hk, s.Hka, s.st)); c->launches += 3; }
+        else { CUDA_TRY(launch_fourier_dense(c->fp, m, ks, s.Hk, s.Hka, s.st)); c->launches += 1; }
+        if (H_k) CUDA_TRY(cudaMemcpyAsync(H_k + 2 * nw2 * k0, s.Hk, sizeof(double2) * nw2 * n, cudaMemcpyDeviceToHost, s.st));
+        if (H_ka) {
+            CUDA_TRY(launch_hka_to_user(s.Hka, c->d_Hka, c->nw * c->nw, n, s.st));
+            CUDA_TRY(cudaMemcpyAsync(H_ka + 2 * 3 * nw2 * k0, c->d_Hka, sizeof(double2) * 3 * nw2 * n, cudaMemcpyDeviceToHost, s.st));
+        }
+        CUDA_TRY(cudaStreamSynchronize(s.st));
+    }
+    return MEPB_OK;
 }
 
 int mepb_update_model(mepb_ctx *c, const mepb_model *model) {

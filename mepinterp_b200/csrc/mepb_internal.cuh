@@ -116,6 +116,31 @@ struct FourierPlan {
 };
 
 // ---------------------------------------------------------------------------------------------------------
+// mesh-separable Fourier sums (mepb_large.cu, mesh mode): on a Monkhorst-Pack mesh the phase factorises over the axes,
+// e^{2 pi i k.R} = p1(q1, R1) p2(q2, R2) p3(q3, R3), so the nR-term sum per k-point is contracted axis by axis:
+//   stage A  per mesh plane q3:        G1(a,b; t)   = sum_c p3(q3,c) {1, u3(c)} H(a,b,c)            t = 0, 1
+//   stage B  per mesh line (q2,q3):    G2(a; t)     = sum_b p2(q2,b) {G1(a,b;0), u2(b) G1(a,b;0), G1(a,b;1)}   t = 0, 1, 2
+//   stage C  per k-point of the line:  H, d_aH      = sum_{a,t} p1(q1,a) w(a,t) G2(a;t)      (3 n1 terms instead of nR)
+// (a, b, c index the distinct lattice coordinates u1, u2, u3 of the R set; the weights w carry c_a(R) = (M.R)_a, which is
+// linear in R.)  Stage C is the dense contraction kernel run on the per-line table.
+// ---------------------------------------------------------------------------------------------------------
+struct SepPlan {
+    int on;                  // 0 -> not available (explicit k lists, or too many distinct coordinates)
+    int n1, n2, n3;          // distinct lattice coordinates per axis
+    int nrp;                 // rows of a line table: 3 n1 padded to kFourierRC
+    int nelp;                // ntiles * kFourierTN
+    double u2[32], u3[32];   // distinct coordinates of axes 2, 3 (axis 1 enters through cw4)
+    const int *map3;         // [n1*n2*n3] index into the R list or -1
+    const double2 *P1, *P2, *P3;   // [n_a][N_a] e^{2 pi i k_a(q) u_a}
+    const double *cw4;       // [nrp][4] weights (H, d_1, d_2, d_3) of a line-table row
+    const int *ra;           // [nrp] axis-1 coordinate index of a line-table row
+    double2 *G1;             // [planes][n1*n2][2][nelp]      (per stream)
+    double2 *G2;             // [lines][ntiles][nrp][kFourierTN] (per stream)
+    long long line0;         // first mesh line (q2 + N2 q3) covered by G2
+    int nlines, q3_0, nq3;
+};
+
+// ---------------------------------------------------------------------------------------------------------
 // Householder + implicit-QL eigensolver of the general path (mepb_tri.cu): per-k intermediates in HBM
 //   tridiag_kernel   H(k) -> reflectors v_s, tau_s, real tridiagonal (d, e)           (LAPACK zhetd2 'L' arithmetic)
 //   tql_kernel       thread per k: implicit QL on (d, e); eigenvalues, sort ranks, and the LOG of plane rotations
@@ -261,6 +286,10 @@ bool large_supported(int nw);
 size_t fourier_dense_smem(const FourierPlan &fp, int nw, bool has_tau);
 cudaError_t launch_fourier_dense(const FourierPlan &fp, const DevModel &m, const KSource &ks, double2 *Hk, double2 *Hka,
                                  cudaStream_t st);
+// mesh mode: stages A, B, C of the separable transform for the k range of ks (sp.G1/G2 sized by the caller); 3 launches
+cudaError_t launch_fourier_mesh(const FourierPlan &fp, SepPlan sp, const DevModel &m, const KSource &ks, double2 *Hk,
+                                double2 *Hka, cudaStream_t st);
+cudaError_t launch_phase_table(double2 *P, const double *u, int n, int N, cudaStream_t st);
 cudaError_t launch_hka_to_user(const double2 *in, double2 *out, int nw2, long long nk, cudaStream_t st);
 int eig_large_grid(int sm_count, long long nk);
 cudaError_t launch_eig_rot_large(const DevModel &m, const KSource &ks, const Jobs &jobs, const InterpOut &out, int max_pairs,

@@ -39,31 +39,57 @@ constexpr int F_THREADS = 256;
 struct FourierSmem {                 // fixed part; the axis tables (Utot x F_TK complex) follow
     double2 ph[2][F_RC][F_TK];       // 2 x 16 KB
     double2 h[2][F_RC][F_TN];        // 2 x  8 KB   (TMA destination)
-    double cw[2][F_RC][4];           // c_a(R) = (M.R)_a
+    double cw[2][F_RC][4];           // c_a(R) = (M.R)_a ; [3] = weight of the row in H itself (line mode)
     uint64_t bar[2];
 };
 
+// LINE = false: explicit k list or mesh points, all nR terms per k-point (phases from per-axis tables or sincospi).
+// LINE = true : stage C of the mesh-separable transform — one CTA works on 64 k-points of ONE mesh line (q2, q3) and
+//               contracts that line's table G2 (sp.nrp rows) with the axis-1 phases.
+template <bool LINE>
 __global__ void __launch_bounds__(F_THREADS, 1)
-fourier_dense_kernel(const FourierPlan fp, const DevModel m, const KSource ks, double2 *__restrict__ Hk_out,
+fourier_dense_kernel(const FourierPlan fp, const SepPlan sp, const DevModel m, const KSource ks, double2 *__restrict__ Hk_out,
                      double2 *__restrict__ Hka_out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FourierSmem &S = *reinterpret_cast<FourierSmem *>(smem_raw);
     double2 *tab = reinterpret_cast<double2 *>(smem_raw + sizeof(FourierSmem));      // [Utot][F_TK]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lk = lane & 7, ln = lane >> 3, wk = warp & 1, wn = warp >> 1;
-    const long long k0 = (long long)blockIdx.x * F_TK;
     const int tile = blockIdx.y;
     const int nw = m.nw, nw2 = nw * nw;
-    const int nchunks = fp.nRp / F_RC;
-    const double2 *Hsrc = fp.Hp + (size_t)tile * fp.nRp * F_TN;
+    // k-points of this CTA: ik = kbase + kk for kk < kcnt (line mode: one mesh line; may start before / end after the range)
+    long long kbase;
+    int q1_0 = 0;
+    const double2 *Hsrc;
+    int nchunks;
+    if (LINE) {
+        const int ktl = (ks.N1 + F_TK - 1) / F_TK;
+        const int li = blockIdx.x / ktl;
+        q1_0 = (blockIdx.x % ktl) * F_TK;
+        kbase = (sp.line0 + li) * (long long)ks.N1 + q1_0 - ks.lin_begin;
+        Hsrc = sp.G2 + ((size_t)li * fp.ntiles + tile) * sp.nrp * F_TN;
+        nchunks = sp.nrp / F_RC;
+    } else {
+        kbase = (long long)blockIdx.x * F_TK;
+        Hsrc = fp.Hp + (size_t)tile * fp.nRp * F_TN;
+        nchunks = fp.nRp / F_RC;
+    }
+    auto kvalid = [&](int kk) -> bool {
+        const long long ik = kbase + kk;
+        if (LINE && q1_0 + kk >= ks.N1) return false;
+        return ik >= 0 && ik < ks.nk;
+    };
+    auto kclamp = [&](int kk) -> long long {
+        long long ik = kbase + kk;
+        return ik < 0 ? 0 : (ik >= ks.nk ? ks.nk - 1 : ik);
+    };
 
     if (tid == 0) { mbar_init(&S.bar[0], 1); mbar_init(&S.bar[1], 1); mbar_fence_init(); }
     // ---- per-axis phase tables: tab[u][k] = e^{2 pi i k_a(u) * uval[u]}   (or nothing in direct mode)
-    if (!fp.direct) {
+    if (!LINE && !fp.direct) {
         for (int idx = tid; idx < fp.utot * F_TK; idx += F_THREADS) {
             const int u = idx / F_TK, kk = idx % F_TK;
-            long long ik = k0 + kk; if (ik >= ks.nk) ik = ks.nk - 1;
-            double k1, k2, k3; mesh_k(ks, ik, k1, k2, k3);
+            double k1, k2, k3; mesh_k(ks, kclamp(kk), k1, k2, k3);
             const int ax = u < fp.u1 ? 0 : (u < fp.u1 + fp.u2 ? 1 : 2);
             const double kc = ax == 0 ? k1 : (ax == 1 ? k2 : k3);
             double s, c; sincospi(2.0 * kc * fp.uval[u], &s, &c);
@@ -82,9 +108,11 @@ fourier_dense_kernel(const FourierPlan fp, const DevModel m, const KSource ks, d
             const int r = idx / F_TK, kk = idx % F_TK;
             const int R = c * F_RC + r;
             double2 p;
-            if (fp.direct) {
-                long long ik = k0 + kk; if (ik >= ks.nk) ik = ks.nk - 1;
-                double k1, k2, k3; mesh_k(ks, ik, k1, k2, k3);
+            if (LINE) {
+                const int q1 = min(q1_0 + kk, ks.N1 - 1);
+                p = sp.P1[(size_t)sp.ra[R] * ks.N1 + q1];
+            } else if (fp.direct) {
+                double k1, k2, k3; mesh_k(ks, kclamp(kk), k1, k2, k3);
                 const double x = 2.0 * (k1 * fp.Rf[3 * R] + k2 * fp.Rf[3 * R + 1] + k3 * fp.Rf[3 * R + 2]);
                 double s, cc; sincospi(x, &s, &cc);
                 p = make_double2(cc, s);
@@ -96,7 +124,8 @@ fourier_dense_kernel(const FourierPlan fp, const DevModel m, const KSource ks, d
             }
             S.ph[b][r][kk] = p;
         }
-        if (tid < F_RC * 3) { const int r = tid / 3, a = tid % 3; S.cw[b][r][a] = fp.cR[3 * (c * F_RC + r) + a]; }
+        if (LINE) { if (tid < F_RC * 4) { const int r = tid / 4, a = tid % 4; S.cw[b][r][a] = sp.cw4[4 * (c * F_RC + r) + a]; } }
+        else if (tid < F_RC * 3) { const int r = tid / 3, a = tid % 3; S.cw[b][r][a] = fp.cR[3 * (c * F_RC + r) + a]; }
     };
 
     double2 hk[4][2], g[3][4][2];
@@ -118,6 +147,7 @@ fourier_dense_kernel(const FourierPlan fp, const DevModel m, const KSource ks, d
 #pragma unroll 2
         for (int r = 0; r < F_RC; ++r) {
             const double c0 = S.cw[b][r][0], c1 = S.cw[b][r][1], c2 = S.cw[b][r][2];
+            const double ch = LINE ? S.cw[b][r][3] : 1.0;
             double2 p[4], h[2];
 #pragma unroll
             for (int j = 0; j < 4; ++j) p[j] = S.ph[b][r][wk * 32 + lk + 8 * j];
@@ -129,7 +159,8 @@ fourier_dense_kernel(const FourierPlan fp, const DevModel m, const KSource ks, d
                 for (int e = 0; e < 2; ++e) {
                     const double tx = fma(p[j].x, h[e].x, -(p[j].y * h[e].y));
                     const double ty = fma(p[j].x, h[e].y, p[j].y * h[e].x);
-                    hk[j][e].x += tx; hk[j][e].y += ty;
+                    if (LINE) { hk[j][e].x = fma(ch, tx, hk[j][e].x); hk[j][e].y = fma(ch, ty, hk[j][e].y); }
+                    else { hk[j][e].x += tx; hk[j][e].y += ty; }
                     g[0][j][e].x = fma(c0, tx, g[0][j][e].x); g[0][j][e].y = fma(c0, ty, g[0][j][e].y);
                     g[1][j][e].x = fma(c1, tx, g[1][j][e].x); g[1][j][e].y = fma(c1, ty, g[1][j][e].y);
                     g[2][j][e].x = fma(c2, tx, g[2][j][e].x); g[2][j][e].y = fma(c2, ty, g[2][j][e].y);
@@ -143,8 +174,7 @@ fourier_dense_kernel(const FourierPlan fp, const DevModel m, const KSource ks, d
     if (has_tau) {
         for (int idx = tid; idx < F_TK * nw; idx += F_THREADS) {
             const int kk = idx / nw, n = idx % nw;
-            long long ik = k0 + kk; if (ik >= ks.nk) ik = ks.nk - 1;
-            double k1, k2, k3; mesh_k(ks, ik, k1, k2, k3);
+            double k1, k2, k3; mesh_k(ks, kclamp(kk), k1, k2, k3);
             double s, c; sincospi(2.0 * (k1 * m.tau[3 * n] + k2 * m.tau[3 * n + 1] + k3 * m.tau[3 * n + 2]), &s, &c);
             dn[idx] = make_double2(c, s);
         }
@@ -159,8 +189,8 @@ fourier_dense_kernel(const FourierPlan fp, const DevModel m, const KSource ks, d
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int kk = wk * 32 + lk + 8 * j;
-            const long long ik = k0 + kk;
-            if (ik >= ks.nk) continue;
+            if (!kvalid(kk)) continue;
+            const long long ik = kbase + kk;
             double2 h0 = hk[j][e];
             double2 ga[3];
 #pragma unroll
@@ -184,6 +214,63 @@ fourier_dense_kernel(const FourierPlan fp, const DevModel m, const KSource ks, d
                 for (int a = 0; a < 3; ++a) Hka_out[((size_t)ik * 3 + a) * nw2 + mm + nw * n] = cconj(ga[a]);
             }
         }
+    }
+}
+
+// ---- mesh-separable transform, stages A and B (cheap: O(nR nel) per mesh plane, O(n1 n2 nel) per mesh line) ----
+__global__ void phase_table_kernel(double2 *__restrict__ P, const double *__restrict__ u, int n, int N) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * N) return;
+    const int a = idx / N, q = idx % N + 1;
+    const double k = (2.0 * (double)q - (double)N - 1.0) / (2.0 * (double)N);                   // k_space.f90:351-375
+    double s, c; sincospi(2.0 * k * u[a], &s, &c);
+    P[idx] = make_double2(c, s);
+}
+
+__global__ void __launch_bounds__(256)
+sep_stage_a_kernel(const FourierPlan fp, const SepPlan sp, const int N3) {
+    const int n12 = sp.n1 * sp.n2;
+    const long long total = (long long)sp.nq3 * n12 * sp.nelp;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int el = (int)(idx % sp.nelp);
+        const int ab = (int)((idx / sp.nelp) % n12);
+        const int qi = (int)(idx / ((long long)sp.nelp * n12));
+        const int q3 = min(sp.q3_0 + qi, N3 - 1);
+        const double2 *Hel = fp.Hp + (size_t)(el / F_TN) * fp.nRp * F_TN + (el % F_TN);
+        double2 g0 = make_double2(0.0, 0.0), g1 = g0;
+        for (int c = 0; c < sp.n3; ++c) {
+            const int R = sp.map3[ab * sp.n3 + c];
+            if (R < 0) continue;
+            const double2 t = cmul(sp.P3[(size_t)c * N3 + q3], Hel[(size_t)R * F_TN]);
+            g0 = cadd(g0, t);
+            g1.x = fma(sp.u3[c], t.x, g1.x); g1.y = fma(sp.u3[c], t.y, g1.y);
+        }
+        double2 *o = sp.G1 + ((size_t)(qi * n12 + ab) * 2) * sp.nelp + el;
+        o[0] = g0; o[sp.nelp] = g1;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+sep_stage_b_kernel(const FourierPlan fp, const SepPlan sp, const int N2) {
+    const long long total = (long long)sp.nlines * sp.nrp * sp.nelp;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int el = (int)(idx % sp.nelp);
+        const int r = (int)((idx / sp.nelp) % sp.nrp);
+        const int li = (int)(idx / ((long long)sp.nelp * sp.nrp));
+        double2 acc = make_double2(0.0, 0.0);
+        if (r < 3 * sp.n1) {
+            const int t = r / sp.n1, a = r % sp.n1;
+            const long long line = sp.line0 + li;
+            const int q2 = (int)(line % N2);
+            const int qi = (int)(line / N2) - sp.q3_0;
+            const double2 *src = sp.G1 + ((size_t)(qi * sp.n1 * sp.n2 + a * sp.n2) * 2 + (t == 2 ? 1 : 0)) * sp.nelp + el;
+            for (int b = 0; b < sp.n2; ++b) {
+                const double2 tt = cmul(sp.P2[(size_t)b * N2 + q2], src[(size_t)b * 2 * sp.nelp]);
+                const double w = (t == 1) ? sp.u2[b] : 1.0;
+                acc.x = fma(w, tt.x, acc.x); acc.y = fma(w, tt.y, acc.y);
+            }
+        }
+        sp.G2[(((size_t)li * fp.ntiles + el / F_TN) * sp.nrp + r) * F_TN + (el % F_TN)] = acc;
     }
 }
 
@@ -719,10 +806,44 @@ size_t fourier_dense_smem(const FourierPlan &fp, int nw, bool has_tau) {
 cudaError_t launch_fourier_dense(const FourierPlan &fp, const DevModel &m, const KSource &ks, double2 *Hk, double2 *Hka,
                                  cudaStream_t st) {
     const size_t smem = fourier_dense_smem(fp, m.nw, m.tau != nullptr);
-    cudaError_t e = cudaFuncSetAttribute(fourier_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(fourier_dense_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((unsigned)((ks.nk + F_TK - 1) / F_TK), (unsigned)fp.ntiles);
-    fourier_dense_kernel<<<grid, F_THREADS, smem, st>>>(fp, m, ks, Hk, Hka);
+    SepPlan sp; sp.on = 0;
+    fourier_dense_kernel<false><<<grid, F_THREADS, smem, st>>>(fp, sp, m, ks, Hk, Hka);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_phase_table(double2 *P, const double *u, int n, int N, cudaStream_t st) {
+    phase_table_kernel<<<(n * N + 255) / 256, 256, 0, st>>>(P, u, n, N);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fourier_mesh(const FourierPlan &fp, SepPlan sp, const DevModel &m, const KSource &ks, double2 *Hk,
+                                double2 *Hka, cudaStream_t st) {
+    if (ks.nk <= 0) return cudaSuccess;
+    const long long lin_end = ks.lin_begin + ks.nk - 1;
+    sp.line0 = ks.lin_begin / ks.N1;
+    sp.nlines = (int)(lin_end / ks.N1 - sp.line0 + 1);
+    sp.q3_0 = (int)(sp.line0 / ks.N2);
+    sp.nq3 = (int)((sp.line0 + sp.nlines - 1) / ks.N2) - sp.q3_0 + 1;
+    {
+        const long long total = (long long)sp.nq3 * sp.n1 * sp.n2 * sp.nelp;
+        const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 32);
+        sep_stage_a_kernel<<<grid, 256, 0, st>>>(fp, sp, ks.N3);
+    }
+    {
+        const long long total = (long long)sp.nlines * sp.nrp * sp.nelp;
+        const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 32);
+        sep_stage_b_kernel<<<grid, 256, 0, st>>>(fp, sp, ks.N2);
+    }
+    FourierPlan f0 = fp; f0.direct = 1; f0.utot = 0;        // no per-axis tables in shared memory
+    const size_t smem = fourier_dense_smem(f0, m.nw, m.tau != nullptr);
+    cudaError_t e = cudaFuncSetAttribute(fourier_dense_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int ktl = (ks.N1 + F_TK - 1) / F_TK;
+    dim3 grid((unsigned)(ktl * sp.nlines), (unsigned)fp.ntiles);
+    fourier_dense_kernel<true><<<grid, F_THREADS, smem, st>>>(fp, sp, m, ks, Hk, Hka);
     return cudaGetLastError();
 }
 

@@ -175,6 +175,26 @@ def test_general_path_fourier_and_eigen(libmepb, name):
         assert rel_err(V, V_r) < 1e-13
 
 
+@pytest.mark.parametrize("name", list(CASES_LARGE) + ["femn_all_jobs_T300_neF3_ragged", "syn_nw8_tb_cart_velo"])
+def test_general_path_mesh_separable_fourier(libmepb, name):
+    """Mesh mode of the general path: the axis-by-axis (separable) Fourier transform on Monkhorst-Pack points equals the
+    oracle's nR-term sums element-wise (1e-13), on a ragged range that starts and ends inside mesh lines."""
+    (model, params), force = _case(name)
+    N1, N2, N3 = params.mp_grid
+    nk_mesh = N1 * N2 * N3
+    b0, b1 = min(2, nk_mesh - 1), nk_mesh - min(1, nk_mesh - 2)
+    q = np.arange(b0, b1)
+    kp = np.stack([(2.0 * (q % N1 + 1) - N1 - 1) / (2.0 * N1), (2.0 * ((q // N1) % N2 + 1) - N2 - 1) / (2.0 * N2),
+                   (2.0 * (q // (N1 * N2) + 1) - N3 - 1) / (2.0 * N3)], axis=1)                  # k_space.f90:351-375
+    _, _, Hk_r, Hka_r = cpu_ref.Handle(model, params).interp(kp, want_V=True, want_H=True)
+    with force_path(force):
+        ctx = libmepb.Context(model, params)
+    Hk, Hka = ctx.fourier_mesh(b0, b1 - b0)
+    ctx.close()
+    assert rel_err(Hk, Hk_r) < 1e-13
+    assert rel_err(Hka, Hka_r) < 1e-13
+
+
 @pytest.mark.parametrize("name", list(CASES_LARGE) + FORCED_LARGE)
 def test_general_path_run_mesh_parity(libmepb, name):
     (model, params), force = _case(name)
