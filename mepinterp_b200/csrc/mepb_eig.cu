@@ -10,6 +10,18 @@
 //      (conflict-free LDS.128/STS.128)
 //   3. writes the ascending eigenvalues and the matching eigenvector columns to HBM for the band-sum kernel.
 // The rotation formulas are those of the warp-per-k solver in mepb_small.cu (validated against zheevd to 1e-15).
+//
+// Default solver since r01h: HOUSEHOLDER + IMPLICIT QL, still one thread per k and every index a compile-time constant:
+//   a. zhetd2('L') arithmetic on the register-resident lower triangle (reflector + p = tau A v + rank-2 update per column);
+//      the reflectors (v_s, tau_s) are parked in shared memory ([slot][thread], 448 B per thread at nw = 8)
+//   b. implicit-shift QL (EISPACK tql2 recurrence) on (d, e) with the REAL eigenvector matrix Z of the tridiagonal in
+//      registers: the chase over planes i = m-1 .. l is unrolled over all planes and each plane guarded by (l <= i < m),
+//      so a warp skips the planes none of its threads needs; dynamic d[l], e[l], d[m] accesses are select chains
+//   c. back-transformation u_j = H_0 H_1 ... H_{n-2} z_j one column at a time, written at its ascending rank.
+// ~4x fewer FP64 instructions than the cyclic Jacobi (6 sweeps x 7 rounds x ~1000 DFMA); Jacobi stays selectable with
+// MEPB_SMALL_EIG=jacobi (it is the independent cross-check of the parity tests).
+#include <cstdlib>
+#include <string>
 #include "mepb_internal.cuh"
 
 namespace mepb {
@@ -103,6 +115,62 @@ __device__ __forceinline__ void tournament_permute(double (&ar)[NW][NW], double 
     }
 }
 
+// k-point of the launch (k_space.f90:351-375) and the upper triangle of H(k) (wann_interp.f90:206-279), in registers
+template <int NW>
+__device__ __forceinline__ void fourier_upper(const DevModel &m, const KSource &ks, const long long ik, const int nR,
+                                              const bool has_tau, double (&ar)[NW][NW], double (&ai)[NW][NW]) {
+    constexpr int NW2 = NW * NW;
+    // ------------------------------------------------------------------ k-point (k_space.f90:351-375)
+    double k1, k2, k3;
+    if (ks.list) { k1 = ks.list[3 * ik]; k2 = ks.list[3 * ik + 1]; k3 = ks.list[3 * ik + 2]; }
+    else {
+        const long long lin = ks.lin_begin + ik;
+        long long q1, q2, q3;
+        if (lin < 0x7fffffffLL) {     // 32-bit divisions (a 64-bit one is ~60 instructions)
+            const unsigned l32 = (unsigned)lin, n1 = (unsigned)ks.N1, n2 = (unsigned)ks.N2;
+            const unsigned t = l32 / n1;
+            q1 = l32 - t * n1 + 1; const unsigned t2 = t / n2; q2 = t - t2 * n2 + 1; q3 = t2 + 1;
+        } else { q1 = lin % ks.N1 + 1; q2 = (lin / ks.N1) % ks.N2 + 1; q3 = lin / ((long long)ks.N1 * ks.N2) + 1; }
+        k1 = (2.0 * (double)q1 - (double)ks.N1 - 1.0) / (2.0 * (double)ks.N1);
+        k2 = (2.0 * (double)q2 - (double)ks.N2 - 1.0) / (2.0 * (double)ks.N2);
+        k3 = (2.0 * (double)q3 - (double)ks.N3 - 1.0) / (2.0 * (double)ks.N3);
+    }
+    // ------------------------------------------------------------------ Fourier sum, upper triangle (zheevd 'U')
+#pragma unroll
+    for (int p = 0; p < NW; ++p)
+#pragma unroll
+        for (int q = 0; q < NW; ++q) { ar[p][q] = 0.0; ai[p][q] = 0.0; }
+    for (int R = 0; R < nR; ++R) {
+        const double x = 2.0 * (k1 * __ldg(&m.Rf[3 * R]) + k2 * __ldg(&m.Rf[3 * R + 1]) + k3 * __ldg(&m.Rf[3 * R + 2]));
+        double s, c; sincospi(x, &s, &c);
+        const double2 *HR = m.H + (size_t)R * NW2;
+#pragma unroll
+        for (int q = 0; q < NW; ++q)
+#pragma unroll
+            for (int p = 0; p <= q; ++p) {
+                const double2 h = __ldg(&HR[p + NW * q]);
+                ar[p][q] = fma(c, h.x, ar[p][q]); ar[p][q] = fma(-s, h.y, ar[p][q]);
+                if (p != q) { ai[p][q] = fma(c, h.y, ai[p][q]); ai[p][q] = fma(s, h.x, ai[p][q]); }
+            }
+    }
+    if (has_tau) {   // tight-binding convention: H(n,m) <- conj(d_n) H(n,m) d_m, d_n = e^{2 pi i k.tau_n}
+        double dr[NW], di[NW];
+#pragma unroll
+        for (int n = 0; n < NW; ++n) {
+            const double x = 2.0 * (k1 * __ldg(&m.tau[3 * n]) + k2 * __ldg(&m.tau[3 * n + 1]) + k3 * __ldg(&m.tau[3 * n + 2]));
+            sincospi(x, &di[n], &dr[n]);
+        }
+#pragma unroll
+        for (int q = 0; q < NW; ++q)
+#pragma unroll
+            for (int p = 0; p < q; ++p) {
+                const double wr = dr[q] * dr[p] + di[q] * di[p], wi = di[q] * dr[p] - dr[q] * di[p];   // d_q conj(d_p)
+                const double hr = ar[p][q], hi = ai[p][q];
+                ar[p][q] = hr * wr - hi * wi; ai[p][q] = hr * wi + hi * wr;
+            }
+    }
+}
+
 template <int NW>
 __global__ void __launch_bounds__(EigCfg<NW>::TPB, 1)
 eig_small_kernel(const DevModel m, const KSource ks, double *__restrict__ E_out, double2 *__restrict__ U_out,
@@ -114,56 +182,8 @@ eig_small_kernel(const DevModel m, const KSource ks, double *__restrict__ E_out,
     const bool has_tau = (m.tau != nullptr);
 
     for (long long ik = (long long)blockIdx.x * TPB + tid; ik < ks.nk; ik += (long long)gridDim.x * TPB) {
-        // ------------------------------------------------------------------ k-point (k_space.f90:351-375)
-        double k1, k2, k3;
-        if (ks.list) { k1 = ks.list[3 * ik]; k2 = ks.list[3 * ik + 1]; k3 = ks.list[3 * ik + 2]; }
-        else {
-            const long long lin = ks.lin_begin + ik;
-            long long q1, q2, q3;
-            if (lin < 0x7fffffffLL) {     // 32-bit divisions (a 64-bit one is ~60 instructions)
-                const unsigned l32 = (unsigned)lin, n1 = (unsigned)ks.N1, n2 = (unsigned)ks.N2;
-                const unsigned t = l32 / n1;
-                q1 = l32 - t * n1 + 1; const unsigned t2 = t / n2; q2 = t - t2 * n2 + 1; q3 = t2 + 1;
-            } else { q1 = lin % ks.N1 + 1; q2 = (lin / ks.N1) % ks.N2 + 1; q3 = lin / ((long long)ks.N1 * ks.N2) + 1; }
-            k1 = (2.0 * (double)q1 - (double)ks.N1 - 1.0) / (2.0 * (double)ks.N1);
-            k2 = (2.0 * (double)q2 - (double)ks.N2 - 1.0) / (2.0 * (double)ks.N2);
-            k3 = (2.0 * (double)q3 - (double)ks.N3 - 1.0) / (2.0 * (double)ks.N3);
-        }
-        // ------------------------------------------------------------------ Fourier sum, upper triangle (zheevd 'U')
         double ar[NW][NW], ai[NW][NW];                         // [p][q], p <= q used
-#pragma unroll
-        for (int p = 0; p < NW; ++p)
-#pragma unroll
-            for (int q = 0; q < NW; ++q) { ar[p][q] = 0.0; ai[p][q] = 0.0; }
-        for (int R = 0; R < nR; ++R) {
-            const double x = 2.0 * (k1 * __ldg(&m.Rf[3 * R]) + k2 * __ldg(&m.Rf[3 * R + 1]) + k3 * __ldg(&m.Rf[3 * R + 2]));
-            double s, c; sincospi(x, &s, &c);
-            const double2 *HR = m.H + (size_t)R * NW2;
-#pragma unroll
-            for (int q = 0; q < NW; ++q)
-#pragma unroll
-                for (int p = 0; p <= q; ++p) {
-                    const double2 h = __ldg(&HR[p + NW * q]);
-                    ar[p][q] = fma(c, h.x, ar[p][q]); ar[p][q] = fma(-s, h.y, ar[p][q]);
-                    if (p != q) { ai[p][q] = fma(c, h.y, ai[p][q]); ai[p][q] = fma(s, h.x, ai[p][q]); }
-                }
-        }
-        if (has_tau) {   // tight-binding convention: H(n,m) <- conj(d_n) H(n,m) d_m, d_n = e^{2 pi i k.tau_n}
-            double dr[NW], di[NW];
-#pragma unroll
-            for (int n = 0; n < NW; ++n) {
-                const double x = 2.0 * (k1 * __ldg(&m.tau[3 * n]) + k2 * __ldg(&m.tau[3 * n + 1]) + k3 * __ldg(&m.tau[3 * n + 2]));
-                sincospi(x, &di[n], &dr[n]);
-            }
-#pragma unroll
-            for (int q = 0; q < NW; ++q)
-#pragma unroll
-                for (int p = 0; p < q; ++p) {
-                    const double wr = dr[q] * dr[p] + di[q] * di[p], wi = di[q] * dr[p] - dr[q] * di[p];   // d_q conj(d_p)
-                    const double hr = ar[p][q], hi = ai[p][q];
-                    ar[p][q] = hr * wr - hi * wi; ai[p][q] = hr * wi + hi * wr;
-                }
-        }
+        fourier_upper<NW>(m, ks, ik, nR, has_tau, ar, ai);
         // ------------------------------------------------------------------ Jacobi
         double nrm = 0.0;
 #pragma unroll
@@ -267,12 +287,248 @@ cudaError_t launch_eig_t(const DevModel &m, const KSource &ks, double *E_out, do
     return cudaGetLastError();
 }
 
+// ================================================================================================ Householder + QL
+template <int NW> struct HqCfg {
+    static constexpr int TPB = 256;
+    static constexpr int NV = (NW - 1) * (NW - 2) / 2;     // parked reflector entries v_s(r), r >= s+2
+    static constexpr int SLOTS = NV + (NW - 1);            // + tau_s
+    __host__ __device__ static constexpr int voff(int s) { return s * (NW - 2) - s * (s - 1) / 2; }   // first slot of v_s
+};
+
+// implicit-shift QL on the real symmetric tridiagonal (d, e) (e[i] couples i and i+1, e[NW-1] is scratch), Z <- Z * rotations.
+// EISPACK tql2 recurrence; the same arithmetic as tql_kernel in mepb_tri.cu.
+template <int NW>
+__device__ __forceinline__ bool tql_regs(double (&d)[NW], double (&e)[NW], double (&z)[NW][NW]) {
+    const double eps = 1.1102230246251565e-16;
+    int l = 0, iter = 0;
+    while (l < NW - 1) {
+        int m = NW - 1;                                       // smallest m >= l with a negligible e[m]
+#pragma unroll
+        for (int i = NW - 2; i >= 0; --i) {
+            const bool small = fabs(e[i]) <= eps * (fabs(d[i]) + fabs(d[i + 1]));
+            if (i >= l && small) m = i;
+        }
+        if (m == l) { ++l; iter = 0; continue; }
+        if (++iter > 60) return false;
+        double dl = d[0], dl1 = d[1], el = e[0], dm = d[NW - 1];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            if (i == l) { dl = d[i]; el = e[i]; }
+            if (i == l + 1) dl1 = d[i];
+            if (i == m) dm = d[i];
+        }
+        double g = (dl1 - dl) / (2.0 * el);
+        double r = sqrt(fma(g, g, 1.0));
+        g = dm - dl + el / (g + copysign(r, g));
+        double s = 1.0, c = 1.0, p = 0.0;
+        bool brk = false;
+#pragma unroll
+        for (int i = NW - 2; i >= 0; --i) {
+            if (i < m && i >= l && !brk) {
+                const double f = s * e[i], b = c * e[i];
+                const double hh = fma(f, f, g * g);
+                if (!(hh > 1e-290)) {                         // r == 0: deflate here
+                    e[i + 1] = 0.0; d[i + 1] -= p; brk = true;
+                } else {
+                    const double rr = fast_rsqrt3(hh);
+                    e[i + 1] = hh * rr;
+                    s = f * rr; c = g * rr;
+                    g = d[i + 1] - p;
+                    r = fma(d[i] - g, s, 2.0 * c * b);
+                    p = s * r;
+                    d[i + 1] = g + p;
+                    g = fma(c, r, -b);
+#pragma unroll
+                    for (int k = 0; k < NW; ++k) {
+                        const double zf = z[k][i + 1], zi = z[k][i];
+                        z[k][i + 1] = fma(s, zi, c * zf);
+                        z[k][i] = fma(c, zi, -(s * zf));
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            if (i == m) e[i] = 0.0;
+            if (i == l && !brk) { d[i] -= p; e[i] = g; }
+        }
+    }
+    return true;
+}
+
+template <int NW>
+__global__ void __launch_bounds__(HqCfg<NW>::TPB, 1)
+eig_small_hq_kernel(const DevModel m, const KSource ks, double *__restrict__ E_out, double2 *__restrict__ U_out,
+                    int *__restrict__ err_flag) {
+    using Cfg = HqCfg<NW>;
+    constexpr int TPB = Cfg::TPB, NW2 = NW * NW;
+    extern __shared__ __align__(16) double2 park[];          // [SLOTS][TPB]
+    const int tid = threadIdx.x;
+    const int nR = m.nR;
+    const bool has_tau = (m.tau != nullptr);
+    double2 *pk = park + tid;
+
+    for (long long ik = (long long)blockIdx.x * TPB + tid; ik < ks.nk; ik += (long long)gridDim.x * TPB) {
+        double d[NW], e[NW];
+        bool ok = true;
+        {
+            // lower triangle L(r,c), r >= c, from the upper one the Fourier sum fills (zheevd 'U': only it is referenced)
+            double lr[NW][NW], li[NW][NW];
+            {
+                double ar[NW][NW], ai[NW][NW];
+                fourier_upper<NW>(m, ks, ik, nR, has_tau, ar, ai);
+#pragma unroll
+                for (int r = 0; r < NW; ++r)
+#pragma unroll
+                    for (int c = 0; c <= r; ++c) { lr[r][c] = ar[c][r]; li[r][c] = (r == c) ? 0.0 : -ai[c][r]; }
+            }
+            // -------------------------------------------------------------- zhetd2('L'): T = Q^H A Q, Q = H_0 ... H_{n-2}
+#pragma unroll
+            for (int s = 0; s < NW - 1; ++s) {
+                const double alr = lr[s + 1][s], ali = li[s + 1][s];
+                double xn = 0.0;
+#pragma unroll
+                for (int r = s + 2; r < NW; ++r) xn = fma(lr[r][s], lr[r][s], fma(li[r][s], li[r][s], xn));
+                const bool ident = (xn == 0.0 && ali == 0.0);                    // zlarfg: H = 1
+                const double nrm = sqrt(fma(alr, alr, fma(ali, ali, xn)));
+                const double beta = ident ? alr : -copysign(nrm, alr);
+                const double rb = ident ? 0.0 : 1.0 / beta;
+                const double tr = (beta - alr) * rb, ti = -ali * rb;             // tau (0 when ident)
+                const double sr0 = alr - beta, den = fma(sr0, sr0, ali * ali);
+                const double rden = ident ? 0.0 : 1.0 / den;
+                const double scr = sr0 * rden, sci = -ali * rden;                // 1 / (alpha - beta)
+                double vr[NW], vi[NW];
+                vr[s + 1] = 1.0; vi[s + 1] = 0.0;
+#pragma unroll
+                for (int r = s + 2; r < NW; ++r) {
+                    vr[r] = fma(lr[r][s], scr, -(li[r][s] * sci));
+                    vi[r] = fma(lr[r][s], sci, li[r][s] * scr);
+                }
+                d[s] = lr[s][s]; e[s] = beta;
+                // p = tau A v
+                double pr[NW], pi[NW];
+#pragma unroll
+                for (int r = s + 1; r < NW; ++r) {
+                    double xr = 0.0, xi = 0.0;
+#pragma unroll
+                    for (int c = s + 1; c < NW; ++c) {
+                        const double a_r = (r >= c) ? lr[r][c] : lr[c][r];
+                        const double a_i = (r > c) ? li[r][c] : ((r == c) ? 0.0 : -li[c][r]);
+                        xr = fma(a_r, vr[c], xr); xi = fma(a_r, vi[c], xi);
+                        if (r != c) { xr = fma(-a_i, vi[c], xr); xi = fma(a_i, vr[c], xi); }
+                    }
+                    pr[r] = fma(tr, xr, -(ti * xi)); pi[r] = fma(tr, xi, ti * xr);
+                }
+                // alc = -1/2 tau (p^H v);  w = p + alc v
+                double dr_ = 0.0, di_ = 0.0;
+#pragma unroll
+                for (int r = s + 1; r < NW; ++r) {
+                    dr_ = fma(pr[r], vr[r], fma(pi[r], vi[r], dr_));
+                    di_ = fma(pr[r], vi[r], fma(-pi[r], vr[r], di_));
+                }
+                const double acr = -0.5 * fma(tr, dr_, -(ti * di_)), aci = -0.5 * fma(tr, di_, ti * dr_);
+#pragma unroll
+                for (int r = s + 1; r < NW; ++r) {
+                    const double wr = fma(acr, vr[r], fma(-aci, vi[r], pr[r]));
+                    const double wi = fma(acr, vi[r], fma(aci, vr[r], pi[r]));
+                    pr[r] = wr; pi[r] = wi;
+                }
+                // A -= v w^H + w v^H   (lower triangle; the diagonal stays real)
+#pragma unroll
+                for (int r = s + 1; r < NW; ++r)
+#pragma unroll
+                    for (int c = s + 1; c <= r; ++c) {
+                        lr[r][c] -= fma(vr[r], pr[c], vi[r] * pi[c]) + fma(pr[r], vr[c], pi[r] * vi[c]);
+                        if (r != c) li[r][c] -= fma(vi[r], pr[c], -(vr[r] * pi[c])) + fma(pi[r], vr[c], -(pr[r] * vi[c]));
+                    }
+                // park the reflector
+#pragma unroll
+                for (int r = s + 2; r < NW; ++r) pk[(Cfg::voff(s) + (r - s - 2)) * TPB] = make_double2(vr[r], vi[r]);
+                pk[(Cfg::NV + s) * TPB] = make_double2(tr, ti);
+            }
+            d[NW - 1] = lr[NW - 1][NW - 1]; e[NW - 1] = 0.0;
+        }
+        // ------------------------------------------------------------------ implicit QL, Z in registers
+        double z[NW][NW];
+#pragma unroll
+        for (int r = 0; r < NW; ++r)
+#pragma unroll
+            for (int c = 0; c < NW; ++c) z[r][c] = (r == c) ? 1.0 : 0.0;
+        ok = tql_regs<NW>(d, e, z);
+        if (!ok) atomicExch(err_flag, 1);
+        // ------------------------------------------------------------------ ascending order (zheevd), ties by index
+        double *Eo = E_out + (size_t)ik * NW;
+        double2 *Uo = U_out + (size_t)ik * NW2;
+#pragma unroll
+        for (int j = 0; j < NW; ++j) {
+            const double ej = d[j];
+            int rank = 0;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) rank += (d[i] < ej || (d[i] == ej && i < j)) ? 1 : 0;
+            Eo[rank] = ej;
+            // u_j = H_0 H_1 ... H_{n-2} z_j
+            double xr[NW], xi[NW];
+#pragma unroll
+            for (int r = 0; r < NW; ++r) { xr[r] = z[r][j]; xi[r] = 0.0; }
+#pragma unroll
+            for (int s = NW - 2; s >= 0; --s) {
+                const double2 tau = pk[(Cfg::NV + s) * TPB];
+                double2 v[NW];
+#pragma unroll
+                for (int r = s + 2; r < NW; ++r) v[r] = pk[(Cfg::voff(s) + (r - s - 2)) * TPB];
+                double dtr = xr[s + 1], dti = xi[s + 1];                         // v^H x
+#pragma unroll
+                for (int r = s + 2; r < NW; ++r) {
+                    dtr = fma(v[r].x, xr[r], fma(v[r].y, xi[r], dtr));
+                    dti = fma(v[r].x, xi[r], fma(-v[r].y, xr[r], dti));
+                }
+                const double tr = fma(tau.x, dtr, -(tau.y * dti)), ti = fma(tau.x, dti, tau.y * dtr);
+                xr[s + 1] -= tr; xi[s + 1] -= ti;
+#pragma unroll
+                for (int r = s + 2; r < NW; ++r) {
+                    xr[r] -= fma(tr, v[r].x, -(ti * v[r].y));
+                    xi[r] -= fma(tr, v[r].y, ti * v[r].x);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < NW; ++r) Uo[r + NW * rank] = make_double2(xr[r], xi[r]);
+        }
+    }
+}
+
+template <int NW>
+cudaError_t launch_eig_hq_t(const DevModel &m, const KSource &ks, double *E_out, double2 *U_out, int *err_flag, int sm_count,
+                            cudaStream_t st) {
+    using Cfg = HqCfg<NW>;
+    const size_t smem = sizeof(double2) * Cfg::SLOTS * Cfg::TPB;
+    cudaError_t e = cudaFuncSetAttribute(eig_small_hq_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eig_small_hq_kernel<NW>, Cfg::TPB, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (ks.nk + Cfg::TPB - 1) / Cfg::TPB;
+    const long long cap = (long long)sm_count * per_sm;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    eig_small_hq_kernel<NW><<<(int)grid, Cfg::TPB, smem, st>>>(m, ks, E_out, U_out, err_flag);
+    return cudaGetLastError();
+}
+
 }  // namespace
 
 bool eig_thread_supported(int nw) { return nw == 4 || nw == 8; }
 
 cudaError_t launch_eig_small(const DevModel &m, const KSource &ks, double *E_out, double2 *U_out, int *err_flag, int sm_count,
                              cudaStream_t st) {
+    static const bool jacobi = [] { const char *e = getenv("MEPB_SMALL_EIG"); return e && std::string(e) == "jacobi"; }();
+    if (!jacobi) {
+        switch (m.nw) {
+            case 4: return launch_eig_hq_t<4>(m, ks, E_out, U_out, err_flag, sm_count, st);
+            case 8: return launch_eig_hq_t<8>(m, ks, E_out, U_out, err_flag, sm_count, st);
+            default: return cudaErrorInvalidValue;
+        }
+    }
     switch (m.nw) {
         case 4: return launch_eig_t<4>(m, ks, E_out, U_out, err_flag, sm_count, st);
         case 8: return launch_eig_t<8>(m, ks, E_out, U_out, err_flag, sm_count, st);
