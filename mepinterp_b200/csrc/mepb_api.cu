@@ -142,6 +142,8 @@ struct mepb_ctx {
     double Mmat[9];            // c_a(R) = sum_j Mmat[a + 3 j] R_j
     int *d_sp_ptr = nullptr, *d_sp_R = nullptr; double2 *d_sp_val = nullptr;   // sparse H(R) (warp-per-k Fourier sums)
     bool sparse = false; int sp_nnz = 0;
+    int *d_ell_R = nullptr; double2 *d_ell_val = nullptr; double *d_ell_x = nullptr; int ell_n = 0, ell_nR = 0;   // mepb_eig.cu
+    std::vector<double> h_Rf, h_tau;   // host copies (fractional R, centres) for rebuilding the sparse forms in update_model
     double a_latt[9];
     // device model
     double2 *d_H = nullptr; double *d_Rf = nullptr, *d_cR = nullptr, *d_tau = nullptr, *d_tM = nullptr, *d_hw = nullptr;
@@ -179,6 +181,8 @@ DevModel dev_model(const mepb_ctx *c) {
     m.nw = c->nw; m.nR = c->nR; m.H = c->d_H; m.Rf = c->d_Rf; m.cR = c->d_cR;
     m.tau = c->has_tau ? c->d_tau : nullptr; m.tM = c->d_tM;
     m.sp_ptr = c->sparse ? c->d_sp_ptr : nullptr; m.sp_R = c->d_sp_R; m.sp_val = c->d_sp_val; m.sp_nnz = c->sp_nnz;
+    m.ell_n = c->ell_n; m.ell_nR = c->ell_nR;
+    m.ell_R = (c->sparse && c->ell_n > 0) ? c->d_ell_R : nullptr; m.ell_val = c->d_ell_val; m.ell_x = c->d_ell_x;
     return m;
 }
 Jobs make_jobs(const mepb_ctx *c, int ief, bool response) {
@@ -376,12 +380,48 @@ cudaError_t build_sparse(mepb_ctx *c, const mepb_model *model) {
     if ((e = cudaMalloc((void **)&c->d_sp_val, sizeof(double2) * n)) != cudaSuccess) return e;
     if ((e = cudaMemcpy(c->d_sp_ptr, ptr.data(), sizeof(int) * ptr.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
     if ((e = cudaMemcpy(c->d_sp_R, col.data(), sizeof(int) * n, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
-    return cudaMemcpy(c->d_sp_val, val.data(), sizeof(double2) * n, cudaMemcpyHostToDevice);
+    if ((e = cudaMemcpy(c->d_sp_val, val.data(), sizeof(double2) * n, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+    // ELL form of the upper triangle over the compact list of used R points (thread-per-k eigensolver)
+    cudaFree(c->d_ell_R); cudaFree(c->d_ell_val); cudaFree(c->d_ell_x);
+    c->d_ell_R = nullptr; c->d_ell_val = nullptr; c->d_ell_x = nullptr; c->ell_n = 0; c->ell_nR = 0;
+    const int nw = c->nw, nel = nw * (nw + 1) / 2;
+    std::vector<int> rmap(nR, -1), used;
+    int emax = 0;
+    for (int q = 0; q < nw; ++q)
+        for (int pp = 0; pp <= q; ++pp) {
+            const int idx = pp + nw * q;
+            emax = std::max(emax, ptr[idx + 1] - ptr[idx]);
+            for (int t = ptr[idx]; t < ptr[idx + 1]; ++t)
+                if (rmap[col[t]] < 0) { rmap[col[t]] = (int)used.size(); used.push_back(col[t]); }
+        }
+    if (used.empty()) { used.push_back(0); rmap[0] = 0; }
+    // worth it only when the padded work (4 DFMA per slot) stays well below the dense loops (4 DFMA per (R, element))
+    if (emax == 0 || 3 * emax > nR || (int)c->h_Rf.size() != 3 * nR) return cudaSuccess;
+    std::vector<int> eR((size_t)emax * nel, 0);
+    std::vector<double2> eV((size_t)emax * nel, make_double2(0.0, 0.0));
+    int el = 0;
+    for (int q = 0; q < nw; ++q)
+        for (int pp = 0; pp <= q; ++pp, ++el) {
+            const int idx = pp + nw * q;
+            for (int t = ptr[idx], j = 0; t < ptr[idx + 1]; ++t, ++j) { eR[(size_t)j * nel + el] = rmap[col[t]]; eV[(size_t)j * nel + el] = val[t]; }
+        }
+    std::vector<double> ex;
+    for (int R : used) for (int a = 0; a < 3; ++a) ex.push_back(c->h_Rf[3 * R + a]);
+    if (c->has_tau) ex.insert(ex.end(), c->h_tau.begin(), c->h_tau.end());
+    if ((e = cudaMalloc((void **)&c->d_ell_R, sizeof(int) * eR.size())) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void **)&c->d_ell_val, sizeof(double2) * eV.size())) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void **)&c->d_ell_x, sizeof(double) * ex.size())) != cudaSuccess) return e;
+    if ((e = cudaMemcpy(c->d_ell_R, eR.data(), sizeof(int) * eR.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+    if ((e = cudaMemcpy(c->d_ell_val, eV.data(), sizeof(double2) * eV.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+    if ((e = cudaMemcpy(c->d_ell_x, ex.data(), sizeof(double) * ex.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+    c->ell_n = emax; c->ell_nR = (int)used.size();
+    return cudaSuccess;
 }
 
 void free_all(mepb_ctx *c) {
     cudaSetDevice(c->device);
     cudaFree(c->d_sp_ptr); cudaFree(c->d_sp_R); cudaFree(c->d_sp_val);
+    cudaFree(c->d_ell_R); cudaFree(c->d_ell_val); cudaFree(c->d_ell_x);
     cudaFree(c->d_H); cudaFree(c->d_Rf); cudaFree(c->d_cR); cudaFree(c->d_tau); cudaFree(c->d_tM); cudaFree(c->d_hw);
     for (auto &s : c->sb) {
         cudaFree(s.items_ahc); cudaFree(s.cnt_ahc); cudaFree(s.items_photo); cudaFree(s.cnt_photo);
@@ -507,6 +547,7 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
     for (int r = 0; r < nR; ++r) { for (int i = 0; i < 3; ++i) Rf[3 * r + i] = model->R[3 * r + i]; applyM(&model->R[3 * r], &cR[3 * r]); }
     if (c->has_tau)
         for (int n = 0; n < nw; ++n) { for (int i = 0; i < 3; ++i) tau[3 * n + i] = model->wf_centers[3 * n + i]; applyM(&tau[3 * n], &tM[3 * n]); }
+    c->h_Rf = Rf; c->h_tau = tau;
     auto up = [&](void **dst, const void *src, size_t bytes) -> cudaError_t {
         cudaError_t e = cudaMalloc(dst, bytes);
         if (e != cudaSuccess) return e;
@@ -521,7 +562,7 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
     CT(up((void **)&c->d_hw, c->hw_lst.data(), sizeof(double) * p.n_hw));
     CT(cudaMalloc((void **)&c->d_err, sizeof(int)));
     CT(cudaMemset(c->d_err, 0, sizeof(int)));
-    // schedule: chunk sized so the item buffers stay below ~768 MB per stream
+    // schedule: chunk (k-points per launch wave) sized from the HBM budget below
     c->max_pairs = nw * (nw - 1) / 2;
     c->max_photo = nw * (nw - 1);
     const long long nk_mesh = (long long)p.mp_grid[0] * p.mp_grid[1] * p.mp_grid[2];
@@ -537,14 +578,19 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
     if (c->tri) per_k += (size_t)tne * tne * (sizeof(double2) + sizeof(double)) + sizeof(double2) * tri_log_cap(tne) +
                          sizeof(unsigned int) * kTriHdrCap + (size_t)tne * 48;
     long long chunk = 1 << 18;
-    if (per_k) chunk = std::min<long long>(chunk, (long long)(((c->large ? 6144ull : 768ull) << 20) / per_k));
+    {   // per-stream budget for the per-k intermediates: an eighth of the free HBM, at most 8 GB (180 GB per B200; two streams)
+        size_t free_b = 0, total_b = 0;
+        CT(cudaMemGetInfo(&free_b, &total_b));
+        const size_t budget = std::max<size_t>(256ull << 20, std::min<size_t>(free_b / 8, (c->large ? 6144ull : 8192ull) << 20));
+        if (per_k) chunk = std::min<long long>(chunk, (long long)(budget / per_k));
+    }
     chunk = std::max<long long>(c->large ? 296 : 1024, std::min(chunk, std::max<long long>(nk_mesh, 1024)));
     c->chunk = chunk;
     if (!c->large) CT(build_sparse(c, model));
     c->grid_interp = c->large ? eig_large_grid(c->sm_count, chunk) : interp_small_grid(nw, nR, c->sm_count, chunk);
     if (c->use_sub) c->grid_interp = std::max(c->grid_interp, bands_sub_grid(nw, nR, c->sm_count, chunk));
-    c->grid_sweep = sweep_ahc_grid(c->sm_count, chunk, p.n_hw, &c->ns_sweep);
-    c->grid_photo = sweep_photo_grid(c->sm_count, chunk, p.n_hw, &c->ns_photo);
+    c->grid_sweep = sweep_ahc_grid(c->sm_count, chunk, p.n_hw, &c->ns_sweep, c->herm, c->max_pairs);
+    c->grid_photo = sweep_photo_grid(c->sm_count, chunk, p.n_hw, &c->ns_photo, c->max_photo);
     c->cs.ns = static_size(nw); c->cs.sweep = p.n_hw * kSweepAcc; c->cs.photo = p.n_hw * kPhotoAcc;
     c->cs.per_ef = c->cs.ns + c->cs.sweep + c->cs.photo;
     c->L = make_layout(p);
@@ -686,7 +732,7 @@ int mepb_accumulate(mepb_ctx *c, int64_t lin_begin, int64_t lin_end) {
               CUDA_TRY(launch_reduce_rows(s.block_static, gi, ns, s.compact + (size_t)ief * c->cs.per_ef, ns, 0, 0, s.st)); }
             c->launches += 1;
             if (jb.do_ahc) {
-                int nsl; const int gs = sweep_ahc_grid(c->sm_count, nk, p.n_hw, &nsl);
+                int nsl; const int gs = sweep_ahc_grid(c->sm_count, nk, p.n_hw, &nsl, c->herm, c->max_pairs);
                 { ProfScope ps(c, s.st, MEPB_PROF_SWEEP_AHC);
                   CUDA_TRY(launch_sweep_ahc(c->herm, s.items_ahc, s.cnt_ahc, c->max_pairs, nk, p.n_hw, c->d_hw, p.eta, s.block_sweep, gs, s.st)); }
                 const int nacc = c->herm ? kSweepAccH : kSweepAcc;          // Hermitian kernel fills X2,Y1 = slots [6,24)
@@ -696,7 +742,7 @@ int mepb_accumulate(mepb_ctx *c, int64_t lin_begin, int64_t lin_end) {
                 c->launches += 2;
             }
             if (jb.do_opt) {
-                int nsl; const int gs = sweep_photo_grid(c->sm_count, nk, p.n_hw, &nsl);
+                int nsl; const int gs = sweep_photo_grid(c->sm_count, nk, p.n_hw, &nsl, c->max_photo);
                 { ProfScope ps(c, s.st, MEPB_PROF_SWEEP_PHOTO);
                   CUDA_TRY(launch_sweep_photo(s.items_photo, s.cnt_photo, c->max_photo, nk, p.n_hw, c->d_hw, p.eta, s.block_photo, gs, s.st)); }
                 { ProfScope ps(c, s.st, MEPB_PROF_REDUCE);

@@ -118,7 +118,8 @@ __device__ __forceinline__ void tournament_permute(double (&ar)[NW][NW], double 
 // k-point of the launch (k_space.f90:351-375) and the upper triangle of H(k) (wann_interp.f90:206-279), in registers
 template <int NW>
 __device__ __forceinline__ void fourier_upper(const DevModel &m, const KSource &ks, const long long ik, const int nR,
-                                              const bool has_tau, double (&ar)[NW][NW], double (&ai)[NW][NW]) {
+                                              const bool has_tau, double (&ar)[NW][NW], double (&ai)[NW][NW],
+                                              double2 *phase = nullptr, const int pstride = 0) {
     constexpr int NW2 = NW * NW;
     // ------------------------------------------------------------------ k-point (k_space.f90:351-375)
     double k1, k2, k3;
@@ -140,6 +141,49 @@ __device__ __forceinline__ void fourier_upper(const DevModel &m, const KSource &
     for (int p = 0; p < NW; ++p)
 #pragma unroll
         for (int q = 0; q < NW; ++q) { ar[p][q] = 0.0; ai[p][q] = 0.0; }
+    if (phase) {
+        // sparse H(R) (FeMn: 110 of 1728 entries, 19 of 27 R points used): the phases of the used R points and of the
+        // centres tau_n go to this thread's shared-memory column in ONE rolled loop (a single inlined sincospi), then the
+        // padded element lists (ELL, warp-uniform) are summed slot by slot: per slot 36 independent (index, value, phase)
+        // loads and 4 DFMA each — no dependent pointer chasing, ~10x fewer DFMA than the dense loops
+        const int nx = m.ell_nR + (has_tau ? NW : 0);
+#pragma unroll 1
+        for (int R = 0; R < nx; ++R) {
+            const double x = 2.0 * (k1 * __ldg(&m.ell_x[3 * R]) + k2 * __ldg(&m.ell_x[3 * R + 1]) + k3 * __ldg(&m.ell_x[3 * R + 2]));
+            double s, c; sincospi(x, &s, &c);
+            phase[R * pstride] = make_double2(c, s);
+        }
+        constexpr int NEL = NW * (NW + 1) / 2;
+#pragma unroll 1
+        for (int j = 0; j < m.ell_n; ++j) {
+            const int *Rj = m.ell_R + j * NEL;
+            const double2 *Vj = m.ell_val + j * NEL;
+#pragma unroll
+            for (int q = 0; q < NW; ++q)
+#pragma unroll
+                for (int p = 0; p <= q; ++p) {
+                    const int el = q * (q + 1) / 2 + p;
+                    const double2 ph = phase[__ldg(Rj + el) * pstride];
+                    const double2 h = __ldg(Vj + el);
+                    ar[p][q] = fma(ph.x, h.x, ar[p][q]); ar[p][q] = fma(-ph.y, h.y, ar[p][q]);
+                    if (p != q) { ai[p][q] = fma(ph.x, h.y, ai[p][q]); ai[p][q] = fma(ph.y, h.x, ai[p][q]); }
+                }
+        }
+        if (has_tau) {   // H(n,m) <- conj(d_n) H(n,m) d_m, d_n = e^{2 pi i k.tau_n}
+            double dr[NW], di[NW];
+#pragma unroll
+            for (int n = 0; n < NW; ++n) { const double2 dn = phase[(m.ell_nR + n) * pstride]; dr[n] = dn.x; di[n] = dn.y; }
+#pragma unroll
+            for (int q = 0; q < NW; ++q)
+#pragma unroll
+                for (int p = 0; p < q; ++p) {
+                    const double wr = dr[q] * dr[p] + di[q] * di[p], wi = di[q] * dr[p] - dr[q] * di[p];   // d_q conj(d_p)
+                    const double hr = ar[p][q], hi = ai[p][q];
+                    ar[p][q] = hr * wr - hi * wi; ai[p][q] = hr * wi + hi * wr;
+                }
+        }
+        return;
+    }
     for (int R = 0; R < nR; ++R) {
         const double x = 2.0 * (k1 * __ldg(&m.Rf[3 * R]) + k2 * __ldg(&m.Rf[3 * R + 1]) + k3 * __ldg(&m.Rf[3 * R + 2]));
         double s, c; sincospi(x, &s, &c);
@@ -288,6 +332,7 @@ cudaError_t launch_eig_t(const DevModel &m, const KSource &ks, double *E_out, do
 }
 
 // ================================================================================================ Householder + QL
+constexpr int kEigSparseMaxR = 48;       // 48 x 16 B x 256 threads = 192 KB of shared memory
 template <int NW> struct HqCfg {
     static constexpr int TPB = 256;
     static constexpr int NV = (NW - 1) * (NW - 2) / 2;     // parked reflector entries v_s(r), r >= s+2
@@ -356,7 +401,7 @@ __device__ __forceinline__ bool tql_regs(double (&d)[NW], double (&e)[NW], doubl
     return true;
 }
 
-template <int NW>
+template <int NW, bool SPARSE>
 __global__ void __launch_bounds__(HqCfg<NW>::TPB, 1)
 eig_small_hq_kernel(const DevModel m, const KSource ks, double *__restrict__ E_out, double2 *__restrict__ U_out,
                     int *__restrict__ err_flag) {
@@ -376,7 +421,7 @@ eig_small_hq_kernel(const DevModel m, const KSource ks, double *__restrict__ E_o
             double lr[NW][NW], li[NW][NW];
             {
                 double ar[NW][NW], ai[NW][NW];
-                fourier_upper<NW>(m, ks, ik, nR, has_tau, ar, ai);
+                fourier_upper<NW>(m, ks, ik, nR, has_tau, ar, ai, SPARSE ? pk : nullptr, TPB);   // phases share the park
 #pragma unroll
                 for (int r = 0; r < NW; ++r)
 #pragma unroll
@@ -459,60 +504,79 @@ eig_small_hq_kernel(const DevModel m, const KSource ks, double *__restrict__ E_o
         // ------------------------------------------------------------------ ascending order (zheevd), ties by index
         double *Eo = E_out + (size_t)ik * NW;
         double2 *Uo = U_out + (size_t)ik * NW2;
+        // u_j = H_0 H_1 ... H_{n-2} z_j, two columns per pass (each reflector is read once per pair; two independent chains)
 #pragma unroll
-        for (int j = 0; j < NW; ++j) {
-            const double ej = d[j];
-            int rank = 0;
+        for (int j = 0; j < NW; j += 2) {
+            int rank[2];
 #pragma unroll
-            for (int i = 0; i < NW; ++i) rank += (d[i] < ej || (d[i] == ej && i < j)) ? 1 : 0;
-            Eo[rank] = ej;
-            // u_j = H_0 H_1 ... H_{n-2} z_j
-            double xr[NW], xi[NW];
+            for (int t = 0; t < 2; ++t) {
+                const double ej = d[j + t];
+                int rk = 0;
 #pragma unroll
-            for (int r = 0; r < NW; ++r) { xr[r] = z[r][j]; xi[r] = 0.0; }
+                for (int i = 0; i < NW; ++i) rk += (d[i] < ej || (d[i] == ej && i < j + t)) ? 1 : 0;
+                Eo[rk] = ej; rank[t] = rk;
+            }
+            double xr[2][NW], xi[2][NW];
+#pragma unroll
+            for (int r = 0; r < NW; ++r) { xr[0][r] = z[r][j]; xi[0][r] = 0.0; xr[1][r] = z[r][j + 1]; xi[1][r] = 0.0; }
 #pragma unroll
             for (int s = NW - 2; s >= 0; --s) {
                 const double2 tau = pk[(Cfg::NV + s) * TPB];
                 double2 v[NW];
 #pragma unroll
                 for (int r = s + 2; r < NW; ++r) v[r] = pk[(Cfg::voff(s) + (r - s - 2)) * TPB];
-                double dtr = xr[s + 1], dti = xi[s + 1];                         // v^H x
 #pragma unroll
-                for (int r = s + 2; r < NW; ++r) {
-                    dtr = fma(v[r].x, xr[r], fma(v[r].y, xi[r], dtr));
-                    dti = fma(v[r].x, xi[r], fma(-v[r].y, xr[r], dti));
-                }
-                const double tr = fma(tau.x, dtr, -(tau.y * dti)), ti = fma(tau.x, dti, tau.y * dtr);
-                xr[s + 1] -= tr; xi[s + 1] -= ti;
+                for (int t = 0; t < 2; ++t) {
+                    double dtr = xr[t][s + 1], dti = xi[t][s + 1];                   // v^H x
 #pragma unroll
-                for (int r = s + 2; r < NW; ++r) {
-                    xr[r] -= fma(tr, v[r].x, -(ti * v[r].y));
-                    xi[r] -= fma(tr, v[r].y, ti * v[r].x);
+                    for (int r = s + 2; r < NW; ++r) {
+                        dtr = fma(v[r].x, xr[t][r], fma(v[r].y, xi[t][r], dtr));
+                        dti = fma(v[r].x, xi[t][r], fma(-v[r].y, xr[t][r], dti));
+                    }
+                    const double tr = fma(tau.x, dtr, -(tau.y * dti)), ti = fma(tau.x, dti, tau.y * dtr);
+                    xr[t][s + 1] -= tr; xi[t][s + 1] -= ti;
+#pragma unroll
+                    for (int r = s + 2; r < NW; ++r) {
+                        xr[t][r] -= fma(tr, v[r].x, -(ti * v[r].y));
+                        xi[t][r] -= fma(tr, v[r].y, ti * v[r].x);
+                    }
                 }
             }
 #pragma unroll
-            for (int r = 0; r < NW; ++r) Uo[r + NW * rank] = make_double2(xr[r], xi[r]);
+            for (int t = 0; t < 2; ++t)
+#pragma unroll
+                for (int r = 0; r < NW; ++r) Uo[r + NW * rank[t]] = make_double2(xr[t][r], xi[t][r]);
         }
     }
 }
 
-template <int NW>
-cudaError_t launch_eig_hq_t(const DevModel &m, const KSource &ks, double *E_out, double2 *U_out, int *err_flag, int sm_count,
-                            cudaStream_t st) {
+template <int NW, bool SPARSE>
+cudaError_t launch_eig_hq_ts(const DevModel &m, const KSource &ks, double *E_out, double2 *U_out, int *err_flag, int sm_count,
+                             cudaStream_t st) {
     using Cfg = HqCfg<NW>;
-    const size_t smem = sizeof(double2) * Cfg::SLOTS * Cfg::TPB;
-    cudaError_t e = cudaFuncSetAttribute(eig_small_hq_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int nx = m.ell_nR + (m.tau ? NW : 0);                 // phase slots of the sparse Fourier sum (they share the park)
+    const int slots = (SPARSE && nx > Cfg::SLOTS) ? nx : Cfg::SLOTS;
+    const size_t smem = sizeof(double2) * slots * Cfg::TPB;
+    cudaError_t e = cudaFuncSetAttribute(eig_small_hq_kernel<NW, SPARSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eig_small_hq_kernel<NW>, Cfg::TPB, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eig_small_hq_kernel<NW, SPARSE>, Cfg::TPB, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     long long grid = (ks.nk + Cfg::TPB - 1) / Cfg::TPB;
     const long long cap = (long long)sm_count * per_sm;
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
-    eig_small_hq_kernel<NW><<<(int)grid, Cfg::TPB, smem, st>>>(m, ks, E_out, U_out, err_flag);
+    eig_small_hq_kernel<NW, SPARSE><<<(int)grid, Cfg::TPB, smem, st>>>(m, ks, E_out, U_out, err_flag);
     return cudaGetLastError();
+}
+template <int NW>
+cudaError_t launch_eig_hq_t(const DevModel &m, const KSource &ks, double *E_out, double2 *U_out, int *err_flag, int sm_count,
+                            cudaStream_t st) {
+    // sparse Fourier sum: the per-thread phase table must fit beside nothing else (it shares the reflector park)
+    const bool sparse = m.ell_R != nullptr && m.ell_nR + NW <= kEigSparseMaxR;
+    return sparse ? launch_eig_hq_ts<NW, true>(m, ks, E_out, U_out, err_flag, sm_count, st)
+                  : launch_eig_hq_ts<NW, false>(m, ks, E_out, U_out, err_flag, sm_count, st);
 }
 
 }  // namespace

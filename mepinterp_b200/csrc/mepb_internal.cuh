@@ -59,6 +59,14 @@ struct DevModel {
     const int *sp_R;     // [nnz] R index
     const double2 *sp_val;   // [nnz]
     int sp_nnz;
+    // padded (ELL) form of the UPPER triangle for the thread-per-k eigensolver (mepb_eig.cu): every element p <= q, in the
+    // order q-major / p-minor, has ell_n slots (R index into the compact list of R points that carry any entry, value);
+    // empty slots are (0, 0+0i).  ell_x = coordinates whose phases a thread needs: the ell_nR used R points, then
+    // (tight-binding convention) the nw centres tau_n.  nullptr -> dense loops.
+    int ell_n, ell_nR;
+    const int *ell_R;        // [ell_n][nw(nw+1)/2]
+    const double2 *ell_val;  // [ell_n][nw(nw+1)/2]
+    const double *ell_x;     // [ell_nR (+ nw)][3]
 };
 
 struct KSource {          // where the k-points of a launch come from
@@ -273,10 +281,20 @@ cudaError_t launch_eig_small(const DevModel &m, const KSource &ks, double *E_out
 
 cudaError_t launch_sweep_ahc(bool herm, const double *items, const int *cnt, int max_pairs, long long nk, int n_hw,
                              const double *hw, double eta, double *block_out, int grid, cudaStream_t st);
-int sweep_ahc_grid(int sm_count, long long nk, int n_hw, int *slots_out);
+int sweep_ahc_grid(int sm_count, long long nk, int n_hw, int *slots_out, bool herm, int max_pairs);
 cudaError_t launch_sweep_photo(const double *items, const int *cnt, int max_items, long long nk, int n_hw, const double *hw,
                                double eta, double *block_out, int grid, cudaStream_t st);
-int sweep_photo_grid(int sm_count, long long nk, int n_hw, int *slots_out);
+int sweep_photo_grid(int sm_count, long long nk, int n_hw, int *slots_out, int max_items);
+// tensor-core (DMMA) formulation of both sweeps (mepb_sweep_mma.cu), used for n_hw >= 16 unless MEPB_SWEEP_FMA is set
+struct MmaShape { int NT, G, wtiles, warps, passes; };     // tiles per warp, k-groups, warps per group, warps per CTA, grid.y
+constexpr int kMmaAhcWarps = 8, kMmaPhotoWarps = 14;
+MmaShape sweep_mma_shape(int n_hw, int wmax, int nt_max);
+bool sweep_mma_enabled(int n_hw);
+int sweep_ahc_mma_bps(bool herm, int NT);
+cudaError_t launch_sweep_ahc_mma(bool herm, const double *items, const int *cnt, int max_pairs, long long nk, int n_hw,
+                                 const double *hw, double eta, double *block_out, int grid, int KC, cudaStream_t st);
+cudaError_t launch_sweep_photo_mma(const double *items, const int *cnt, int max_items, long long nk, int n_hw, const double *hw,
+                                   double eta, double *block_out, int grid, cudaStream_t st);
 // out[(c / group) * out_stride + out_off + c % group] += sum_r in[r*cols + c]
 cudaError_t launch_reduce_rows(const double *in, int rows, int cols, double *out_accum, int group, int out_stride, int out_off,
                                cudaStream_t st);

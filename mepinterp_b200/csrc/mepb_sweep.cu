@@ -74,7 +74,7 @@ sweep_ahc_kernel(const double2 *__restrict__ items, const int *__restrict__ cnt,
 constexpr int kSweepStages = 3;
 
 template <bool HERM>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, HERM ? 3 : 2)
 sweep_ahc_staged_kernel(const double2 *__restrict__ items, const int *__restrict__ cnt, const int max_pairs, const long long nk,
                         const int n_hw, const double *__restrict__ hw, const double eta, double *__restrict__ block_out,
                         const int G, const int NS, const int KC) {
@@ -197,8 +197,11 @@ sweep_photo_kernel(const double2 *__restrict__ items, const int *__restrict__ cn
 }
 
 // ------------------------------------------------------------------------------------------------ staged photo sweep
-// One k-point (nw(nw-1) items x 448 bytes) per TMA stage; 256 frequency-threads per CTA (grid.y passes for more).
-__global__ void __launch_bounds__(256, 1)
+// One k-point (nw(nw-1) items x 448 bytes) per TMA stage; up to 256 threads per CTA, one CTA per SM (178 registers; two CTAs
+// of 224 threads at 128 registers measured 10 % slower, profiles/r01j): thread = (frequency, item group g of G) — the G
+// groups share a stage and split its items (grid.y passes for n_hw > 256).
+constexpr int kPhotoThreads = 256;
+__global__ void __launch_bounds__(kPhotoThreads, 1)
 sweep_photo_staged_kernel(const double2 *__restrict__ items, const int *__restrict__ cnt, const int max_items, const long long nk,
                           const int n_hw, const double *__restrict__ hw, const double eta, double *__restrict__ block_out,
                           const int G, const int NS) {
@@ -239,11 +242,11 @@ sweep_photo_staged_kernel(const double2 *__restrict__ items, const int *__restri
     for (int c = 0; c < nchunks; ++c) {
         const int st = c % kSweepStages;
         mbar_wait(&bar[st], (uint32_t)((c / kSweepStages) & 1));
-        if (active && (c % G) == g) {
+        if (active) {
             const unsigned char *base = stage0 + (size_t)st * stage_bytes;
-            const double2 *it = reinterpret_cast<const double2 *>(base);
+            const double2 *it = reinterpret_cast<const double2 *>(base) + (size_t)g * ISTR;
             const int n_it = reinterpret_cast<const int *>(base + item_bytes)[(kb0 + c) & 3];
-            for (int j = 0; j < n_it; ++j, it += ISTR) {
+            for (int j = g; j < n_it; j += G, it += (size_t)G * ISTR) {
                 const double xr = it[27].x;
                 // h = (1/w^2) * 2x/(x^2 - w^2),  x = xr - 2 i eta
                 const double a = xr * xr - e2 * e2 - om2, b = -2.0 * xr * e2;
@@ -295,10 +298,19 @@ void sweep_shape(int n_hw, int T, int *G, int *NS, int *threads) {
 
 }  // namespace
 
-int sweep_ahc_grid(int sm_count, long long nk, int n_hw, int *slots_out) {
+int sweep_ahc_kc(bool herm, int max_pairs);
+int sweep_ahc_grid(int sm_count, long long nk, int n_hw, int *slots_out, bool herm, int max_pairs) {
+    if (sweep_mma_enabled(n_hw) && !getenv("MEPB_SWEEP_DIRECT") && sweep_ahc_kc(herm, max_pairs) > 0) {
+        const MmaShape s = sweep_mma_shape(n_hw, kMmaAhcWarps, 4);
+        if (slots_out) *slots_out = s.G * n_hw;
+        long long g = (long long)sm_count * sweep_ahc_mma_bps(herm, s.NT);
+        const long long need = (nk + s.G - 1) / s.G;
+        if (g > need) g = need;
+        return (int)(g < 1 ? 1 : g);
+    }
     int G, NS, T; sweep_shape(n_hw, 256, &G, &NS, &T);
     if (slots_out) *slots_out = NS;
-    long long g = (long long)sm_count * 2;
+    long long g = (long long)sm_count * (herm ? 3 : 2);         // resident CTAs per SM of the staged kernel (80 / 128 registers)
     long long need = (nk + G - 1) / G;      // at least G k-points per block to give every group work
     if (g > need) g = need;
     if (g < 1) g = 1;
@@ -318,6 +330,8 @@ cudaError_t launch_sweep_ahc(bool herm, const double *items, const int *cnt, int
                              const double *hw, double eta, double *block_out, int grid, cudaStream_t st) {
     int G, NS, T; sweep_shape(n_hw, 256, &G, &NS, &T);
     const int KC = getenv("MEPB_SWEEP_DIRECT") ? 0 : sweep_ahc_kc(herm, max_pairs);
+    if (KC > 0 && sweep_mma_enabled(n_hw))
+        return launch_sweep_ahc_mma(herm, items, cnt, max_pairs, nk, n_hw, hw, eta, block_out, grid, KC, st);
     if (KC > 0) {
         const size_t item_bytes = sizeof(double) * (herm ? kAhcItemH : kAhcItemG) * (size_t)max_pairs * KC;
         const size_t stage_bytes = (item_bytes + 16 * ((KC * sizeof(int) + 15) / 16) + 127) / 128 * 128;
@@ -340,26 +354,34 @@ cudaError_t launch_sweep_ahc(bool herm, const double *items, const int *cnt, int
         sweep_ahc_kernel<false><<<grid, T, 0, st>>>(reinterpret_cast<const double2 *>(items), cnt, max_pairs, nk, n_hw, hw, eta, block_out, G, NS);
     return cudaGetLastError();
 }
-int sweep_photo_grid(int sm_count, long long nk, int n_hw, int *slots_out) {
-    int G, NS, T; sweep_shape(n_hw, 256, &G, &NS, &T);          // staged kernel shape; the direct kernel loops over its slots
+int sweep_photo_grid(int sm_count, long long nk, int n_hw, int *slots_out, int max_items) {
+    if (sweep_mma_enabled(n_hw) && !getenv("MEPB_SWEEP_DIRECT") && sizeof(double) * kPhotoItem * (size_t)max_items <= 64 * 1024) {
+        const MmaShape s = sweep_mma_shape(n_hw, kMmaPhotoWarps, 2);
+        if (slots_out) *slots_out = s.G * n_hw;
+        long long g = sm_count;                                  // one CTA of up to 448 threads per SM
+        if (g > nk) g = nk;
+        return (int)(g < 1 ? 1 : g);
+    }
+    int G, NS, T; sweep_shape(n_hw, kPhotoThreads, &G, &NS, &T);   // staged kernel shape; the direct kernel loops over its slots
     if (slots_out) *slots_out = NS;
     long long g = (long long)sm_count * 2;
-    long long need = (nk + G - 1) / G;
-    if (g > need) g = need;
+    if (g > nk) g = nk;
     if (g < 1) g = 1;
     return (int)g;
 }
 cudaError_t launch_sweep_photo(const double *items, const int *cnt, int max_items, long long nk, int n_hw, const double *hw,
                                double eta, double *block_out, int grid, cudaStream_t st) {
-    int G, NS, T; sweep_shape(n_hw, 256, &G, &NS, &T);          // same (G, NS) as sweep_photo_grid
+    int G, NS, T; sweep_shape(n_hw, kPhotoThreads, &G, &NS, &T);   // same (G, NS) as sweep_photo_grid
     const size_t item_bytes = sizeof(double) * kPhotoItem * (size_t)max_items;
+    if (!getenv("MEPB_SWEEP_DIRECT") && item_bytes <= 64 * 1024 && sweep_mma_enabled(n_hw))
+        return launch_sweep_photo_mma(items, cnt, max_items, nk, n_hw, hw, eta, block_out, grid, st);
     if (!getenv("MEPB_SWEEP_DIRECT") && item_bytes <= 64 * 1024) {
         const size_t stage_bytes = (item_bytes + 16 + 127) / 128 * 128;
         const size_t smem = 128 + kSweepStages * stage_bytes;
         cudaError_t e = cudaFuncSetAttribute(sweep_photo_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        sweep_photo_staged_kernel<<<dim3(grid, (NS + 255) / 256), 256, smem, st>>>(reinterpret_cast<const double2 *>(items), cnt, max_items, nk,
-                                                                                   n_hw, hw, eta, block_out, G, NS);
+        sweep_photo_staged_kernel<<<dim3(grid, (NS + T - 1) / T), T, smem, st>>>(reinterpret_cast<const double2 *>(items), cnt, max_items, nk,
+                                                                                 n_hw, hw, eta, block_out, G, NS);
         return cudaGetLastError();
     }
     if (T > 128) T = 128;                                        // direct kernel: 128 threads loop over the NS slots
