@@ -230,6 +230,9 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -287,9 +290,10 @@ cudaError_t launch_sweep_photo(const double *items, const int *cnt, int max_item
 int sweep_photo_grid(int sm_count, long long nk, int n_hw, int *slots_out, int max_items);
 // tensor-core (DMMA) formulation of both sweeps (mepb_sweep_mma.cu), used for n_hw >= 16 unless MEPB_SWEEP_FMA is set
 struct MmaShape { int NT, G, wtiles, warps, passes; };     // tiles per warp, k-groups, warps per group, warps per CTA, grid.y
-constexpr int kMmaAhcWarps = 8, kMmaPhotoWarps = 14;
+constexpr int kMmaAhcWarps = 8, kMmaPhotoWarps = 13;      // consumer warps per CTA (+ one TMA producer warp)
 MmaShape sweep_mma_shape(int n_hw, int wmax, int nt_max);
 bool sweep_mma_enabled(int n_hw);
+bool sweep_photo_mma_fits(int max_items);
 int sweep_ahc_mma_bps(bool herm, int NT);
 cudaError_t launch_sweep_ahc_mma(bool herm, const double *items, const int *cnt, int max_pairs, long long nk, int n_hw,
                                  const double *hw, double eta, double *block_out, int grid, int KC, cudaStream_t st);

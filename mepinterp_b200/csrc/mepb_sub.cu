@@ -232,15 +232,16 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
                         for (int j = 0; j < 3; ++j)
 #pragma unroll
                             for (int i = 0; i < 3; ++i) P[i + 3 * j] = cmul(vnm[i], vmn[j]);
+                        const double rdE = 1.0 / dE;                                        // unguarded like kubo.f90:65,186
                         if (valid && (f_n != 0.0 || f_m != 0.0 || dE == 0.0)) {          // kubo.f90:58-73, unguarded
-                            const double inv2 = 2.0 / (dE * dE);
+                            const double inv2 = 2.0 * rdE * rdE;
 #pragma unroll
                             for (int j = 0; j < 3; ++j)
 #pragma unroll
                                 for (int i = 0; i < 3; ++i) acc_ahc[i + 3 * j] += inv2 * (f_n * P[i + 3 * j].y + f_m * P[j + 3 * i].y);
                         }
                         if (fdm != 0.0 || dE == 0.0) {
-                            const double wa = fdm / dE;                                   // unguarded like kubo.f90:186
+                            const double wa = fdm * rdE;
                             item[0] = fma(dE, dE, jb.eta * jb.eta);
                             const int ai[3] = {0, 0, 1}, aj[3] = {1, 2, 2};
                             const int si[6] = {0, 1, 2, 0, 0, 1}, sj[6] = {0, 1, 2, 1, 2, 2};

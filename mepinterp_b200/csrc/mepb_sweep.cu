@@ -301,7 +301,7 @@ void sweep_shape(int n_hw, int T, int *G, int *NS, int *threads) {
 int sweep_ahc_kc(bool herm, int max_pairs);
 int sweep_ahc_grid(int sm_count, long long nk, int n_hw, int *slots_out, bool herm, int max_pairs) {
     if (sweep_mma_enabled(n_hw) && !getenv("MEPB_SWEEP_DIRECT") && sweep_ahc_kc(herm, max_pairs) > 0) {
-        const MmaShape s = sweep_mma_shape(n_hw, kMmaAhcWarps, 4);
+        const MmaShape s = sweep_mma_shape(n_hw, kMmaAhcWarps, herm ? 4 : 2);
         if (slots_out) *slots_out = s.G * n_hw;
         long long g = (long long)sm_count * sweep_ahc_mma_bps(herm, s.NT);
         const long long need = (nk + s.G - 1) / s.G;
@@ -355,7 +355,7 @@ cudaError_t launch_sweep_ahc(bool herm, const double *items, const int *cnt, int
     return cudaGetLastError();
 }
 int sweep_photo_grid(int sm_count, long long nk, int n_hw, int *slots_out, int max_items) {
-    if (sweep_mma_enabled(n_hw) && !getenv("MEPB_SWEEP_DIRECT") && sizeof(double) * kPhotoItem * (size_t)max_items <= 64 * 1024) {
+    if (sweep_mma_enabled(n_hw) && !getenv("MEPB_SWEEP_DIRECT") && sweep_photo_mma_fits(max_items)) {
         const MmaShape s = sweep_mma_shape(n_hw, kMmaPhotoWarps, 2);
         if (slots_out) *slots_out = s.G * n_hw;
         long long g = sm_count;                                  // one CTA of up to 448 threads per SM
@@ -373,7 +373,7 @@ cudaError_t launch_sweep_photo(const double *items, const int *cnt, int max_item
                                double eta, double *block_out, int grid, cudaStream_t st) {
     int G, NS, T; sweep_shape(n_hw, kPhotoThreads, &G, &NS, &T);   // same (G, NS) as sweep_photo_grid
     const size_t item_bytes = sizeof(double) * kPhotoItem * (size_t)max_items;
-    if (!getenv("MEPB_SWEEP_DIRECT") && item_bytes <= 64 * 1024 && sweep_mma_enabled(n_hw))
+    if (!getenv("MEPB_SWEEP_DIRECT") && sweep_photo_mma_fits(max_items) && sweep_mma_enabled(n_hw))
         return launch_sweep_photo_mma(items, cnt, max_items, nk, n_hw, hw, eta, block_out, grid, st);
     if (!getenv("MEPB_SWEEP_DIRECT") && item_bytes <= 64 * 1024) {
         const size_t stage_bytes = (item_bytes + 16 + 127) / 128 * 128;

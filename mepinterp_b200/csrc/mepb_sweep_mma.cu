@@ -13,8 +13,9 @@
 //   * components beyond a multiple of 8 (the 9th AHC weight, T(24..26) of the photo tensor) are accumulated per lane with
 //     plain DFMAs on the lane's own (item, frequency) and reduced over the 4 item lanes at the end.
 // DFMA and DMMA share one pipe on B200 (tools/fp64_mixed.cu: 37.1 TF each, 36 TF interleaved), so the gain is operand
-// bandwidth and issue slots, not peak.  Items stream through shared memory exactly as in the staged FMA kernels (TMA bulk
-// copies, 3-stage mbarrier ring, one elected producer thread).
+// bandwidth and issue slots, not peak.  Items stream through shared memory by TMA bulk copies into a ring of stages with
+// full/empty mbarriers: a dedicated producer warp refills a stage as soon as every consumer warp has released it, so the
+// consumer warps (which own different numbers of frequency tiles) never meet at a CTA-wide barrier.
 #include <cstdlib>
 
 #include "mepb_internal.cuh"
@@ -23,7 +24,8 @@ namespace mepb {
 
 namespace {
 
-constexpr int kMmaStages = 3;
+constexpr int kMmaStages = 3;          // AHC sweep (KC k-points per stage)
+constexpr int kMmaPhotoStages = 6;     // photo sweep (one k-point, 25 KB at nw = 8, per stage; one CTA per SM)
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, const double a, const double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
@@ -31,6 +33,8 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, const double a, 
 
 // ------------------------------------------------------------------------------------------------ AHC / OHC sweep
 // MT full 8-row tiles + REM remainder weights: Hermitian items (9 weights) MT = 1, REM = 1; general items (18) MT = 2, REM = 2.
+// (CTA-wide barrier per stage and one elected producer thread: the full/empty ring of the photo kernel with a producer warp
+// measured 10 % slower here — 288-thread CTAs, 96-register cap — profiles/r01m.)
 // Warp w of the CTA: k-group g = w / wtiles, frequency tiles [(w % wtiles) NT, +NT) (+ blockIdx.y * wtiles_per_pass * NT).
 template <bool HERM, int NT>
 __global__ void __launch_bounds__(256, (HERM && NT <= 2) ? 3 : 2)
@@ -179,20 +183,27 @@ sweep_photo_mma_kernel(const double2 *__restrict__ items, const int *__restrict_
     const long long kb0 = (long long)blockIdx.x * per;
     const long long kb1 = (kb0 + per < nk) ? kb0 + per : nk;
     const int nchunks = kb0 < kb1 ? (int)(kb1 - kb0) : 0;
+    const int n_cons = (int)(blockDim.x >> 5) - 1;              // consumer warps; the last warp is the TMA producer
+    uint64_t *full = bar, *empty = bar + kMmaPhotoStages;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kMmaStages; ++s) mbar_init(&bar[s], 1);
+        for (int s = 0; s < kMmaPhotoStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], n_cons); }
         mbar_fence_init();
     }
     __syncthreads();
-    auto issue = [&](int c) {
-        unsigned char *dst = stage0 + (size_t)(c % kMmaStages) * stage_bytes;
-        const long long k = kb0 + c;
-        mbar_expect_tx(&bar[c % kMmaStages], (uint32_t)item_bytes + 16u);
-        tma_bulk_g2s(dst, items + (size_t)k * max_items * ISTR, (uint32_t)item_bytes, &bar[c % kMmaStages]);
-        tma_bulk_g2s(dst + item_bytes, cnt + (k & ~3LL), 16u, &bar[c % kMmaStages]);
-    };
-    if (threadIdx.x == 0)
-        for (int c = 0; c < kMmaStages && c < nchunks; ++c) issue(c);
+    if ((int)(threadIdx.x >> 5) == n_cons) {                    // producer warp
+        if ((threadIdx.x & 31) == 0) {
+            for (int c = 0; c < nchunks; ++c) {
+                const int st = c % kMmaPhotoStages;
+                if (c >= kMmaPhotoStages) mbar_wait(&empty[st], (uint32_t)(((c / kMmaPhotoStages) + 1) & 1));
+                unsigned char *dst = stage0 + (size_t)st * stage_bytes;
+                const long long k = kb0 + c;
+                mbar_expect_tx(&full[st], (uint32_t)item_bytes + 16u);
+                tma_bulk_g2s(dst, items + (size_t)k * max_items * ISTR, (uint32_t)item_bytes, &full[st]);
+                tma_bulk_g2s(dst + item_bytes, cnt + (k & ~3LL), 16u, &full[st]);
+            }
+        }
+        return;
+    }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kq = lane & 3, nq = lane >> 2;
@@ -216,8 +227,8 @@ sweep_photo_mma_kernel(const double2 *__restrict__ items, const int *__restrict_
         for (int q = 0; q < REM; ++q) { rr[t][q] = 0.0; ri[t][q] = 0.0; }
     }
     for (int c = 0; c < nchunks; ++c) {
-        const int st = c % kMmaStages;
-        mbar_wait(&bar[st], (uint32_t)((c / kMmaStages) & 1));
+        const int st = c % kMmaPhotoStages;
+        mbar_wait(&full[st], (uint32_t)((c / kMmaPhotoStages) & 1));
         if (active) {
             const unsigned char *base = stage0 + (size_t)st * stage_bytes;
             const double2 *its = reinterpret_cast<const double2 *>(base);
@@ -240,10 +251,13 @@ sweep_photo_mma_kernel(const double2 *__restrict__ items, const int *__restrict_
                     const double hr = 2.0 * (xr * aa - e2 * bb) * inv, hi = -2.0 * (xr * bb + e2 * aa) * inv;
                     const double nhi = -hi;
 #pragma unroll
-                    for (int q = 0; q < MT; ++q) {
+                    for (int q = 0; q < MT; ++q) {                             // dependent pairs (same accumulator) kept 6 MMAs apart
                         dmma884(cr[t][q][0], cr[t][q][1], a[q].x, hr);
-                        dmma884(cr[t][q][0], cr[t][q][1], a[q].y, nhi);
                         dmma884(ci[t][q][0], ci[t][q][1], a[q].x, hi);
+                    }
+#pragma unroll
+                    for (int q = 0; q < MT; ++q) {
+                        dmma884(cr[t][q][0], cr[t][q][1], a[q].y, nhi);
                         dmma884(ci[t][q][0], ci[t][q][1], a[q].y, hr);
                     }
 #pragma unroll
@@ -254,8 +268,8 @@ sweep_photo_mma_kernel(const double2 *__restrict__ items, const int *__restrict_
                 }
             }
         }
-        __syncthreads();
-        if (threadIdx.x == 0 && c + kMmaStages < nchunks) issue(c + kMmaStages);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);                    // this warp is done with stage st
     }
     if (!active) return;
     double2 *out = reinterpret_cast<double2 *>(block_out) + ((size_t)blockIdx.x * ((size_t)G * n_hw) + (size_t)g * n_hw) * (kPhotoAcc / 2);
@@ -302,6 +316,10 @@ MmaShape sweep_mma_shape(int n_hw, int wmax, int nt_max) {
     return best;
 }
 int sweep_ahc_mma_bps(bool herm, int NT) { return (herm && NT <= 2) ? 3 : 2; }   // resident CTAs per SM (launch bounds above)
+bool sweep_photo_mma_fits(int max_items) {      // the ring of kMmaPhotoStages one-k-point stages must fit one CTA's shared memory
+    const size_t stage_bytes = (sizeof(double) * kPhotoItem * (size_t)max_items + 16 + 127) / 128 * 128;
+    return 128 + kMmaPhotoStages * stage_bytes <= 200 * 1024;
+}
 bool sweep_mma_enabled(int n_hw) {
     static const bool off = getenv("MEPB_SWEEP_FMA") != nullptr;
     return !off && n_hw >= 16;
@@ -309,7 +327,7 @@ bool sweep_mma_enabled(int n_hw) {
 
 cudaError_t launch_sweep_ahc_mma(bool herm, const double *items, const int *cnt, int max_pairs, long long nk, int n_hw,
                                  const double *hw, double eta, double *block_out, int grid, int KC, cudaStream_t st) {
-    const MmaShape s = sweep_mma_shape(n_hw, kMmaAhcWarps, 4);
+    const MmaShape s = sweep_mma_shape(n_hw, kMmaAhcWarps, herm ? 4 : 2);   // general items at NT = 4 spill (96-register cap)
     const size_t item_bytes = sizeof(double) * (herm ? kAhcItemH : kAhcItemG) * (size_t)max_pairs * KC;
     const size_t stage_bytes = (item_bytes + 16 * ((KC * sizeof(int) + 15) / 16) + 127) / 128 * 128;
     const size_t smem = 128 + kMmaStages * stage_bytes;
@@ -332,8 +350,9 @@ cudaError_t launch_sweep_photo_mma(const double *items, const int *cnt, int max_
     const MmaShape s = sweep_mma_shape(n_hw, kMmaPhotoWarps, 2);
     const size_t item_bytes = sizeof(double) * kPhotoItem * (size_t)max_items;
     const size_t stage_bytes = (item_bytes + 16 + 127) / 128 * 128;
-    const size_t smem = 128 + kMmaStages * stage_bytes;
-    const dim3 g(grid, s.passes), b(32 * s.warps);
+    int stages = kMmaPhotoStages;
+    const size_t smem = 128 + stages * stage_bytes;              // <= 6 x 64 KB would not fit: sweep_photo_mma_fits() gates this path
+    const dim3 g(grid, s.passes), b(32 * (s.warps + 1));         // + the producer warp
     const double2 *it2 = reinterpret_cast<const double2 *>(items);
 #define MEPB_LAUNCH_PHOTO(N)                                                                                                   \
     do {                                                                                                                       \

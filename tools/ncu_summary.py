@@ -3,7 +3,7 @@
 
   launches  <launches.csv>                      per-kernel count / total ms / share of the step
   raw       <file.ncu-rep> [kernel-regex]       the raw-page metrics the roofline discussion uses, per captured launch
-  lines     <file.ncu-rep> <cubin.sass> <mangled-substr> <source.cu> [N]   executed instructions / stall samples by source line
+  lines     <file.ncu-rep> <cubin.sass> <mangled-substr> <source.cu> [N [kernel-regex]]   executed instructions / stall samples by source line
 (sass file: `cuobjdump -xelf all libmepb.so; nvdisasm -g -c x.cubin > x.sass`)
 """
 import collections
@@ -57,11 +57,15 @@ def raw(rep, pat=None):
                 print(f"   {w:70s} {r[i]:>18s} {units[i]}")
 
 
-def lines(rep, sass, func, src, top=40):
+def lines(rep, sass, func, src, top=40, kernel=None):
+    """kernel: regex on the (demangled) kernel name of the report; default = first captured launch"""
     top = int(top)
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+    start = 0
+    if kernel:
+        start = next(i for i, r in enumerate(rows) if r and r[0] == "Kernel Name" and re.search(kernel, r[1]))
+    hdr_i = next(i for i, r in enumerate(rows) if i >= start and r and r[0] == "Address")
     hdr = rows[hdr_i]
     data = []
     for r in rows[hdr_i + 1:]:
