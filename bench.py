@@ -70,19 +70,46 @@ def make_workload(name: str, n_gpus: int, mesh: int = 0):
     return model, params, desc
 
 
+def hermitian_closed(model) -> bool:
+    """H(-R) = H(R)^dagger for every R (mirror of hermitian_closed in mepb_api.cu): decides which pair-item format the library uses."""
+    H, R = np.asarray(model.H), np.asarray(model.R).reshape(3, -1, order="F")
+    tol = 4e-16 * max(float(np.abs(H).max()), 1e-300)
+    for r in range(H.shape[2]):
+        partner = np.where(np.all(np.abs(R + R[:, r:r + 1]) < 1e-9, axis=0))[0]
+        if partner.size == 0:
+            if np.abs(H[:, :, r]).max() > tol:
+                return False
+            continue
+        if np.abs(H[:, :, r] - H[:, :, partner[0]].conj().T).max() > tol:
+            return False
+    return True
+
+
 def flops_model(model, params):
-    """Algorithmic FP64 flops per unit for each kernel class (DESIGN.md 'Kernels and rooflines')."""
+    """Algorithmic FP64 flops per unit for each kernel class (DESIGN.md 'Kernels and rooflines').
+
+    Sparse H(R) (FeMn: 110 of 1728 entries): the library sums only the non-zero entries (the reference adds the zeros,
+    file_io.f90:732-741 keeps them in H_tb), so the Fourier terms are counted per NON-ZERO entry — counting the dense
+    8*nR*nw^2 of SURVEY 8(d) would credit the kernels with work they do not do."""
     nw, nR = model.nw, model.nR
+    H = np.asarray(model.H)
+    nz = (H != 0)
+    nnz = int(nz.sum())
+    sparse = nw in (4, 8, 16) and 2 * nnz < nw * nw * nR                  # mepb_api.cu build_sparse
+    nnz_up = int(sum(nz[p, q, :].sum() for q in range(nw) for p in range(q + 1)))
     split = nw in (4, 8)                                              # thread-per-k eigensolver kernel (mepb_eig.cu)
-    eig = 8.0 * nR * (nw * (nw + 1) // 2) + 36.0 * nw ** 3            # Fourier sum of H (upper triangle) + LAPACK-convention eigensolve
-    interp = 8.0 * nR * nw * nw * 4 + (0.0 if split else 36.0 * nw ** 3)   # Fourier sums (H, 3 dH)
+    # eigensolver kernel: Fourier sum of H (upper triangle; 1 complex MAC = 8 flops) + LAPACK-convention 36 nw^3 eigensolve
+    eig = 8.0 * (nnz_up if sparse else nR * (nw * (nw + 1) // 2)) + 36.0 * nw ** 3
+    # band-sum kernel: Fourier sums of the three d_aH — per entry one complex multiply (6), the H accumulate (2) and three
+    # real x complex multiply-adds (12) = 20 flops (dense: per (R, element))
+    interp = 20.0 * (nnz if sparse else nR * nw * nw) + (0.0 if split else 36.0 * nw ** 3)
     if params.do_gauge_trafo:
         interp += 48.0 * nw ** 3                                      # U^dagger (d_a H) U, a = 1..3
     if params.do_ahc:
         interp += 60.0 * nw * nw
     if params.do_mep or params.do_kubo:
         interp += 130.0 * nw * (nw - 1) ** 2
-    herm = True
+    herm = hermitian_closed(model)                                    # mepb_api.cu hermitian_closed: 10-double items, else 20
     large = nw not in (4, 8, 16)
     nel = nw * (nw + 1) // 2
     return {"interp_per_k": interp, "eig_per_k": eig if split else 0.0,
@@ -92,7 +119,8 @@ def flops_model(model, params):
             "fourier_per_k": 20.0 * nR * nel if large else 0.0,
             "eig_rot_per_k": (36.0 + 48.0) * nw ** 3 + 60.0 * nw * nw if large else 0.0,
             "sweep_ahc_per_item_hw": 56.0 if herm else 92.0,          # 1 complex reciprocal + 18 (36) accumulate FMAs
-            "sweep_photo_per_item_hw": 246.0}                          # 27 complex MACs + the two-pole factor
+            "sweep_photo_per_item_hw": 246.0,                          # 27 complex MACs + the two-pole factor
+            "sparse": sparse, "nnz": nnz, "herm": herm}
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -303,6 +331,8 @@ def main():
         traffic = json.load(open(tpath)).get(args.workload, {}).get(top)
     roofline = {"kernel": top, "bound": "fp64", "achieved": kernels[top]["tflops"], "peak": peak, "unit": "TFLOP/s",
                 "frac": kernels[top]["tflops"] / peak, "traffic": traffic,
+                "traffic_note": "DRAM bytes per launch of the dominant kernel (ncu --set full, profiles/traffic.json); the path is "
+                                "FP64-pipe bound, HBM < 10 % of its peak in every kernel",
                 "peak_source": "MEASURED_PEAKS_FP64.json (tools/fp64_peaks.cu on this pool's B200: DFMA = DMMA = 37.1 TF; "
                                "MEASURED_PEAKS.json has no FP64 figure; HBM is not a bound for this path)",
                 "avg_launch_ms": kernels[top]["ms_per_pass"] / kernels[top]["launches"],

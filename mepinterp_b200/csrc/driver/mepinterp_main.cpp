@@ -98,7 +98,7 @@ struct Inputs {
     double a_latt[9];                       // Fortran a_latt(3,3): a_latt(i,:) = a_i * a0 -> column-major storage
     std::vector<double> wf_centers;         // (3, N_wf) or empty
     std::string seed;
-    bool plot_bands = false;
+    bool plot_bands = false, do_write_velo = false;
     int nw = 0, nR = 0;
     std::vector<double> R, H;               // (3,nR), (nw,nw,nR) complex interleaved, Hartree
 };
@@ -120,6 +120,7 @@ void read_inputs_cfg(const std::string &path, Inputs &I) {
     }
     I.seed = c.str("wannBase%seed_name", "wf1");
     I.plot_bands = c.logical("jobs%plot_bands", false);
+    I.do_write_velo = c.logical("jobs%do_write_velo", false);
     mepb_params &p = I.p;
     const auto g = c.reals("wannInterp%mp_grid", 3);
     for (int i = 0; i < 3; ++i) p.mp_grid[i] = (int)g[i];
@@ -191,6 +192,69 @@ void check(int rc, const char *what) {
 
 }  // namespace
 
+// Band-structure mode (band_calc.f90:30-92): `kpts` (kptsgen.pl format, file_io.f90:451-478: "num_kpts x" then
+// "k1 k2 k3 weight" rows, fractional) -> raw/enK.<7-digit ki> (raw stream of nw doubles, file_io.f90:57-72), optionally
+// out/velo/velo_Vka.<ki> (file_io.f90:146-185), then out/eBands.dat (file_io.f90:116-143).  One batched mepb_interp call
+// replaces the per-k get_wann_interp loop.
+int band_mode(const std::string &dir, const Inputs &I, const mepb_model &M, int device) {
+    std::ifstream f(dir + "/kpts");
+    if (!f) throw std::runtime_error("for bandstructure calculations a kpts file has to be provided");   // band_calc.f90:86
+    long long nk = 0; double dummy = 0.0;
+    { std::string line; std::getline(f, line); std::stringstream ss(line); if (!(ss >> nk >> dummy) || nk < 1) throw std::runtime_error("kpts: bad header"); }
+    std::vector<double> kpt(3 * (size_t)nk);
+    for (long long k = 0; k < nk; ++k) {
+        std::string line;
+        if (!std::getline(f, line)) throw std::runtime_error("kpts: fewer rows than the header announces");
+        std::stringstream ss(line);
+        if (!(ss >> kpt[3 * k] >> kpt[3 * k + 1] >> kpt[3 * k + 2])) throw std::runtime_error("kpts: bad row " + std::to_string(k + 1));
+    }
+    mepb_ctx *ctx = nullptr;
+    check(mepb_create(&M, &I.p, device, &ctx), "mepb_create");
+    const int nw = I.nw;
+    std::vector<double> en((size_t)nw * nk), V;
+    if (I.do_write_velo) V.resize(2 * 3 * (size_t)nw * nw * nk);
+    check(mepb_interp(ctx, nk, kpt.data(), en.data(), I.do_write_velo ? V.data() : nullptr), "mepb_interp");
+    mepb_destroy(ctx);
+    mkdir((dir + "/out").c_str(), 0755); mkdir((dir + "/raw").c_str(), 0755);
+    if (I.do_write_velo) mkdir((dir + "/out/velo").c_str(), 0755);
+    char name[64];
+    for (long long k = 0; k < nk; ++k) {
+        std::snprintf(name, sizeof(name), "/raw/enK.%07lld", k + 1);
+        FILE *o = std::fopen((dir + name).c_str(), "wb");
+        if (!o) throw std::runtime_error(std::string("cannot write ") + name);
+        std::fwrite(&en[(size_t)nw * k], sizeof(double), nw, o);
+        std::fclose(o);
+        if (I.do_write_velo) {
+            std::snprintf(name, sizeof(name), "/out/velo/velo_Vka.%07lld", k + 1);
+            FILE *v = std::fopen((dir + name).c_str(), "w");
+            if (!v) throw std::runtime_error(std::string("cannot write ") + name);
+            std::fprintf(v, " #interpolated velocities\n # x |\t n\t\t|\tm \t|\treal(V^x_nm)  |\t\timag(Vx_nm)\n");
+            std::fprintf(v, " #-----------------------------------------------------------------------\n");
+            const double *Vk = &V[2 * 3 * (size_t)nw * nw * k];                // V_ka(x,n,m): x + 3 (n + nw m)
+            for (int x = 0; x < 3; ++x) {
+                for (int m = 0; m < nw; ++m)
+                    for (int n = 0; n < nw; ++n) {
+                        const double *z = Vk + 2 * (x + 3 * (n + (size_t)nw * m));
+                        std::fprintf(v, "\t%1d\t\t%3d\t\t%3d\t\t%16.8f\t%16.8f\n", x + 1, n + 1, m + 1, z[0], z[1]);
+                    }
+                std::fprintf(v, " #----------------------------------------------------------------------\n");
+            }
+            std::fclose(v);
+        }
+    }
+    FILE *o = std::fopen((dir + "/out/eBands.dat").c_str(), "w");
+    if (!o) throw std::runtime_error("cannot write out/eBands.dat");
+    std::fprintf(o, " # energies interpolated by mepinterp-b200 (band mode of MEPinterp)\n");
+    std::fprintf(o, " # first 3 columns give the relative k-mesh, 4th column are the enegies\n");
+    std::fprintf(o, " # Kpt_idx  K_x (frac)       K_y (frac)        K_z (frac)       Energy (Hartree)  \n");
+    for (long long k = 0; k < nk; ++k)
+        for (int b = 0; b < nw; ++b)                                           // '(i7,a)' '(200(f16.8))' '(a,f18.8)'
+            std::fprintf(o, "%7lld\t%16.8f%16.8f%16.8f\t%18.8f\n", k + 1, kpt[3 * k], kpt[3 * k + 1], kpt[3 * k + 2], en[(size_t)nw * k + b]);
+    std::fclose(o);
+    std::printf("[mepInterp] band mode: %lld k-points, %d bands; wrote %s/raw/enK.* and %s/out/eBands.dat\n", nk, nw, dir.c_str(), dir.c_str());
+    return 0;
+}
+
 int main(int argc, char **argv) {
     std::vector<int> devices = {0};
     bool check_only = false;
@@ -225,11 +289,11 @@ int main(int argc, char **argv) {
             std::printf("checksums %.17g %.17g %.17g\n", sr, sh, sa);
             return 0;
         }
-        if (I.plot_bands) throw std::runtime_error("plot_bands = T selects band mode (band_calc.f90); this driver runs the response path");
         mepb_model M{};
         M.nw = I.nw; M.nR = I.nR; M.R = I.R.data(); M.H = I.H.data(); M.r = nullptr;
         M.wf_centers = I.wf_centers.empty() ? nullptr : I.wf_centers.data();
         std::memcpy(M.a_latt, I.a_latt, sizeof(M.a_latt));
+        if (I.plot_bands) return band_mode(dir, I, M, devices[0]);            // main.f90:32-36
         const long long nk = (long long)p.mp_grid[0] * p.mp_grid[1] * p.mp_grid[2];
         const int G = (int)devices.size();
         std::vector<mepb_ctx *> ctx(G, nullptr);

@@ -588,7 +588,7 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
     c->chunk = chunk;
     if (!c->large) CT(build_sparse(c, model));
     c->grid_interp = c->large ? eig_large_grid(c->sm_count, chunk) : interp_small_grid(nw, nR, c->sm_count, chunk);
-    if (c->use_sub) c->grid_interp = std::max(c->grid_interp, bands_sub_grid(nw, nR, c->sm_count, chunk));
+    if (c->use_sub) c->grid_interp = std::max(c->grid_interp, bands_sub_grid(nw, nR, c->sm_count, chunk, c->sparse ? c->sp_nnz : 0, p.do_mep || p.do_kubo));
     c->grid_sweep = sweep_ahc_grid(c->sm_count, chunk, p.n_hw, &c->ns_sweep, c->herm, c->max_pairs);
     c->grid_photo = sweep_photo_grid(c->sm_count, chunk, p.n_hw, &c->ns_photo, c->max_photo);
     c->cs.ns = static_size(nw); c->cs.sweep = p.n_hw * kSweepAcc; c->cs.photo = p.n_hw * kPhotoAcc;
@@ -696,7 +696,7 @@ int mepb_accumulate(mepb_ctx *c, int64_t lin_begin, int64_t lin_end) {
             o.items_photo = jb.do_opt ? s.items_photo : nullptr; o.cnt_photo = s.cnt_photo;
             o.block_static = s.block_static; o.err_flag = c->d_err;
             const int gi = c->large ? eig_large_grid(c->sm_count, nk)
-                           : c->use_sub ? bands_sub_grid(c->nw, c->nR, c->sm_count, nk) : interp_small_grid(c->nw, c->nR, c->sm_count, nk);
+                           : c->use_sub ? bands_sub_grid(c->nw, c->nR, c->sm_count, nk, c->sparse ? c->sp_nnz : 0, jb.do_mep || jb.do_kubo) : interp_small_grid(c->nw, c->nR, c->sm_count, nk);
             if (c->large) {
                 if (c->sp.on) {
                     SepPlan sp = c->sp; sp.G1 = s.G1; sp.G2 = s.G2;

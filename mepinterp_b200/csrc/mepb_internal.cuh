@@ -276,7 +276,7 @@ int interp_small_grid(int nw, int nR, int sm_count, long long nk);
 bool eig_thread_supported(int nw);
 // NW-lanes-per-k band-sum kernel (mepb_sub.cu): response mode, num_wann 4 / 8, eigenpairs from launch_eig_small
 bool sub_supported(int nw, int nR);
-int bands_sub_grid(int nw, int nR, int sm_count, long long nk);
+int bands_sub_grid(int nw, int nR, int sm_count, long long nk, int nnz, bool mep);   // nnz: staged sparse records (0: dense)
 cudaError_t launch_bands_sub(const DevModel &m, const KSource &ks, const Jobs &jobs, const InterpOut &out, int max_pairs, int grid,
                              cudaStream_t st);
 cudaError_t launch_eig_small(const DevModel &m, const KSource &ks, double *E_out, double2 *U_out, int *err_flag, int sm_count,

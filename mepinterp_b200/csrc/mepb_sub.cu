@@ -26,8 +26,7 @@ struct SpRec { double2 val; double c0, c1, c2; int R; int pad; };   // 48 bytes:
 template <int NW>
 struct SubL {  // shared-memory layout per GROUP (one k-point), bytes
     static constexpr int LD = NW + 1;             // padded rows: row-strided stores of a group (U load, Fourier) hit distinct banks
-    static constexpr size_t oU = 0;
-    static constexpr size_t oHa = oU + sizeof(double2) * NW * LD;
+    static constexpr size_t oHa = 0;                // U stays in registers (column g per lane): 1.1 KB less per k-point
     static constexpr size_t oEs = oHa + sizeof(double2) * 3 * NW * LD;
     static constexpr size_t oFn = oEs + sizeof(double) * NW;
     static constexpr size_t oDn = oFn + sizeof(double) * NW;
@@ -37,8 +36,9 @@ struct SubL {  // shared-memory layout per GROUP (one k-point), bytes
 };
 
 template <int NW, bool MEP>
-__global__ void __launch_bounds__(kSubWarps * 32, 2)
-bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const InterpOut out, const int max_pairs, const size_t grp_bytes) {
+__global__ void __launch_bounds__(kSubWarps * 32, MEP ? 2 : 3)      // 36 more accumulators with the MEP jobs: 3 CTAs would spill 1.1 KB
+bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const InterpOut out, const int max_pairs, const size_t grp_bytes,
+                 const int rec_cap) {
     using L = SubL<NW>;
     constexpr int LD = L::LD, NW2 = NW * NW, NPAIR = NW * (NW - 1) / 2, NGRP = 32 / NW;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -47,7 +47,6 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
     const unsigned gshift = (unsigned)(grp * NW);
     const unsigned gbits = (NW == 32) ? 0xffffffffu : ((1u << NW) - 1u);
     unsigned char *base = smem_raw + ((size_t)warp * NGRP + grp) * grp_bytes;
-    double2 *Us = reinterpret_cast<double2 *>(base + L::oU);
     double2 *Ha = reinterpret_cast<double2 *>(base + L::oHa);      // [a][n*LD + m]; V_a after the rotation
     double *es = reinterpret_cast<double *>(base + L::oEs);
     double *fn = reinterpret_cast<double *>(base + L::oFn);
@@ -57,7 +56,7 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
     const bool has_tau = (m.tau != nullptr);
     // CTA-wide copy of the sparse H(R) list (after the group buffers)
     SpRec *rec = reinterpret_cast<SpRec *>(smem_raw + (size_t)kSubWarps * NGRP * grp_bytes);
-    int *sptr = reinterpret_cast<int *>(rec + kSubMaxNnz);
+    int *sptr = reinterpret_cast<int *>(rec + rec_cap);
     const bool sp_smem = (m.sp_ptr != nullptr) && (m.sp_nnz <= kSubMaxNnz);
     if (sp_smem) {
         for (int t = threadIdx.x; t < m.sp_nnz; t += blockDim.x) {
@@ -110,10 +109,11 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
             double s, c; sincospi(x, &s, &c);
             dn[g] = make_double2(c, s);
         }
+        double2 u[NW];                                             // column g of U (eigenvector of band g)
         {
-            const double2 *Uk = out.U_in + (size_t)ik * NW2;       // element r + NW*c ; lane g takes row g
+            const double2 *Uk = out.U_in + (size_t)ik * NW2 + (size_t)NW * g;   // element r + NW*c: 128 contiguous bytes per lane
 #pragma unroll
-            for (int c = 0; c < NW; ++c) Us[g * LD + c] = Uk[g + NW * c];
+            for (int q = 0; q < NW; ++q) u[q] = __ldg(Uk + q);
             const double e = out.e_in[(size_t)ik * NW + g];
             const double f = fermi(e, jb);
             es[g] = e; fn[g] = f;
@@ -177,12 +177,10 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
             }
         }
         __syncwarp();
-        // ------------------------------------------------------------------ 4. gauge rotation, column mc = g
+        // ------------------------------------------------------------------ 4. gauge rotation V_a = U^dagger (d_a H) U
+        // lane g: column g of T = H_a U from its own u (registers), written over H_a; then ROW g of V_a = U^dagger T,
+        // again from its own u — U never goes through shared memory.
         if (jb.do_gauge) {
-            const int mc = g;
-            double2 u[NW];
-#pragma unroll
-            for (int q = 0; q < NW; ++q) u[q] = Us[q * LD + mc];
 #pragma unroll 1
             for (int a = 0; a < 3; ++a) {
                 double2 *Hrow = Ha + a * NW * LD;
@@ -194,14 +192,20 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
                     for (int q = 0; q < NW; ++q) cfma(s, Hrow[p * LD + q], u[q]);
                     tmp[p] = s;
                 }
-                __syncwarp();                                       // every lane has read Ha[a]: column mc can be overwritten
+                __syncwarp();                                       // every lane has read H_a: column g can be overwritten
 #pragma unroll
-                for (int n = 0; n < NW; ++n) {
+                for (int p = 0; p < NW; ++p) Hrow[p * LD + g] = tmp[p];
+                __syncwarp();                                       // T complete
+#pragma unroll
+                for (int mm = 0; mm < NW; ++mm) {
                     double2 s = make_double2(0, 0);
 #pragma unroll
-                    for (int p = 0; p < NW; ++p) cfmac(s, Us[p * LD + n], tmp[p]);
-                    Hrow[n * LD + mc] = s;
+                    for (int p = 0; p < NW; ++p) cfmac(s, u[p], Hrow[p * LD + mm]);
+                    tmp[mm] = s;
                 }
+                __syncwarp();                                       // every lane has read T: row g can be overwritten
+#pragma unroll
+                for (int mm = 0; mm < NW; ++mm) Hrow[g * LD + mm] = tmp[mm];
             }
             __syncwarp();
         }
@@ -463,9 +467,11 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
     }
 }
 
+inline int sub_rec_cap(int nnz) { return (nnz > 0 && nnz <= kSubMaxNnz) ? (nnz + 7) / 8 * 8 : 8; }   // staged sparse records
+
 template <int NW>
-size_t sub_smem(int nR) {
-    const size_t groups = (size_t)kSubWarps * (32 / NW) * SubL<NW>::bytes(nR) + sizeof(SpRec) * kSubMaxNnz + sizeof(int) * (NW * NW + 4);
+size_t sub_smem(int nR, int nnz = kSubMaxNnz) {
+    const size_t groups = (size_t)kSubWarps * (32 / NW) * SubL<NW>::bytes(nR) + sizeof(SpRec) * sub_rec_cap(nnz) + sizeof(int) * (NW * NW + 4);
     const size_t stage = sizeof(double) * kSubWarps * (S_NIU + 18 * NW);
     return groups > stage ? groups : stage;
 }
@@ -473,16 +479,17 @@ size_t sub_smem(int nR) {
 template <int NW>
 cudaError_t launch_sub_t(const DevModel &m, const KSource &ks, const Jobs &jobs, const InterpOut &out, int max_pairs, int grid,
                          cudaStream_t st) {
-    const size_t smem = sub_smem<NW>(m.nR);
+    const int rec_cap = sub_rec_cap(m.sp_ptr ? m.sp_nnz : 0);
+    const size_t smem = sub_smem<NW>(m.nR, m.sp_ptr ? m.sp_nnz : 0);
     cudaError_t e;
     if (jobs.do_mep || jobs.do_kubo) {
         e = cudaFuncSetAttribute(bands_sub_kernel<NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        bands_sub_kernel<NW, true><<<grid, kSubWarps * 32, smem, st>>>(m, ks, jobs, out, max_pairs, SubL<NW>::bytes(m.nR));
+        bands_sub_kernel<NW, true><<<grid, kSubWarps * 32, smem, st>>>(m, ks, jobs, out, max_pairs, SubL<NW>::bytes(m.nR), rec_cap);
     } else {
         e = cudaFuncSetAttribute(bands_sub_kernel<NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        bands_sub_kernel<NW, false><<<grid, kSubWarps * 32, smem, st>>>(m, ks, jobs, out, max_pairs, SubL<NW>::bytes(m.nR));
+        bands_sub_kernel<NW, false><<<grid, kSubWarps * 32, smem, st>>>(m, ks, jobs, out, max_pairs, SubL<NW>::bytes(m.nR), rec_cap);
     }
     return cudaGetLastError();
 }
@@ -495,10 +502,10 @@ bool sub_supported(int nw, int nR) {
     return false;
 }
 
-int bands_sub_grid(int nw, int nR, int sm_count, long long nk) {
-    const size_t smem = (nw == 4 ? sub_smem<4>(nR) : sub_smem<8>(nR)) + 1024;
+int bands_sub_grid(int nw, int nR, int sm_count, long long nk, int nnz, bool mep) {
+    const size_t smem = (nw == 4 ? sub_smem<4>(nR, nnz) : sub_smem<8>(nR, nnz)) + 1024;
     int per_sm = (int)((227 * 1024) / smem);
-    if (per_sm > 2) per_sm = 2;                        // __launch_bounds__(128, 2)
+    if (per_sm > (mep ? 2 : 3)) per_sm = mep ? 2 : 3;  // __launch_bounds__(128, MEP ? 2 : 3)
     if (per_sm < 1) per_sm = 1;
     const int kpb = kSubWarps * (32 / nw);
     long long need = (nk + kpb - 1) / kpb;

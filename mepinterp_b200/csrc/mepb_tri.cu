@@ -203,7 +203,7 @@ tql_kernel(const int n, const long long nk, const TriBuf tb, int *__restrict__ e
 
 // ================================================================================================ replay of the rotation log
 template <int NE>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, NE == 64 ? 3 : 4)
 zrot_kernel(const int n, const long long nk, const TriBuf tb) {
     constexpr int GROUPS = 128 / NE;                 // matrices per CTA
     const int tid = threadIdx.x;
@@ -223,12 +223,21 @@ zrot_kernel(const int n, const long long nk, const TriBuf tb) {
 #pragma unroll
             for (int blk = NE / 8 - 1; blk >= 0; --blk) {
                 if (8 * blk < m && 8 * blk + 7 >= l) {
+                    // the 8 rotations of the block are fetched together (clamped to the chase's range): one exposed L2
+                    // latency per 8 rotations instead of one per rotation (the guarded loads could not be hoisted)
+                    double2 csb[8];
+#pragma unroll
+                    for (int ii = 0; ii < 8; ++ii) {
+                        int ic = 8 * blk + ii;
+                        ic = ic < l ? l : (ic > m - 1 ? m - 1 : ic);
+                        csb[ii] = __ldg(src - ic);
+                    }
 #pragma unroll
                     for (int ii = 7; ii >= 0; --ii) {
                         const int i = 8 * blk + ii;
                         if (i <= NE - 2) {
                             if (i < m && i >= l) {
-                                const double2 cs = __ldg(src - i);
+                                const double2 cs = csb[ii];
                                 const double f = z[i + 1 <= NE - 1 ? i + 1 : NE - 1];
                                 const double zi = z[i];
                                 z[i + 1 <= NE - 1 ? i + 1 : NE - 1] = fma(cs.y, zi, cs.x * f);

@@ -95,3 +95,35 @@ def test_driver_end_to_end_files(driver, tmp_path, name, mesh):
     assert hw.shape == (9,) and abs(hw[-1] - p.hw_max * mo.AU_TO_EV) < 1e-12
     occ = (run / "out" / "occ.dat").read_text().split()
     assert abs(float(occ[1]) - ref["Ne"][0]) < 1e-7
+
+
+@pytest.mark.gpu
+def test_driver_band_mode_files(driver, tmp_path):
+    """plot_bands = T (band_calc.f90:30-92): `kpts` file -> raw/enK.<ki> (raw f8 stream), out/eBands.dat, out/velo/velo_Vka.<ki>."""
+    run = tmp_path / "run"
+    shutil.copytree(os.path.join(GOLDEN, "femn_d0.900"), run)
+    cfg = (run / "input.cfg").read_text().splitlines()
+    cfg = [("    plot_bands= T") if ln.strip().startswith("plot_bands") else ln for ln in cfg]
+    cfg = [("    do_write_velo= T") if ln.strip().startswith("do_write_velo") else ln for ln in cfg]
+    (run / "input.cfg").write_text("\n".join(cfg) + "\n")
+    rng = np.random.default_rng(7)
+    kpts = np.vstack([np.zeros((1, 3)), rng.uniform(-0.5, 0.5, size=(36, 3))])          # Gamma + a random path
+    with open(run / "kpts", "w") as f:                                                    # kptsgen.pl format, file_io.f90:451-478
+        f.write("%d 1.0\n" % len(kpts))
+        for k in kpts:
+            f.write("%.15f %.15f %.15f 1.0\n" % tuple(k))
+    r = subprocess.run([driver, "--dir", str(run)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    m, p = mo.load_model(str(run))
+    rows = np.loadtxt(run / "out" / "eBands.dat", comments="#")
+    assert rows.shape == (len(kpts) * m.nw, 5)
+    e_all = mo.get_wann_interp(m, kpts, do_gauge_trafo=p.do_gauge_trafo, use_cart_velo=p.use_cart_velo)[0]
+    for ki, k in enumerate(kpts):
+        e_ref = e_all[ki]
+        e_raw = np.fromfile(run / "raw" / ("enK.%07d" % (ki + 1)), dtype="<f8")
+        assert e_raw.shape == (m.nw,)
+        np.testing.assert_allclose(e_raw, e_ref, rtol=0, atol=1e-10 * max(1.0, np.abs(e_ref).max()))
+        blk = rows[ki * m.nw:(ki + 1) * m.nw]
+        assert np.all(blk[:, 0] == ki + 1) and np.allclose(blk[:, 1:4], k, atol=5e-9) and np.allclose(blk[:, 4], e_ref, atol=5e-9)
+    velo = (run / "out" / "velo" / "velo_Vka.0000001").read_text().splitlines()
+    assert len([ln for ln in velo if not ln.lstrip().startswith("#")]) == 3 * m.nw * m.nw
