@@ -1,6 +1,7 @@
 // mepb_internal.cuh — shared between the kernels and the C-ABI host code of libmepb.so.
 // sm_100a only.  All arithmetic FP64.
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/mepb.h"
@@ -264,6 +265,14 @@ __device__ __forceinline__ double fast_rcp3(double x) {
     const double e = fma(-x, r, 1.0);
     const double t = fma(e, e, e);
     return fma(r, t, r);
+}
+
+// resident-CTAs-per-SM override for co-scheduling experiments (two streams, complementary kernels on one SM)
+inline int env_bpsm(const char *name, int def) {
+    const char *e = getenv(name);
+    if (!e) return def;
+    const int v = atoi(e);
+    return (v >= 1 && v < def) ? v : def;
 }
 
 // ---------------------------------------------------------------------------------------------------------
