@@ -267,14 +267,6 @@ __device__ __forceinline__ double fast_rcp3(double x) {
     return fma(r, t, r);
 }
 
-// resident-CTAs-per-SM override for co-scheduling experiments (two streams, complementary kernels on one SM)
-inline int env_bpsm(const char *name, int def) {
-    const char *e = getenv(name);
-    if (!e) return def;
-    const int v = atoi(e);
-    return (v >= 1 && v < def) ? v : def;
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // launchers (defined in the .cu files)
 // ---------------------------------------------------------------------------------------------------------

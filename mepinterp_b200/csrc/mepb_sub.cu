@@ -506,7 +506,6 @@ int bands_sub_grid(int nw, int nR, int sm_count, long long nk, int nnz, bool mep
     const size_t smem = (nw == 4 ? sub_smem<4>(nR, nnz) : sub_smem<8>(nR, nnz)) + 1024;
     int per_sm = (int)((227 * 1024) / smem);
     if (per_sm > (mep ? 2 : 3)) per_sm = mep ? 2 : 3;  // __launch_bounds__(128, MEP ? 2 : 3)
-    per_sm = env_bpsm("MEPB_BANDS_BPSM", per_sm);
     if (per_sm < 1) per_sm = 1;
     const int kpb = kSubWarps * (32 / nw);
     long long need = (nk + kpb - 1) / kpb;

@@ -303,7 +303,7 @@ int sweep_ahc_grid(int sm_count, long long nk, int n_hw, int *slots_out, bool he
     if (sweep_mma_enabled(n_hw) && !getenv("MEPB_SWEEP_DIRECT") && sweep_ahc_kc(herm, max_pairs) > 0) {
         const MmaShape s = sweep_mma_shape(n_hw, kMmaAhcWarps, herm ? 4 : 2);
         if (slots_out) *slots_out = s.G * n_hw;
-        long long g = (long long)sm_count * env_bpsm("MEPB_SWEEP_BPSM", sweep_ahc_mma_bps(herm, s.NT));
+        long long g = (long long)sm_count * sweep_ahc_mma_bps(herm, s.NT);
         const long long need = (nk + s.G - 1) / s.G;
         if (g > need) g = need;
         return (int)(g < 1 ? 1 : g);

@@ -113,19 +113,24 @@ sweep_ahc_mma_kernel(const double2 *__restrict__ items, const int *__restrict__ 
                     for (int q = 0; q < MT; ++q) a[q] = valid ? it[1 + 8 * q + nq] : 0.0;
 #pragma unroll
                     for (int q = 0; q < REM; ++q) r[q] = valid ? it[1 + 8 * MT + q] : 0.0;
+                    // g = 1/(dE^2 - (w + i eta)^2) = (x - i b)/(x^2 + b^2),  x = dE^2 + eta^2 - w^2,  b = -2 w eta
+                    // (the NT reciprocal chains first, interleaved by the scheduler; then the MMAs, none waiting on a chain)
+                    double inv[NT], xi[NT];
 #pragma unroll
                     for (int t = 0; t < NT; ++t) {
-                        // g = 1/(dE^2 - (w + i eta)^2) = (x - i b)/(x^2 + b^2),  x = dE^2 + eta^2 - w^2,  b = -2 w eta
                         const double x = cit - om2[t];
-                        const double inv = fast_rcp3(fma(x, x, b2[t]));
-                        const double xi = x * inv;
+                        inv[t] = fast_rcp3(fma(x, x, b2[t]));
+                        xi[t] = x * inv[t];
+                    }
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) {
 #pragma unroll
                         for (int q = 0; q < MT; ++q) {
-                            dmma884(c1[t][q][0], c1[t][q][1], a[q], xi);
-                            dmma884(c2[t][q][0], c2[t][q][1], a[q], inv);
+                            dmma884(c1[t][q][0], c1[t][q][1], a[q], xi[t]);
+                            dmma884(c2[t][q][0], c2[t][q][1], a[q], inv[t]);
                         }
 #pragma unroll
-                        for (int q = 0; q < REM; ++q) { r1[t][q] = fma(r[q], xi, r1[t][q]); r2[t][q] = fma(r[q], inv, r2[t][q]); }
+                        for (int q = 0; q < REM; ++q) { r1[t][q] = fma(r[q], xi[t], r1[t][q]); r2[t][q] = fma(r[q], inv[t], r2[t][q]); }
                     }
                 }
             }
@@ -243,27 +248,31 @@ sweep_photo_mma_kernel(const double2 *__restrict__ items, const int *__restrict_
 #pragma unroll
                 for (int q = 0; q < REM; ++q) r[q] = valid ? it[8 * MT + q] : make_double2(0.0, 0.0);
                 const double xx = xr * xr - e22, bb = -2.0 * xr * e2, b2 = bb * bb;
+                // h = (1/w^2) * 2x/(x^2 - w^2),  x = xr - 2 i eta   (all NT chains first, then the MMAs)
+                double hr[NT], hi[NT], nhi[NT];
 #pragma unroll
                 for (int t = 0; t < NT; ++t) {
-                    // h = (1/w^2) * 2x/(x^2 - w^2),  x = xr - 2 i eta
                     const double aa = xx - om2[t];
                     const double inv = fast_rcp(fma(aa, aa, b2)) * iw2[t];
-                    const double hr = 2.0 * (xr * aa - e2 * bb) * inv, hi = -2.0 * (xr * bb + e2 * aa) * inv;
-                    const double nhi = -hi;
+                    hr[t] = 2.0 * (xr * aa - e2 * bb) * inv; hi[t] = -2.0 * (xr * bb + e2 * aa) * inv;
+                    nhi[t] = -hi[t];
+                }
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
 #pragma unroll
                     for (int q = 0; q < MT; ++q) {                             // dependent pairs (same accumulator) kept 6 MMAs apart
-                        dmma884(cr[t][q][0], cr[t][q][1], a[q].x, hr);
-                        dmma884(ci[t][q][0], ci[t][q][1], a[q].x, hi);
+                        dmma884(cr[t][q][0], cr[t][q][1], a[q].x, hr[t]);
+                        dmma884(ci[t][q][0], ci[t][q][1], a[q].x, hi[t]);
                     }
 #pragma unroll
                     for (int q = 0; q < MT; ++q) {
-                        dmma884(cr[t][q][0], cr[t][q][1], a[q].y, nhi);
-                        dmma884(ci[t][q][0], ci[t][q][1], a[q].y, hr);
+                        dmma884(cr[t][q][0], cr[t][q][1], a[q].y, nhi[t]);
+                        dmma884(ci[t][q][0], ci[t][q][1], a[q].y, hr[t]);
                     }
 #pragma unroll
                     for (int q = 0; q < REM; ++q) {
-                        rr[t][q] = fma(r[q].x, hr, rr[t][q]); rr[t][q] = fma(r[q].y, nhi, rr[t][q]);
-                        ri[t][q] = fma(r[q].x, hi, ri[t][q]); ri[t][q] = fma(r[q].y, hr, ri[t][q]);
+                        rr[t][q] = fma(r[q].x, hr[t], rr[t][q]); rr[t][q] = fma(r[q].y, nhi[t], rr[t][q]);
+                        ri[t][q] = fma(r[q].x, hi[t], ri[t][q]); ri[t][q] = fma(r[q].y, hr[t], ri[t][q]);
                     }
                 }
             }

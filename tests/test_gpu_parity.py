@@ -371,3 +371,45 @@ def test_nccl_sharded_if_multi_gpu(libmepb):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "NCCL_SHARDED_OK" in r.stdout
+
+
+def _run_variant(tmp_path, tag, case, over, env):
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / (tag + ".npz"))
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "run_case_worker.py"), case, json.dumps(over), out],
+                       capture_output=True, text=True, timeout=900, cwd=root, env=e)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return dict(np.load(out))
+
+
+def test_full_size_c3_independent_eigensolvers_agree(libmepb, tmp_path):
+    """BASELINE config 3 at full size (FeMn MEP, 256^3 = 16.8 M k-points): the Householder + QL eigensolver and the cyclic
+    Jacobi one (MEPB_SMALL_EIG=jacobi) are independent implementations of zheevd's contract; the guarded MEP tensors
+    (mep_niu, band resolved before the cancellation between bands) must agree.  kubo_mep is left out: it has no
+    degeneracy guard (kubo_mep.f90:73,126) and moves by 1e-2 under a 2-ulp change of the input on FeMn."""
+    over = dict(mp_grid=[256, 256, 256], do_ahc=False, do_mep=True, do_kubo=True, n_hw=1, hw_max=0.0, valence_bands=4,
+                do_write_mep_bands=True)
+    a = _run_variant(tmp_path, "ql", "femn_d0.900", over, {})
+    b = _run_variant(tmp_path, "jacobi", "femn_d0.900", over, {"MEPB_SMALL_EIG": "jacobi"})
+    assert int(a["n_k"]) == int(b["n_k"]) == 256 ** 3 and int(a["eF_idx"]) == int(b["eF_idx"])
+    assert abs(float(a["Ne"][0]) - float(b["Ne"][0])) <= 1e-9 * float(a["Ne"][0])
+    s = np.abs(a["mep_bands"]).max()
+    for k in ("mep_bands", "mep_ic", "mep_lc"):
+        assert np.abs(a[k] - b[k]).max() <= 1e-8 * s, k
+
+
+def test_full_size_c4_dmma_and_fma_sweeps_agree(libmepb, tmp_path):
+    """BASELINE config 4 at full size (FeMn Rashba, photo2 + AHC, n_hw = 200, 128^3): the tensor-core (DMMA) sweeps against
+    the thread-per-frequency FMA sweeps (MEPB_SWEEP_FMA=1) on identical items."""
+    over = dict(mp_grid=[128, 128, 128])
+    a = _run_variant(tmp_path, "dmma", "femn_rashba", over, {})
+    b = _run_variant(tmp_path, "fma", "femn_rashba", over, {"MEPB_SWEEP_FMA": "1"})
+    assert int(a["n_k"]) == int(b["n_k"]) == 128 ** 3
+    for k in ("ahc_tens", "ahcVELO", "ohcVELO", "photoC_2nd"):
+        assert a[k].shape == b[k].shape
+        assert np.abs(a[k] - b[k]).max() <= 1e-10 * np.abs(b[k]).max(), k
