@@ -232,6 +232,12 @@ def main():
         args.gpus = world
     args.warmup = max(args.warmup, 3)
 
+    # stdout carries exactly ONE line (the JSON): libraries that print there (NCCL's version banner at communicator creation)
+    # are sent to stderr for the duration of the run; the saved descriptor is restored for the final print
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     import mepinterp_b200 as mb
@@ -357,7 +363,10 @@ def main():
             line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{n} consecutive k-points of the same mesh ({dt:.1f} s), C restatement of the reference "
                                               "algorithm (dense loops + OpenBLAS zheevd/zgemm per k), one worker per core"}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     ctx.close()
     if world > 1:
         dist.barrier()

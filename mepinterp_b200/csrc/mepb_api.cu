@@ -632,7 +632,7 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
             CT(cudaMalloc((void **)&t.E, sizeof(double) * tne * ck));
             CT(cudaMalloc((void **)&t.rank, (size_t)tne * ck));
             CT(cudaMalloc((void **)&t.hdr, sizeof(unsigned int) * kTriHdrCap * ck));
-            CT(cudaMalloc((void **)&t.nhdr, sizeof(int) * ck));
+            CT(cudaMalloc((void **)&t.nhdr, sizeof(int) * 2 * ck));
             CT(cudaMalloc((void **)&t.log, sizeof(double2) * t.log_cap * ck));
             CT(cudaMalloc((void **)&t.Z, sizeof(double) * tne * tne * ck));
         }

@@ -165,7 +165,7 @@ struct TriBuf {
     double *E;              // [k][ne]      ascending eigenvalues
     unsigned char *rank;    // [k][ne]      position of tql's eigenvalue j in the ascending order
     unsigned int *hdr;      // [k][hdr_cap] one word per QL chase: l | m << 8  (rotations in planes m-1 ... l)
-    int *nhdr;              // [k]
+    int *nhdr;              // [k][2]  number of chases, number of logged rotations
     double2 *log;           // [k][log_cap] (c, s) per rotation, in execution order
     double *Z;              // [k][ne*ne]   Z[col*ne + row], eigenvectors of T in tql's (unsorted) column order
 };

@@ -326,7 +326,7 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
 #pragma unroll
                     for (int j = 0; j < 3; ++j) { Zg[j] = make_double2(0, 0); Zu[j] = make_double2(0, 0); }
                     const double d2 = d0n * d0n;
-#pragma unroll 1
+#pragma unroll 2
                     for (int mm = 0; mm < NW; ++mm) {
                         if (mm == n0) continue;
                         const double den = d2 * (e0 - es[mm]);

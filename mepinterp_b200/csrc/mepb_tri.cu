@@ -187,7 +187,7 @@ tql_kernel(const int n, const long long nk, const TriBuf tb, int *__restrict__ e
         }
     }
     if (failed) { atomicExch(err_flag, 1); nh = 0; }
-    tb.nhdr[ik] = nh;
+    tb.nhdr[2 * ik] = nh; tb.nhdr[2 * ik + 1] = failed ? 0 : pos;
     // ascending order (stable): rank of eigenvalue j, sorted copy
     double *Eo = tb.E + (size_t)ik * ne;
     unsigned char *rk = tb.rank + (size_t)ik * ne;
@@ -202,35 +202,70 @@ tql_kernel(const int n, const long long nk, const TriBuf tb, int *__restrict__ e
 }
 
 // ================================================================================================ replay of the rotation log
+// One thread per ROW of Z, the row in registers; the NE threads of a k-point (a "group": NE/32 warps) consume the same log
+// strictly in order, so it is STREAMED through shared memory: a ring of kLogSlots chunks of kLogChunk rotations per group,
+// filled by TMA bulk copies that lane 0 of the group's first warp issues, full/empty mbarriers per slot.  The rotations are
+// then broadcast LDS.128 (tens of cycles) instead of dependent global loads (an exposed L2/HBM latency per 8 rotations was
+// what bounded the first version: 78 ms per 110 K matrices of order 64, profiles/r01r).
+constexpr int kLogChunk = 256, kLogSlots = 4;         // 4 x 256 x 16 B = 16 KB per k-point in flight
+
 template <int NE>
-__global__ void __launch_bounds__(128, NE == 64 ? 3 : 4)
+__global__ void __launch_bounds__(128, 3)
 zrot_kernel(const int n, const long long nk, const TriBuf tb) {
-    constexpr int GROUPS = 128 / NE;                 // matrices per CTA
-    const int tid = threadIdx.x;
+    constexpr int GROUPS = 128 / NE, GW = NE / 32;    // matrices per CTA, warps per matrix
+    constexpr int RING = kLogChunk * kLogSlots;
+    extern __shared__ __align__(128) unsigned char zsm[];       // [GROUPS][RING] double2, then [GROUPS][2][kLogSlots] mbarriers
+    const int tid = threadIdx.x, lane = tid & 31;
     const int grp = tid / NE, row = tid % NE;
+    const bool producer = (row == 0);                 // lane 0 of the group's first warp
+    double2 *ring = reinterpret_cast<double2 *>(zsm) + (size_t)grp * RING;
+    uint64_t *full = reinterpret_cast<uint64_t *>(zsm + sizeof(double2) * GROUPS * RING) + (size_t)grp * 2 * kLogSlots;
+    uint64_t *empty = full + kLogSlots;
+    if (producer) {
+        for (int s = 0; s < kLogSlots; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], GW); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    // chunk counters run on across the k-points of this group, so the barrier phases stay consistent
+    unsigned acquired = 0, released = 0, issued = 0;  // chunks waited for / handed back / requested (producer only)
     for (long long ik = (long long)blockIdx.x * GROUPS + grp; ik < nk; ik += (long long)gridDim.x * GROUPS) {
         double z[NE];
 #pragma unroll
         for (int j = 0; j < NE; ++j) z[j] = (j == row) ? 1.0 : 0.0;
         const unsigned int *hdr = tb.hdr + (size_t)ik * tb.hdr_cap;
         const double2 *lg = tb.log + (size_t)ik * tb.log_cap;
-        const int nh = tb.nhdr[ik];
+        const int nh = tb.nhdr[2 * ik], nlog = tb.nhdr[2 * ik + 1];
+        const unsigned nchunks = (unsigned)((nlog + kLogChunk - 1) / kLogChunk);
+        const unsigned base = acquired;               // chunk counter value of this matrix's chunk 0 (== released == issued)
+        const unsigned ring0 = base * kLogChunk;      // ring position of this matrix's log position 0
+        auto issue_upto = [&](unsigned want) {        // producer: request chunks [issued, min(want, base + nchunks))
+            while (issued < want && issued - base < nchunks) {
+                const unsigned c = issued - base, slot = issued % kLogSlots;
+                if (issued >= kLogSlots) mbar_wait(&empty[slot], ((issued / kLogSlots) + 1) & 1);
+                const int cnt = (nlog - (int)c * kLogChunk < kLogChunk) ? nlog - (int)c * kLogChunk : kLogChunk;
+                mbar_expect_tx(&full[slot], (uint32_t)cnt * 16u);
+                tma_bulk_g2s(ring + (size_t)slot * kLogChunk, lg + (size_t)c * kLogChunk, (uint32_t)cnt * 16u, &full[slot]);
+                ++issued;
+            }
+        };
+        if (producer) issue_upto(base + kLogSlots);
         int pos0 = 0;
         for (int h = 0; h < nh; ++h) {
             const unsigned int w = __ldg(hdr + h);
             const int l = (int)(w & 0xffu), m = (int)(w >> 8);
-            const double2 *src = lg + pos0 + (m - 1);          // rotation of plane i sits at src[-i]
+            // the chase reads log positions [pos0, pos0 + m - l): make sure their chunks have landed
+            const unsigned need = base + (unsigned)((pos0 + (m - l) - 1) / kLogChunk) + 1;
+            while (acquired < need) { mbar_wait(&full[acquired % kLogSlots], (acquired / kLogSlots) & 1); ++acquired; }
+            const int p_hi = pos0 + (m - 1);          // rotation of plane i sits at log position p_hi - i
 #pragma unroll
             for (int blk = NE / 8 - 1; blk >= 0; --blk) {
                 if (8 * blk < m && 8 * blk + 7 >= l) {
-                    // the 8 rotations of the block are fetched together (clamped to the chase's range): one exposed L2
-                    // latency per 8 rotations instead of one per rotation (the guarded loads could not be hoisted)
                     double2 csb[8];
 #pragma unroll
                     for (int ii = 0; ii < 8; ++ii) {
                         int ic = 8 * blk + ii;
                         ic = ic < l ? l : (ic > m - 1 ? m - 1 : ic);
-                        csb[ii] = __ldg(src - ic);
+                        csb[ii] = ring[(ring0 + (unsigned)(p_hi - ic)) % RING];
                     }
 #pragma unroll
                     for (int ii = 7; ii >= 0; --ii) {
@@ -248,7 +283,22 @@ zrot_kernel(const int n, const long long nk, const TriBuf tb) {
                 }
             }
             pos0 += m - l;
+            // hand back the chunks that lie completely behind pos0
+            while ((int)(released - base + 1) * kLogChunk <= pos0) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[released % kLogSlots]);
+                ++released;
+                if (producer) issue_upto(released + kLogSlots);
+            }
         }
+        // the tail chunk(s) of this matrix
+        while (released - base < nchunks) {
+            if (acquired <= released) { mbar_wait(&full[acquired % kLogSlots], (acquired / kLogSlots) & 1); ++acquired; }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[released % kLogSlots]);
+            ++released;
+        }
+        if (producer) issued = released;              // nothing beyond this matrix's chunks was requested
         double *Zo = tb.Z + (size_t)ik * NE * NE;
 #pragma unroll
         for (int j = 0; j < NE; ++j) Zo[j * NE + row] = z[j];
@@ -279,9 +329,18 @@ cudaError_t launch_tql(int nw, long long nk, const TriBuf &tb, int *err_flag, cu
 cudaError_t launch_zrot(int nw, long long nk, const TriBuf &tb, int sm_count, cudaStream_t st) {
     const int groups = 128 / tb.ne;
     long long grid = (nk + groups - 1) / groups;
-    grid = std::max<long long>(1, std::min<long long>(grid, (long long)sm_count * 8));
-    if (tb.ne == 32) zrot_kernel<32><<<(int)grid, 128, 0, st>>>(nw, nk, tb);
-    else zrot_kernel<64><<<(int)grid, 128, 0, st>>>(nw, nk, tb);
+    grid = std::max<long long>(1, std::min<long long>(grid, (long long)sm_count * (tb.ne == 32 ? 3 : 3)));
+    const size_t smem = sizeof(double2) * groups * kLogChunk * kLogSlots + sizeof(uint64_t) * groups * 2 * kLogSlots;
+    cudaError_t e;
+    if (tb.ne == 32) {
+        e = cudaFuncSetAttribute(zrot_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        zrot_kernel<32><<<(int)grid, 128, smem, st>>>(nw, nk, tb);
+    } else {
+        e = cudaFuncSetAttribute(zrot_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        zrot_kernel<64><<<(int)grid, 128, smem, st>>>(nw, nk, tb);
+    }
     return cudaGetLastError();
 }
 
