@@ -317,6 +317,53 @@ struct LargeSmemLayout {
     }
 };
 
+// C = op(Am) * Bm for nw x nw complex matrices held row-major in shared memory (leading dimension LD), nw % 8 == 0, on the
+// FP64 tensor cores: 8 x 8 output tiles, mma.sync.m8n8k4.f64, four real MMAs per complex k-step (re re, -im im, re im, im re).
+// A warp owns a tile row and up to four tile columns: its A fragment (one LDS.128 per lane and k-step) is reused for the
+// four B fragments.  The 2 x 2 register-blocked FMA loops this replaces issue one LDS.128 per four DFMA and are bound by the
+// shared-memory pipe (20 TF); here it is one LDS.128 per 2.5 DMMA = 640 FMA.
+// CONJT: op(Am) = Am^dagger (element (n, p) = conj(Am[p LD + n])).  Output: Cs row-major in shared memory, or Cg column-major
+// (n + nw j) in global memory.
+template <bool CONJT>
+__device__ __forceinline__ void zgemm_dmma(const int nw, const int LD, const double2 *__restrict__ Am, const double2 *__restrict__ Bm,
+                                           double2 *__restrict__ Cs, double2 *__restrict__ Cg) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kq = lane & 3, nq = lane >> 2;
+    const int nt = nw >> 3, ngrp = (nt + 3) >> 2;
+    for (int item = warp; item < nt * ngrp; item += E_WARPS) {
+        const int tr = item / ngrp, tc0 = (item % ngrp) * 4;
+        double cr[4][2], ci[4][2];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { cr[t][0] = cr[t][1] = ci[t][0] = ci[t][1] = 0.0; }
+        for (int ks = 0; ks < (nw >> 2); ++ks) {
+            double2 a = CONJT ? Am[(4 * ks + kq) * LD + 8 * tr + nq] : Am[(8 * tr + nq) * LD + 4 * ks + kq];
+            if (CONJT) a.y = -a.y;
+            const double nay = -a.y;
+            double2 b[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) b[t] = (tc0 + t < nt) ? Bm[(4 * ks + kq) * LD + 8 * (tc0 + t) + nq] : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(cr[t][0]), "+d"(cr[t][1]) : "d"(a.x), "d"(b[t].x));
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(ci[t][0]), "+d"(ci[t][1]) : "d"(a.x), "d"(b[t].y));
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(cr[t][0]), "+d"(cr[t][1]) : "d"(nay), "d"(b[t].y));
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(ci[t][0]), "+d"(ci[t][1]) : "d"(a.y), "d"(b[t].x));
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            if (tc0 + t < nt) {
+                const int row = 8 * tr + nq, col = 8 * (tc0 + t) + 2 * kq;
+                if (Cs) { Cs[row * LD + col] = make_double2(cr[t][0], ci[t][0]); Cs[row * LD + col + 1] = make_double2(cr[t][1], ci[t][1]); }
+                else { Cg[row + nw * col] = make_double2(cr[t][0], ci[t][0]); Cg[row + nw * (col + 1)] = make_double2(cr[t][1], ci[t][1]); }
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(E_THREADS, 1)
 eig_rot_large_kernel(const DevModel m, const KSource ks, const Jobs jb, const InterpOut out, const int max_pairs,
                      const double2 *__restrict__ Hk_in, const double2 *__restrict__ Hka_in, double2 *__restrict__ Vscr,
@@ -522,6 +569,13 @@ eig_rot_large_kernel(const DevModel m, const KSource ks, const Jobs jb, const In
                 if (jb.do_gauge) {
                     for (int idx = tid; idx < nw2; idx += E_THREADS) { const int n = idx % nw, mm = idx / nw; A[n * LD + mm] = Ha[idx]; }
                     __syncthreads();
+                    if ((nw & 7) == 0) {                            // tensor-core path: U(buffer) <- Ha Us ; V <- Us^dagger U
+                        zgemm_dmma<false>(nw, LD, A, T, U, nullptr);
+                        __syncthreads();
+                        zgemm_dmma<true>(nw, LD, T, U, nullptr, Vg + a * nw2);
+                        __syncthreads();
+                        continue;
+                    }
                     // U(buffer) <- Ha * Us     two rows x two columns per thread
                     const int njb = (nw + 1) / 2;
                     for (int t = tid; t < njb * njb; t += E_THREADS) {
