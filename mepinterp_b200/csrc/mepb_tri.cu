@@ -30,15 +30,21 @@ __device__ __forceinline__ double2 shfl_xor2(double2 v, int o) {
 }
 
 // ================================================================================================ tridiagonalisation
-template <int NE>
-__global__ void __launch_bounds__(NE * 8, 1)
+// PARTS threads per matrix row (thread (i, part) owns A(i, part + PARTS jj)); NE = 64: PARTS = 4 -> 256 threads and 16
+// columns per thread, ~100 registers, TWO matrices resident per SM (the 512-thread / 124-register shape of the first
+// version allowed one, and the kernel is bound by its three barriers per column, not by arithmetic).  The reflector is never
+// materialised per thread: with v = scale x (x = the published column, v(s+1) = 1)
+//   A v = scale sum_{j>s+1} A(:,j) x_j + A(:,s+1),      w_i conj(v_j) = (w_i conj(scale)) conj(x_j)
+// so the column entries come straight from shared memory (one complex multiply per thread instead of one per element).
+template <int NE, int PARTS>
+__global__ void __launch_bounds__(NE * PARTS, 2)
 tridiag_kernel(const int nw, const long long nk, const double2 *__restrict__ Hk_in, const TriBuf tb) {
-    constexpr int JJ = NE / 8, NT = NE * 8, NWARP = NT / 32;
+    constexpr int JJ = NE / PARTS, NT = NE * PARTS, NWARP = NT / 32;
     __shared__ double2 xs[2][NE];
     __shared__ double2 ws[NE];
     __shared__ double2 red[NWARP];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int i = tid >> 3, part = tid & 7;
+    const int i = tid / PARTS, part = tid % PARTS;
     const int nw2 = nw * nw;
 
     for (long long ik = blockIdx.x; ik < nk; ik += gridDim.x) {
@@ -50,7 +56,7 @@ tridiag_kernel(const int nw, const long long nk, const double2 *__restrict__ Hk_
         double2 a[JJ];
 #pragma unroll
         for (int jj = 0; jj < JJ; ++jj) {
-            const int j = part + 8 * jj;
+            const int j = part + PARTS * jj;
             double2 v = make_double2(0.0, 0.0);
             if (i < nw && j < nw) {
                 if (i < j) v = Hk[i + nw * j];
@@ -64,8 +70,8 @@ tridiag_kernel(const int nw, const long long nk, const double2 *__restrict__ Hk_
 
 #pragma unroll
         for (int sb = 0; sb < JJ; ++sb) {
-            for (int sl = 0; sl < 8; ++sl) {
-                const int s = 8 * sb + sl;
+            for (int sl = 0; sl < PARTS; ++sl) {
+                const int s = PARTS * sb + sl;
                 if (s > nw - 1) break;
                 const int buf = s & 1;
                 if (part == sl) {
@@ -90,25 +96,25 @@ tridiag_kernel(const int nw, const long long nk, const double2 *__restrict__ Hk_
                     tau = make_double2((beta - alpha.x) * rb, -alpha.y * rb);
                     scale = crcp(make_double2(alpha.x - beta, alpha.y));
                 }
-                auto vget = [&](int r) -> double2 {
-                    if (r <= s) return make_double2(0.0, 0.0);
-                    if (r == s + 1) return make_double2(1.0, 0.0);
-                    return cmul(xs[buf][r], scale);
-                };
-                const double2 vi = vget(i);
-                double2 vj[JJ];
-#pragma unroll
-                for (int jj = 0; jj < JJ; ++jj) vj[jj] = vget(part + 8 * jj);
+                // own row's reflector entry
+                const double2 vi = (i <= s) ? make_double2(0.0, 0.0) : (i == s + 1) ? make_double2(1.0, 0.0) : cmul(xs[buf][i], scale);
                 // p = tau A v  (rows <= s are finished: p = 0 there)
-                double2 p = make_double2(0.0, 0.0);
+                double2 p1 = make_double2(0.0, 0.0), p2 = make_double2(0.0, 0.0);
 #pragma unroll
-                for (int jj = 0; jj < JJ; ++jj) cfma(p, a[jj], vj[jj]);
-                p = cadd(p, shfl_xor2(p, 1)); p = cadd(p, shfl_xor2(p, 2)); p = cadd(p, shfl_xor2(p, 4));
+                for (int jj = 0; jj < JJ; ++jj) {
+                    const int j = part + PARTS * jj;
+                    if (j > s + 1) cfma(p1, a[jj], xs[buf][j]);
+                    else if (j == s + 1) p2 = a[jj];
+                }
+                double2 p = cadd(cmul(scale, p1), p2);
+#pragma unroll
+                for (int o = 1; o < PARTS; o <<= 1) p = cadd(p, shfl_xor2(p, o));
                 p = cmul(tau, p);
                 if (i <= s) p = make_double2(0.0, 0.0);
                 // p^H v
                 double2 dt = (part == 0) ? cmulc(vi, p) : make_double2(0.0, 0.0);
-                dt = cadd(dt, shfl_xor2(dt, 8)); dt = cadd(dt, shfl_xor2(dt, 16));
+#pragma unroll
+                for (int o = PARTS; o < 32; o <<= 1) dt = cadd(dt, shfl_xor2(dt, o));
                 if (lane == 0) red[warp] = dt;
                 if (part == 0) Vr[(size_t)s * NE + i] = vi;
                 if (tid == 0) { tau_o[s] = tau; e_o[s] = beta; }
@@ -121,11 +127,15 @@ tridiag_kernel(const int nw, const long long nk, const double2 *__restrict__ Hk_
                 cfma(wi, alc, vi);
                 if (part == 0) ws[i] = wi;
                 __syncthreads();                                                            // (3)
+                const double2 wis = cmulc(wi, scale);                                       // w_i conj(scale)
 #pragma unroll
                 for (int jj = 0; jj < JJ; ++jj) {
-                    const double2 wj = ws[part + 8 * jj];
-                    const double2 u1 = cmulc(vi, wj), u2 = cmulc(wi, vj[jj]);
-                    a[jj].x -= u1.x + u2.x; a[jj].y -= u1.y + u2.y;
+                    const int j = part + PARTS * jj;
+                    if (j > s) {
+                        const double2 u1 = cmulc(vi, ws[j]);
+                        const double2 u2 = (j == s + 1) ? wi : cmulc(wis, xs[buf][j]);
+                        a[jj].x -= u1.x + u2.x; a[jj].y -= u1.y + u2.y;
+                    }
                 }
             }
         }
@@ -313,9 +323,9 @@ int tri_padded_size(int nw) { return nw <= 32 ? 32 : 64; }
 size_t tri_log_cap(int ne) { return (size_t)2 * ne * ne; }
 
 cudaError_t launch_tridiag(int nw, long long nk, const double2 *Hk, const TriBuf &tb, int sm_count, cudaStream_t st) {
-    const int grid = (int)std::min<long long>(nk < 1 ? 1 : nk, (long long)sm_count * (tb.ne == 32 ? 4 : 1));
-    if (tb.ne == 32) tridiag_kernel<32><<<grid, 256, 0, st>>>(nw, nk, Hk, tb);
-    else tridiag_kernel<64><<<grid, 512, 0, st>>>(nw, nk, Hk, tb);
+    const int grid = (int)std::min<long long>(nk < 1 ? 1 : nk, (long long)sm_count * 2);      // two CTAs of 256 threads per SM (110 / 128 registers)
+    if (tb.ne == 32) tridiag_kernel<32, 8><<<grid, 256, 0, st>>>(nw, nk, Hk, tb);
+    else tridiag_kernel<64, 4><<<grid, 256, 0, st>>>(nw, nk, Hk, tb);
     return cudaGetLastError();
 }
 
