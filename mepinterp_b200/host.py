@@ -188,3 +188,21 @@ def band_worker(run_dir: str, kpts: np.ndarray, device: int = 0) -> np.ndarray:
     finally:
         ctx.close()
     return np.ascontiguousarray(e.T)
+
+
+def probe_phi(phis, params, device: int = 0) -> list:
+    """The parameter sweep of scripts/probe_phi.py / mep_worker.py without processes or files: the reference writes a run
+    directory and spawns `mpirun mepInterp` per phi (mep_worker.py:142); here ONE live context takes the regenerated H(R)
+    through mepb_update_model (same R set, same FT convention) and reruns the mesh.  Returns the result dict per phi."""
+    from . import models
+    phis = [float(x) for x in phis]
+    ctx = api.Context(models.souza_tb(phis[0]), params, device)
+    out = []
+    try:
+        for i, phi in enumerate(phis):
+            if i:
+                ctx.update_model(models.souza_tb(phi).H)
+            out.append(ctx.run_mesh())
+    finally:
+        ctx.close()
+    return out

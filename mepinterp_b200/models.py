@@ -40,3 +40,51 @@ def synthetic_tb(nw: int = 64, rmax2: int = 61, seed: int = 20261017, tb_centers
         a_latt = np.diag([5.0, 6.0, 7.0])
     wfc = rng.uniform(size=(3, nw)) if tb_centers else None
     return make_model(R, Hs, np.asarray(a_latt, dtype=np.float64), wfc)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Cubic 8-band model of New J. Phys. 12, 053032 (2010) as the reference's generator parametrises it
+# (scripts/souza_tb_model.py:394-442: get_souza_tb(phi_para)).  Restated as a bond table:
+# per axis four bonds, each with an intra-cell hopping H(0)(i,j) = t[a] and an inter-cell hopping H(+-e)(i',j') = t[a'] (the SAME
+# value at +e and -e, as the reference writes it), plus the Hermitian partners.  t[axis][a] = 27.21139 eV * exp(i pi phi[axis][a]).
+# (i, j, a) are 1-based like the _hr.dat columns "m n".
+_SOUZA_BONDS = (
+    ((1, 2, 1, 2, 1, 2), (4, 3, 4, 3, 4, 3), (5, 6, 5, 6, 5, 6), (8, 7, 8, 7, 8, 7)),      # x
+    ((1, 4, 1, 4, 1, 4), (2, 3, 2, 3, 2, 3), (5, 8, 5, 8, 5, 8), (6, 7, 6, 7, 6, 7)),      # y
+    ((1, 5, 1, 5, 1, 5), (2, 6, 2, 6, 2, 6), (3, 7, 3, 7, 3, 7), (4, 8, 4, 8, 4, 8)),      # z
+)
+_SOUZA_ONSITE = (-6.5, 0.9, 1.4, 1.2, -6.0, 1.5, 0.8, 1.2)
+_SOUZA_PHI = ((None, 1.3, 0.8, 0.3, 1.4, 0.6, 0.8, 1.9), (0.5, 0.2, 1.4, 1.9, 0.8, 1.7, 0.6, 0.3), (1.7, 0.5, 0.6, 1.0, 0.3, 0.7, 1.2, 1.4))
+_PY_AU_TO_EV = 27.21139          # the generator's constant; the Fortran reader divides by 27.211385 (keep both)
+
+
+def souza_tb(phi: float = 0.0, as_file: bool = True):
+    """In-memory model of the Souza toy system for the phase parameter `phi` (the knob scripts/probe_phi.py sweeps).
+
+    as_file=True reproduces what the reference pipeline hands to core_worker bit for bit: the generator's eV values rounded to
+    the 8 decimals of tb_input_writer.py ("{:16.8f}"), the reader's |x| < 1e-7 eV -> 0 rule and its division by 27.211385
+    (file_io.f90:732-741).  R points in the writer's (sorted) order; cubic cell a = 2 Bohr; Wannier FT convention (N_wf = 0)."""
+    R = np.array([(-1, 0, 0), (0, -1, 0), (0, 0, -1), (0, 0, 0), (0, 0, 1), (0, 1, 0), (1, 0, 0)], dtype=np.float64).T
+    index = {tuple(int(x) for x in R[:, i]): i for i in range(7)}
+    H = np.zeros((8, 8, 7), dtype=np.complex128)
+    for n, e in enumerate(_SOUZA_ONSITE):
+        H[n, n, index[(0, 0, 0)]] = e * _PY_AU_TO_EV
+    for ax in range(3):
+        t = [_PY_AU_TO_EV * np.exp(1j * np.pi * (phi if p is None else p)) for p in _SOUZA_PHI[ax]]
+        e = [0, 0, 0]
+        e[ax] = 1
+        for (i0, j0, a0, i1, j1, a1) in _SOUZA_BONDS[ax]:
+            H[i0 - 1, j0 - 1, index[(0, 0, 0)]] = t[a0 - 1]
+            H[j0 - 1, i0 - 1, index[(0, 0, 0)]] = np.conj(t[a0 - 1])
+            for sgn in (-1, 1):
+                r = index[tuple(sgn * x for x in e)]
+                H[i1 - 1, j1 - 1, r] = t[a1 - 1]
+                H[j1 - 1, i1 - 1, r] = np.conj(t[a1 - 1])
+    if as_file:
+        re = np.vectorize(lambda v: float("{:.8f}".format(v)))(H.real)
+        im = np.vectorize(lambda v: float("{:.8f}".format(v)))(H.imag)
+        re[np.abs(re) < 1e-7] = 0.0
+        im[np.abs(im) < 1e-7] = 0.0
+        H = re + 1j * im
+    H = H / AU_TO_EV
+    return make_model(R, H, np.diag([2.0, 2.0, 2.0]), None)

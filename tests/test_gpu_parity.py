@@ -413,3 +413,21 @@ def test_full_size_c4_dmma_and_fma_sweeps_agree(libmepb, tmp_path):
     for k in ("ahc_tens", "ahcVELO", "ohcVELO", "photoC_2nd"):
         assert a[k].shape == b[k].shape
         assert np.abs(a[k] - b[k]).max() <= 1e-10 * np.abs(b[k]).max(), k
+
+
+def test_probe_phi_live_context_equals_fresh_contexts(libmepb):
+    """scripts/probe_phi.py as a library call: H(R) regenerated per phi and re-uploaded into ONE context
+    gives bit-identical tensors to a fresh context per phi, and phi = 0 matches the oracle on the reference-generated fixture."""
+    from mepinterp_b200 import host, models
+    m0, p = load_case("souza_phi0", mp_grid=(12, 12, 12), do_kubo=True)
+    phis = [0.0, 0.3, 0.85]
+    sweep = host.probe_phi(phis, p)
+    for phi, res in zip(phis, sweep):
+        ctx = libmepb.Context(models.souza_tb(phi), p)
+        fresh = ctx.run_mesh()
+        ctx.close()
+        for k, v in fresh.items():
+            assert np.array_equal(np.asarray(v), np.asarray(res[k])), (phi, k)
+    ref, scale, sens = oracle_reference(m0, p)
+    assert_parity(sweep[0], ref, scale, sens, tol=TENS_TOL, label="souza phi=0")
+    assert np.abs(sweep[1]["mep_tens"] - sweep[0]["mep_tens"]).max() > 1e-6 * np.abs(sweep[0]["mep_bands"]).max()   # phi matters

@@ -69,3 +69,23 @@ def test_output_writer_format(tmp_path):
     np.testing.assert_allclose(np.load(os.path.join(out, "hw_lst.npy")), [0.0, 1.0, 2.0], atol=1e-14)
     rows = open(os.path.join(out, "occ.dat")).read().splitlines()
     assert len(rows) == 2 and rows[0].split() == ["-2.72113850", "3.50000000"]
+
+
+def test_souza_generator_equals_the_reference_generated_fixture():
+    """mepinterp_b200.models.souza_tb against tests/golden/souza_phi0, which make_fixtures.py produced by
+    running the reference's scripts/souza_tb_model.py + tb_input_writer.py unchanged: bit-identical H(R), R, lattice."""
+    import numpy as np
+    from mepinterp_b200 import host, models
+    from tests.cases import GOLDEN
+    ref, _, _ = host.load_run_dir(os.path.join(GOLDEN, "souza_phi0"))
+    gen = models.souza_tb(0.0)
+    assert gen.nw == ref.nw == 8 and gen.nR == ref.nR == 7 and gen.wf_centers is None and ref.wf_centers is None
+    assert np.array_equal(np.asarray(gen.R), np.asarray(ref.R))
+    assert np.array_equal(np.asarray(gen.a_latt), np.asarray(ref.a_latt))
+    assert np.array_equal(np.asarray(gen.H), np.asarray(ref.H))
+    other = models.souza_tb(0.35)                                   # phi enters exactly one hopping phase (x bond of site 1)
+    changed = np.argwhere(np.asarray(other.H) != np.asarray(gen.H))
+    assert {(int(a), int(b)) for a, b, _ in changed} == {(0, 1), (1, 0)} and {int(r) for _, _, r in changed} == {3}
+    Hh = np.asarray(other.H)
+    for r, rm in ((0, 6), (1, 5), (2, 4), (3, 3)):                  # Hermitian closure H(-R) = H(R)^dagger
+        assert np.array_equal(Hh[:, :, r], Hh[:, :, rm].conj().T)
