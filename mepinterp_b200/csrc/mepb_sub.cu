@@ -288,12 +288,13 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
             if (valid && out.cnt_ahc && g == 0) { out.cnt_ahc[ik] = n_items_before; acc_nit += (double)n_items_before; }
         }
         // ------------------------------------------------------------------ MEP sums, band n0 = g (mep_niu.f90, kubo_mep.f90)
-        if (MEP && (jb.do_mep || jb.do_kubo)) {
+        if (MEP && (jb.do_mep || jb.do_kubo) && valid) {               // idle groups (past the end of the launch) contribute nothing
             const int n0 = g;
             const double e0 = es[n0];
-            double lc_g[9], lc_u[9], ic_g[9], ic_u[9];
-#pragma unroll
-            for (int q = 0; q < 9; ++q) { lc_g[q] = 0; lc_u[q] = 0; ic_g[q] = 0; ic_u[q] = 0; }
+            // the per-k terms go straight into the launch-long accumulators with their weights (1 for band n0 <= nval of
+            // mep_niu, f_n0 for kubo_mep): 36 fewer live doubles in a kernel that spills at 255 registers
+            const double w_niu = (jb.do_mep && n0 < jb.nval) ? 1.0 : 0.0;
+            const double w_kub = jb.do_kubo ? fn[n0] : 0.0;
             double2 v00[3];
 #pragma unroll
             for (int a = 0; a < 3; ++a) v00[a] = Vs[a * NW * LD + n0 * LD + n0];
@@ -317,8 +318,9 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
                         const double c0 = re(Q[1], v00[2]) - re(Q[2], v00[1]);
                         const double c1 = re(Q[2], v00[0]) - re(Q[0], v00[2]);
                         const double c2 = re(Q[0], v00[1]) - re(Q[1], v00[0]);
-                        lc_u[i] += c0 * inv; lc_u[i + 3] += c1 * inv; lc_u[i + 6] += c2 * inv;
-                        if (pass) { lc_g[i] += c0 * inv; lc_g[i + 3] += c1 * inv; lc_g[i + 6] += c2 * inv; }
+                        const double iu = inv * w_kub, ig = pass ? inv * w_niu : 0.0;
+                        kub_lc[i] = fma(c0, iu, kub_lc[i]); kub_lc[i + 3] = fma(c1, iu, kub_lc[i + 3]); kub_lc[i + 6] = fma(c2, iu, kub_lc[i + 6]);
+                        niu_lc[i] = fma(c0, ig, niu_lc[i]); niu_lc[i + 3] = fma(c1, ig, niu_lc[i + 3]); niu_lc[i + 6] = fma(c2, ig, niu_lc[i + 6]);
                     }
                 }
                 {   // itinerant term: - sum_{m != n0} eps_jkl Re[V(i,n0,n) V(k,n,m) V(l,m,n0)] / ((E_n0-E_n)^2 (E_n0-E_m))
@@ -349,20 +351,9 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
                     for (int j = 0; j < 3; ++j)
 #pragma unroll
                         for (int i = 0; i < 3; ++i) {
-                            ic_u[i + 3 * j] -= (v0n[i].x * Zu[j].x - v0n[i].y * Zu[j].y);
-                            ic_g[i + 3 * j] -= (v0n[i].x * Zg[j].x - v0n[i].y * Zg[j].y);
+                            kub_ic[i + 3 * j] -= w_kub * (v0n[i].x * Zu[j].x - v0n[i].y * Zu[j].y);
+                            niu_ic[i + 3 * j] -= w_niu * (v0n[i].x * Zg[j].x - v0n[i].y * Zg[j].y);
                         }
-                }
-            }
-            if (valid) {
-                const double f0 = fn[n0];
-                if (jb.do_mep && n0 < jb.nval) {
-#pragma unroll
-                    for (int q = 0; q < NM; ++q) { niu_ic[q] += ic_g[q]; niu_lc[q] += lc_g[q]; }
-                }
-                if (jb.do_kubo) {
-#pragma unroll
-                    for (int q = 0; q < NM; ++q) { kub_ic[q] += f0 * ic_u[q]; kub_lc[q] += f0 * lc_u[q]; }
                 }
             }
         }
