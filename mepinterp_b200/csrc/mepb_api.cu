@@ -578,10 +578,13 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
     if (c->tri) per_k += (size_t)tne * tne * (sizeof(double2) + sizeof(double)) + sizeof(double2) * tri_log_cap(tne) +
                          sizeof(unsigned int) * kTriHdrCap + (size_t)tne * 48;
     long long chunk = 1 << 18;
-    {   // per-stream budget for the per-k intermediates: an eighth of the free HBM, at most 8 GB (180 GB per B200; two streams)
+    {   // per-stream budget for the per-k intermediates (180 GB per B200; two streams): small path an eighth of the free HBM,
+        // at most 8 GB; general path a fifth, at most 24 GB (0.4 MB per k-point at nw = 64: 60 K k-points per wave — the
+        // thread-per-k QL kernel needs tens of thousands of k-points in flight to hide its serial recurrence)
         size_t free_b = 0, total_b = 0;
         CT(cudaMemGetInfo(&free_b, &total_b));
-        const size_t budget = std::max<size_t>(256ull << 20, std::min<size_t>(free_b / 8, (c->large ? 6144ull : 8192ull) << 20));
+        const size_t budget = std::max<size_t>(256ull << 20, c->large ? std::min<size_t>(free_b / 5, 24576ull << 20)
+                                                                      : std::min<size_t>(free_b / 8, 8192ull << 20));
         if (per_k) chunk = std::min<long long>(chunk, (long long)(budget / per_k));
     }
     chunk = std::max<long long>(c->large ? 296 : 1024, std::min(chunk, std::max<long long>(nk_mesh, 1024)));
