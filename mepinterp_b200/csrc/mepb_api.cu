@@ -578,6 +578,7 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
     if (c->tri) per_k += (size_t)tne * tne * (sizeof(double2) + sizeof(double)) + sizeof(double2) * tri_log_cap(tne) +
                          sizeof(unsigned int) * kTriHdrCap + (size_t)tne * 48;
     long long chunk = 1 << 18;
+    if (const char *e = getenv("MEPB_CHUNK_LOG2")) { const int v = atoi(e); if (v >= 10 && v <= 24) chunk = 1LL << v; }   // tuning knob
     {   // per-stream budget for the per-k intermediates (180 GB per B200; two streams): small path an eighth of the free HBM,
         // at most 8 GB; general path a fifth, at most 24 GB (0.4 MB per k-point at nw = 64: 60 K k-points per wave — the
         // thread-per-k QL kernel needs tens of thousands of k-points in flight to hide its serial recurrence)
