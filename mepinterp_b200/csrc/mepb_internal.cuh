@@ -290,9 +290,9 @@ cudaError_t launch_sweep_photo(const double *items, const int *cnt, int max_item
                                double eta, double *block_out, int grid, cudaStream_t st);
 int sweep_photo_grid(int sm_count, long long nk, int n_hw, int *slots_out, int max_items);
 // tensor-core (DMMA) formulation of both sweeps (mepb_sweep_mma.cu), used for n_hw >= 16 unless MEPB_SWEEP_FMA is set
-struct MmaShape { int NT, G, wtiles, warps, passes; };     // tiles per warp, k-groups, warps per group, warps per CTA, grid.y
+struct MmaShape { int NT, G, wtiles, warps, passes, shared; };   // tiles per warp, k-groups, warps per group, warps per CTA, grid.y, shared tile
 constexpr int kMmaAhcWarps = 8, kMmaPhotoWarps = 13;      // consumer warps per CTA (+ one TMA producer warp)
-MmaShape sweep_mma_shape(int n_hw, int wmax, int nt_max);
+MmaShape sweep_mma_shape(int n_hw, int wmax, int nt_max, bool shared_ok);
 bool sweep_mma_enabled(int n_hw);
 bool sweep_photo_mma_fits(int max_items);
 int sweep_ahc_mma_bps(bool herm, int NT);

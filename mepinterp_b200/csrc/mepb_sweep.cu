@@ -301,7 +301,7 @@ void sweep_shape(int n_hw, int T, int *G, int *NS, int *threads) {
 int sweep_ahc_kc(bool herm, int max_pairs);
 int sweep_ahc_grid(int sm_count, long long nk, int n_hw, int *slots_out, bool herm, int max_pairs) {
     if (sweep_mma_enabled(n_hw) && !getenv("MEPB_SWEEP_DIRECT") && sweep_ahc_kc(herm, max_pairs) > 0) {
-        const MmaShape s = sweep_mma_shape(n_hw, kMmaAhcWarps, herm ? 4 : 2);
+        const MmaShape s = sweep_mma_shape(n_hw, kMmaAhcWarps, herm ? 4 : 2, false);
         if (slots_out) *slots_out = s.G * n_hw;
         long long g = (long long)sm_count * sweep_ahc_mma_bps(herm, s.NT);
         const long long need = (nk + s.G - 1) / s.G;
@@ -356,7 +356,7 @@ cudaError_t launch_sweep_ahc(bool herm, const double *items, const int *cnt, int
 }
 int sweep_photo_grid(int sm_count, long long nk, int n_hw, int *slots_out, int max_items) {
     if (sweep_mma_enabled(n_hw) && !getenv("MEPB_SWEEP_DIRECT") && sweep_photo_mma_fits(max_items)) {
-        const MmaShape s = sweep_mma_shape(n_hw, kMmaPhotoWarps, 2);
+        const MmaShape s = sweep_mma_shape(n_hw, kMmaPhotoWarps, 2, true);
         if (slots_out) *slots_out = s.G * n_hw;
         long long g = sm_count;                                  // one CTA of up to 448 threads per SM
         if (g > nk) g = nk;

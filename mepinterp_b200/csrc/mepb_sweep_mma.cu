@@ -16,6 +16,7 @@
 // bandwidth and issue slots, not peak.  Items stream through shared memory by TMA bulk copies into a ring of stages with
 // full/empty mbarriers: a dedicated producer warp refills a stage as soon as every consumer warp has released it, so the
 // consumer warps (which own different numbers of frequency tiles) never meet at a CTA-wide barrier.
+#include <algorithm>
 #include <cstdlib>
 
 #include "mepb_internal.cuh"
@@ -172,8 +173,11 @@ sweep_ahc_mma_kernel(const double2 *__restrict__ items, const int *__restrict__ 
 // ------------------------------------------------------------------------------------------------ photo sweep
 // 27 complex components = 3 tiles of 8 + 3 remainder; one k-point per TMA stage.  The G k-groups of a CTA take the items of a
 // stage in turn in blocks of 4 (item block jb belongs to group jb % G).
-template <int NT>
-__global__ void __launch_bounds__(448, 1)
+// SH: one more frequency tile (index wtiles * NT) is SHARED by all consumer warps — warp w takes it for the item blocks whose
+// running number is w modulo the number of warps — and reduced in fixed order at the end.  With 25 tiles (n_hw = 200) twelve
+// warps then carry 2 + 1/12 tiles each, 6.25 per SM sub-partition, where 13 warps x 2 tiles leave one sub-partition with 7.
+template <int NT, bool SH>
+__global__ void __launch_bounds__(SH ? 384 : 448, 1)             // SH: 12 warps, no producer warp (168 registers; a 13th warp would cap them at 128)
 sweep_photo_mma_kernel(const double2 *__restrict__ items, const int *__restrict__ cnt, const int max_items, const long long nk,
                        const int n_hw, const double *__restrict__ hw, const double eta, double *__restrict__ block_out,
                        const int G, const int wtiles) {
@@ -188,27 +192,31 @@ sweep_photo_mma_kernel(const double2 *__restrict__ items, const int *__restrict_
     const long long kb0 = (long long)blockIdx.x * per;
     const long long kb1 = (kb0 + per < nk) ? kb0 + per : nk;
     const int nchunks = kb0 < kb1 ? (int)(kb1 - kb0) : 0;
-    const int n_cons = (int)(blockDim.x >> 5) - 1;              // consumer warps; the last warp is the TMA producer
+    // consumer warps; without SH the last warp is a dedicated TMA producer, with SH thread 0 refills a stage one k-point after
+    // it was consumed (by then the other warps have normally released it)
+    const int n_cons = SH ? (int)(blockDim.x >> 5) : (int)(blockDim.x >> 5) - 1;
     uint64_t *full = bar, *empty = bar + kMmaPhotoStages;
     if (threadIdx.x == 0) {
         for (int s = 0; s < kMmaPhotoStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], n_cons); }
         mbar_fence_init();
     }
     __syncthreads();
-    if ((int)(threadIdx.x >> 5) == n_cons) {                    // producer warp
-        if ((threadIdx.x & 31) == 0) {
-            for (int c = 0; c < nchunks; ++c) {
-                const int st = c % kMmaPhotoStages;
-                if (c >= kMmaPhotoStages) mbar_wait(&empty[st], (uint32_t)(((c / kMmaPhotoStages) + 1) & 1));
-                unsigned char *dst = stage0 + (size_t)st * stage_bytes;
-                const long long k = kb0 + c;
-                mbar_expect_tx(&full[st], (uint32_t)item_bytes + 16u);
-                tma_bulk_g2s(dst, items + (size_t)k * max_items * ISTR, (uint32_t)item_bytes, &full[st]);
-                tma_bulk_g2s(dst + item_bytes, cnt + (k & ~3LL), 16u, &full[st]);
-            }
-        }
+    auto produce = [&](int c) {
+        const int st = c % kMmaPhotoStages;
+        if (c >= kMmaPhotoStages) mbar_wait(&empty[st], (uint32_t)(((c / kMmaPhotoStages) + 1) & 1));
+        unsigned char *dst = stage0 + (size_t)st * stage_bytes;
+        const long long k = kb0 + c;
+        mbar_expect_tx(&full[st], (uint32_t)item_bytes + 16u);
+        tma_bulk_g2s(dst, items + (size_t)k * max_items * ISTR, (uint32_t)item_bytes, &full[st]);
+        tma_bulk_g2s(dst + item_bytes, cnt + (k & ~3LL), 16u, &full[st]);
+    };
+    if (!SH && (int)(threadIdx.x >> 5) == n_cons) {             // producer warp
+        if ((threadIdx.x & 31) == 0)
+            for (int c = 0; c < nchunks; ++c) produce(c);
         return;
     }
+    if (SH && threadIdx.x == 0)
+        for (int c = 0; c < kMmaPhotoStages && c < nchunks; ++c) produce(c);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kq = lane & 3, nq = lane >> 2;
@@ -231,8 +239,23 @@ sweep_photo_mma_kernel(const double2 *__restrict__ items, const int *__restrict_
 #pragma unroll
         for (int q = 0; q < REM; ++q) { rr[t][q] = 0.0; ri[t][q] = 0.0; }
     }
+    // shared tile (SH): its own frequency constants and accumulators
+    const int sh_tile = wtiles * NT;
+    double som2 = 1.0, siw2 = 1.0, scr[MT][2], sci[MT][2], srr[REM], sri[REM];
+    if (SH) {
+        const int f = 8 * sh_tile + nq;
+        const double om = (f < n_hw) ? hw[f] : 1.0;
+        som2 = om * om; siw2 = 1.0 / som2;
+    }
+#pragma unroll
+    for (int q = 0; q < MT; ++q) { scr[q][0] = scr[q][1] = sci[q][0] = sci[q][1] = 0.0; }
+#pragma unroll
+    for (int q = 0; q < REM; ++q) { srr[q] = 0.0; sri[q] = 0.0; }
+    int sh_turn = warp;                                           // item blocks until this warp's next turn at the shared tile
     for (int c = 0; c < nchunks; ++c) {
         const int st = c % kMmaPhotoStages;
+        if (SH && threadIdx.x == 0 && c >= 1 && c - 1 + kMmaPhotoStages < nchunks) produce(c - 1 + kMmaPhotoStages);
+        if (SH) __syncwarp();
         mbar_wait(&full[st], (uint32_t)((c / kMmaPhotoStages) & 1));
         if (active) {
             const unsigned char *base = stage0 + (size_t)st * stage_bytes;
@@ -275,6 +298,30 @@ sweep_photo_mma_kernel(const double2 *__restrict__ items, const int *__restrict_
                         ri[t][q] = fma(r[q].x, hi[t], ri[t][q]); ri[t][q] = fma(r[q].y, hr[t], ri[t][q]);
                     }
                 }
+                if (SH) {
+                    if (sh_turn == 0) {                                        // this item block's shared-tile contribution is ours
+                        sh_turn = n_cons;
+                        const double aa = xx - som2;
+                        const double inv = fast_rcp(fma(aa, aa, b2)) * siw2;
+                        const double shr = 2.0 * (xr * aa - e2 * bb) * inv, shi = -2.0 * (xr * bb + e2 * aa) * inv, snhi = -shi;
+#pragma unroll
+                        for (int q = 0; q < MT; ++q) {
+                            dmma884(scr[q][0], scr[q][1], a[q].x, shr);
+                            dmma884(sci[q][0], sci[q][1], a[q].x, shi);
+                        }
+#pragma unroll
+                        for (int q = 0; q < MT; ++q) {
+                            dmma884(scr[q][0], scr[q][1], a[q].y, snhi);
+                            dmma884(sci[q][0], sci[q][1], a[q].y, shr);
+                        }
+#pragma unroll
+                        for (int q = 0; q < REM; ++q) {
+                            srr[q] = fma(r[q].x, shr, srr[q]); srr[q] = fma(r[q].y, snhi, srr[q]);
+                            sri[q] = fma(r[q].x, shi, sri[q]); sri[q] = fma(r[q].y, shr, sri[q]);
+                        }
+                    }
+                    --sh_turn;
+                }
             }
         }
         __syncwarp();
@@ -300,6 +347,33 @@ sweep_photo_mma_kernel(const double2 *__restrict__ items, const int *__restrict_
             if (kq == 0 && f < n_hw) out[(size_t)f * (kPhotoAcc / 2) + 8 * MT + q] = make_double2(pr, pi);
         }
     }
+    if (SH) {
+        // partial sums of the shared tile -> shared memory (the stage ring is free once every consumer warp is here),
+        // summed over the warps in fixed order (bit-reproducible), written by the first 8 x 27 threads
+        constexpr int NC = kPhotoAcc / 2;                          // 27 complex components
+        double2 *scratch = reinterpret_cast<double2 *>(stage0);    // [n_cons][8][NC]
+        const int nthr = n_cons * 32;
+        asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
+        double2 *mine = scratch + (size_t)warp * 8 * NC;
+#pragma unroll
+        for (int q = 0; q < MT; ++q)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) mine[(2 * kq + h) * NC + 8 * q + nq] = make_double2(scr[q][h], sci[q][h]);
+#pragma unroll
+        for (int q = 0; q < REM; ++q) {
+            double pr = srr[q], pi = sri[q];
+            pr += __shfl_xor_sync(0xffffffffu, pr, 1); pi += __shfl_xor_sync(0xffffffffu, pi, 1);
+            pr += __shfl_xor_sync(0xffffffffu, pr, 2); pi += __shfl_xor_sync(0xffffffffu, pi, 2);
+            if (kq == 0) mine[nq * NC + 8 * MT + q] = make_double2(pr, pi);
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
+        for (int e = threadIdx.x; e < 8 * NC; e += nthr) {
+            double2 sum = make_double2(0.0, 0.0);
+            for (int w = 0; w < n_cons; ++w) { const double2 v = scratch[(size_t)w * 8 * NC + e]; sum.x += v.x; sum.y += v.y; }
+            const int f = 8 * sh_tile + e / NC;
+            if (f < n_hw) out[(size_t)f * NC + e % NC] = sum;
+        }
+    }
 }
 
 }  // namespace
@@ -307,20 +381,44 @@ sweep_photo_mma_kernel(const double2 *__restrict__ items, const int *__restrict_
 // ------------------------------------------------------------------------------------------------ shapes
 // ntile = ceil(n_hw / 8) frequency tiles; a warp owns NT of them -> wt = ceil(ntile / NT) warps cover every frequency once.
 // wt <= wmax: G = wmax / wt k-groups share a CTA of G wt warps; else the frequencies are split over grid.y passes.
-MmaShape sweep_mma_shape(int n_hw, int wmax, int nt_max) {
+// shared_ok (photo sweep, one CTA per SM): efficiency = useful tiles / (4 x the busiest SM sub-partition's tiles), warps
+// being dealt round-robin to the four sub-partitions, and the shape "W warps x NT tiles + one tile shared by all warps" is
+// also tried.
+MmaShape sweep_mma_shape(int n_hw, int wmax, int nt_max, bool shared_ok) {
     MmaShape best{}; double best_eff = -1.0;
     const int ntile = (n_hw + 7) / 8;
     if (const char *e = getenv("MEPB_MMA_NT")) { const int v = atoi(e); if (v >= 1 && v < nt_max) nt_max = v; }   // tuning knob
+    static const bool no_shared = getenv("MEPB_MMA_NOSHARED") != nullptr;
     for (int NT : {4, 2, 1}) {
         if (NT > nt_max) continue;
         MmaShape s{};
-        s.NT = NT;
+        s.NT = NT; s.shared = 0;
         const int wt = (ntile + NT - 1) / NT;
         if (wt <= wmax) { s.passes = 1; s.wtiles = wt; s.G = wmax / wt; }
         else { s.passes = (wt + wmax - 1) / wmax; s.wtiles = (wt + s.passes - 1) / s.passes; s.G = 1; }
         s.warps = s.G * s.wtiles;
-        const double eff = (double)n_hw * s.G / (8.0 * s.passes * s.warps * NT) * (s.warps >= 4 ? 1.0 : 0.25 * s.warps);
+        double busiest = 0.0;
+        for (int y = 0; y < s.passes; ++y) {
+            int load[4] = {0, 0, 0, 0};
+            for (int w = 0; w < s.warps; ++w) {
+                const int first = ((w % s.wtiles) + y * s.wtiles) * NT;
+                const int valid = ntile - first < 0 ? 0 : (ntile - first > NT ? NT : ntile - first);
+                load[w & 3] += valid;
+            }
+            busiest += (double)std::max(std::max(load[0], load[1]), std::max(load[2], load[3]));
+        }
+        // one CTA per SM (photo sweep): the busiest sub-partition sets the pace; several co-resident CTAs and grid.y passes
+        // (AHC sweep) even that out, there the plain tile-slot utilisation ranks the shapes
+        const double eff = (shared_ok ? (double)ntile * s.G / (4.0 * busiest) : (double)n_hw * s.G / (8.0 * s.passes * s.warps * NT)) *
+                           (s.warps >= 4 ? 1.0 : 0.25 * s.warps);
         if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+        if (shared_ok && !no_shared && (ntile - 1) % NT == 0) {
+            const int W = (ntile - 1) / NT;
+            if (W >= 4 && W <= wmax - 1 && W % 4 == 0) {
+                const double effs = (double)ntile / (W * NT + 1.0);
+                if (effs > best_eff + 1e-9) { best_eff = effs; best = MmaShape{NT, 1, W, W, 1, 1}; }
+            }
+        }
     }
     return best;
 }
@@ -336,7 +434,7 @@ bool sweep_mma_enabled(int n_hw) {
 
 cudaError_t launch_sweep_ahc_mma(bool herm, const double *items, const int *cnt, int max_pairs, long long nk, int n_hw,
                                  const double *hw, double eta, double *block_out, int grid, int KC, cudaStream_t st) {
-    const MmaShape s = sweep_mma_shape(n_hw, kMmaAhcWarps, herm ? 4 : 2);   // general items at NT = 4 spill (96-register cap)
+    const MmaShape s = sweep_mma_shape(n_hw, kMmaAhcWarps, herm ? 4 : 2, false);   // general items at NT = 4 spill (96-register cap)
     const size_t item_bytes = sizeof(double) * (herm ? kAhcItemH : kAhcItemG) * (size_t)max_pairs * KC;
     const size_t stage_bytes = (item_bytes + 16 * ((KC * sizeof(int) + 15) / 16) + 127) / 128 * 128;
     const size_t smem = 128 + kMmaStages * stage_bytes;
@@ -356,20 +454,21 @@ cudaError_t launch_sweep_ahc_mma(bool herm, const double *items, const int *cnt,
 
 cudaError_t launch_sweep_photo_mma(const double *items, const int *cnt, int max_items, long long nk, int n_hw, const double *hw,
                                    double eta, double *block_out, int grid, cudaStream_t st) {
-    const MmaShape s = sweep_mma_shape(n_hw, kMmaPhotoWarps, 2);
+    const MmaShape s = sweep_mma_shape(n_hw, kMmaPhotoWarps, 2, true);
     const size_t item_bytes = sizeof(double) * kPhotoItem * (size_t)max_items;
     const size_t stage_bytes = (item_bytes + 16 + 127) / 128 * 128;
     int stages = kMmaPhotoStages;
     const size_t smem = 128 + stages * stage_bytes;              // <= 6 x 64 KB would not fit: sweep_photo_mma_fits() gates this path
-    const dim3 g(grid, s.passes), b(32 * (s.warps + 1));         // + the producer warp
+    const dim3 g(grid, s.passes), b(32 * (s.warps + (s.shared ? 0 : 1)));   // + the producer warp (none in the shared-tile shape)
     const double2 *it2 = reinterpret_cast<const double2 *>(items);
-#define MEPB_LAUNCH_PHOTO(N)                                                                                                   \
-    do {                                                                                                                       \
-        cudaError_t e = cudaFuncSetAttribute(sweep_photo_mma_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e != cudaSuccess) return e;                                                                                        \
-        sweep_photo_mma_kernel<N><<<g, b, smem, st>>>(it2, cnt, max_items, nk, n_hw, hw, eta, block_out, s.G, s.wtiles);        \
+#define MEPB_LAUNCH_PHOTO(N, S)                                                                                                  \
+    do {                                                                                                                          \
+        cudaError_t e = cudaFuncSetAttribute(sweep_photo_mma_kernel<N, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return e;                                                                                           \
+        sweep_photo_mma_kernel<N, S><<<g, b, smem, st>>>(it2, cnt, max_items, nk, n_hw, hw, eta, block_out, s.G, s.wtiles);        \
     } while (0)
-    if (s.NT == 2) MEPB_LAUNCH_PHOTO(2); else MEPB_LAUNCH_PHOTO(1);
+    if (s.shared) { if (s.NT == 2) MEPB_LAUNCH_PHOTO(2, true); else MEPB_LAUNCH_PHOTO(1, true); }
+    else { if (s.NT == 2) MEPB_LAUNCH_PHOTO(2, false); else MEPB_LAUNCH_PHOTO(1, false); }
 #undef MEPB_LAUNCH_PHOTO
     return cudaGetLastError();
 }
