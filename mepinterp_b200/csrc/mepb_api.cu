@@ -688,12 +688,16 @@ int mepb_accumulate(mepb_ctx *c, int64_t lin_begin, int64_t lin_end) {
     CUDA_TRY(cudaEventRecord(c->ev0, c->sb[0].st));
     CUDA_TRY(cudaStreamWaitEvent(c->sb[1].st, c->ev0, 0));
     int which = 0;
-    for (int ief = 0; ief < p.n_eF; ++ief) {
-        const Jobs jb = make_jobs(c, ief, true);
-        for (long long k0 = lin_begin; k0 < lin_end; k0 += c->chunk) {
-            const long long nk = std::min<long long>(c->chunk, lin_end - k0);
-            StreamBuf &s = c->sb[which];
-            if (!c->profiling) which ^= 1;
+    // wave of k-points outermost: everything that does not depend on E_F (Fourier sums, eigenpairs) is computed once per wave
+    // and reused for the n_eF Fermi levels (the reference recomputes nothing either: its E_F loop sits inside the k-loop,
+    // core.f90:187-253)
+    for (long long k0 = lin_begin; k0 < lin_end; k0 += c->chunk) {
+        const long long nk = std::min<long long>(c->chunk, lin_end - k0);
+        StreamBuf &s = c->sb[which];
+        if (!c->profiling) which ^= 1;
+        for (int ief = 0; ief < p.n_eF; ++ief) {
+            const Jobs jb = make_jobs(c, ief, true);
+            const bool first_ef = (ief == 0);
             KSource ks; ks.list = nullptr; ks.lin_begin = k0; ks.nk = nk; ks.N1 = p.mp_grid[0]; ks.N2 = p.mp_grid[1]; ks.N3 = p.mp_grid[2];
             InterpOut o; std::memset(&o, 0, sizeof(o));
             o.items_ahc = jb.do_ahc ? s.items_ahc : nullptr; o.cnt_ahc = s.cnt_ahc;
@@ -702,7 +706,8 @@ int mepb_accumulate(mepb_ctx *c, int64_t lin_begin, int64_t lin_end) {
             const int gi = c->large ? eig_large_grid(c->sm_count, nk)
                            : c->use_sub ? bands_sub_grid(c->nw, c->nR, c->sm_count, nk, c->sparse ? c->sp_nnz : 0, jb.do_mep || jb.do_kubo) : interp_small_grid(c->nw, c->nR, c->sm_count, nk);
             if (c->large) {
-                if (c->sp.on) {
+                if (!first_ef) {
+                } else if (c->sp.on) {
                     SepPlan sp = c->sp; sp.G1 = s.G1; sp.G2 = s.G2;
                     ProfScope ps(c, s.st, MEPB_PROF_FOURIER);
                     CUDA_TRY(launch_fourier_mesh(c->fp, sp, m, ks, s.Hk, s.Hka, s.st));
@@ -710,7 +715,7 @@ int mepb_accumulate(mepb_ctx *c, int64_t lin_begin, int64_t lin_end) {
                 } else {
                     ProfScope ps(c, s.st, MEPB_PROF_FOURIER); CUDA_TRY(launch_fourier_dense(c->fp, m, ks, s.Hk, s.Hka, s.st));
                 }
-                if (c->tri) {
+                if (c->tri && first_ef) {
                     { ProfScope ps(c, s.st, MEPB_PROF_TRIDIAG); CUDA_TRY(launch_tridiag(c->nw, nk, s.Hk, s.tb, c->sm_count, s.st)); }
                     { ProfScope ps(c, s.st, MEPB_PROF_TQL); CUDA_TRY(launch_tql(c->nw, nk, s.tb, c->d_err, s.st)); }
                     { ProfScope ps(c, s.st, MEPB_PROF_ZROT); CUDA_TRY(launch_zrot(c->nw, nk, s.tb, c->sm_count, s.st)); }
@@ -721,10 +726,12 @@ int mepb_accumulate(mepb_ctx *c, int64_t lin_begin, int64_t lin_end) {
                 c->launches += 2;
             }
             if (c->eig_thread) {
-                ProfScope ps(c, s.st, MEPB_PROF_EIG);
-                CUDA_TRY(launch_eig_small(m, ks, s.eig_E, s.eig_U, c->d_err, c->sm_count, s.st));
+                if (first_ef) {
+                    ProfScope ps(c, s.st, MEPB_PROF_EIG);
+                    CUDA_TRY(launch_eig_small(m, ks, s.eig_E, s.eig_U, c->d_err, c->sm_count, s.st));
+                    c->launches += 1;
+                }
                 o.e_in = s.eig_E; o.U_in = s.eig_U;
-                c->launches += 1;
             }
             if (!c->large) {
                 ProfScope ps(c, s.st, MEPB_PROF_INTERP);
