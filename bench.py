@@ -119,7 +119,9 @@ def flops_model(model, params):
             "fourier_per_k": 20.0 * nR * nel if large else 0.0,
             "eig_rot_per_k": (36.0 + 48.0) * nw ** 3 + 60.0 * nw * nw if large else 0.0,
             "sweep_ahc_per_item_hw": 56.0 if herm else 92.0,          # 1 complex reciprocal + 18 (36) accumulate FMAs
-            "sweep_photo_per_item_hw": 246.0,                          # 27 complex MACs + the two-pole factor
+            # 27 complex MACs + the two-pole factor per (item, frequency); the tensor-core sweep contracts the items of the band
+            # pairs (n, l) and (l, n) together (h(l,n) = -conj h(n,l)): 246 flops per PAIR of items
+            "sweep_photo_per_item_hw": 123.0 if (split and params.n_hw >= 16) else 246.0,
             "sparse": sparse, "nnz": nnz, "herm": herm}
 
 

@@ -755,7 +755,7 @@ int mepb_accumulate(mepb_ctx *c, int64_t lin_begin, int64_t lin_end) {
             if (jb.do_opt) {
                 int nsl; const int gs = sweep_photo_grid(c->sm_count, nk, p.n_hw, &nsl, c->max_photo);
                 { ProfScope ps(c, s.st, MEPB_PROF_SWEEP_PHOTO);
-                  CUDA_TRY(launch_sweep_photo(s.items_photo, s.cnt_photo, c->max_photo, nk, p.n_hw, c->d_hw, p.eta, s.block_photo, gs, s.st)); }
+                  CUDA_TRY(launch_sweep_photo(s.items_photo, s.cnt_photo, c->max_photo, nk, p.n_hw, c->d_hw, p.eta, s.block_photo, gs, c->use_sub, s.st)); }
                 { ProfScope ps(c, s.st, MEPB_PROF_REDUCE);
                   CUDA_TRY(launch_reduce_rows(s.block_photo, gs * (nsl / p.n_hw), p.n_hw * kPhotoAcc,
                                               s.compact + (size_t)ief * c->cs.per_ef + ns + c->cs.sweep, kPhotoAcc, kPhotoAcc, 0, s.st)); }

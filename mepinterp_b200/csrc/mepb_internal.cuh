@@ -286,8 +286,9 @@ cudaError_t launch_eig_small(const DevModel &m, const KSource &ks, double *E_out
 cudaError_t launch_sweep_ahc(bool herm, const double *items, const int *cnt, int max_pairs, long long nk, int n_hw,
                              const double *hw, double eta, double *block_out, int grid, cudaStream_t st);
 int sweep_ahc_grid(int sm_count, long long nk, int n_hw, int *slots_out, bool herm, int max_pairs);
+// paired: items of the band pairs (n, l), (l, n) sit in consecutive slots (written by bands_sub_kernel)
 cudaError_t launch_sweep_photo(const double *items, const int *cnt, int max_items, long long nk, int n_hw, const double *hw,
-                               double eta, double *block_out, int grid, cudaStream_t st);
+                               double eta, double *block_out, int grid, bool paired, cudaStream_t st);
 int sweep_photo_grid(int sm_count, long long nk, int n_hw, int *slots_out, int max_items);
 // tensor-core (DMMA) formulation of both sweeps (mepb_sweep_mma.cu), used for n_hw >= 16 unless MEPB_SWEEP_FMA is set
 struct MmaShape { int NT, G, wtiles, warps, passes, shared; };   // tiles per warp, k-groups, warps per group, warps per CTA, grid.y, shared tile
@@ -299,7 +300,7 @@ int sweep_ahc_mma_bps(bool herm, int NT);
 cudaError_t launch_sweep_ahc_mma(bool herm, const double *items, const int *cnt, int max_pairs, long long nk, int n_hw,
                                  const double *hw, double eta, double *block_out, int grid, int KC, cudaStream_t st);
 cudaError_t launch_sweep_photo_mma(const double *items, const int *cnt, int max_items, long long nk, int n_hw, const double *hw,
-                                   double eta, double *block_out, int grid, cudaStream_t st);
+                                   double eta, double *block_out, int grid, bool paired, cudaStream_t st);
 // out[(c / group) * out_stride + out_off + c % group] += sum_r in[r*cols + c]
 cudaError_t launch_reduce_rows(const double *in, int rows, int cols, double *out_accum, int group, int out_stride, int out_off,
                                cudaStream_t st);

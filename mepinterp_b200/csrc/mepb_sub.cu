@@ -35,7 +35,8 @@ struct SubL {  // shared-memory layout per GROUP (one k-point), bytes
     static size_t bytes(int nR) { size_t b = oPh + sizeof(double2) * nR; return (b + 127) / 128 * 128 + 16; }
 };
 
-template <int NW, bool MEP>
+// MEP: build with the MEP sums (two CTAs per SM, 255 registers; otherwise three CTAs, 168); PH: build with the photo items
+template <int NW, bool MEP, bool PH>
 __global__ void __launch_bounds__(kSubWarps * 32, MEP ? 2 : 3)      // 36 more accumulators with the MEP jobs: 3 CTAs would spill 1.1 KB
 bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const InterpOut out, const int max_pairs, const size_t grp_bytes,
                  const int rec_cap) {
@@ -358,22 +359,38 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
             }
         }
         // ------------------------------------------------------------------ photo items (photo.f90:44-81)
-        if (jb.do_opt && out.items_photo) {
+        // PAIRED ORDER: the items of the ordered band pairs (n, l) and (l, n) go into two consecutive slots (2p, 2p + 1).
+        // Their frequency factors obey h(l,n; w) = -conj h(n,l; w) (x -> -conj x in 2x/(x^2 - w^2), x = E_n - E_l - 2 i eta),
+        // which lets the tensor-core sweep (mepb_sweep_mma.cu, PAIRED) contract both with ONE evaluation of h and half the
+        // multiply-adds; the FMA sweeps simply see ordinary items.  The emitting pairs (f_l != f_n) are first compacted into a
+        // list so that the lanes of a group share them evenly (16 pairs on 8 lanes at half filling: 2 each).
+        if (PH && jb.do_opt && out.items_photo) {
             constexpr int NORD = NW * (NW - 1);
-            int n_before = 0;
+            unsigned char *plist = reinterpret_cast<unsigned char *>(dn);          // the centre phases are dead by now: NW x 16 B >= NPAIR bytes
+            int n_pairs = 0;
 #pragma unroll 1
-            for (int p0 = 0; p0 < NORD; p0 += NW) {
+            for (int p0 = 0; p0 < NPAIR; p0 += NW) {
                 const int pidx = p0 + g;
                 bool emit = false;
-                int n = 0, l = 0;
-                double df = 0.0;
-                if (pidx < NORD) {
-                    n = pidx / (NW - 1); l = pidx % (NW - 1); if (l >= n) ++l;
-                    df = fn[l] - fn[n];
-                    emit = valid && (df != 0.0);
+                int n0 = 0, l0 = 0;
+                if (pidx < NPAIR) {
+                    int mm = 1, rem = pidx;
+                    while (rem >= mm) { rem -= mm; ++mm; }
+                    n0 = rem; l0 = mm;                                          // n0 < l0
+                    emit = valid && (fn[l0] - fn[n0] != 0.0);
                 }
                 const unsigned bal = (__ballot_sync(0xffffffffu, emit) >> gshift) & gbits;
-                if (emit) {
+                if (emit) plist[n_pairs + __popc(bal & ((1u << g) - 1u))] = (unsigned char)(n0 | (l0 << 4));
+                n_pairs += __popc(bal);
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (int idx = g; idx < n_pairs; idx += NW) {
+                const int code = plist[idx], n0 = code & 15, l0 = code >> 4;
+#pragma unroll 1
+                for (int dir = 0; dir < 2; ++dir) {
+                    const int n = dir ? l0 : n0, l = dir ? n0 : l0;
+                    const double df = fn[l] - fn[n];
                     double2 W[9];
 #pragma unroll
                     for (int q = 0; q < 9; ++q) W[q] = make_double2(0, 0);
@@ -390,8 +407,7 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
                             for (int c = 0; c < 3; ++c) cfma(W[b + 3 * c], vb, qc[c]);
                         }
                     }
-                    const int slot = n_before + __popc(bal & ((1u << g) - 1u));
-                    double2 *dst = reinterpret_cast<double2 *>(out.items_photo + ((size_t)ik * NORD + slot) * kPhotoItem);
+                    double2 *dst = reinterpret_cast<double2 *>(out.items_photo + ((size_t)ik * NORD + 2 * idx + dir) * kPhotoItem);
 #pragma unroll
                     for (int a = 0; a < 3; ++a) {
                         const double2 va = cscale(df, Vs[a * NW * LD + n * LD + l]);
@@ -400,9 +416,8 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
                     }
                     dst[27] = make_double2(es[n] - es[l], 0.0);
                 }
-                n_before += __popc(bal);
             }
-            if (valid && g == 0) { out.cnt_photo[ik] = n_before; acc_nph += (double)n_before; }
+            if (valid && g == 0) { out.cnt_photo[ik] = 2 * n_pairs; acc_nph += (double)(2 * n_pairs); }
         }
         __syncwarp();                                                   // the group's buffers are reused by the next k
     }
@@ -473,15 +488,17 @@ cudaError_t launch_sub_t(const DevModel &m, const KSource &ks, const Jobs &jobs,
     const int rec_cap = sub_rec_cap(m.sp_ptr ? m.sp_nnz : 0);
     const size_t smem = sub_smem<NW>(m.nR, m.sp_ptr ? m.sp_nnz : 0);
     cudaError_t e;
-    if (jobs.do_mep || jobs.do_kubo) {
-        e = cudaFuncSetAttribute(bands_sub_kernel<NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        bands_sub_kernel<NW, true><<<grid, kSubWarps * 32, smem, st>>>(m, ks, jobs, out, max_pairs, SubL<NW>::bytes(m.nR), rec_cap);
-    } else {
-        e = cudaFuncSetAttribute(bands_sub_kernel<NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        bands_sub_kernel<NW, false><<<grid, kSubWarps * 32, smem, st>>>(m, ks, jobs, out, max_pairs, SubL<NW>::bytes(m.nR), rec_cap);
-    }
+    const bool mep = jobs.do_mep || jobs.do_kubo, ph = jobs.do_opt != 0;
+#define MEPB_LAUNCH_SUB(M, P)                                                                                                  \
+    do {                                                                                                                        \
+        e = cudaFuncSetAttribute(bands_sub_kernel<NW, M, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
+        if (e != cudaSuccess) return e;                                                                                         \
+        bands_sub_kernel<NW, M, P><<<grid, kSubWarps * 32, smem, st>>>(m, ks, jobs, out, max_pairs, SubL<NW>::bytes(m.nR), rec_cap); \
+    } while (0)
+    if (mep) MEPB_LAUNCH_SUB(true, true);
+    else if (ph) MEPB_LAUNCH_SUB(false, true);
+    else MEPB_LAUNCH_SUB(false, false);
+#undef MEPB_LAUNCH_SUB
     return cudaGetLastError();
 }
 

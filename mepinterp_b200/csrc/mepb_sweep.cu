@@ -356,7 +356,7 @@ cudaError_t launch_sweep_ahc(bool herm, const double *items, const int *cnt, int
 }
 int sweep_photo_grid(int sm_count, long long nk, int n_hw, int *slots_out, int max_items) {
     if (sweep_mma_enabled(n_hw) && !getenv("MEPB_SWEEP_DIRECT") && sweep_photo_mma_fits(max_items)) {
-        const MmaShape s = sweep_mma_shape(n_hw, kMmaPhotoWarps, 2, true);
+        const MmaShape s = sweep_mma_shape(n_hw, kMmaPhotoWarps, 3, true);
         if (slots_out) *slots_out = s.G * n_hw;
         long long g = sm_count;                                  // one CTA of up to 448 threads per SM
         if (g > nk) g = nk;
@@ -370,22 +370,22 @@ int sweep_photo_grid(int sm_count, long long nk, int n_hw, int *slots_out, int m
     return (int)g;
 }
 cudaError_t launch_sweep_photo(const double *items, const int *cnt, int max_items, long long nk, int n_hw, const double *hw,
-                               double eta, double *block_out, int grid, cudaStream_t st) {
+                               double eta, double *block_out, int grid, bool paired, cudaStream_t st) {
     int G, NS, T; sweep_shape(n_hw, kPhotoThreads, &G, &NS, &T);   // same (G, NS) as sweep_photo_grid
     const size_t item_bytes = sizeof(double) * kPhotoItem * (size_t)max_items;
     if (!getenv("MEPB_SWEEP_DIRECT") && sweep_photo_mma_fits(max_items) && sweep_mma_enabled(n_hw))
-        return launch_sweep_photo_mma(items, cnt, max_items, nk, n_hw, hw, eta, block_out, grid, st);
+        return launch_sweep_photo_mma(items, cnt, max_items, nk, n_hw, hw, eta, block_out, grid, paired, st);
     if (!getenv("MEPB_SWEEP_DIRECT") && item_bytes <= 64 * 1024) {
         const size_t stage_bytes = (item_bytes + 16 + 127) / 128 * 128;
         const size_t smem = 128 + kSweepStages * stage_bytes;
         cudaError_t e = cudaFuncSetAttribute(sweep_photo_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         sweep_photo_staged_kernel<<<dim3(grid, (NS + T - 1) / T), T, smem, st>>>(reinterpret_cast<const double2 *>(items), cnt, max_items, nk,
-                                                                                 n_hw, hw, eta, block_out, G, NS);
+                                                                                 n_hw, hw, eta, block_out, G, NS);   // (items in paired order are ordinary items)
         return cudaGetLastError();
     }
     if (T > 128) T = 128;                                        // direct kernel: 128 threads loop over the NS slots
-    sweep_photo_kernel<<<grid, T, 0, st>>>(reinterpret_cast<const double2 *>(items), cnt, max_items, nk, n_hw, hw, eta, block_out, G, NS);
+    sweep_photo_kernel<<<grid, T, 0, st>>>(reinterpret_cast<const double2 *>(items), cnt, max_items, nk, n_hw, hw, eta, block_out, G, NS);   // (items in paired order are ordinary items)
     return cudaGetLastError();
 }
 cudaError_t launch_reduce_rows(const double *in, int rows, int cols, double *out_accum, int group, int out_stride, int out_off,

@@ -176,8 +176,13 @@ sweep_ahc_mma_kernel(const double2 *__restrict__ items, const int *__restrict__ 
 // SH: one more frequency tile (index wtiles * NT) is SHARED by all consumer warps — warp w takes it for the item blocks whose
 // running number is w modulo the number of warps — and reduced in fixed order at the end.  With 25 tiles (n_hw = 200) twelve
 // warps then carry 2 + 1/12 tiles each, 6.25 per SM sub-partition, where 13 warps x 2 tiles leave one sub-partition with 7.
-template <int NT, bool SH>
-__global__ void __launch_bounds__(SH ? 384 : 448, 1)             // SH: 12 warps, no producer warp (168 registers; a 13th warp would cap them at 128)
+// PAIRED: the producer (bands_sub_kernel) wrote the items of the band pairs (n, l) and (l, n) into consecutive slots.  Their
+// factors obey h(l,n; w) = -conj h(n,l; w)  (x -> -conj x in 2x/(x^2 - w^2), x = E_n - E_l - 2 i eta), so with T1, T2 the two items
+//   T1 h + T2 h' = [(T1re - T2re) hr - (T1im + T2im) hi] + i [(T1re + T2re) hi + (T1im - T2im) hr]
+// — the four MMAs per tile of ONE item serve two, on operands formed with four additions at fragment-load time: half the
+// reciprocals and half the multiply-adds of the unpaired sweep.
+template <int NT, bool SH, bool PAIRED>
+__global__ void __launch_bounds__(SH ? (NT == 3 ? 256 : 384) : 448, 1)   // SH: 12 warps x 2 tiles (168 registers) or 8 warps x 3 tiles (255), no producer warp
 sweep_photo_mma_kernel(const double2 *__restrict__ items, const int *__restrict__ cnt, const int max_items, const long long nk,
                        const int n_hw, const double *__restrict__ hw, const double eta, double *__restrict__ block_out,
                        const int G, const int wtiles) {
@@ -261,15 +266,26 @@ sweep_photo_mma_kernel(const double2 *__restrict__ items, const int *__restrict_
             const unsigned char *base = stage0 + (size_t)st * stage_bytes;
             const double2 *its = reinterpret_cast<const double2 *>(base);
             const int n_it = reinterpret_cast<const int *>(base + item_bytes)[(kb0 + c) & 3];
-            for (int j0 = 4 * g; j0 < n_it; j0 += 4 * G) {
-                const bool valid = (j0 + kq) < n_it;
-                const double2 *it = its + (size_t)(valid ? j0 + kq : 0) * ISTR;
-                const double xr = valid ? it[27].x : 1e3;                      // padding items: T = 0, finite h
-                double2 a[MT], r[REM];
+            const int n_units = PAIRED ? (n_it >> 1) : n_it;                   // contraction units: merged pairs or single items
+            for (int j0 = 4 * g; j0 < n_units; j0 += 4 * G) {
+                const bool valid = (j0 + kq) < n_units;
+                const int ju = valid ? j0 + kq : 0;
+                const double2 *it = its + (size_t)(PAIRED ? 2 * ju : ju) * ISTR;
+                const double xr = valid ? it[27].x : 1e3;                      // padding units: T = 0, finite h
+                // operands: A1 pairs with hr (real part), A2 with -hi (real part), A3 with hi (imaginary), A4 with hr (imaginary)
+                double A1[MT], A2[MT], A3[MT], A4[MT], R1[REM], R2[REM], R3[REM], R4[REM];
 #pragma unroll
-                for (int q = 0; q < MT; ++q) a[q] = valid ? it[8 * q + nq] : make_double2(0.0, 0.0);
-#pragma unroll
-                for (int q = 0; q < REM; ++q) r[q] = valid ? it[8 * MT + q] : make_double2(0.0, 0.0);
+                for (int q = 0; q < MT + REM; ++q) {
+                    const int comp = (q < MT) ? 8 * q + nq : 8 * MT + (q - MT);
+                    const double2 t1 = valid ? it[comp] : make_double2(0.0, 0.0);
+                    double o1 = t1.x, o2 = t1.y, o3 = t1.x, o4 = t1.y;
+                    if (PAIRED) {
+                        const double2 t2 = valid ? it[ISTR + comp] : make_double2(0.0, 0.0);
+                        o1 = t1.x - t2.x; o2 = t1.y + t2.y; o3 = t1.x + t2.x; o4 = t1.y - t2.y;
+                    }
+                    if (q < MT) { A1[q] = o1; A2[q] = o2; A3[q] = o3; A4[q] = o4; }
+                    else { R1[q - MT] = o1; R2[q - MT] = o2; R3[q - MT] = o3; R4[q - MT] = o4; }
+                }
                 const double xx = xr * xr - e22, bb = -2.0 * xr * e2, b2 = bb * bb;
                 // h = (1/w^2) * 2x/(x^2 - w^2),  x = xr - 2 i eta   (all NT chains first, then the MMAs)
                 double hr[NT], hi[NT], nhi[NT];
@@ -284,40 +300,40 @@ sweep_photo_mma_kernel(const double2 *__restrict__ items, const int *__restrict_
                 for (int t = 0; t < NT; ++t) {
 #pragma unroll
                     for (int q = 0; q < MT; ++q) {                             // dependent pairs (same accumulator) kept 6 MMAs apart
-                        dmma884(cr[t][q][0], cr[t][q][1], a[q].x, hr[t]);
-                        dmma884(ci[t][q][0], ci[t][q][1], a[q].x, hi[t]);
+                        dmma884(cr[t][q][0], cr[t][q][1], A1[q], hr[t]);
+                        dmma884(ci[t][q][0], ci[t][q][1], A3[q], hi[t]);
                     }
 #pragma unroll
                     for (int q = 0; q < MT; ++q) {
-                        dmma884(cr[t][q][0], cr[t][q][1], a[q].y, nhi[t]);
-                        dmma884(ci[t][q][0], ci[t][q][1], a[q].y, hr[t]);
+                        dmma884(cr[t][q][0], cr[t][q][1], A2[q], nhi[t]);
+                        dmma884(ci[t][q][0], ci[t][q][1], A4[q], hr[t]);
                     }
 #pragma unroll
                     for (int q = 0; q < REM; ++q) {
-                        rr[t][q] = fma(r[q].x, hr[t], rr[t][q]); rr[t][q] = fma(r[q].y, nhi[t], rr[t][q]);
-                        ri[t][q] = fma(r[q].x, hi[t], ri[t][q]); ri[t][q] = fma(r[q].y, hr[t], ri[t][q]);
+                        rr[t][q] = fma(R1[q], hr[t], rr[t][q]); rr[t][q] = fma(R2[q], nhi[t], rr[t][q]);
+                        ri[t][q] = fma(R3[q], hi[t], ri[t][q]); ri[t][q] = fma(R4[q], hr[t], ri[t][q]);
                     }
                 }
                 if (SH) {
-                    if (sh_turn == 0) {                                        // this item block's shared-tile contribution is ours
+                    if (sh_turn == 0) {                                        // this unit block's shared-tile contribution is ours
                         sh_turn = n_cons;
                         const double aa = xx - som2;
                         const double inv = fast_rcp(fma(aa, aa, b2)) * siw2;
                         const double shr = 2.0 * (xr * aa - e2 * bb) * inv, shi = -2.0 * (xr * bb + e2 * aa) * inv, snhi = -shi;
 #pragma unroll
                         for (int q = 0; q < MT; ++q) {
-                            dmma884(scr[q][0], scr[q][1], a[q].x, shr);
-                            dmma884(sci[q][0], sci[q][1], a[q].x, shi);
+                            dmma884(scr[q][0], scr[q][1], A1[q], shr);
+                            dmma884(sci[q][0], sci[q][1], A3[q], shi);
                         }
 #pragma unroll
                         for (int q = 0; q < MT; ++q) {
-                            dmma884(scr[q][0], scr[q][1], a[q].y, snhi);
-                            dmma884(sci[q][0], sci[q][1], a[q].y, shr);
+                            dmma884(scr[q][0], scr[q][1], A2[q], snhi);
+                            dmma884(sci[q][0], sci[q][1], A4[q], shr);
                         }
 #pragma unroll
                         for (int q = 0; q < REM; ++q) {
-                            srr[q] = fma(r[q].x, shr, srr[q]); srr[q] = fma(r[q].y, snhi, srr[q]);
-                            sri[q] = fma(r[q].x, shi, sri[q]); sri[q] = fma(r[q].y, shr, sri[q]);
+                            srr[q] = fma(R1[q], shr, srr[q]); srr[q] = fma(R2[q], snhi, srr[q]);
+                            sri[q] = fma(R3[q], shi, sri[q]); sri[q] = fma(R4[q], shr, sri[q]);
                         }
                     }
                     --sh_turn;
@@ -389,8 +405,8 @@ MmaShape sweep_mma_shape(int n_hw, int wmax, int nt_max, bool shared_ok) {
     const int ntile = (n_hw + 7) / 8;
     if (const char *e = getenv("MEPB_MMA_NT")) { const int v = atoi(e); if (v >= 1 && v < nt_max) nt_max = v; }   // tuning knob
     static const bool no_shared = getenv("MEPB_MMA_NOSHARED") != nullptr;
-    for (int NT : {4, 2, 1}) {
-        if (NT > nt_max) continue;
+    for (int NT : {4, 3, 2, 1}) {
+        if (NT > nt_max || (NT == 3 && !shared_ok)) continue;
         MmaShape s{};
         s.NT = NT; s.shared = 0;
         const int wt = (ntile + NT - 1) / NT;
@@ -411,10 +427,10 @@ MmaShape sweep_mma_shape(int n_hw, int wmax, int nt_max, bool shared_ok) {
         // (AHC sweep) even that out, there the plain tile-slot utilisation ranks the shapes
         const double eff = (shared_ok ? (double)ntile * s.G / (4.0 * busiest) : (double)n_hw * s.G / (8.0 * s.passes * s.warps * NT)) *
                            (s.warps >= 4 ? 1.0 : 0.25 * s.warps);
-        if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+        if (NT != 3 && eff > best_eff + 1e-9) { best_eff = eff; best = s; }       // three tiles per warp only in the shared shape
         if (shared_ok && !no_shared && (ntile - 1) % NT == 0) {
             const int W = (ntile - 1) / NT;
-            if (W >= 4 && W <= wmax - 1 && W % 4 == 0) {
+            if (W >= 4 && W <= (NT == 3 ? 8 : wmax - 1) && W % 4 == 0) {
                 const double effs = (double)ntile / (W * NT + 1.0);
                 if (effs > best_eff + 1e-9) { best_eff = effs; best = MmaShape{NT, 1, W, W, 1, 1}; }
             }
@@ -453,22 +469,24 @@ cudaError_t launch_sweep_ahc_mma(bool herm, const double *items, const int *cnt,
 }
 
 cudaError_t launch_sweep_photo_mma(const double *items, const int *cnt, int max_items, long long nk, int n_hw, const double *hw,
-                                   double eta, double *block_out, int grid, cudaStream_t st) {
-    const MmaShape s = sweep_mma_shape(n_hw, kMmaPhotoWarps, 2, true);
+                                   double eta, double *block_out, int grid, bool paired, cudaStream_t st) {
+    const MmaShape s = sweep_mma_shape(n_hw, kMmaPhotoWarps, 3, true);
     const size_t item_bytes = sizeof(double) * kPhotoItem * (size_t)max_items;
     const size_t stage_bytes = (item_bytes + 16 + 127) / 128 * 128;
     int stages = kMmaPhotoStages;
     const size_t smem = 128 + stages * stage_bytes;              // <= 6 x 64 KB would not fit: sweep_photo_mma_fits() gates this path
     const dim3 g(grid, s.passes), b(32 * (s.warps + (s.shared ? 0 : 1)));   // + the producer warp (none in the shared-tile shape)
     const double2 *it2 = reinterpret_cast<const double2 *>(items);
-#define MEPB_LAUNCH_PHOTO(N, S)                                                                                                  \
-    do {                                                                                                                          \
-        cudaError_t e = cudaFuncSetAttribute(sweep_photo_mma_kernel<N, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e != cudaSuccess) return e;                                                                                           \
-        sweep_photo_mma_kernel<N, S><<<g, b, smem, st>>>(it2, cnt, max_items, nk, n_hw, hw, eta, block_out, s.G, s.wtiles);        \
+#define MEPB_LAUNCH_PHOTO(N, S, P)                                                                                                  \
+    do {                                                                                                                             \
+        cudaError_t e = cudaFuncSetAttribute(sweep_photo_mma_kernel<N, S, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return e;                                                                                              \
+        sweep_photo_mma_kernel<N, S, P><<<g, b, smem, st>>>(it2, cnt, max_items, nk, n_hw, hw, eta, block_out, s.G, s.wtiles);        \
     } while (0)
-    if (s.shared) { if (s.NT == 2) MEPB_LAUNCH_PHOTO(2, true); else MEPB_LAUNCH_PHOTO(1, true); }
-    else { if (s.NT == 2) MEPB_LAUNCH_PHOTO(2, false); else MEPB_LAUNCH_PHOTO(1, false); }
+#define MEPB_LAUNCH_PHOTO_P(N, S) do { if (paired) MEPB_LAUNCH_PHOTO(N, S, true); else MEPB_LAUNCH_PHOTO(N, S, false); } while (0)
+    if (s.shared) { if (s.NT == 3) MEPB_LAUNCH_PHOTO_P(3, true); else if (s.NT == 2) MEPB_LAUNCH_PHOTO_P(2, true); else MEPB_LAUNCH_PHOTO_P(1, true); }
+    else { if (s.NT == 2) MEPB_LAUNCH_PHOTO_P(2, false); else MEPB_LAUNCH_PHOTO_P(1, false); }
+#undef MEPB_LAUNCH_PHOTO_P
 #undef MEPB_LAUNCH_PHOTO
     return cudaGetLastError();
 }

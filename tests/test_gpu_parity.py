@@ -433,11 +433,12 @@ def test_probe_phi_live_context_equals_fresh_contexts(libmepb):
     assert np.abs(sweep[1]["mep_tens"] - sweep[0]["mep_tens"]).max() > 1e-6 * np.abs(sweep[0]["mep_bands"]).max()   # phi matters
 
 
-@pytest.mark.parametrize("n_hw", [16, 17, 40, 64, 130, 300])
+@pytest.mark.parametrize("n_hw", [16, 17, 40, 64, 100, 130, 200, 300])
 @pytest.mark.parametrize("name", ["femn_d0.900", "femn_rashba"])
 def test_dmma_sweep_shapes(libmepb, name, n_hw):
     """Every launch shape of the tensor-core sweeps (mepb_sweep_mma.cu) against the oracle: one frequency tile per warp with
-    several k-groups per CTA (n_hw = 16, 17), partly filled tiles (17, 40, 130), full CTAs (64), several grid.y passes (300);
+    several k-groups per CTA (n_hw = 16, 17), partly filled tiles (17, 40, 130), full CTAs (64), the shared-tile shapes of the
+    photo sweep (100, 200: 3 tiles per warp + 1 shared; 130: 2 + 1), several grid.y passes (300);
     Hermitian-closed items (FeMn: 9 weights) and general items (Rashba: 18 weights), the photo sweep included."""
     m, p = load_case(name, mp_grid=(6, 5, 4), n_hw=n_hw, do_ahc=True, do_opt=True, hw_min=ev(0.04), hw_max=ev(5.0), eta=ev(0.1))
     ctx = libmepb.Context(m, p)
