@@ -408,12 +408,13 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
                         }
                     }
                     double2 *dst = reinterpret_cast<double2 *>(out.items_photo + ((size_t)ik * NORD + 2 * idx + dir) * kPhotoItem);
+                    double2 va[3];
 #pragma unroll
-                    for (int a = 0; a < 3; ++a) {
-                        const double2 va = cscale(df, Vs[a * NW * LD + n * LD + l]);
+                    for (int a = 0; a < 3; ++a) va[a] = cscale(df, Vs[a * NW * LD + n * LD + l]);
 #pragma unroll
-                        for (int q = 0; q < 9; ++q) dst[a + 3 * q] = cmul(va, W[q]);
-                    }
+                    for (int q = 0; q < 9; ++q)                                 // ascending addresses: consecutive 16-byte stores
+#pragma unroll
+                        for (int a = 0; a < 3; ++a) dst[a + 3 * q] = cmul(va[a], W[q]);     // fill whole 32-byte sectors
                     dst[27] = make_double2(es[n] - es[l], 0.0);
                 }
             }
