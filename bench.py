@@ -337,7 +337,11 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(args.workload, {}).get(top)
-    roofline = {"kernel": top, "bound": "fp64", "achieved": kernels[top]["tflops"], "peak": peak, "unit": "TFLOP/s",
+    # the frequency sweeps (n_hw >= 16) and the general path's rotation (nw % 8 == 0) run on the FP64 tensor cores (DMMA), which
+    # share the FP64 pipe and its 37.1 TF peak with DFMA (tools/fp64_mixed.cu); the other kernels are plain FP64 FMA code
+    dmma = (top in ("sweep_ahc", "sweep_photo") and params.n_hw >= 16) or (top == "eig_rot" and model.nw % 8 == 0)
+    roofline = {"kernel": top, "bound": "tensor" if dmma else "fp64", "pipe": "FP64 (DFMA and DMMA share one pipe on B200)",
+                "achieved": kernels[top]["tflops"], "peak": peak, "unit": "TFLOP/s",
                 "frac": kernels[top]["tflops"] / peak, "traffic": traffic,
                 "traffic_note": "DRAM bytes per launch of the dominant kernel (ncu --set full, profiles/traffic.json); the path is "
                                 "FP64-pipe bound, HBM < 10 % of its peak in every kernel",
