@@ -342,10 +342,11 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
                         X[0] = csub(cmul(a_[1], b_[2]), cmul(a_[2], b_[1]));
                         X[1] = csub(cmul(a_[2], b_[0]), cmul(a_[0], b_[2]));
                         X[2] = csub(cmul(a_[0], b_[1]), cmul(a_[1], b_[0]));
+                        const double wg = pass ? inv : 0.0;                    // guarded weight: one select instead of six predicated FMAs
 #pragma unroll
                         for (int j = 0; j < 3; ++j) {
                             Zu[j].x = fma(X[j].x, inv, Zu[j].x); Zu[j].y = fma(X[j].y, inv, Zu[j].y);
-                            if (pass) { Zg[j].x = fma(X[j].x, inv, Zg[j].x); Zg[j].y = fma(X[j].y, inv, Zg[j].y); }
+                            Zg[j].x = fma(X[j].x, wg, Zg[j].x); Zg[j].y = fma(X[j].y, wg, Zg[j].y);
                         }
                     }
 #pragma unroll
