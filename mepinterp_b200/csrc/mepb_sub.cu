@@ -32,7 +32,11 @@ struct SubL {  // shared-memory layout per GROUP (one k-point), bytes
     static constexpr size_t oDn = oFn + sizeof(double) * NW;
     static constexpr size_t oPh = oDn + sizeof(double2) * NW;
     // group stride = 16 mod 128 bytes, so that the same element of the 32/NW groups of a warp falls into different banks
-    static size_t bytes(int nR) { size_t b = oPh + sizeof(double2) * nR; return (b + 127) / 128 * 128 + 16; }
+    // MEP builds append a table of reciprocals 1/(E_n0 - E_n), NW rows of NW + 1 doubles (conflict-free), after the nR phases
+    static size_t bytes(int nR, bool mep) {
+        size_t b = oPh + sizeof(double2) * nR + (mep ? sizeof(double) * NW * (NW + 1) : 0);
+        return (b + 127) / 128 * 128 + 16;
+    }
 };
 
 // MEP: build with the MEP sums (two CTAs per SM, 255 registers; otherwise three CTAs, 168); PH: build with the photo items
@@ -292,6 +296,10 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
         if (MEP && (jb.do_mep || jb.do_kubo) && valid) {               // idle groups (past the end of the launch) contribute nothing
             const int n0 = g;
             const double e0 = es[n0];
+            // reciprocals 1/(E_n0 - E_n): one division per band and lane (row n0 of the table) instead of one per (n, m) term
+            double *rt = reinterpret_cast<double *>(base + L::oPh + sizeof(double2) * nR) + n0 * (NW + 1);
+#pragma unroll
+            for (int n = 0; n < NW; ++n) rt[n] = 1.0 / (e0 - es[n]);          // entry n0 is inf and never used
             // the per-k terms go straight into the launch-long accumulators with their weights (1 for band n0 <= nval of
             // mep_niu, f_n0 for kubo_mep): 36 fewer live doubles in a kernel that spills at 255 registers
             const double w_niu = (jb.do_mep && n0 < jb.nval) ? 1.0 : 0.0;
@@ -306,10 +314,11 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
                 double2 v0n[3], vn0[3];
 #pragma unroll
                 for (int a = 0; a < 3; ++a) { v0n[a] = Vs[a * NW * LD + n0 * LD + n]; vn0[a] = Vs[a * NW * LD + n * LD + n0]; }
+                const double rn = rt[n], rn2 = rn * rn;
                 {   // local term: sum_kl eps_jkl Re[V(i,n0,n) V(k,n,n0) V(l,n0,n0)] / (E_n0-E_n)^3
                     const double den = d0n * d0n * d0n;
                     const bool pass = fabs(den) > jb.kubo_tol;
-                    const double inv = 1.0 / den;
+                    const double inv = rn2 * rn;
                     auto re = [](double2 x, double2 y) { return x.x * y.x - x.y * y.y; };
 #pragma unroll
                     for (int i = 0; i < 3; ++i) {
@@ -333,7 +342,7 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
                     for (int mm = 0; mm < NW; ++mm) {
                         if (mm == n0) continue;
                         const double den = d2 * (e0 - es[mm]);
-                        const double inv = 1.0 / den;
+                        const double inv = rn2 * rt[mm];
                         const bool pass = fabs(den) > jb.kubo_tol;
                         double2 a_[3], b_[3];
 #pragma unroll
@@ -478,8 +487,8 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
 inline int sub_rec_cap(int nnz) { return (nnz > 0 && nnz <= kSubMaxNnz) ? (nnz + 7) / 8 * 8 : 8; }   // staged sparse records
 
 template <int NW>
-size_t sub_smem(int nR, int nnz = kSubMaxNnz) {
-    const size_t groups = (size_t)kSubWarps * (32 / NW) * SubL<NW>::bytes(nR) + sizeof(SpRec) * sub_rec_cap(nnz) + sizeof(int) * (NW * NW + 4);
+size_t sub_smem(int nR, int nnz = kSubMaxNnz, bool mep = true) {
+    const size_t groups = (size_t)kSubWarps * (32 / NW) * SubL<NW>::bytes(nR, mep) + sizeof(SpRec) * sub_rec_cap(nnz) + sizeof(int) * (NW * NW + 4);
     const size_t stage = sizeof(double) * kSubWarps * (S_NIU + 18 * NW);
     return groups > stage ? groups : stage;
 }
@@ -488,14 +497,14 @@ template <int NW>
 cudaError_t launch_sub_t(const DevModel &m, const KSource &ks, const Jobs &jobs, const InterpOut &out, int max_pairs, int grid,
                          cudaStream_t st) {
     const int rec_cap = sub_rec_cap(m.sp_ptr ? m.sp_nnz : 0);
-    const size_t smem = sub_smem<NW>(m.nR, m.sp_ptr ? m.sp_nnz : 0);
-    cudaError_t e;
     const bool mep = jobs.do_mep || jobs.do_kubo, ph = jobs.do_opt != 0;
+    const size_t smem = sub_smem<NW>(m.nR, m.sp_ptr ? m.sp_nnz : 0, mep);
+    cudaError_t e;
 #define MEPB_LAUNCH_SUB(M, P)                                                                                                  \
     do {                                                                                                                        \
         e = cudaFuncSetAttribute(bands_sub_kernel<NW, M, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
         if (e != cudaSuccess) return e;                                                                                         \
-        bands_sub_kernel<NW, M, P><<<grid, kSubWarps * 32, smem, st>>>(m, ks, jobs, out, max_pairs, SubL<NW>::bytes(m.nR), rec_cap); \
+        bands_sub_kernel<NW, M, P><<<grid, kSubWarps * 32, smem, st>>>(m, ks, jobs, out, max_pairs, SubL<NW>::bytes(m.nR, M), rec_cap); \
     } while (0)
     if (mep) MEPB_LAUNCH_SUB(true, true);
     else if (ph) MEPB_LAUNCH_SUB(false, true);
@@ -513,7 +522,7 @@ bool sub_supported(int nw, int nR) {
 }
 
 int bands_sub_grid(int nw, int nR, int sm_count, long long nk, int nnz, bool mep) {
-    const size_t smem = (nw == 4 ? sub_smem<4>(nR, nnz) : sub_smem<8>(nR, nnz)) + 1024;
+    const size_t smem = (nw == 4 ? sub_smem<4>(nR, nnz, mep) : sub_smem<8>(nR, nnz, mep)) + 1024;
     int per_sm = (int)((227 * 1024) / smem);
     if (per_sm > (mep ? 2 : 3)) per_sm = mep ? 2 : 3;  // __launch_bounds__(128, MEP ? 2 : 3)
     if (per_sm < 1) per_sm = 1;
