@@ -446,3 +446,16 @@ def test_dmma_sweep_shapes(libmepb, name, n_hw):
     ctx.close()
     ref, scale, sens = oracle_reference(m, p)
     assert_parity(out, ref, scale, sens, tol=TENS_TOL, label=f"{name} n_hw={n_hw}")
+
+
+@pytest.mark.parametrize("name", ["femn_d0.900", "femn_rashba"])
+def test_dmma_sweeps_at_finite_temperature(libmepb, name):
+    """T = 300 K: every band pair has f_n != f_m, so each k-point emits the maximum number of items (28 AHC pairs, 28 + 28 photo
+    items in paired order) — the full-slot case of the tensor-core sweeps, against the oracle."""
+    m, p = load_case(name, mp_grid=(5, 4, 6), n_hw=40, do_ahc=True, do_opt=True, hw_min=ev(0.04), hw_max=ev(5.0), eta=ev(0.1),
+                     T_kelvin=300.0)
+    ctx = libmepb.Context(m, p)
+    out = ctx.run_mesh()
+    ctx.close()
+    ref, scale, sens = oracle_reference(m, p)
+    assert_parity(out, ref, scale, sens, tol=TENS_TOL, label=f"{name} T=300K")
