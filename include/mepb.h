@@ -109,6 +109,16 @@ int mepb_fourier(mepb_ctx *ctx, int64_t nk, const double *kpt, double *H_k, doub
  * harness for that path; MEPB_ERR_UNSUPPORTED on the small-num_wann path, whose kernels never materialise H(k). */
 int mepb_fourier_mesh(mepb_ctx *ctx, int64_t lin_begin, int64_t nk, double *H_k, double *H_ka);
 
+/* Band sums on caller-supplied eigenpairs: e_k (nw,nk) and the H-gauge velocities V_ka (3,nw,nw,nk) complex, as
+ * get_wann_interp returns them (wann_interp.f90:56-108).  Runs the band-sum sections of the same kernels mepb_accumulate
+ * uses (occupations, kubo_ahc_tens, mep_niu_*, kubo_mep_*, pair / photo items) and the frequency sweeps — the per-k
+ * response functions of core.f90:187-253 without interpolation, eigensolve and rotation — and ADDS the un-normalised
+ * sums to the context's accumulators exactly like mepb_accumulate (mepb_reset first; mepb_get_partials / mepb_finalize
+ * follow).  Parity harness: fed the oracle's own (e, V) it removes the eigensolver from the comparison, so the response
+ * formulas are checked at rounding level even where the reference's unguarded 1/dE^2, 1/dE^3 factors amplify
+ * eigenvector rounding (kubo.f90:65, kubo_mep.f90:73,126).  Also the consumer of the position-operator kernels. */
+int mepb_band_sums(mepb_ctx *ctx, int64_t nk, const double *e_k, const double *V_ka);
+
 /* Re-upload H(R) from a host buffer into an existing context (same nw, nR, R set, FT convention): the per-call input
  * of a parameter sweep — the reference re-reads w90files/<seed>_hr.dat in a fresh process per parameter value
  * (scripts/mep_worker.py:133-150, scripts/probe_phi.py). */

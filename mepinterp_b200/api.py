@@ -21,7 +21,7 @@ ERR_ARG, ERR_CUDA, ERR_NOT_HERMITIAN, ERR_UNSUPPORTED, ERR_EIG, ERR_STATE = -1, 
 
 EXPORTS = ["mepb_create", "mepb_destroy", "mepb_run_mesh", "mepb_reset", "mepb_accumulate", "mepb_partials_size",
            "mepb_get_partials", "mepb_set_partials", "mepb_partials_device_ptr", "mepb_finalize", "mepb_interp",
-           "mepb_fourier", "mepb_fourier_mesh", "mepb_update_model", "mepb_timer_start", "mepb_timer_stop", "mepb_set_profiling",
+           "mepb_fourier", "mepb_fourier_mesh", "mepb_band_sums", "mepb_update_model", "mepb_timer_start", "mepb_timer_stop", "mepb_set_profiling",
            "mepb_get_profile", "mepb_work_items", "mepb_last_kernel_ms", "mepb_kernel_launches", "mepb_strerror", "mepb_last_error", "mepb_version"]
 
 
@@ -75,6 +75,7 @@ def lib():
         L.mepb_interp.argtypes = [vp, C.c_int64, vp, vp, vp]
         L.mepb_fourier.argtypes = [vp, C.c_int64, vp, vp, vp]
         L.mepb_fourier_mesh.argtypes = [vp, C.c_int64, C.c_int64, vp, vp]
+        L.mepb_band_sums.argtypes = [vp, C.c_int64, vp, vp]
         L.mepb_update_model.argtypes = [vp, C.POINTER(CModel)]
         L.mepb_timer_start.argtypes = [vp]
         L.mepb_timer_stop.argtypes = [vp, C.POINTER(C.c_double)]
@@ -256,6 +257,13 @@ class Context:
         Hka = np.zeros((3, nw, nw, nk), dtype=np.complex128, order="F")
         _check(lib().mepb_fourier_mesh(self._h, lin_begin, nk, Hk.ctypes.data, Hka.ctypes.data))
         return Hk, Hka
+
+    def band_sums(self, e_k, V_ka):
+        """Response functions on supplied eigenpairs e_k (nw,nk), V_ka (3,nw,nw,nk): adds to the accumulators (reset first)."""
+        e = _f(e_k, np.float64)
+        V = _f(V_ka, np.complex128)
+        assert e.shape[0] == self.nw and V.shape == (3, self.nw, self.nw, e.shape[1])
+        _check(lib().mepb_band_sums(self._h, e.shape[1], e.ctypes.data, V.ctypes.data))
 
     def update_model(self, H):
         """Re-upload H(R) (nw,nw,nR complex, Hartree) from host memory; same R set and FT convention."""

@@ -12,49 +12,29 @@
 #include <string>
 #include <vector>
 
-#include "mepb_internal.cuh"
+#include "mepb_ctx.cuh"
 
 using namespace mepb;
 
-namespace {
-
+namespace mepb {
 thread_local std::string g_last_error;
-
 int fail(int code, const std::string &msg) { g_last_error = msg; return code; }
-#define CUDA_TRY(expr)                                                                                   \
-    do {                                                                                                 \
-        cudaError_t e_ = (expr);                                                                         \
-        if (e_ != cudaSuccess)                                                                           \
-            return fail(MEPB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));              \
-    } while (0)
+const std::string &last_error_text() { return g_last_error; }
+}  // namespace mepb
 
-struct PackedLayout {  // identical to oracle/cpu_ref.c make_layout (documented in include/mepb.h)
-    long long total, ne, mep_ic, mep_lc, kmep_ic, kmep_lc, ahc, velo, ohc, photo;
-};
-PackedLayout make_layout(const mepb_params &p) {
-    PackedLayout L;
-    long long o = 2;
-    L.ne = o; o += p.n_eF;
-    L.mep_ic = L.mep_lc = L.kmep_ic = L.kmep_lc = L.ahc = L.velo = L.ohc = L.photo = -1;
-    if (p.do_mep) { L.mep_ic = o; o += 9LL * p.valence_bands; L.mep_lc = o; o += 9LL * p.valence_bands; }
-    if (p.do_kubo) { L.kmep_ic = o; o += 9LL * p.n_eF; L.kmep_lc = o; o += 9LL * p.n_eF; }
-    if (p.do_ahc) { L.ahc = o; o += 9LL * p.n_eF; L.velo = o; o += 18LL * p.n_hw * p.n_eF; L.ohc = o; o += 18LL * p.n_hw * p.n_eF; }
-    if (p.do_opt) { L.photo = o; o += 54LL * p.n_hw * p.n_eF; }
-    L.total = o;
-    return L;
-}
-
-// compact per-eF accumulator block on the device: [static NS | sweep n_hw*18 | photo n_hw*54]
-struct CompactShape {
-    int ns, sweep, photo, per_ef;
-};
+namespace {
 
 __global__ void pack_kernel(const double *__restrict__ c0, const double *__restrict__ c1, CompactShape cs, int nw, int nval,
                             int n_hw, int n_eF, int do_mep, int do_kubo, int do_ahc, int do_opt, PackedLayout L,
                             double *__restrict__ packed) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     auto C = [&](int ief, int i) { return c0[(size_t)ief * cs.per_ef + i] + c1[(size_t)ief * cs.per_ef + i]; };
-    if (tid == 0) { packed[0] = C(0, S_NK); packed[1] = C(0, S_NDEG); }
+    if (tid == 0) {
+        packed[0] = C(0, S_NK); packed[1] = C(0, S_NDEG);
+        double nit = 0.0, nph = 0.0;                    // items handed to the sweeps, all E_F (behind the packed layout)
+        for (int ief = 0; ief < n_eF; ++ief) { nit += C(ief, S_NIT); nph += C(ief, S_NPH); }
+        packed[L.total] = nit; packed[L.total + 1] = nph;
+    }
     for (int i = tid; i < n_eF; i += nth) packed[L.ne + i] = C(i, S_NE);
     if (do_mep)
         for (int i = tid; i < 9 * nval; i += nth) {
@@ -109,70 +89,7 @@ __global__ void pack_kernel(const double *__restrict__ c0, const double *__restr
     }
 }
 
-struct StreamBuf {
-    cudaStream_t st = nullptr;
-    cudaEvent_t done = nullptr;
-    double *items_ahc = nullptr; int *cnt_ahc = nullptr;
-    double *items_photo = nullptr; int *cnt_photo = nullptr;
-    double *block_static = nullptr, *block_sweep = nullptr, *block_photo = nullptr;
-    double *compact = nullptr;   // [n_eF][per_ef]
-    double *eig_E = nullptr; double2 *eig_U = nullptr;   // [chunk][nw], [chunk][nw*nw] from the thread-per-k eigensolver
-    double2 *Hk = nullptr, *Hka = nullptr, *Vscr = nullptr;   // general path: [chunk][nw^2], [chunk][3][nw^2], [grid][3][nw^2]
-    TriBuf tb{};                                                // general path: Householder + QL intermediates (mepb_tri.cu)
-    double2 *G1 = nullptr, *G2 = nullptr;                       // general path, mesh mode: separable-transform tables
-};
-
 }  // namespace
-
-struct mepb_ctx {
-    int device = 0, sm_count = 0;
-    mepb_params p{};
-    int nw = 0, nR = 0;
-    bool has_tau = false;
-    bool herm = true;      // H(R) Hermitian-closed: V_a Hermitian -> compact items / 18-accumulator sweep
-    bool eig_thread = false;   // eigenpairs from the thread-per-k kernel (nw 4, 8)
-    bool large = false;        // general path (mepb_large.cu)
-    bool use_sub = false;      // NW-lanes-per-k band-sum kernel (mepb_sub.cu) in mesh mode
-    bool tri = false;          // general path: Householder + QL eigensolver (default) instead of the in-kernel Jacobi
-    FourierPlan fp{};
-    int *d_ridx = nullptr, *d_elem = nullptr; double2 *d_Hp = nullptr; double *d_Rfp = nullptr, *d_cRp = nullptr;
-    double2 *d_Hka_int = nullptr;
-    SepPlan sp{};              // mesh-separable Fourier transform (general path, mesh mode)
-    int *d_map3 = nullptr, *d_ra = nullptr; double2 *d_P1 = nullptr, *d_P2 = nullptr, *d_P3 = nullptr; double *d_cw4 = nullptr;
-    double Mmat[9];            // c_a(R) = sum_j Mmat[a + 3 j] R_j
-    int *d_sp_ptr = nullptr, *d_sp_R = nullptr; double2 *d_sp_val = nullptr;   // sparse H(R) (warp-per-k Fourier sums)
-    bool sparse = false; int sp_nnz = 0;
-    int *d_ell_R = nullptr; double2 *d_ell_val = nullptr; double *d_ell_x = nullptr; int ell_n = 0, ell_nR = 0;   // mepb_eig.cu
-    std::vector<double> h_Rf, h_tau;   // host copies (fractional R, centres) for rebuilding the sparse forms in update_model
-    double a_latt[9];
-    // device model
-    double2 *d_H = nullptr; double *d_Rf = nullptr, *d_cR = nullptr, *d_tau = nullptr, *d_tM = nullptr, *d_hw = nullptr;
-    std::vector<double> ef_lst, hw_lst;
-    // schedule
-    long long chunk = 0;
-    int max_pairs = 0, max_photo = 0;
-    int grid_interp = 0, grid_sweep = 0, ns_sweep = 0, grid_photo = 0, ns_photo = 0;
-    CompactShape cs{};
-    PackedLayout L{};
-    StreamBuf sb[2];
-    double *d_packed = nullptr;
-    int *d_err = nullptr;
-    bool packed_from_host = false, have_data = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    double last_ms = 0.0;
-    long long launches = 0;
-    long long n_items_ahc = 0, n_items_photo = 0;
-    // optional per-kernel-class timing (serialises the schedule onto one stream; used by bench.py for the roofline)
-    bool profiling = false;
-    std::vector<cudaEvent_t> prof_ev;          // pairs (start, stop)
-    std::vector<int> prof_kind;
-    double prof_ms[MEPB_PROF_KINDS] = {};
-    long long prof_n[MEPB_PROF_KINDS] = {};
-    cudaEvent_t tm0 = nullptr, tm1 = nullptr;  // mepb_timer_start / stop
-    // list-mode scratch
-    double *d_kpt = nullptr, *d_e = nullptr; double2 *d_V = nullptr, *d_Hk = nullptr, *d_Hka = nullptr;
-    long long list_cap = 0;
-};
 
 namespace {
 
@@ -437,6 +354,7 @@ void free_all(mepb_ctx *c) {
     cudaFree(c->d_map3); cudaFree(c->d_ra); cudaFree(c->d_P1); cudaFree(c->d_P2); cudaFree(c->d_P3); cudaFree(c->d_cw4);
     cudaFree(c->d_ridx); cudaFree(c->d_elem); cudaFree(c->d_Hp); cudaFree(c->d_Rfp); cudaFree(c->d_cRp); cudaFree(c->d_Hka_int);
     cudaFree(c->d_kpt); cudaFree(c->d_e); cudaFree(c->d_V); cudaFree(c->d_Hk); cudaFree(c->d_Hka);
+    cudaFree(c->d_bs_e); cudaFree(c->d_bs_V);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->tm0) cudaEventDestroy(c->tm0);
@@ -592,7 +510,9 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
     c->chunk = chunk;
     if (!c->large) CT(build_sparse(c, model));
     c->grid_interp = c->large ? eig_large_grid(c->sm_count, chunk) : interp_small_grid(nw, nR, c->sm_count, chunk);
-    if (c->use_sub) c->grid_interp = std::max(c->grid_interp, bands_sub_grid(nw, nR, c->sm_count, chunk, c->sparse ? c->sp_nnz : 0, p.do_mep || p.do_kubo));
+    if (c->use_sub)      // block_static holds grid_interp rows: the largest grid any variant of the band-sum kernel is launched with
+        c->grid_interp = std::max(c->grid_interp, std::max(bands_sub_grid(nw, nR, c->sm_count, chunk, c->sparse ? c->sp_nnz : 0, true),
+                                                           bands_sub_grid(nw, nR, c->sm_count, chunk, c->sparse ? c->sp_nnz : 0, false)));
     c->grid_sweep = sweep_ahc_grid(c->sm_count, chunk, p.n_hw, &c->ns_sweep, c->herm, c->max_pairs);
     c->grid_photo = sweep_photo_grid(c->sm_count, chunk, p.n_hw, &c->ns_photo, c->max_photo);
     c->cs.ns = static_size(nw); c->cs.sweep = p.n_hw * kSweepAcc; c->cs.photo = p.n_hw * kPhotoAcc;
@@ -648,8 +568,8 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
         CT(cudaMalloc((void **)&s.compact, sizeof(double) * (size_t)c->cs.per_ef * p.n_eF));
         CT(cudaMemset(s.compact, 0, sizeof(double) * (size_t)c->cs.per_ef * p.n_eF));
     }
-    CT(cudaMalloc((void **)&c->d_packed, sizeof(double) * (size_t)c->L.total));
-    CT(cudaMemset(c->d_packed, 0, sizeof(double) * (size_t)c->L.total));
+    CT(cudaMalloc((void **)&c->d_packed, sizeof(double) * (size_t)(c->L.total + 2)));       // + 2 work counters
+    CT(cudaMemset(c->d_packed, 0, sizeof(double) * (size_t)(c->L.total + 2)));
     CT(cudaEventCreate(&c->ev0));
     CT(cudaEventCreate(&c->ev1));
     CT(cudaEventCreate(&c->tm0));
@@ -669,10 +589,92 @@ int mepb_reset(mepb_ctx *c) {
     if (!c) return fail(MEPB_ERR_ARG, "null ctx");
     CUDA_TRY(cudaSetDevice(c->device));
     for (auto &s : c->sb) CUDA_TRY(cudaMemsetAsync(s.compact, 0, sizeof(double) * (size_t)c->cs.per_ef * c->p.n_eF, s.st));
-    CUDA_TRY(cudaMemsetAsync(c->d_packed, 0, sizeof(double) * (size_t)c->L.total, c->sb[0].st));
+    CUDA_TRY(cudaMemsetAsync(c->d_packed, 0, sizeof(double) * (size_t)(c->L.total + 2), c->sb[0].st));
     CUDA_TRY(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->sb[0].st));
     for (auto &s : c->sb) CUDA_TRY(cudaStreamSynchronize(s.st));
     c->packed_from_host = false; c->have_data = false;
+    return MEPB_OK;
+}
+
+// One wave of k-points on stream buffer s: everything that does not depend on E_F (Fourier sums, eigenpairs) once, then for
+// every trial Fermi level the band-sum kernel, the block reductions and the frequency sweeps (the reference's E_F loop sits
+// inside its k-loop, core.f90:187-253, and recomputes nothing either).  With V_in != nullptr the eigenpairs are supplied
+// (device pointers: e_in (nw, nk), V_in (3, nw, nw, nk)) and only the band-sum sections of the same kernels run.
+static int launch_wave(mepb_ctx *c, StreamBuf &s, long long k0, long long nk, const double *e_in, const double2 *V_in) {
+    const mepb_params &p = c->p;
+    const DevModel m = dev_model(c);
+    const int ns = c->cs.ns;
+    for (int ief = 0; ief < p.n_eF; ++ief) {
+        const Jobs jb = make_jobs(c, ief, true);
+        const bool first_ef = (ief == 0);
+        KSource ks; ks.list = nullptr; ks.lin_begin = k0; ks.nk = nk; ks.N1 = p.mp_grid[0]; ks.N2 = p.mp_grid[1]; ks.N3 = p.mp_grid[2];
+        InterpOut o; std::memset(&o, 0, sizeof(o));
+        o.items_ahc = jb.do_ahc ? s.items_ahc : nullptr; o.cnt_ahc = s.cnt_ahc;
+        o.items_photo = jb.do_opt ? s.items_photo : nullptr; o.cnt_photo = s.cnt_photo;
+        o.block_static = s.block_static; o.err_flag = c->d_err;
+        o.e_in = e_in; o.V_in = V_in;
+        int gi = c->large ? eig_large_grid(c->sm_count, nk)
+                 : c->use_sub ? bands_sub_grid(c->nw, c->nR, c->sm_count, nk, c->sparse ? c->sp_nnz : 0, V_in ? true : (jb.do_mep || jb.do_kubo))
+                              : interp_small_grid(c->nw, c->nR, c->sm_count, nk);
+        gi = std::min(gi, c->grid_interp);                          // block_static holds grid_interp rows
+        if (c->large) {
+            if (V_in || !first_ef) {
+            } else if (c->sp.on) {
+                SepPlan sp = c->sp; sp.G1 = s.G1; sp.G2 = s.G2;
+                ProfScope ps(c, s.st, MEPB_PROF_FOURIER);
+                CUDA_TRY(launch_fourier_mesh(c->fp, sp, m, ks, s.Hk, s.Hka, s.st));
+                c->launches += 3;
+            } else {
+                ProfScope ps(c, s.st, MEPB_PROF_FOURIER); CUDA_TRY(launch_fourier_dense(c->fp, m, ks, s.Hk, s.Hka, s.st));
+                c->launches += 1;
+            }
+            if (c->tri && first_ef && !V_in) {
+                { ProfScope ps(c, s.st, MEPB_PROF_TRIDIAG); CUDA_TRY(launch_tridiag(c->nw, nk, s.Hk, s.tb, c->sm_count, s.st)); }
+                { ProfScope ps(c, s.st, MEPB_PROF_TQL); CUDA_TRY(launch_tql(c->nw, nk, s.tb, c->d_err, s.st)); }
+                { ProfScope ps(c, s.st, MEPB_PROF_ZROT); CUDA_TRY(launch_zrot(c->nw, nk, s.tb, c->sm_count, s.st)); }
+                c->launches += 3;
+            }
+            { ProfScope ps(c, s.st, MEPB_PROF_EIGROT);
+              CUDA_TRY(launch_eig_rot_large(m, ks, jb, o, c->max_pairs, s.Hk, s.Hka, s.Vscr, s.tb, gi, s.st)); }
+            c->launches += 1;
+        }
+        if (c->eig_thread && !V_in) {
+            if (first_ef) {
+                ProfScope ps(c, s.st, MEPB_PROF_EIG);
+                CUDA_TRY(launch_eig_small(m, ks, s.eig_E, s.eig_U, c->d_err, c->sm_count, s.st));
+                c->launches += 1;
+            }
+            o.e_in = s.eig_E; o.U_in = s.eig_U;
+        }
+        if (!c->large) {
+            ProfScope ps(c, s.st, MEPB_PROF_INTERP);
+            if (c->use_sub) CUDA_TRY(launch_bands_sub(m, ks, jb, o, c->max_pairs, gi, s.st));
+            else CUDA_TRY(launch_interp_small(m, ks, jb, o, c->max_pairs, gi, s.st));
+            c->launches += 1;
+        }
+        { ProfScope ps(c, s.st, MEPB_PROF_REDUCE);
+          CUDA_TRY(launch_reduce_rows(s.block_static, gi, ns, s.compact + (size_t)ief * c->cs.per_ef, ns, 0, 0, s.st)); }
+        c->launches += 1;
+        if (jb.do_ahc) {
+            int nsl; const int gs = sweep_ahc_grid(c->sm_count, nk, p.n_hw, &nsl, c->herm, c->max_pairs);
+            { ProfScope ps(c, s.st, MEPB_PROF_SWEEP_AHC);
+              CUDA_TRY(launch_sweep_ahc(c->herm, s.items_ahc, s.cnt_ahc, c->max_pairs, nk, p.n_hw, c->d_hw, p.eta, s.block_sweep, gs, s.st)); }
+            const int nacc = c->herm ? kSweepAccH : kSweepAcc;          // Hermitian kernel fills X2,Y1 = slots [6,24)
+            { ProfScope ps(c, s.st, MEPB_PROF_REDUCE);
+              CUDA_TRY(launch_reduce_rows(s.block_sweep, gs * (nsl / p.n_hw), p.n_hw * nacc,
+                                          s.compact + (size_t)ief * c->cs.per_ef + ns, nacc, kSweepAcc, c->herm ? 6 : 0, s.st)); }
+            c->launches += 2;
+        }
+        if (jb.do_opt) {
+            int nsl; const int gs = sweep_photo_grid(c->sm_count, nk, p.n_hw, &nsl, c->max_photo);
+            { ProfScope ps(c, s.st, MEPB_PROF_SWEEP_PHOTO);
+              CUDA_TRY(launch_sweep_photo(s.items_photo, s.cnt_photo, c->max_photo, nk, p.n_hw, c->d_hw, p.eta, s.block_photo, gs, c->use_sub, s.st)); }
+            { ProfScope ps(c, s.st, MEPB_PROF_REDUCE);
+              CUDA_TRY(launch_reduce_rows(s.block_photo, gs * (nsl / p.n_hw), p.n_hw * kPhotoAcc,
+                                          s.compact + (size_t)ief * c->cs.per_ef + ns + c->cs.sweep, kPhotoAcc, kPhotoAcc, 0, s.st)); }
+            c->launches += 2;
+        }
+    }
     return MEPB_OK;
 }
 
@@ -683,85 +685,15 @@ int mepb_accumulate(mepb_ctx *c, int64_t lin_begin, int64_t lin_end) {
     if (lin_begin < 0 || lin_end > nk_mesh || lin_begin > lin_end) return fail(MEPB_ERR_ARG, "k range outside the mesh");
     if (c->packed_from_host) return fail(MEPB_ERR_STATE, "accumulate after set_partials; call mepb_reset first");
     CUDA_TRY(cudaSetDevice(c->device));
-    const DevModel m = dev_model(c);
-    const int ns = c->cs.ns;
     CUDA_TRY(cudaEventRecord(c->ev0, c->sb[0].st));
     CUDA_TRY(cudaStreamWaitEvent(c->sb[1].st, c->ev0, 0));
     int which = 0;
-    // wave of k-points outermost: everything that does not depend on E_F (Fourier sums, eigenpairs) is computed once per wave
-    // and reused for the n_eF Fermi levels (the reference recomputes nothing either: its E_F loop sits inside the k-loop,
-    // core.f90:187-253)
-    for (long long k0 = lin_begin; k0 < lin_end; k0 += c->chunk) {
+    for (long long k0 = lin_begin; k0 < lin_end; k0 += c->chunk) {       // waves alternate over the two streams
         const long long nk = std::min<long long>(c->chunk, lin_end - k0);
         StreamBuf &s = c->sb[which];
         if (!c->profiling) which ^= 1;
-        for (int ief = 0; ief < p.n_eF; ++ief) {
-            const Jobs jb = make_jobs(c, ief, true);
-            const bool first_ef = (ief == 0);
-            KSource ks; ks.list = nullptr; ks.lin_begin = k0; ks.nk = nk; ks.N1 = p.mp_grid[0]; ks.N2 = p.mp_grid[1]; ks.N3 = p.mp_grid[2];
-            InterpOut o; std::memset(&o, 0, sizeof(o));
-            o.items_ahc = jb.do_ahc ? s.items_ahc : nullptr; o.cnt_ahc = s.cnt_ahc;
-            o.items_photo = jb.do_opt ? s.items_photo : nullptr; o.cnt_photo = s.cnt_photo;
-            o.block_static = s.block_static; o.err_flag = c->d_err;
-            const int gi = c->large ? eig_large_grid(c->sm_count, nk)
-                           : c->use_sub ? bands_sub_grid(c->nw, c->nR, c->sm_count, nk, c->sparse ? c->sp_nnz : 0, jb.do_mep || jb.do_kubo) : interp_small_grid(c->nw, c->nR, c->sm_count, nk);
-            if (c->large) {
-                if (!first_ef) {
-                } else if (c->sp.on) {
-                    SepPlan sp = c->sp; sp.G1 = s.G1; sp.G2 = s.G2;
-                    ProfScope ps(c, s.st, MEPB_PROF_FOURIER);
-                    CUDA_TRY(launch_fourier_mesh(c->fp, sp, m, ks, s.Hk, s.Hka, s.st));
-                    c->launches += 2;
-                } else {
-                    ProfScope ps(c, s.st, MEPB_PROF_FOURIER); CUDA_TRY(launch_fourier_dense(c->fp, m, ks, s.Hk, s.Hka, s.st));
-                }
-                if (c->tri && first_ef) {
-                    { ProfScope ps(c, s.st, MEPB_PROF_TRIDIAG); CUDA_TRY(launch_tridiag(c->nw, nk, s.Hk, s.tb, c->sm_count, s.st)); }
-                    { ProfScope ps(c, s.st, MEPB_PROF_TQL); CUDA_TRY(launch_tql(c->nw, nk, s.tb, c->d_err, s.st)); }
-                    { ProfScope ps(c, s.st, MEPB_PROF_ZROT); CUDA_TRY(launch_zrot(c->nw, nk, s.tb, c->sm_count, s.st)); }
-                    c->launches += 3;
-                }
-                { ProfScope ps(c, s.st, MEPB_PROF_EIGROT);
-                  CUDA_TRY(launch_eig_rot_large(m, ks, jb, o, c->max_pairs, s.Hk, s.Hka, s.Vscr, s.tb, gi, s.st)); }
-                c->launches += 2;
-            }
-            if (c->eig_thread) {
-                if (first_ef) {
-                    ProfScope ps(c, s.st, MEPB_PROF_EIG);
-                    CUDA_TRY(launch_eig_small(m, ks, s.eig_E, s.eig_U, c->d_err, c->sm_count, s.st));
-                    c->launches += 1;
-                }
-                o.e_in = s.eig_E; o.U_in = s.eig_U;
-            }
-            if (!c->large) {
-                ProfScope ps(c, s.st, MEPB_PROF_INTERP);
-                if (c->use_sub) CUDA_TRY(launch_bands_sub(m, ks, jb, o, c->max_pairs, gi, s.st));
-                else CUDA_TRY(launch_interp_small(m, ks, jb, o, c->max_pairs, gi, s.st));
-                c->launches += 1;
-            }
-            { ProfScope ps(c, s.st, MEPB_PROF_REDUCE);
-              CUDA_TRY(launch_reduce_rows(s.block_static, gi, ns, s.compact + (size_t)ief * c->cs.per_ef, ns, 0, 0, s.st)); }
-            c->launches += 1;
-            if (jb.do_ahc) {
-                int nsl; const int gs = sweep_ahc_grid(c->sm_count, nk, p.n_hw, &nsl, c->herm, c->max_pairs);
-                { ProfScope ps(c, s.st, MEPB_PROF_SWEEP_AHC);
-                  CUDA_TRY(launch_sweep_ahc(c->herm, s.items_ahc, s.cnt_ahc, c->max_pairs, nk, p.n_hw, c->d_hw, p.eta, s.block_sweep, gs, s.st)); }
-                const int nacc = c->herm ? kSweepAccH : kSweepAcc;          // Hermitian kernel fills X2,Y1 = slots [6,24)
-                { ProfScope ps(c, s.st, MEPB_PROF_REDUCE);
-                  CUDA_TRY(launch_reduce_rows(s.block_sweep, gs * (nsl / p.n_hw), p.n_hw * nacc,
-                                              s.compact + (size_t)ief * c->cs.per_ef + ns, nacc, kSweepAcc, c->herm ? 6 : 0, s.st)); }
-                c->launches += 2;
-            }
-            if (jb.do_opt) {
-                int nsl; const int gs = sweep_photo_grid(c->sm_count, nk, p.n_hw, &nsl, c->max_photo);
-                { ProfScope ps(c, s.st, MEPB_PROF_SWEEP_PHOTO);
-                  CUDA_TRY(launch_sweep_photo(s.items_photo, s.cnt_photo, c->max_photo, nk, p.n_hw, c->d_hw, p.eta, s.block_photo, gs, c->use_sub, s.st)); }
-                { ProfScope ps(c, s.st, MEPB_PROF_REDUCE);
-                  CUDA_TRY(launch_reduce_rows(s.block_photo, gs * (nsl / p.n_hw), p.n_hw * kPhotoAcc,
-                                              s.compact + (size_t)ief * c->cs.per_ef + ns + c->cs.sweep, kPhotoAcc, kPhotoAcc, 0, s.st)); }
-                c->launches += 2;
-            }
-        }
+        const int rc = launch_wave(c, s, k0, nk, nullptr, nullptr);
+        if (rc) return rc;
     }
     CUDA_TRY(cudaEventRecord(c->sb[1].done, c->sb[1].st));
     CUDA_TRY(cudaStreamWaitEvent(c->sb[0].st, c->sb[1].done, 0));
@@ -775,25 +707,48 @@ int mepb_accumulate(mepb_ctx *c, int64_t lin_begin, int64_t lin_end) {
     return check_err_flag(c);
 }
 
-static int pack_now(mepb_ctx *c) {
-    const mepb_params &p = c->p;
-    {   // work counters (items emitted to the frequency sweeps), summed over both stream buffers and all eF
-        c->n_items_ahc = c->n_items_photo = 0;
-        for (auto &s : c->sb)
-            for (int ief = 0; ief < p.n_eF; ++ief) {
-                double h2[2];
-                CUDA_TRY(cudaMemcpyAsync(h2, s.compact + (size_t)ief * c->cs.per_ef + S_NIT, sizeof(h2), cudaMemcpyDeviceToHost, c->sb[0].st));
-                CUDA_TRY(cudaStreamSynchronize(c->sb[0].st));
-                c->n_items_ahc += (long long)h2[0]; c->n_items_photo += (long long)h2[1];
-            }
+// Band sums on caller-supplied eigenpairs (include/mepb.h).  Waves of at most `chunk` k-points through stream buffer 0.
+int mepb_band_sums(mepb_ctx *c, int64_t nk, const double *e_k, const double *V_ka) {
+    if (!c || !e_k || !V_ka || nk < 0) return fail(MEPB_ERR_ARG, "bad argument");
+    if (c->packed_from_host) return fail(MEPB_ERR_STATE, "band_sums after set_partials; call mepb_reset first");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t nw = c->nw;
+    const long long cap = std::min<long long>(std::max<long long>(nk, 1), c->chunk);
+    if (cap > c->bs_cap) {
+        cudaFree(c->d_bs_e); cudaFree(c->d_bs_V); c->d_bs_e = nullptr; c->d_bs_V = nullptr; c->bs_cap = 0;
+        CUDA_TRY(cudaMalloc((void **)&c->d_bs_e, sizeof(double) * nw * cap));
+        CUDA_TRY(cudaMalloc((void **)&c->d_bs_V, sizeof(double2) * 3 * nw * nw * cap));
+        c->bs_cap = cap;
     }
+    StreamBuf &s = c->sb[0];
+    for (long long k0 = 0; k0 < nk; k0 += cap) {
+        const long long n = std::min<long long>(cap, nk - k0);
+        CUDA_TRY(cudaMemcpyAsync(c->d_bs_e, e_k + nw * k0, sizeof(double) * nw * n, cudaMemcpyHostToDevice, s.st));
+        CUDA_TRY(cudaMemcpyAsync(c->d_bs_V, V_ka + 2 * 3 * nw * nw * k0, sizeof(double2) * 3 * nw * nw * n, cudaMemcpyHostToDevice, s.st));
+        const int rc = launch_wave(c, s, 0, n, c->d_bs_e, c->d_bs_V);
+        if (rc) return rc;
+        CUDA_TRY(cudaStreamSynchronize(s.st));
+    }
+    c->have_data = true;
+    if (c->profiling) prof_collect(c);
+    return check_err_flag(c);
+}
+
+}  // extern "C"
+// Compact accumulators of both streams -> the packed buffer, on stream 0 (asynchronous: callers that read d_packed on the
+// host synchronise themselves; an NCCL all-reduce enqueued on the same stream needs no host round trip).  The work counters
+// of the roofline figures ride along in two extra slots behind the packed layout and are only fetched by mepb_work_items.
+int mepb::pack_now(mepb_ctx *c) {
+    const mepb_params &p = c->p;
     pack_kernel<<<32, 256, 0, c->sb[0].st>>>(c->sb[0].compact, c->sb[1].compact, c->cs, c->nw, p.valence_bands, p.n_hw, p.n_eF,
                                               p.do_mep, p.do_kubo, p.do_ahc, p.do_opt, c->L, c->d_packed);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaStreamSynchronize(c->sb[0].st));
     c->launches += 1;
+    c->counters_valid = true;
     return MEPB_OK;
 }
+
+extern "C" {
 
 int64_t mepb_partials_size(const mepb_ctx *c) { return c ? c->L.total : 0; }
 
@@ -801,13 +756,15 @@ int mepb_get_partials(mepb_ctx *c, double *buf) {
     if (!c || !buf) return fail(MEPB_ERR_ARG, "null argument");
     CUDA_TRY(cudaSetDevice(c->device));
     if (!c->packed_from_host) { int rc = pack_now(c); if (rc) return rc; }
-    CUDA_TRY(cudaMemcpy(buf, c->d_packed, sizeof(double) * (size_t)c->L.total, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpyAsync(buf, c->d_packed, sizeof(double) * (size_t)c->L.total, cudaMemcpyDeviceToHost, c->sb[0].st));
+    CUDA_TRY(cudaStreamSynchronize(c->sb[0].st));
     return MEPB_OK;
 }
 int mepb_set_partials(mepb_ctx *c, const double *buf) {
     if (!c || !buf) return fail(MEPB_ERR_ARG, "null argument");
     CUDA_TRY(cudaSetDevice(c->device));
-    CUDA_TRY(cudaMemcpy(c->d_packed, buf, sizeof(double) * (size_t)c->L.total, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpyAsync(c->d_packed, buf, sizeof(double) * (size_t)c->L.total, cudaMemcpyHostToDevice, c->sb[0].st));
+    CUDA_TRY(cudaStreamSynchronize(c->sb[0].st));
     c->packed_from_host = true; c->have_data = true;
     return MEPB_OK;
 }
@@ -815,6 +772,7 @@ int mepb_partials_device_ptr(mepb_ctx *c, double **dptr) {
     if (!c || !dptr) return fail(MEPB_ERR_ARG, "null argument");
     CUDA_TRY(cudaSetDevice(c->device));
     if (!c->packed_from_host) { int rc = pack_now(c); if (rc) return rc; }
+    CUDA_TRY(cudaStreamSynchronize(c->sb[0].st));      // the caller's stream is not ours
     c->packed_from_host = true;    // the caller may all-reduce in place; finalize reads d_packed as is
     *dptr = c->d_packed;
     return MEPB_OK;
@@ -828,7 +786,8 @@ int mepb_finalize(mepb_ctx *c, mepb_result *out) {
     {
         CUDA_TRY(cudaSetDevice(c->device));
         if (!c->packed_from_host) { int rc = pack_now(c); if (rc) return rc; }
-        CUDA_TRY(cudaMemcpy(h.data(), c->d_packed, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpyAsync(h.data(), c->d_packed, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, c->sb[0].st));
+        CUDA_TRY(cudaStreamSynchronize(c->sb[0].st));
     }
     const PackedLayout &L = c->L;
     const int n_ef = p.n_eF, n_hw = p.n_hw, nval = p.valence_bands;
@@ -1042,8 +1001,17 @@ int mepb_get_profile(const mepb_ctx *c, int kind, double *ms_total, int64_t *lau
     return MEPB_OK;
 }
 
-int64_t mepb_work_items(const mepb_ctx *c, int kind) {
+int64_t mepb_work_items(const mepb_ctx *cc, int kind) {
+    mepb_ctx *c = const_cast<mepb_ctx *>(cc);
     if (!c) return 0;
+    if (c->counters_valid) {                                 // fetched lazily: two doubles behind the packed layout
+        double h2[2] = {0.0, 0.0};
+        if (cudaSetDevice(c->device) == cudaSuccess && cudaStreamSynchronize(c->sb[0].st) == cudaSuccess &&
+            cudaMemcpy(h2, c->d_packed + c->L.total, sizeof(h2), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            c->n_items_ahc = (long long)h2[0]; c->n_items_photo = (long long)h2[1];
+        }
+        c->counters_valid = false;
+    }
     return kind == MEPB_PROF_SWEEP_AHC ? c->n_items_ahc : kind == MEPB_PROF_SWEEP_PHOTO ? c->n_items_photo : 0;
 }
 

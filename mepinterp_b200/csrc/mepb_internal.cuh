@@ -89,6 +89,7 @@ struct InterpOut {
     // list-mode outputs (any may be nullptr)
     double *e_out;        // (nw, nk)
     double2 *V_out;       // (3, nw, nw, nk)
+    double2 *U_out;       // (nw, nw, nk) eigenvectors in columns (general path only; consumed by the position-operator kernels)
     double2 *Hk_out;      // (nw, nw, nk)      W gauge
     double2 *Hka_out;     // (3, nw, nw, nk)   W gauge
     // response-mode outputs
@@ -101,6 +102,10 @@ struct InterpOut {
     // inputs from the thread-per-k eigensolver (mepb_eig.cu); nullptr -> the kernel runs its own warp-level Jacobi
     const double *e_in;   // (nw, nk) ascending
     const double2 *U_in;  // (nw, nw, nk) eigenvectors in columns, same order
+    // band sums on supplied eigenpairs (mepb_band_sums, position-operator branch): H-gauge velocities V_ka(a,n,m) in the
+    // user layout a + 3 (n + nw m) per k-point, with e_in the energies; the kernels then skip Fourier sums, eigensolve
+    // and rotation and run only their band-sum sections
+    const double2 *V_in;  // (3, nw, nw, nk) or nullptr
 };
 
 // ---------------------------------------------------------------------------------------------------------

@@ -386,7 +386,7 @@ eig_rot_large_kernel(const DevModel m, const KSource ks, const Jobs jb, const In
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double2 *Vg = Vscr + (size_t)blockIdx.x * 3 * nw2;          // V_ka(a, n, m) at a*nw2 + n + nw*m
     const bool response = (out.block_static != nullptr);
-    const bool need_eig = (out.e_out != nullptr) || response;
+    const bool need_eig = (out.e_out != nullptr) || (out.U_out != nullptr) || response;
 
     for (int i = tid; i < 18 * nw; i += E_THREADS) mep[i] = 0.0;
     for (int i = tid; i < 18 * E_WARPS; i += E_THREADS) kub[i] = 0.0;
@@ -396,7 +396,12 @@ eig_rot_large_kernel(const DevModel m, const KSource ks, const Jobs jb, const In
     __syncthreads();
 
     for (long long ik = blockIdx.x; ik < ks.nk && need_eig; ik += gridDim.x) {
-      if (tb.ne) {
+      if (out.V_in) {
+        // ------------------------------------------------------------------ supplied eigenpairs (mepb_band_sums, position-operator
+        // branch): energies from e_in, velocities copied below; no eigensolve, no rotation
+        if (tid < nw) es[tid] = out.e_in[(size_t)ik * nw + tid];
+        __syncthreads();
+      } else if (tb.ne) {
         // ------------------------------------------------------------------ U = H_0 H_1 ... H_{n-2} Z  (zunmtr 'L','N')
         // eigenpairs of the tridiagonal matrix come from mepb_tri.cu; thread (col, part) owns rows part + 8 rr of one
         // column of Z in registers, reflectors are broadcast from shared memory, no barrier inside the loop
@@ -561,8 +566,15 @@ eig_rot_large_kernel(const DevModel m, const KSource ks, const Jobs jb, const In
         }
         if (warp < 2) { f_loc = warp_sum(f_loc); if (lane == 0) acc_ne += f_loc; }     // nw <= 64: warps 0, 1
         __syncthreads();
+        if (out.U_out && !out.V_in)                               // eigenvectors in columns, ascending order: U(r, j) at r + nw j
+            for (int idx = tid; idx < nw2; idx += E_THREADS) { const int r = idx % nw, j = idx / nw; out.U_out[(size_t)ik * nw2 + idx] = T[r * LD + j]; }
         const bool want_V = response || (out.V_out != nullptr);
-        if (want_V) {
+        if (want_V && out.V_in) {
+            const double2 *Vk = out.V_in + (size_t)ik * 3 * nw2;     // user layout a + 3 (n + nw m)
+            for (int idx = tid; idx < 3 * nw2; idx += E_THREADS) { const int a = idx % 3, e = idx / 3; Vg[a * nw2 + e] = Vk[idx]; }
+            __threadfence_block();
+            __syncthreads();
+        } else if (want_V) {
             // -------------------------------------------------------------- V_a = Us^dagger (d_a H) Us   (Us = T)
             for (int a = 0; a < 3; ++a) {
                 const double2 *Ha = Hka_in + ((size_t)ik * 3 + a) * nw2;

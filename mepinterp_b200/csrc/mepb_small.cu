@@ -234,20 +234,21 @@ interp_small_kernel(const DevModel m, const KSource ks, const Jobs jb, const Int
             k2 = (2.0 * (double)q2 - (double)ks.N2 - 1.0) / (2.0 * (double)ks.N2);
             k3 = (2.0 * (double)q3 - (double)ks.N3 - 1.0) / (2.0 * (double)ks.N3);
         }
+        const bool vin = (out.V_in != nullptr);                   // band sums on supplied (e, V): sections 1-4 are skipped
         // ------------------------------------------------------------------ 1. phases
-        for (int R = lane; R < nR; R += 32) {
+        for (int R = lane; R < nR && !vin; R += 32) {
             const double x = 2.0 * (k1 * m.Rf[3 * R] + k2 * m.Rf[3 * R + 1] + k3 * m.Rf[3 * R + 2]);
             double s, c; sincospi(x, &s, &c);
             ph[R] = make_double2(c, s);
         }
-        if (has_tau && lane < NW) {
+        if (has_tau && lane < NW && !vin) {
             const double x = 2.0 * (k1 * m.tau[3 * lane] + k2 * m.tau[3 * lane + 1] + k3 * m.tau[3 * lane + 2]);
             double s, c; sincospi(x, &s, &c);
             dn[lane] = make_double2(c, s);
         }
         __syncwarp();
         // ------------------------------------------------------------------ 2. Fourier sums
-        for (int e0 = 0; e0 < NW2; e0 += 64) {
+        for (int e0 = 0; e0 < NW2 && !vin; e0 += 64) {
             const int idx0 = e0 + lane, idx1 = e0 + 32 + lane;       // two matrix elements per lane
             const bool v0 = idx0 < NW2, v1 = idx1 < NW2;
             double2 hk0 = make_double2(0, 0), hk1 = hk0;
@@ -330,7 +331,13 @@ interp_small_kernel(const DevModel m, const KSource ks, const Jobs jb, const Int
         __syncwarp();
         if (!need_eig) continue;
         // ------------------------------------------------------------------ 3. eigensolve
-        if (out.U_in) {   // eigenpairs come from the thread-per-k solver (mepb_eig.cu), already in ascending order
+        if (vin) {        // supplied energies and velocities (user layout a + 3 (n + NW m))
+            if (lane < NW) { es[lane] = out.e_in[(size_t)ik * NW + lane]; perm[lane] = lane; }
+            for (int idx = lane; idx < 3 * NW2; idx += 32) {
+                const int a = idx % 3, n = (idx / 3) % NW, mm = idx / (3 * NW);
+                Ha[a * NW * LD + n * LD + mm] = out.V_in[(size_t)ik * 3 * NW2 + idx];
+            }
+        } else if (out.U_in) {   // eigenpairs come from the thread-per-k solver (mepb_eig.cu), already in ascending order
             for (int idx = lane; idx < NW2; idx += 32) Us[(idx % NW) * LD + idx / NW] = out.U_in[(size_t)ik * NW2 + idx];
             if (lane < NW) { es[lane] = out.e_in[(size_t)ik * NW + lane]; perm[lane] = lane; }
         } else {
@@ -355,7 +362,7 @@ interp_small_kernel(const DevModel m, const KSource ks, const Jobs jb, const Int
             if (out.e_out) out.e_out[(size_t)ik * NW + lane] = es[lane];
         }
         // ------------------------------------------------------------------ 4. gauge rotation (in place in Ha)
-        if (jb.do_gauge) {
+        if (jb.do_gauge && !vin) {
             for (int t0 = 0; t0 < 3 * NW; t0 += 32) {
                 const int t = t0 + lane;
                 const bool act = t < 3 * NW;

@@ -40,7 +40,8 @@ struct SubL {  // shared-memory layout per GROUP (one k-point), bytes
 };
 
 // MEP: build with the MEP sums (two CTAs per SM, 255 registers; otherwise three CTAs, 168); PH: build with the photo items
-template <int NW, bool MEP, bool PH>
+// VIN: band sums on supplied eigenpairs (out.e_in, out.V_in) — Fourier sums and rotation compiled out
+template <int NW, bool MEP, bool PH, bool VIN>
 __global__ void __launch_bounds__(kSubWarps * 32, MEP ? 2 : 3)      // 36 more accumulators with the MEP jobs: 3 CTAs would spill 1.1 KB
 bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const InterpOut out, const int max_pairs, const size_t grp_bytes,
                  const int rec_cap) {
@@ -59,6 +60,7 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
     double2 *ph = reinterpret_cast<double2 *>(base + L::oPh);
     const int nR = m.nR;
     const bool has_tau = (m.tau != nullptr);
+    constexpr bool vin = VIN;                                     // band sums on supplied (e, V): no Fourier sums, no rotation
     // CTA-wide copy of the sparse H(R) list (after the group buffers)
     SpRec *rec = reinterpret_cast<SpRec *>(smem_raw + (size_t)kSubWarps * NGRP * grp_bytes);
     int *sptr = reinterpret_cast<int *>(rec + rec_cap);
@@ -104,21 +106,23 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
             k3 = (2.0 * (double)q3 - (double)ks.N3 - 1.0) / (2.0 * (double)ks.N3);
         }
         // ------------------------------------------------------------------ 1. phases; 3. eigenpairs (loads issued early)
-        for (int R = g; R < nR; R += NW) {
+        for (int R = g; R < nR && !vin; R += NW) {
             const double x = 2.0 * (k1 * __ldg(&m.Rf[3 * R]) + k2 * __ldg(&m.Rf[3 * R + 1]) + k3 * __ldg(&m.Rf[3 * R + 2]));
             double s, c; sincospi(x, &s, &c);
             ph[R] = make_double2(c, s);
         }
-        if (has_tau) {
+        if (has_tau && !vin) {
             const double x = 2.0 * (k1 * __ldg(&m.tau[3 * g]) + k2 * __ldg(&m.tau[3 * g + 1]) + k3 * __ldg(&m.tau[3 * g + 2]));
             double s, c; sincospi(x, &s, &c);
             dn[g] = make_double2(c, s);
         }
         double2 u[NW];                                             // column g of U (eigenvector of band g)
         {
-            const double2 *Uk = out.U_in + (size_t)ik * NW2 + (size_t)NW * g;   // element r + NW*c: 128 contiguous bytes per lane
+            if (!vin) {
+                const double2 *Uk = out.U_in + (size_t)ik * NW2 + (size_t)NW * g;   // element r + NW*c: 128 contiguous bytes per lane
 #pragma unroll
-            for (int q = 0; q < NW; ++q) u[q] = __ldg(Uk + q);
+                for (int q = 0; q < NW; ++q) u[q] = __ldg(Uk + q);
+            }
             const double e = out.e_in[(size_t)ik * NW + g];
             const double f = fermi(e, jb);
             es[g] = e; fn[g] = f;
@@ -126,7 +130,13 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
         }
         __syncwarp();
         // ------------------------------------------------------------------ 2. Fourier sums of d_a H, row n = g
-        {
+        if (vin) {                                                  // supplied velocities: user layout a + 3 (n + NW m)
+            const double2 *Vk = out.V_in + (size_t)ik * 3 * NW2;
+            for (int idx = g; idx < 3 * NW2; idx += NW) {
+                const int a = idx % 3, n = (idx / 3) % NW, mm = idx / (3 * NW);
+                Ha[a * NW * LD + n * LD + mm] = __ldg(Vk + idx);
+            }
+        } else {
             const int n = g;
 #pragma unroll 1
             for (int mm = 0; mm < NW; ++mm) {
@@ -185,7 +195,7 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
         // ------------------------------------------------------------------ 4. gauge rotation V_a = U^dagger (d_a H) U
         // lane g: column g of T = H_a U from its own u (registers), written over H_a; then ROW g of V_a = U^dagger T,
         // again from its own u — U never goes through shared memory.
-        if (jb.do_gauge) {
+        if (jb.do_gauge && !vin) {
 #pragma unroll 1
             for (int a = 0; a < 3; ++a) {
                 double2 *Hrow = Ha + a * NW * LD;
@@ -500,15 +510,21 @@ cudaError_t launch_sub_t(const DevModel &m, const KSource &ks, const Jobs &jobs,
     const bool mep = jobs.do_mep || jobs.do_kubo, ph = jobs.do_opt != 0;
     const size_t smem = sub_smem<NW>(m.nR, m.sp_ptr ? m.sp_nnz : 0, mep);
     cudaError_t e;
-#define MEPB_LAUNCH_SUB(M, P)                                                                                                  \
+#define MEPB_LAUNCH_SUB(M, P, V)                                                                                               \
     do {                                                                                                                        \
-        e = cudaFuncSetAttribute(bands_sub_kernel<NW, M, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
+        e = cudaFuncSetAttribute(bands_sub_kernel<NW, M, P, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
         if (e != cudaSuccess) return e;                                                                                         \
-        bands_sub_kernel<NW, M, P><<<grid, kSubWarps * 32, smem, st>>>(m, ks, jobs, out, max_pairs, SubL<NW>::bytes(m.nR, M), rec_cap); \
+        bands_sub_kernel<NW, M, P, V><<<grid, kSubWarps * 32, smem, st>>>(m, ks, jobs, out, max_pairs, SubL<NW>::bytes(m.nR, M), rec_cap); \
     } while (0)
-    if (mep) MEPB_LAUNCH_SUB(true, true);
-    else if (ph) MEPB_LAUNCH_SUB(false, true);
-    else MEPB_LAUNCH_SUB(false, false);
+    if (out.V_in) {                                        // supplied eigenpairs: one build with every job compiled in
+        const size_t smem_v = sub_smem<NW>(m.nR, m.sp_ptr ? m.sp_nnz : 0, true);
+        e = cudaFuncSetAttribute(bands_sub_kernel<NW, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v);
+        if (e != cudaSuccess) return e;
+        bands_sub_kernel<NW, true, true, true><<<grid, kSubWarps * 32, smem_v, st>>>(m, ks, jobs, out, max_pairs, SubL<NW>::bytes(m.nR, true), rec_cap);
+    }
+    else if (mep) MEPB_LAUNCH_SUB(true, true, false);
+    else if (ph) MEPB_LAUNCH_SUB(false, true, false);
+    else MEPB_LAUNCH_SUB(false, false, false);
 #undef MEPB_LAUNCH_SUB
     return cudaGetLastError();
 }

@@ -339,6 +339,34 @@ static void mesh_kpt(const int32_t *g, int64_t lin, double *kpt) {
     kpt[2] = (2.0 * (double)kiz - (double)g[2] - 1.0) / (2.0 * (double)g[2]);
 }
 
+/* The per-k response functions of core.f90:187-253 on one set of eigenpairs (en, V): occupations, MEP, Kubo-MEP, AHC,
+ * optical sums, all += into the packed partials. */
+static void band_sums_k(const mepb_model *mo, const mepb_params *p, const layout_t *Lp, const double *ef_lst, const double *hw_lst,
+                        const double *en, const zc *V, double *fd, zc *scr, double *partials) {
+    const int nw = mo->nw, n_ef = p->n_eF, n_hw = p->n_hw;
+    const layout_t L = *Lp;
+    zc i_eta = I * p->eta;
+    for (int n = 0; n < nw; ++n) for (int ef = 0; ef < n_ef; ++ef) { /* core.f90:187-193 */
+        double f = fd_stat(en[n], ef_lst[ef], p->T_kelvin);
+        FD(ef, n) = f; partials[L.ne + ef] += f;
+    }
+    for (int n = 0; n < nw; ++n) for (int m = n + 1; m < nw; ++m) if (en[n] == en[m]) partials[1] += 1.0;
+    if (p->do_mep) {
+        mep_niu_IC(nw, p->valence_bands, p->kubo_tol, en, V, partials + L.mep_ic);
+        mep_niu_LC(nw, p->valence_bands, p->kubo_tol, en, V, partials + L.mep_lc);
+    }
+    if (p->do_kubo) {
+        kubo_mep_IC(nw, n_ef, en, V, fd, partials + L.kmep_ic);
+        kubo_mep_LC(nw, n_ef, en, V, fd, partials + L.kmep_lc);
+    }
+    if (p->do_ahc) {
+        kubo_ahc_tens(nw, n_ef, en, V, fd, partials + L.ahc);
+        velo_ahc_tens(nw, n_ef, n_hw, en, V, hw_lst, fd, i_eta, (zc *)(partials + L.velo), scr);
+        kubo_ohc_tens(nw, n_ef, n_hw, en, V, hw_lst, fd, i_eta, (zc *)(partials + L.ohc), scr);
+    }
+    if (p->do_opt) photo_2nd_cond(nw, n_ef, n_hw, en, V, hw_lst, fd, i_eta, (zc *)(partials + L.photo), scr);
+}
+
 /* One "rank": k-points lin_begin + rank, + rank + nranks, ... < lin_end  (mpi_comm.f90:80-99 round-robin).  partials += */
 int cpu_ref_accumulate(const mepb_model *mo, const mepb_params *p, int64_t lin_begin, int64_t lin_end, int rank, int nranks,
                        double *partials) {
@@ -350,7 +378,6 @@ int cpu_ref_accumulate(const mepb_model *mo, const mepb_params *p, int64_t lin_b
     double *ef_lst = (double *)malloc(sizeof(double) * n_ef), *hw_lst = (double *)malloc(sizeof(double) * n_hw);
     get_linspace(p->eF_min, p->eF_max, n_ef, ef_lst); /* core.f90:124-125 */
     get_linspace(p->hw_min, p->hw_max, n_hw, hw_lst);
-    zc i_eta = I * p->eta;
     double *en = (double *)malloc(sizeof(double) * nw), *fd = (double *)malloc(sizeof(double) * n_ef * nw);
     zc *V = (zc *)malloc(sizeof(zc) * 3 * nw * nw), *U = (zc *)malloc(sizeof(zc) * nw * nw), *H_ka = (zc *)malloc(sizeof(zc) * 3 * nw * nw);
     zc *tmp = (zc *)malloc(sizeof(zc) * nw * nw), *M_in = (zc *)malloc(sizeof(zc) * nw * nw), *U_dag = (zc *)malloc(sizeof(zc) * nw * nw);
@@ -360,29 +387,28 @@ int cpu_ref_accumulate(const mepb_model *mo, const mepb_params *p, int64_t lin_b
         double kpt[3]; mesh_kpt(p->mp_grid, lin, kpt);
         int info = get_wann_interp(mo, p, recip, kpt, en, V, U, H_ka, tmp, M_in, U_dag);
         if (info != 0) { rc = -5; break; }
-        for (int n = 0; n < nw; ++n) for (int ef = 0; ef < n_ef; ++ef) { /* core.f90:187-193 */
-            double f = fd_stat(en[n], ef_lst[ef], p->T_kelvin);
-            FD(ef, n) = f; partials[L.ne + ef] += f;
-        }
-        for (int n = 0; n < nw; ++n) for (int m = n + 1; m < nw; ++m) if (en[n] == en[m]) partials[1] += 1.0;
-        if (p->do_mep) {
-            mep_niu_IC(nw, p->valence_bands, p->kubo_tol, en, V, partials + L.mep_ic);
-            mep_niu_LC(nw, p->valence_bands, p->kubo_tol, en, V, partials + L.mep_lc);
-        }
-        if (p->do_kubo) {
-            kubo_mep_IC(nw, n_ef, en, V, fd, partials + L.kmep_ic);
-            kubo_mep_LC(nw, n_ef, en, V, fd, partials + L.kmep_lc);
-        }
-        if (p->do_ahc) {
-            kubo_ahc_tens(nw, n_ef, en, V, fd, partials + L.ahc);
-            velo_ahc_tens(nw, n_ef, n_hw, en, V, hw_lst, fd, i_eta, (zc *)(partials + L.velo), scr);
-            kubo_ohc_tens(nw, n_ef, n_hw, en, V, hw_lst, fd, i_eta, (zc *)(partials + L.ohc), scr);
-        }
-        if (p->do_opt) photo_2nd_cond(nw, n_ef, n_hw, en, V, hw_lst, fd, i_eta, (zc *)(partials + L.photo), scr);
+        band_sums_k(mo, p, &L, ef_lst, hw_lst, en, V, fd, scr, partials);
         partials[0] += 1.0;
     }
     free(ef_lst); free(hw_lst); free(en); free(fd); free(V); free(U); free(H_ka); free(tmp); free(M_in); free(U_dag); free(scr);
     return rc;
+}
+
+/* Band sums on supplied eigenpairs: e_k (nw,nk), V_ka (3,nw,nw,nk).  partials += (test helper mirroring mepb_band_sums) */
+int cpu_ref_band_sums(const mepb_model *mo, const mepb_params *p, int64_t nk, const double *e_k, const double *V_ka, double *partials) {
+    const int nw = mo->nw, n_ef = p->n_eF, n_hw = p->n_hw;
+    layout_t L = make_layout(p);
+    double *ef_lst = (double *)malloc(sizeof(double) * n_ef), *hw_lst = (double *)malloc(sizeof(double) * n_hw);
+    get_linspace(p->eF_min, p->eF_max, n_ef, ef_lst);
+    get_linspace(p->hw_min, p->hw_max, n_hw, hw_lst);
+    double *fd = (double *)malloc(sizeof(double) * n_ef * nw);
+    zc *scr = (zc *)malloc(sizeof(zc) * 27 * n_hw);
+    for (int64_t ik = 0; ik < nk; ++ik) {
+        band_sums_k(mo, p, &L, ef_lst, hw_lst, e_k + (int64_t)nw * ik, (const zc *)V_ka + (int64_t)3 * nw * nw * ik, fd, scr, partials);
+        partials[0] += 1.0;
+    }
+    free(ef_lst); free(hw_lst); free(fd); free(scr);
+    return 0;
 }
 
 /* nthreads workers standing in for MPI ranks; private accumulators summed at the end like MPI_REDUCE (core.f90:467-526) */
@@ -473,27 +499,36 @@ int cpu_ref_finalize(const mepb_model *mo, const mepb_params *p, const double *p
     return 0;
 }
 
-/* explicit k list: e_k (nw,nk), V_ka (3,nw,nw,nk) or NULL, H_k (nw,nw,nk) or NULL, H_ka_W (3,nw,nw,nk) or NULL (W gauge) */
+/* explicit k list: e_k (nw,nk), V_ka (3,nw,nw,nk) or NULL, H_k (nw,nw,nk) or NULL, H_ka_W (3,nw,nw,nk) or NULL (W gauge);
+ * k-points are independent: OpenMP over k with private scratch (test helper speed only) */
 int cpu_ref_interp(const mepb_model *mo, const mepb_params *p, int64_t nk, const double *kpt, double *e_k, double *V_ka,
                    double *H_k_out, double *H_ka_out) {
     if (!p_zheevd) return -1;
     const int nw = mo->nw;
     double recip[9]; set_recip_latt(mo->a_latt, recip);
-    zc *V = (zc *)malloc(sizeof(zc) * 3 * nw * nw), *U = (zc *)malloc(sizeof(zc) * nw * nw), *H_ka = (zc *)malloc(sizeof(zc) * 3 * nw * nw);
-    zc *tmp = (zc *)malloc(sizeof(zc) * nw * nw), *M_in = (zc *)malloc(sizeof(zc) * nw * nw), *U_dag = (zc *)malloc(sizeof(zc) * nw * nw);
     int rc = 0;
-    for (int64_t ik = 0; ik < nk && rc == 0; ++ik) {
-        if (H_k_out || H_ka_out) {
-            ft_R_to_k(mo, p->use_cart_velo, recip, kpt + 3 * ik, U, H_ka);
-            if (H_k_out) memcpy(H_k_out + 2 * (int64_t)nw * nw * ik, U, sizeof(zc) * nw * nw);
-            if (H_ka_out) memcpy(H_ka_out + 2 * (int64_t)3 * nw * nw * ik, H_ka, sizeof(zc) * 3 * nw * nw);
+#ifdef _OPENMP
+#pragma omp parallel
+#endif
+    {
+        zc *V = (zc *)malloc(sizeof(zc) * 3 * nw * nw), *U = (zc *)malloc(sizeof(zc) * nw * nw), *H_ka = (zc *)malloc(sizeof(zc) * 3 * nw * nw);
+        zc *tmp = (zc *)malloc(sizeof(zc) * nw * nw), *M_in = (zc *)malloc(sizeof(zc) * nw * nw), *U_dag = (zc *)malloc(sizeof(zc) * nw * nw);
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 4)
+#endif
+        for (int64_t ik = 0; ik < nk; ++ik) {
+            if (H_k_out || H_ka_out) {
+                ft_R_to_k(mo, p->use_cart_velo, recip, kpt + 3 * ik, U, H_ka);
+                if (H_k_out) memcpy(H_k_out + 2 * (int64_t)nw * nw * ik, U, sizeof(zc) * nw * nw);
+                if (H_ka_out) memcpy(H_ka_out + 2 * (int64_t)3 * nw * nw * ik, H_ka, sizeof(zc) * 3 * nw * nw);
+            }
+            if (e_k) {
+                int info = get_wann_interp(mo, p, recip, kpt + 3 * ik, e_k + (int64_t)nw * ik, V, U, H_ka, tmp, M_in, U_dag);
+                if (info) rc = -5;
+                if (V_ka) memcpy(V_ka + 2 * (int64_t)3 * nw * nw * ik, V, sizeof(zc) * 3 * nw * nw);
+            }
         }
-        if (e_k) {
-            int info = get_wann_interp(mo, p, recip, kpt + 3 * ik, e_k + (int64_t)nw * ik, V, U, H_ka, tmp, M_in, U_dag);
-            if (info) rc = -5;
-            if (V_ka) memcpy(V_ka + 2 * (int64_t)3 * nw * nw * ik, V, sizeof(zc) * 3 * nw * nw);
-        }
+        free(V); free(U); free(H_ka); free(tmp); free(M_in); free(U_dag);
     }
-    free(V); free(U); free(H_ka); free(tmp); free(M_in); free(U_dag);
     return rc;
 }

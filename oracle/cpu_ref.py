@@ -65,6 +65,7 @@ def lib():
         L.cpu_ref_accumulate_abs.argtypes = [C.POINTER(CModel), C.POINTER(CParams), C.c_int64, C.c_int64, C.c_int, C.c_void_p]
         L.cpu_ref_finalize.argtypes = [C.POINTER(CModel), C.POINTER(CParams), C.c_void_p, C.POINTER(CResult)]
         L.cpu_ref_interp.argtypes = [C.POINTER(CModel), C.POINTER(CParams), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.cpu_ref_band_sums.argtypes = [C.POINTER(CModel), C.POINTER(CParams), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         rc = L.cpu_ref_init(openblas_path().encode())
         if rc != 0:
             raise RuntimeError(f"cpu_ref_init failed rc={rc}")
@@ -125,6 +126,18 @@ class Handle:
         if rc != 0:
             raise RuntimeError(f"cpu_ref_accumulate_abs rc={rc}")
         return buf
+
+    def band_sums(self, e_k, V_ka, partials=None):
+        """The per-k response functions on supplied eigenpairs: e_k (nw,nk), V_ka (3,nw,nw,nk); partials += ."""
+        e = _f(e_k, np.float64)
+        V = _f(V_ka, np.complex128)
+        if partials is None:
+            partials = np.zeros(self.partials_size())
+        with np.errstate(all="ignore"):
+            rc = lib().cpu_ref_band_sums(C.byref(self.cm), C.byref(self.cp), e.shape[1], e.ctypes.data, V.ctypes.data, partials.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f"cpu_ref_band_sums rc={rc}")
+        return partials
 
     def finalize(self, partials) -> dict:
         return finalize_with(lambda res: lib().cpu_ref_finalize(C.byref(self.cm), C.byref(self.cp), partials.ctypes.data, C.byref(res)),

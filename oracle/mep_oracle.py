@@ -345,19 +345,23 @@ def _offdiag_mask(nw):
     return ~np.eye(nw, dtype=bool)
 
 
-def kubo_ahc_tens(e, V, fd):
-    """kubo.f90:37-78 -> (K,3,3,n_eF).  No degeneracy guard (inf/NaN propagate)."""
+def kubo_ahc_tens(e, V, fd, mag=False):
+    """kubo.f90:37-78 -> (K,3,3,n_eF).  No degeneracy guard (inf/NaN propagate).
+    mag=True (every band-sum function here): the same sum with every TERM replaced by its magnitude — the un-cancelled
+    size of the sum, the yardstick floating-point reassociation errors are measured against in the tests."""
     nw = e.shape[1]
     dE2 = (e[:, None, :] - e[:, :, None]) ** 2                        # [k,n,np] = (e_np - e_n)^2
     W = np.imag(np.einsum("kinp,kjpn->kijnp", V, V))                  # Im[V(i,n,np) V(j,np,n)]
     with np.errstate(divide="ignore", invalid="ignore"):
         T = -2.0 * W / dE2[:, None, None, :, :]
     T = np.where(_offdiag_mask(nw)[None, None, None], T, 0.0)
+    if mag:
+        return np.einsum("kijn,ken->kije", np.abs(T).sum(axis=-1), np.abs(fd))
     curv = T.sum(axis=-1)                                             # (k,i,j,n)
     return -np.einsum("kijn,ken->kije", curv, fd)
 
 
-def velo_ahc_tens(e, V, hw, fd, eta):
+def velo_ahc_tens(e, V, hw, fd, eta, mag=False):
     """kubo.f90:86-140 -> (K,3,3,n_hw,n_eF) complex."""
     nw = e.shape[1]
     z = hw + 1j * eta
@@ -370,11 +374,14 @@ def velo_ahc_tens(e, V, hw, fd, eta):
         with np.errstate(divide="ignore", invalid="ignore"):
             g = 1.0 / (dE2 - z[h] ** 2)                               # (k,n,np)
         g = np.where(mask[None], g, 0.0)
+        if mag:
+            out[:, :, :, h, :] = np.einsum("kijnp,knp,kenp->kije", np.abs(W), np.abs(g), np.abs(np.where(mask[None, None], dfd, 0.0)))
+            continue
         out[:, :, :, h, :] = np.einsum("kijnp,knp,kenp->kije", W, g, np.where(mask[None, None], dfd, 0.0))
     return out
 
 
-def kubo_ohc_tens(e, V, hw, fd, eta):
+def kubo_ohc_tens(e, V, hw, fd, eta, mag=False):
     """kubo.f90:145-198 -> (K,3,3,n_hw,n_eF) complex."""
     nw = e.shape[1]
     dE = e[:, :, None] - e[:, None, :]                                # [k,m,n] = e_m - e_n
@@ -387,11 +394,14 @@ def kubo_ohc_tens(e, V, hw, fd, eta):
         with np.errstate(divide="ignore", invalid="ignore"):
             g = 1.0 / (dE * (dE - hw[h] - 1j * eta))
         g = np.where(mask[None], g, 0.0)
+        if mag:
+            out[:, :, :, h, :] = np.einsum("kijmn,kmn,kemn->kije", np.abs(P), np.abs(g), np.abs(df))
+            continue
         out[:, :, :, h, :] = 1j * np.einsum("kijmn,kmn,kemn->kije", P, g, df)
     return out
 
 
-def photo_2nd_cond(e, V, hw, fd, eta):
+def photo_2nd_cond(e, V, hw, fd, eta, mag=False):
     """photo.f90:16-86 -> (K,3,3,3,n_hw,n_eF) complex.  m==n included, l==n skipped."""
     K, nw = e.shape
     i_eta = 1j * eta
@@ -412,48 +422,56 @@ def photo_2nd_cond(e, V, hw, fd, eta):
         # weight by df_ln (per eF) and contract
         for ef in range(fd.shape[1]):
             w = s * df_ln[:, ef, :, :, None]                          # [k,n,l,m]
+            if mag:
+                Va = np.abs(V)
+                out[:, :, :, :, h, ef] = np.einsum("kanl,kblm,kcmn,knlm->kabc", Va, Va, Va, np.abs(w), optimize=True)
+                continue
             out[:, :, :, :, h, ef] = np.einsum("kanl,kblm,kcmn,knlm->kabc", V, V, V, w, optimize=True)
     return out
 
 
-def _mep_lc_terms(e, V):
+def _mep_lc_terms(e, V, mag=False):
     """Common kernel of mep_niu_LC (mep_niu.f90:69-95) and kubo_mep_LC (kubo_mep.f90:67-94):
     returns num[k,i,j,n0,n] = sum_kl eps_jkl Re[V(i,n0,n) V(k,n,n0) V(l,n0,n0)] and den[k,n0,n] = (e_n0-e_n)^3."""
     lc = levi_civita()
     nw = e.shape[1]
     Vd = np.einsum("klnn->kln", V)                                    # V(l,n0,n0)
     t = np.einsum("kion,kbno,kco->kibcon", V, V, Vd, optimize=True)   # V(i,n0,n) V(b,n,n0) V(c,n0,n0) [o=n0]
+    if mag:                                                           # |term| per epsilon entry, |den|
+        return np.einsum("jbc,kibcon->kijon", np.abs(lc), np.abs(t), optimize=True), np.abs((e[:, :, None] - e[:, None, :]) ** 3)
     num = np.einsum("jbc,kibcon->kijon", lc, t.real, optimize=True)
     den = (e[:, :, None] - e[:, None, :]) ** 3
     return num, den
 
 
-def _mep_ic_terms(e, V):
+def _mep_ic_terms(e, V, mag=False):
     """Common kernel of mep_niu_IC (mep_niu.f90:125-155) and kubo_mep_IC (kubo_mep.f90:119-146):
     num[k,i,j,n0,n,m] = - sum_kl eps_jkl Re[V(i,n0,n) V(k,n,m) V(l,m,n0)],
     den[k,n0,n,m] = (e_n0-e_n)^2 (e_n0-e_m)."""
     lc = levi_civita()
     t = np.einsum("kion,kbnm,kcmo->kibconm", V, V, V, optimize=True)
-    num = -np.einsum("jbc,kibconm->kijonm", lc, t.real, optimize=True)
     d = e[:, :, None] - e[:, None, :]                                 # [k,n0,x] = e_n0 - e_x
     den = (d ** 2)[:, :, :, None] * d[:, :, None, :]
+    if mag:
+        return np.einsum("jbc,kibconm->kijonm", np.abs(lc), np.abs(t), optimize=True), np.abs(den)
+    num = -np.einsum("jbc,kibconm->kijonm", lc, t.real, optimize=True)
     return num, den
 
 
-def mep_niu_LC(e, V, valence_bands, kubo_tol):
+def mep_niu_LC(e, V, valence_bands, kubo_tol, mag=False):
     """mep_niu.f90:47-99 -> (K,3,3,nval).  Terms with |den| <= kubo_tol skipped."""
     nw = e.shape[1]
-    num, den = _mep_lc_terms(e, V)
+    num, den = _mep_lc_terms(e, V, mag)
     ok = (np.abs(den) > kubo_tol) & _offdiag_mask(nw)[None]
     with np.errstate(divide="ignore", invalid="ignore"):
         T = np.where(ok[:, None, None], num / den[:, None, None], 0.0)
     return T.sum(axis=-1)[:, :, :, :valence_bands]
 
 
-def mep_niu_IC(e, V, valence_bands, kubo_tol):
+def mep_niu_IC(e, V, valence_bands, kubo_tol, mag=False):
     """mep_niu.f90:102-159 -> (K,3,3,nval)."""
     nw = e.shape[1]
-    num, den = _mep_ic_terms(e, V)
+    num, den = _mep_ic_terms(e, V, mag)
     off = _offdiag_mask(nw)
     ok = (np.abs(den) > kubo_tol) & off[None, :, :, None] & off[None, :, None, :]   # n/=n0 and m/=n0
     with np.errstate(divide="ignore", invalid="ignore"):
@@ -461,20 +479,20 @@ def mep_niu_IC(e, V, valence_bands, kubo_tol):
     return T.sum(axis=(-1, -2))[:, :, :, :valence_bands]
 
 
-def kubo_mep_LC(e, V, fd):
+def kubo_mep_LC(e, V, fd, mag=False):
     """kubo_mep.f90:51-97 -> (K,3,3,n_eF).  All n0, Fermi weight f_n0, no tolerance guard."""
     nw = e.shape[1]
-    num, den = _mep_lc_terms(e, V)
+    num, den = _mep_lc_terms(e, V, mag)
     with np.errstate(divide="ignore", invalid="ignore"):
         T = num / den[:, None, None]
     T = np.where(_offdiag_mask(nw)[None, None, None], T, 0.0).sum(axis=-1)   # (k,i,j,n0)
     return np.einsum("kijo,keo->kije", T, fd)
 
 
-def kubo_mep_IC(e, V, fd):
+def kubo_mep_IC(e, V, fd, mag=False):
     """kubo_mep.f90:100-149 -> (K,3,3,n_eF)."""
     nw = e.shape[1]
-    num, den = _mep_ic_terms(e, V)
+    num, den = _mep_ic_terms(e, V, mag)
     off = _offdiag_mask(nw)
     ok = off[None, :, :, None] & off[None, :, None, :]
     with np.errstate(divide="ignore", invalid="ignore"):
@@ -499,37 +517,71 @@ class Partials:
         return self
 
 
-def accumulate(model: Model, p: Params, lin_begin: int, lin_end: int, batch: int = 2048) -> Partials:
-    """The k-loop body of core.f90:165-270 over the 0-based linear mesh range [lin_begin, lin_end)."""
+def band_sums(p: Params, e: np.ndarray, V: np.ndarray, part: Optional[Partials] = None, mag: bool = False) -> Partials:
+    """The per-k response functions of core.f90:187-253 on a batch of eigenpairs e (K,nw), V (K,3,nw,nw), summed over the
+    batch into `part`.  mag=True: every term replaced by its magnitude (test yardstick, see kubo_ahc_tens)."""
     ef_lst = get_linspace(p.eF_min, p.eF_max, p.n_eF)                # core.f90:124
     hw_lst = get_linspace(p.hw_min, p.hw_max, p.n_hw)                # :125
-    part = Partials(n_k=0, Ne=np.zeros(p.n_eF))
+    if part is None:
+        part = Partials(n_k=0, Ne=np.zeros(p.n_eF))
     acc = part.arrays
 
     def add(name, val):
         s = val.sum(axis=0)
         acc[name] = s if name not in acc else acc[name] + s
 
+    fd = fd_stat(e, ef_lst, p.T_kelvin)                              # (K, n_eF, nw)
+    part.Ne += fd.sum(axis=(0, 2))                                   # core.f90:187
+    part.n_k += e.shape[0]
+    if p.do_mep:                                                     # :198-202
+        add("mep_bands_ic", mep_niu_IC(e, V, p.valence_bands, p.kubo_tol, mag))
+        add("mep_bands_lc", mep_niu_LC(e, V, p.valence_bands, p.kubo_tol, mag))
+    if p.do_kubo:                                                    # :207-216
+        add("kubo_mep_ic", kubo_mep_IC(e, V, fd, mag))
+        add("kubo_mep_lc", kubo_mep_LC(e, V, fd, mag))
+    if p.do_ahc:                                                     # :221-230
+        add("kubo_ahc", kubo_ahc_tens(e, V, fd, mag))
+        add("velo_ahc", velo_ahc_tens(e, V, hw_lst, fd, p.eta, mag))
+        add("kubo_ohc", kubo_ohc_tens(e, V, hw_lst, fd, p.eta, mag))
+    if p.do_opt:                                                     # :235-242 (kubo_opt_tens == 0 without A_ka)
+        add("photo2", photo_2nd_cond(e, V, hw_lst, fd, p.eta, mag))
+    return part
+
+
+def accumulate(model: Model, p: Params, lin_begin: int, lin_end: int, batch: int = 2048) -> Partials:
+    """The k-loop body of core.f90:165-270 over the 0-based linear mesh range [lin_begin, lin_end)."""
+    part = Partials(n_k=0, Ne=np.zeros(p.n_eF))
     for b0 in range(lin_begin, lin_end, batch):
         b1 = min(lin_end, b0 + batch)
         kpts = mesh_kpts(p.mp_grid, b0, b1)
         e, V, _ = get_wann_interp(model, kpts, p.do_gauge_trafo, p.use_cart_velo)
-        fd = fd_stat(e, ef_lst, p.T_kelvin)                          # (K, n_eF, nw)
-        part.Ne += fd.sum(axis=(0, 2))                               # core.f90:187
-        part.n_k += (b1 - b0)
-        if p.do_mep:                                                 # :198-202
-            add("mep_bands_ic", mep_niu_IC(e, V, p.valence_bands, p.kubo_tol))
-            add("mep_bands_lc", mep_niu_LC(e, V, p.valence_bands, p.kubo_tol))
-        if p.do_kubo:                                                # :207-216
-            add("kubo_mep_ic", kubo_mep_IC(e, V, fd))
-            add("kubo_mep_lc", kubo_mep_LC(e, V, fd))
-        if p.do_ahc:                                                 # :221-230
-            add("kubo_ahc", kubo_ahc_tens(e, V, fd))
-            add("velo_ahc", velo_ahc_tens(e, V, hw_lst, fd, p.eta))
-            add("kubo_ohc", kubo_ohc_tens(e, V, hw_lst, fd, p.eta))
-        if p.do_opt:                                                 # :235-242 (kubo_opt_tens == 0 without A_ka)
-            add("photo2", photo_2nd_cond(e, V, hw_lst, fd, p.eta))
+        band_sums(p, e, V, part)
     return part
+
+
+def pack_partials(p: Params, part: Partials, nw: int) -> np.ndarray:
+    """Partials -> the packed FP64 buffer of include/mepb.h / oracle/cpu_ref.c (same order; complex = re, im)."""
+    a = part.arrays
+    out = [np.array([float(part.n_k), 0.0]), np.asarray(part.Ne, dtype=np.float64)]
+
+    def put(x):
+        x = np.asarray(x)
+        x = np.asfortranarray(x)
+        out.append(x.view(np.float64).ravel(order="K") if np.iscomplexobj(x) else x.ravel(order="F"))
+
+    def putc(x):                                                     # complex, Fortran order, interleaved
+        x = np.asarray(x, dtype=np.complex128).ravel(order="F")
+        out.append(np.stack([x.real, x.imag], axis=1).ravel())
+
+    if p.do_mep:
+        out.append(np.asarray(a["mep_bands_ic"]).ravel(order="F")); out.append(np.asarray(a["mep_bands_lc"]).ravel(order="F"))
+    if p.do_kubo:
+        out.append(np.asarray(a["kubo_mep_ic"]).ravel(order="F")); out.append(np.asarray(a["kubo_mep_lc"]).ravel(order="F"))
+    if p.do_ahc:
+        out.append(np.asarray(a["kubo_ahc"]).ravel(order="F")); putc(a["velo_ahc"]); putc(a["kubo_ohc"])
+    if p.do_opt:
+        putc(a["photo2"])
+    return np.concatenate(out)
 
 
 def fermi_selector(n_ki_glob: int, Ne_sum: np.ndarray, valence_bands: int) -> int:

@@ -140,3 +140,44 @@ def assert_parity(out, ref, scale, sens, tol=1e-8, k_sens=20.0, label=""):
         report[k] = (err, scale[k], sens[k])
         assert err <= allowed, f"{label} {k}: |gpu-oracle| {err:.3e} > {allowed:.3e} (scale {scale[k]:.3e}, sens {sens[k]:.3e})"
     return report
+
+
+def packed_slices(params, nw=None):
+    """name -> slice of the packed partial-sum buffer (include/mepb.h; identical in oracle/cpu_ref.c and mep_oracle.pack_partials)."""
+    p = params
+    o, sl = 2, {"n_k": slice(0, 1), "n_degenerate": slice(1, 2)}
+
+    def take(name, n):
+        nonlocal o
+        sl[name] = slice(o, o + n)
+        o += n
+
+    take("Ne", p.n_eF)
+    if p.do_mep:
+        take("mep_bands_ic", 9 * p.valence_bands); take("mep_bands_lc", 9 * p.valence_bands)
+    if p.do_kubo:
+        take("kubo_mep_ic", 9 * p.n_eF); take("kubo_mep_lc", 9 * p.n_eF)
+    if p.do_ahc:
+        take("kubo_ahc", 9 * p.n_eF); take("velo_ahc", 18 * p.n_hw * p.n_eF); take("kubo_ohc", 18 * p.n_hw * p.n_eF)
+    if p.do_opt:
+        take("photo2", 54 * p.n_hw * p.n_eF)
+    return sl, o
+
+
+def oracle_eigenpairs(model, params, kpts):
+    """(e (nw,nk), V (3,nw,nw,nk)) of the C oracle (zheevd + zgemm) on a k list."""
+    from oracle import cpu_ref
+    e, V, _, _ = cpu_ref.Handle(model, params).interp(kpts, want_V=True)
+    return e, V
+
+
+def band_sum_reference(model, params, e, V):
+    """Oracle band sums on supplied eigenpairs + the per-tensor yardstick sum |term| (numpy oracle, mag=True)."""
+    from oracle import cpu_ref
+    ref = cpu_ref.Handle(model, params).band_sums(e, V)
+    with np.errstate(all="ignore"):
+        mg = mo.pack_partials(params, mo.band_sums(params, np.ascontiguousarray(e.T), np.ascontiguousarray(np.moveaxis(V, 3, 0)), mag=True),
+                              model.nw)
+    sl, n = packed_slices(params)
+    assert n == ref.size == mg.size
+    return ref, {k: float(np.nanmax(mg[v])) if mg[v].size else 0.0 for k, v in sl.items()}, sl

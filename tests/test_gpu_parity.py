@@ -15,7 +15,8 @@ import pytest
 
 from oracle import cpu_ref
 from oracle import mep_oracle as mo
-from tests.cases import GOLDEN, assert_parity, ev, load_case, oracle_reference, rel_err, synthetic_model
+from tests.cases import (GOLDEN, assert_parity, band_sum_reference, ev, load_case, oracle_eigenpairs, oracle_reference, rel_err,
+                         synthetic_model)
 
 pytestmark = pytest.mark.gpu
 
@@ -193,6 +194,86 @@ def test_general_path_mesh_separable_fourier(libmepb, name):
     ctx.close()
     assert rel_err(Hk, Hk_r) < 1e-13
     assert rel_err(Hka, Hka_r) < 1e-13
+
+
+class chunk_log2:
+    """MEPB_CHUNK_LOG2=n makes mepb_create schedule the mesh in waves of 2^n k-points (tuning knob): with n = 10 even the small test
+    meshes run as many waves alternating over the two CUDA streams, like the BASELINE meshes do with the default 2^18."""
+
+    def __init__(self, n):
+        self.n = n
+
+    def __enter__(self):
+        self.old = os.environ.get("MEPB_CHUNK_LOG2")
+        os.environ["MEPB_CHUNK_LOG2"] = str(self.n)
+
+    def __exit__(self, *a):
+        os.environ.pop("MEPB_CHUNK_LOG2", None)
+        if self.old is not None:
+            os.environ["MEPB_CHUNK_LOG2"] = self.old
+
+
+def _mesh_points(grid, b0, b1):
+    N1, N2, N3 = grid
+    q = np.arange(b0, b1)
+    return np.stack([(2.0 * (q % N1 + 1) - N1 - 1) / (2.0 * N1), (2.0 * ((q // N1) % N2 + 1) - N2 - 1) / (2.0 * N2),
+                     (2.0 * (q // (N1 * N2) + 1) - N3 - 1) / (2.0 * N3)], axis=1)                  # k_space.f90:351-375
+
+
+@pytest.mark.parametrize("grid,span", [((200, 2, 2), (3, 797)), ((72, 5, 3), (70, 1011)), ((65, 3, 2), (0, 390)), ((130, 1, 3), (64, 325))])
+def test_mesh_separable_fourier_long_lines_c5(libmepb, grid, span):
+    """BASELINE config 5's model (nw = 64, nR = 2007) on meshes whose lines are LONGER than one 64-k CTA tile (N1 = 65, 72, 130,
+    200 — C5 itself is 200^3): second and third tiles of a line (q1_0 > 0), partial last tiles, ranges that start and end inside a
+    line, against the oracle's 2007-term sums element-wise (wann_interp.f90:254-279)."""
+    model = synthetic_model(64, 61)
+    params = mo.Params(mp_grid=grid, do_ahc=True, T_kelvin=300.0)
+    b0, b1 = span
+    kp = _mesh_points(grid, b0, b1)
+    _, _, Hk_r, Hka_r = cpu_ref.Handle(model, params).interp(kp, want_V=False, want_H=True)
+    ctx = libmepb.Context(model, params)
+    Hk, Hka = ctx.fourier_mesh(b0, b1 - b0)
+    ctx.close()
+    assert rel_err(Hk, Hk_r) < 1e-13
+    assert rel_err(Hka, Hka_r) < 1e-13
+
+
+def test_c5_run_mesh_2160_kpoints_three_waves(libmepb):
+    """BASELINE config 5 (synthetic nw = 64, nR = 2007, AHC, T = 300 K) against the oracle on 72 x 5 x 6 = 2160 k-points, scheduled
+    in waves of 1024 (MEPB_CHUNK_LOG2=10): mesh lines of two CTA tiles, waves that start and end inside lines and alternate over
+    both streams — the schedule the 200^3 run uses (core.f90:165-270 on the whole mesh)."""
+    model = synthetic_model(64, 61)
+    params = mo.Params(mp_grid=(72, 5, 6), do_ahc=True, T_kelvin=300.0)
+    from tests.cases import oracle_reference as oref
+    ref, scale, sens = oref(model, params, n_perturb=1)
+    with chunk_log2(10):
+        ctx = libmepb.Context(model, params)
+    out = ctx.run_mesh()
+    launches = ctx.kernel_launches
+    ctx.close()
+    assert launches >= 3 * 7                              # three waves of the seven-kernel general path
+    rep = assert_parity(out, ref, scale, sens, tol=TENS_TOL, label="C5 72x5x6")
+    # the allowance actually needed with the conditioning term switched off (sigma = 0): printed for the record
+    print("[C5 2160 k] error / (1e-8 sum|term|) with sigma = 0: " +
+          " ".join(f"{k}={e / max(1e-8 * s, 1e-300):.2e}" for k, (e, s, _) in rep.items()))
+
+
+MULTIWAVE = ["C2_femn_ahc_nhw121_16^3", "C3_femn_mep_kubo_16^3", "C4_rashba_opt_ahc_nhw200_8^3", "femn_all_jobs_T300_neF3_ragged",
+             "syn_nw16_tb_neF2", "C1_souza_kubo_16^3"]
+
+
+@pytest.mark.parametrize("force", [None, "large"])
+@pytest.mark.parametrize("name", MULTIWAVE)
+def test_run_mesh_parity_many_waves(libmepb, name, force):
+    """The same oracle comparison as test_run_mesh_parity with the mesh cut into waves of 1024 k-points (4 waves for 16^3, ragged
+    last waves for 11x12x13 and 8^3) on both paths (thread-per-k + band-sum kernels, and the general kernels): the two-stream
+    wave schedule of mepb_accumulate, which the BASELINE-size runs use, against the oracle."""
+    model, params = CASES[name]
+    ref, scale, sens = oracle_reference(model, params)
+    with force_path(force), chunk_log2(10):
+        ctx = libmepb.Context(model, params)
+    out = ctx.run_mesh()
+    ctx.close()
+    assert_parity(out, ref, scale, sens, tol=TENS_TOL, label=f"{name} waves of 1024 ({force or 'small'} path)")
 
 
 @pytest.mark.parametrize("name", list(CASES_LARGE) + FORCED_LARGE)
@@ -459,3 +540,57 @@ def test_dmma_sweeps_at_finite_temperature(libmepb, name):
     ctx.close()
     ref, scale, sens = oracle_reference(m, p)
     assert_parity(out, ref, scale, sens, tol=TENS_TOL, label=f"{name} T=300K")
+
+
+# ------------------------------------------------------------------------------------------------ band sums on identical eigenpairs
+BAND_SUM_TOL = 1e-12
+
+
+def _band_sum_cases():
+    jobs = dict(do_mep=True, do_kubo=True, do_ahc=True, do_opt=True, n_hw=21, hw_min=ev(0.03), hw_max=ev(6.0), eta=ev(0.1))
+    yield "femn_T0", load_case("femn_d0.900", mp_grid=(12, 12, 12), valence_bands=4, **jobs), None
+    yield "femn_T300_neF2", load_case("femn_d0.900", mp_grid=(10, 10, 10), valence_bands=4, T_kelvin=300.0, n_eF=2, eF_min=ev(-0.3),
+                                      eF_max=ev(0.2), **jobs), None
+    yield "rashba_T0", load_case("femn_rashba", mp_grid=(10, 10, 10), valence_bands=4, **jobs), None
+    yield "rashba_T300", load_case("femn_rashba", mp_grid=(9, 8, 7), valence_bands=4, T_kelvin=300.0, **jobs), None
+    yield "souza_T0", load_case("souza_phi0", mp_grid=(12, 12, 12), **dict(jobs, do_opt=True)), None
+    yield "syn_nw16_T200", (synthetic_model(16, 3), mo.Params(mp_grid=(6, 6, 6), valence_bands=7, T_kelvin=200.0, **dict(jobs, n_hw=17))), None
+    yield "syn_nw32_T300", (synthetic_model(32, 4), mo.Params(mp_grid=(3, 3, 3), valence_bands=14, T_kelvin=300.0, **dict(jobs, n_hw=16))), None
+    yield "syn_nw64_T300_no_photo", (synthetic_model(64, 4), mo.Params(mp_grid=(3, 3, 2), valence_bands=30, T_kelvin=300.0,
+                                                                      **dict(jobs, n_hw=16, do_opt=False))), None
+    yield "femn_general_path", load_case("femn_d0.900", mp_grid=(8, 8, 8), valence_bands=4, **jobs), "large"
+
+
+BS_CASES = {n: (c, f) for n, c, f in _band_sum_cases()}
+
+
+@pytest.mark.parametrize("name", list(BS_CASES))
+def test_band_sums_on_oracle_eigenpairs(libmepb, name, capsys):
+    """kubo_ahc_tens, velo_ahc_tens, kubo_ohc_tens, photo_2nd_cond, mep_niu_IC/LC, kubo_mep_IC/LC (kubo.f90:37-198, photo.f90:44-81,
+    mep_niu.f90:47-159, kubo_mep.f90:51-149) through mepb_band_sums: the production band-sum kernels and frequency sweeps fed the
+    ORACLE'S OWN eigenpairs (zheevd energies, zgemm-rotated velocities).  The eigensolver is out of the comparison, so the
+    near-degenerate FeMn band pairs no longer need the 20-sigma conditioning allowance of test_run_mesh_parity: every tensor must
+    agree to 1e-12 of its un-cancelled magnitude sum |term|."""
+    (model, params), force = BS_CASES[name]
+    kp = mo.mesh_kpts(params.mp_grid)
+    e, V = oracle_eigenpairs(model, params, kp)
+    ref, scale, sl = band_sum_reference(model, params, e, V)
+    with force_path(force):
+        ctx = libmepb.Context(model, params)
+    ctx.reset()
+    half = e.shape[1] // 2                                   # two calls: the sums accumulate like mepb_accumulate
+    ctx.band_sums(e[:, :half], V[..., :half])
+    ctx.band_sums(e[:, half:], V[..., half:])
+    out = ctx.get_partials().copy()
+    ctx.close()
+    assert out[0] == ref[0] == e.shape[1] and out[1] == ref[1]
+    worst = {}
+    for k, v in sl.items():
+        if k in ("n_k", "n_degenerate") or out[v].size == 0:
+            continue
+        s = max(scale[k], 1e-300)
+        worst[k] = float(np.abs(out[v] - ref[v]).max()) / s
+    with capsys.disabled():
+        print(f"\n[band_sums {name}] " + " ".join(f"{k}={w:.1e}" for k, w in worst.items()))
+    for k, w in worst.items():
+        assert w <= BAND_SUM_TOL, f"{name} {k}: {w:.3e} of sum|term| (scale {scale[k]:.3e})"
