@@ -31,6 +31,8 @@ extern "C" {
 #define MEPB_ERR_EIG          (-5)   /* eigensolver did not converge for some k (reference: zheevd info/=0 -> stop,
                                         src/matrix_math.f90:224)                                              */
 #define MEPB_ERR_STATE        (-6)   /* call order (finalize before accumulate, ...)                         */
+#define MEPB_ERR_NCCL         (-7)   /* libnccl.so.2 not loadable, or an NCCL call failed (reference: MPI ierr /= 0 -> stop,
+                                        src/mpi_comm.f90:124)                                                 */
 
 /* == what read_tb_basis (src/file_io.f90:800) + init_parameters (src/input_paras.f90:79) hand to core_worker */
 typedef struct {
@@ -81,19 +83,50 @@ void mepb_destroy(mepb_ctx *ctx);
  * and integrate_over_k_space for a 1-rank run (core.f90:165-292). */
 int mepb_run_mesh(mepb_ctx *ctx, mepb_result *out);
 
-/* The MPI-host / multi-GPU variant: each rank accumulates a contiguous slab [lin_begin, lin_end) of the 0-based
- * linear mesh index lin = (kix-1) + N1*((kiy-1) + N2*(kiz-1)) (loop order of core.f90:165-167), exports its
- * un-normalised partial sums as one packed FP64 buffer, the host sums the buffers across ranks (MPI_Allreduce /
- * ncclAllReduce — the reference's mpi_reduce_sum calls, core.f90:467-526, fused into one), imports the sum, and
- * finalizes (fermi_selector + normalize_k_int). */
+/* The MPI-host / multi-GPU variant: each rank accumulates its share of the 0-based linear mesh index
+ * lin = (kix-1) + N1*((kiy-1) + N2*(kiz-1)) (loop order of core.f90:165-167) and holds its un-normalised partial sums as one
+ * packed FP64 buffer; the buffers are summed across ranks — the reference's mpi_reduce_sum calls, core.f90:467-526, fused
+ * into one — either by the library itself (mepb_allreduce_partials: NCCL, below) or by the host (mepb_get_partials /
+ * MPI_Allreduce / mepb_set_partials); every rank then finalizes (fermi_selector + normalize_k_int) redundantly. */
 int     mepb_reset(mepb_ctx *ctx);
-int     mepb_accumulate(mepb_ctx *ctx, int64_t lin_begin, int64_t lin_end);
+int     mepb_accumulate(mepb_ctx *ctx, int64_t lin_begin, int64_t lin_end);     /* contiguous slab                    */
+/* k ownership by round-robin BLOCKS: rank takes the blocks j = rank, rank + nranks, ... of `block` consecutive k-points of
+ * [lin_begin, lin_end).  The reference deals single k-points round-robin (mpi_ki_selector, mpi_comm.f90:80-99), which is
+ * load-balanced by construction; block = mepb_balanced_block(ctx, nk, nranks) keeps that property with waves as large as
+ * the context schedules them.  block <= 0: the whole range as one block. */
+int     mepb_accumulate_strided(mepb_ctx *ctx, int64_t lin_begin, int64_t lin_end, int64_t block, int rank, int nranks);
+int64_t mepb_chunk_size(const mepb_ctx *ctx);                       /* k-points per launch wave                 */
+int64_t mepb_balanced_block(const mepb_ctx *ctx, int64_t nk, int nranks);
 int64_t mepb_partials_size(const mepb_ctx *ctx);                    /* number of doubles                        */
 int     mepb_get_partials(mepb_ctx *ctx, double *buf);              /* host buffer                              */
 int     mepb_set_partials(mepb_ctx *ctx, const double *buf);        /* host buffer                              */
-/* same, but the packed buffer lives in device memory of this context's device (for NCCL all-reduce in place) */
+/* same, but the packed buffer lives in device memory of this context's device (for a caller-side all-reduce in place) */
 int     mepb_partials_device_ptr(mepb_ctx *ctx, double **dptr);
 int     mepb_finalize(mepb_ctx *ctx, mepb_result *out);
+
+/* The exchange step inside the library (replaces src/mpi_comm.f90:118-367): one ncclAllReduce(sum, double) of the packed
+ * buffer over NVLink, enqueued on the context's launch stream behind the packing kernel.  libnccl.so.2 is bound at run time.
+ * One process per GPU: rank 0 calls mepb_comm_unique_id (128 bytes), the host broadcasts them (MPI_Bcast, a file, a
+ * torch.distributed store), every rank calls mepb_comm_init_rank; then per run
+ *     mepb_reset, mepb_accumulate_strided(..., rank, nranks), mepb_allreduce_partials, mepb_finalize. */
+int     mepb_comm_unique_id(void *id128, int nbytes);
+int     mepb_comm_init_rank(mepb_ctx *ctx, int nranks, int rank, const void *id128);
+int     mepb_comm_size(const mepb_ctx *ctx);
+int     mepb_comm_rank(const mepb_ctx *ctx);
+int     mepb_allreduce_partials(mepb_ctx *ctx);
+/* device time of the stages of the last run on this rank since mepb_reset (ms): k-loop, all-reduce, finalize (host) */
+int     mepb_get_timing(const mepb_ctx *ctx, double *accumulate_ms, double *allreduce_ms, double *finalize_ms);
+
+/* One process, several B200s (what `mpirun -np N ./mepInterp` is to the reference): a context per device, ncclCommInitAll,
+ * round-robin blocks of the mesh per device on one host thread each, one all-reduce, finalize. */
+typedef struct mepb_multi mepb_multi;
+int       mepb_create_multi(const mepb_model *model, const mepb_params *params, int n_devices, const int *devices /* NULL: 0..n-1 */,
+                            mepb_multi **out);
+int       mepb_multi_run_mesh(mepb_multi *mm, mepb_result *out);
+int       mepb_multi_update_model(mepb_multi *mm, const mepb_model *model);
+int       mepb_multi_size(const mepb_multi *mm);
+mepb_ctx *mepb_multi_ctx(mepb_multi *mm, int i);
+void      mepb_multi_destroy(mepb_multi *mm);
 
 /* Batched get_wann_interp (wann_interp.f90:56-108) on an explicit list of fractional k-points: band mode
  * (band_calc.f90:67-75) and the parity harness.  kpt (3,nk); e_k (nw,nk); V_ka (3,nw,nw,nk) complex or NULL.
@@ -123,6 +156,17 @@ int mepb_band_sums(mepb_ctx *ctx, int64_t nk, const double *e_k, const double *V
  * of a parameter sweep — the reference re-reads w90files/<seed>_hr.dat in a fresh process per parameter value
  * (scripts/mep_worker.py:133-150, scripts/probe_phi.py). */
 int mepb_update_model(mepb_ctx *ctx, const mepb_model *model);
+/* Same for the scalars of a frequency / smearing / Fermi-level / temperature sweep (scripts/probe_hw.py:167-208 starts a fresh
+ * process per value): hw_min, hw_max, eF_min, eF_max, T_kelvin, eta, kubo_tol (and valence_bands unless do_mep) may change;
+ * mp_grid, the job flags, n_hw and n_eF are fixed per context (MEPB_ERR_ARG otherwise). */
+int mepb_update_params(mepb_ctx *ctx, const mepb_params *params);
+/* What mepb_create decided for the model: herm_closed = 1 when H(-R) = H(R)^dagger holds bit for bit (compact pair items,
+ * upper-triangle Fourier sums; a 6-decimal _hr.dat whose (n,m,R) and (m,n,-R) entries differ in the last digit gets 0 and the
+ * general, slower formulation — results are the reference's either way), sparse = 1 when only non-zero H(R) entries are summed,
+ * path = 0 / 1 / 2 (thread-per-k kernels for num_wann 4, 8 / warp-per-k kernel up to 16 / general path up to 64).  `why`
+ * (may be NULL) receives the reason the closure test failed.  mepb_update_model keeps the flag fixed: a model that flips it is
+ * refused with MEPB_ERR_UNSUPPORTED. */
+int mepb_model_info(const mepb_ctx *ctx, int *herm_closed, int *sparse, int *path, char *why, int why_len);
 
 /* CUDA-event stopwatch on the context's launch stream (brackets any sequence of mepb_* calls; ms on the device). */
 int mepb_timer_start(mepb_ctx *ctx);

@@ -17,11 +17,14 @@ LIB_PATH = os.path.join(_HERE, "libmepb.so")
 _LIB = None
 
 OK = 0
-ERR_ARG, ERR_CUDA, ERR_NOT_HERMITIAN, ERR_UNSUPPORTED, ERR_EIG, ERR_STATE = -1, -2, -3, -4, -5, -6
+ERR_ARG, ERR_CUDA, ERR_NOT_HERMITIAN, ERR_UNSUPPORTED, ERR_EIG, ERR_STATE, ERR_NCCL = -1, -2, -3, -4, -5, -6, -7
 
-EXPORTS = ["mepb_create", "mepb_destroy", "mepb_run_mesh", "mepb_reset", "mepb_accumulate", "mepb_partials_size",
+EXPORTS = ["mepb_create", "mepb_destroy", "mepb_run_mesh", "mepb_reset", "mepb_accumulate", "mepb_accumulate_strided",
+           "mepb_chunk_size", "mepb_balanced_block", "mepb_comm_unique_id", "mepb_comm_init_rank", "mepb_comm_size", "mepb_comm_rank",
+           "mepb_allreduce_partials", "mepb_get_timing", "mepb_create_multi", "mepb_multi_run_mesh", "mepb_multi_update_model",
+           "mepb_multi_size", "mepb_multi_ctx", "mepb_multi_destroy", "mepb_partials_size",
            "mepb_get_partials", "mepb_set_partials", "mepb_partials_device_ptr", "mepb_finalize", "mepb_interp",
-           "mepb_fourier", "mepb_fourier_mesh", "mepb_band_sums", "mepb_update_model", "mepb_timer_start", "mepb_timer_stop", "mepb_set_profiling",
+           "mepb_fourier", "mepb_fourier_mesh", "mepb_band_sums", "mepb_update_model", "mepb_update_params", "mepb_model_info", "mepb_timer_start", "mepb_timer_stop", "mepb_set_profiling",
            "mepb_get_profile", "mepb_work_items", "mepb_last_kernel_ms", "mepb_kernel_launches", "mepb_strerror", "mepb_last_error", "mepb_version"]
 
 
@@ -66,6 +69,25 @@ def lib():
         L.mepb_run_mesh.argtypes = [vp, C.POINTER(CResult)]
         L.mepb_reset.argtypes = [vp]
         L.mepb_accumulate.argtypes = [vp, C.c_int64, C.c_int64]
+        L.mepb_accumulate_strided.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int]
+        L.mepb_chunk_size.argtypes = [vp]
+        L.mepb_chunk_size.restype = C.c_int64
+        L.mepb_balanced_block.argtypes = [vp, C.c_int64, C.c_int]
+        L.mepb_balanced_block.restype = C.c_int64
+        L.mepb_comm_unique_id.argtypes = [vp, C.c_int]
+        L.mepb_comm_init_rank.argtypes = [vp, C.c_int, C.c_int, vp]
+        L.mepb_comm_size.argtypes = [vp]
+        L.mepb_comm_rank.argtypes = [vp]
+        L.mepb_allreduce_partials.argtypes = [vp]
+        L.mepb_get_timing.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.mepb_create_multi.argtypes = [C.POINTER(CModel), C.POINTER(CParams), C.c_int, C.POINTER(C.c_int), C.POINTER(vp)]
+        L.mepb_multi_run_mesh.argtypes = [vp, C.POINTER(CResult)]
+        L.mepb_multi_update_model.argtypes = [vp, C.POINTER(CModel)]
+        L.mepb_multi_size.argtypes = [vp]
+        L.mepb_multi_ctx.argtypes = [vp, C.c_int]
+        L.mepb_multi_ctx.restype = vp
+        L.mepb_multi_destroy.argtypes = [vp]
+        L.mepb_multi_destroy.restype = None
         L.mepb_partials_size.argtypes = [vp]
         L.mepb_partials_size.restype = C.c_int64
         L.mepb_get_partials.argtypes = [vp, vp]
@@ -77,6 +99,8 @@ def lib():
         L.mepb_fourier_mesh.argtypes = [vp, C.c_int64, C.c_int64, vp, vp]
         L.mepb_band_sums.argtypes = [vp, C.c_int64, vp, vp]
         L.mepb_update_model.argtypes = [vp, C.POINTER(CModel)]
+        L.mepb_update_params.argtypes = [vp, C.POINTER(CParams)]
+        L.mepb_model_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p, C.c_int]
         L.mepb_timer_start.argtypes = [vp]
         L.mepb_timer_stop.argtypes = [vp, C.POINTER(C.c_double)]
         L.mepb_set_profiling.argtypes = [vp, C.c_int]
@@ -121,10 +145,17 @@ def make_model(R, H, a_latt, wf_centers=None) -> SimpleNamespace:
                            a_latt=np.asarray(a_latt, dtype=np.float64), wf_centers=wf_centers)
 
 
-class Context:
-    """One mepb_ctx: a model + parameter set resident on one B200."""
+def comm_unique_id() -> bytes:
+    """128-byte NCCL unique id (rank 0 creates it, the host broadcasts it, every rank passes it to Context.comm_init_rank)."""
+    buf = C.create_string_buffer(128)
+    _check(lib().mepb_comm_unique_id(buf, 128))
+    return buf.raw
 
-    def __init__(self, model, params, device: int = 0):
+
+class _Marshal:
+    """numpy model / parameter bundle -> the plain-pointer structs of the ABI (keeps the arrays alive)."""
+
+    def _marshal(self, model, params):
         self.nw, self.nR = int(model.nw), int(model.nR)
         self._R = _f(model.R, np.float64)
         self._H = _f(model.H, np.complex128)
@@ -146,50 +177,6 @@ class Context:
         for k in ("hw_min", "hw_max", "eF_min", "eF_max", "T_kelvin", "eta", "kubo_tol"):
             setattr(p, k, float(getattr(params, k)))
         self.cm, self.cp, self.params = m, p, params
-        self._h = C.c_void_p()
-        _check(lib().mepb_create(C.byref(m), C.byref(p), int(device), C.byref(self._h)))
-
-    def close(self):
-        if self._h:
-            lib().mepb_destroy(self._h)
-            self._h = C.c_void_p()
-
-    def __del__(self):
-        try:
-            self.close()
-        except Exception:
-            pass
-
-    # ---- mesh runs
-    @property
-    def n_kpts(self) -> int:
-        g = self.params.mp_grid
-        return int(g[0]) * int(g[1]) * int(g[2])
-
-    def reset(self):
-        _check(lib().mepb_reset(self._h))
-
-    def accumulate(self, lin_begin: int, lin_end: int):
-        _check(lib().mepb_accumulate(self._h, int(lin_begin), int(lin_end)))
-
-    def partials_size(self) -> int:
-        return int(lib().mepb_partials_size(self._h))
-
-    def get_partials(self, out=None) -> np.ndarray:
-        if out is None:
-            out = np.zeros(self.partials_size())
-        _check(lib().mepb_get_partials(self._h, out.ctypes.data))
-        return out
-
-    def set_partials(self, buf: np.ndarray):
-        buf = np.ascontiguousarray(buf, dtype=np.float64)
-        assert buf.size == self.partials_size()
-        _check(lib().mepb_set_partials(self._h, buf.ctypes.data))
-
-    def partials_device_ptr(self) -> int:
-        p = C.c_void_p()
-        _check(lib().mepb_partials_device_ptr(self._h, C.byref(p)))
-        return int(p.value)
 
     def _result(self, call) -> dict:
         P = self.params
@@ -226,6 +213,121 @@ class Context:
         if P.do_kubo:
             out["kubo_mep_tens"] = out["kubo_mep_ic"] + out["kubo_mep_lc"] + out["kubo_mep_cs"]
         return out
+
+
+class MultiContext(_Marshal):
+    """mepb_multi: one process driving several B200s (a context per device + NCCL all-reduce inside the library)."""
+
+    def __init__(self, model, params, devices):
+        self._marshal(model, params)
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        self._h = C.c_void_p()
+        _check(lib().mepb_create_multi(C.byref(self.cm), C.byref(self.cp), len(devices), devs, C.byref(self._h)))
+
+    def run_mesh(self) -> dict:
+        return self._result(lambda res: lib().mepb_multi_run_mesh(self._h, C.byref(res)))
+
+    def update_model(self, H):
+        self._H = _f(H, np.complex128)
+        self.cm.H = self._H.ctypes.data
+        _check(lib().mepb_multi_update_model(self._h, C.byref(self.cm)))
+
+    def timings(self):
+        out = []
+        for i in range(int(lib().mepb_multi_size(self._h))):
+            a, b, c = C.c_double(), C.c_double(), C.c_double()
+            _check(lib().mepb_get_timing(lib().mepb_multi_ctx(self._h, i), C.byref(a), C.byref(b), C.byref(c)))
+            out.append({"accumulate_ms": a.value, "allreduce_ms": b.value, "finalize_ms": c.value})
+        return out
+
+    def close(self):
+        if self._h:
+            lib().mepb_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Context(_Marshal):
+    """One mepb_ctx: a model + parameter set resident on one B200."""
+
+    def __init__(self, model, params, device: int = 0):
+        self._marshal(model, params)
+        self._h = C.c_void_p()
+        _check(lib().mepb_create(C.byref(self.cm), C.byref(self.cp), int(device), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().mepb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- mesh runs
+    @property
+    def n_kpts(self) -> int:
+        g = self.params.mp_grid
+        return int(g[0]) * int(g[1]) * int(g[2])
+
+    def reset(self):
+        _check(lib().mepb_reset(self._h))
+
+    def accumulate(self, lin_begin: int, lin_end: int):
+        _check(lib().mepb_accumulate(self._h, int(lin_begin), int(lin_end)))
+
+    def accumulate_strided(self, lin_begin: int, lin_end: int, block: int, rank: int, nranks: int):
+        _check(lib().mepb_accumulate_strided(self._h, int(lin_begin), int(lin_end), int(block), int(rank), int(nranks)))
+
+    @property
+    def chunk_size(self) -> int:
+        return int(lib().mepb_chunk_size(self._h))
+
+    def balanced_block(self, nk: int, nranks: int) -> int:
+        return int(lib().mepb_balanced_block(self._h, int(nk), int(nranks)))
+
+    def comm_init_rank(self, nranks: int, rank: int, unique_id: bytes):
+        assert len(unique_id) == 128
+        _check(lib().mepb_comm_init_rank(self._h, int(nranks), int(rank), C.c_char_p(unique_id)))
+
+    @property
+    def comm_size(self) -> int:
+        return int(lib().mepb_comm_size(self._h))
+
+    def allreduce_partials(self):
+        """pack + NCCL all-reduce of the packed partial sums inside the library (on its launch stream)."""
+        _check(lib().mepb_allreduce_partials(self._h))
+
+    def timings(self) -> dict:
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        _check(lib().mepb_get_timing(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"accumulate_ms": a.value, "allreduce_ms": b.value, "finalize_ms": c.value}
+
+    def partials_size(self) -> int:
+        return int(lib().mepb_partials_size(self._h))
+
+    def get_partials(self, out=None) -> np.ndarray:
+        if out is None:
+            out = np.zeros(self.partials_size())
+        _check(lib().mepb_get_partials(self._h, out.ctypes.data))
+        return out
+
+    def set_partials(self, buf: np.ndarray):
+        buf = np.ascontiguousarray(buf, dtype=np.float64)
+        assert buf.size == self.partials_size()
+        _check(lib().mepb_set_partials(self._h, buf.ctypes.data))
+
+    def partials_device_ptr(self) -> int:
+        p = C.c_void_p()
+        _check(lib().mepb_partials_device_ptr(self._h, C.byref(p)))
+        return int(p.value)
 
     def finalize(self) -> dict:
         return self._result(lambda res: lib().mepb_finalize(self._h, C.byref(res)))
@@ -271,6 +373,32 @@ class Context:
         assert self._H.shape == (self.nw, self.nw, self.nR)
         self.cm.H = self._H.ctypes.data
         _check(lib().mepb_update_model(self._h, C.byref(self.cm)))
+
+    def update_params(self, **kw):
+        """hw_min / hw_max / eF_min / eF_max / T_kelvin / eta / kubo_tol (Hartree, K) of a live context."""
+        import copy
+        P = copy.copy(self.params)
+        for k, v in kw.items():
+            if not hasattr(P, k):
+                raise KeyError(k)
+            setattr(P, k, v)
+        p = CParams.from_buffer_copy(self.cp)
+        for k in ("hw_min", "hw_max", "eF_min", "eF_max", "T_kelvin", "eta", "kubo_tol"):
+            setattr(p, k, float(getattr(P, k)))
+        p.valence_bands, p.n_hw, p.n_eF = int(P.valence_bands), int(P.n_hw), int(P.n_eF)
+        for i in range(3):
+            p.mp_grid[i] = int(P.mp_grid[i])
+        for k in ("do_gauge_trafo", "use_cart_velo", "do_mep", "do_kubo", "do_ahc", "do_opt", "do_write_mep_bands"):
+            setattr(p, k, int(bool(getattr(P, k))))
+        _check(lib().mepb_update_params(self._h, C.byref(p)))
+        self.cp, self.params = p, P
+
+    def model_info(self) -> dict:
+        h, s, pth = C.c_int(), C.c_int(), C.c_int()
+        why = C.create_string_buffer(256)
+        _check(lib().mepb_model_info(self._h, C.byref(h), C.byref(s), C.byref(pth), why, 256))
+        return {"herm_closed": bool(h.value), "sparse": bool(s.value), "path": ("sub", "warp", "general")[pth.value],
+                "why": why.value.decode()}
 
     def timer_start(self):
         _check(lib().mepb_timer_start(self._h))

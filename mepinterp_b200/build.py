@@ -7,7 +7,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["mepb_small.cu", "mepb_sub.cu", "mepb_eig.cu", "mepb_sweep.cu", "mepb_sweep_mma.cu", "mepb_large.cu", "mepb_tri.cu", "mepb_api.cu"]
+SOURCES = ["mepb_small.cu", "mepb_sub.cu", "mepb_eig.cu", "mepb_sweep.cu", "mepb_sweep_mma.cu", "mepb_large.cu", "mepb_tri.cu", "mepb_api.cu", "mepb_comm.cu"]
 LIB = os.path.join(HERE, "libmepb.so")
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3"]
@@ -28,7 +28,7 @@ def _stale(target: str, deps) -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    hdrs = [os.path.join(CSRC, "mepb_internal.cuh"), os.path.join(HERE, "..", "include", "mepb.h")]
+    hdrs = [os.path.join(CSRC, "mepb_internal.cuh"), os.path.join(CSRC, "mepb_ctx.cuh"), os.path.join(HERE, "..", "include", "mepb.h")]
     objs = []
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     for s in srcs:
@@ -39,7 +39,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             subprocess.check_call(cmd)
         objs.append(obj)
     if force or _stale(LIB, objs):
-        subprocess.check_call([nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart"])
+        subprocess.check_call([nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart", "-ldl"])
     return LIB
 
 
@@ -56,6 +56,21 @@ def build_driver(force: bool = False) -> str:
     return DRIVER
 
 
+TOOLS = os.path.join(HERE, "..", "tools")
+
+
+def build_tools(force: bool = False) -> list:
+    """Stand-alone measurement tools (not part of the product): the cuSOLVER heevjBatched yardstick for the eigensolvers."""
+    out = []
+    for name, libs in (("heevj_compare", ["-lcusolver"]),):
+        src, exe = os.path.join(TOOLS, name + ".cu"), os.path.join(TOOLS, name)
+        if os.path.exists(src) and (force or _stale(exe, [src])):
+            subprocess.check_call([nvcc(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-o", exe, src] + libs)
+        out.append(exe)
+    return out
+
+
 if __name__ == "__main__":
     build_driver(force="--force" in sys.argv)
+    build_tools(force="--force" in sys.argv)
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

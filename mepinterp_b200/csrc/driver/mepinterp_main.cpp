@@ -296,27 +296,10 @@ int main(int argc, char **argv) {
         if (I.plot_bands) return band_mode(dir, I, M, devices[0]);            // main.f90:32-36
         const long long nk = (long long)p.mp_grid[0] * p.mp_grid[1] * p.mp_grid[2];
         const int G = (int)devices.size();
-        std::vector<mepb_ctx *> ctx(G, nullptr);
-        for (int g = 0; g < G; ++g) check(mepb_create(&M, &p, devices[g], &ctx[g]), "mepb_create");
-        const long long nbuf = mepb_partials_size(ctx[0]);
-        std::vector<std::vector<double>> bufs(G, std::vector<double>((size_t)nbuf, 0.0));
-        std::vector<int> rcs(G, 0);
-        std::vector<std::string> errs(G);
-        const long long per = (nk + G - 1) / G;
-        std::vector<std::thread> th;
-        for (int g = 0; g < G; ++g)
-            th.emplace_back([&, g]() {     // one host thread per device: contiguous slab of the linear mesh index
-                const long long b0 = std::min(nk, g * per), b1 = std::min(nk, (g + 1) * per);
-                int rc = mepb_reset(ctx[g]);
-                if (!rc) rc = mepb_accumulate(ctx[g], b0, b1);
-                if (!rc) rc = mepb_get_partials(ctx[g], bufs[g].data());
-                rcs[g] = rc;
-                if (rc) errs[g] = mepb_last_error();
-            });
-        for (auto &t : th) t.join();
-        for (int g = 0; g < G; ++g) if (rcs[g]) throw std::runtime_error("device " + std::to_string(devices[g]) + ": " + mepb_strerror(rcs[g]) + " — " + errs[g]);
-        for (int g = 1; g < G; ++g) for (long long i = 0; i < nbuf; ++i) bufs[0][i] += bufs[g][i];     // the MPI_REDUCEs of core.f90:467-526
-        if (G > 1) check(mepb_set_partials(ctx[0], bufs[0].data()), "mepb_set_partials");
+        // what `mpirun -np G` is to the reference: a context per device, round-robin blocks of the mesh, ONE NCCL all-reduce of
+        // the packed partial sums inside the library (the MPI_REDUCEs of core.f90:467-526), finalize on the first device
+        mepb_multi *mm = nullptr;
+        check(mepb_create_multi(&M, &p, G, devices.data(), &mm), "mepb_create_multi");
         // outputs
         const int n_hw = p.n_hw, n_eF = p.n_eF, nval = p.valence_bands;
         std::vector<double> Ne(n_eF), mep_ic(9), mep_lc(9), mep_cs(9), mep_bands(9 * (size_t)std::max(nval, 1)), k_ic(9), k_lc(9), k_cs(9), ahc(9),
@@ -327,7 +310,7 @@ int main(int argc, char **argv) {
         if (p.do_kubo) { r.kubo_mep_ic = k_ic.data(); r.kubo_mep_lc = k_lc.data(); r.kubo_mep_cs = k_cs.data(); }
         if (p.do_ahc) { r.ahc = ahc.data(); r.ahc_velo = velo.data(); r.ohc_velo = ohc.data(); }
         if (p.do_opt) { r.opt_s = opt_s.data(); r.opt_a = opt_a.data(); r.photo2 = photo.data(); }
-        check(mepb_finalize(ctx[0], &r), "mepb_finalize");
+        check(mepb_multi_run_mesh(mm, &r), "mepb_multi_run_mesh");
         const std::string out = dir + "/out";
         mkdir(out.c_str(), 0755);
         mkdir((dir + "/raw").c_str(), 0755);                                    // input_paras.f90:213-215
@@ -370,11 +353,16 @@ int main(int argc, char **argv) {
                 std::fclose(f);
             }
         }
-        double ms = 0.0;
-        for (int g = 0; g < G; ++g) ms = std::max(ms, mepb_last_kernel_ms(ctx[g]));
+        double ms = 0.0, ar_ms = 0.0;
+        for (int g = 0; g < G; ++g) {
+            double a = 0.0, b = 0.0, f = 0.0;
+            mepb_get_timing(mepb_multi_ctx(mm, g), &a, &b, &f);
+            ms = std::max(ms, a + b); ar_ms = std::max(ar_ms, b);
+        }
         std::printf("[mepInterp] %lld k-points on %d GPU(s): %.3f ms on the device (%.4g k-points/s), eF index %d, degenerate pairs %lld; wrote %s/\n",
                     (long long)r.n_k, G, ms, ms > 0 ? (double)nk / (ms * 1e-3) : 0.0, r.eF_idx + 1, (long long)r.n_degenerate, out.c_str());
-        for (auto *c : ctx) mepb_destroy(c);
+        if (G > 1) std::printf("[mepInterp] NCCL all-reduce of the packed partial sums: %.3f ms\n", ar_ms);
+        mepb_multi_destroy(mm);
         return 0;
     } catch (const std::exception &e) {
         std::fprintf(stderr, "[mepInterp] ERROR: %s\n", e.what());

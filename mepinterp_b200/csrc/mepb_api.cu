@@ -5,11 +5,13 @@
 // (interpolation kernel of chunk i+1 overlaps the frequency sweep of chunk i), keeps every accumulator on the
 // device, and only at finalize copies a few KB back.  No CPU compute path exists here.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "mepb_ctx.cuh"
@@ -151,9 +153,14 @@ bool hermitian_closed(const mepb_model *m, std::string *why) {
     return true;
 }
 
-// Host-side plan of the dense Fourier contraction: packed element tiles of H(R), per-axis phase tables.
+// Plan of the dense Fourier contraction: element tiles, per-axis phase tables (host; depends on the R set and the closure flag
+// only), then the packed element tiles Hp of H(R) by a device kernel from the uploaded d_H.
+cudaError_t pack_fourier_operand(mepb_ctx *c, cudaStream_t st) {
+    return launch_pack_hp(c->fp, c->d_H, 1, 0, c->nw, c->nR, c->d_Hp, st);
+}
+
 cudaError_t build_fourier_plan(mepb_ctx *c, const mepb_model *model, const std::vector<double> &cR) {
-    const int nw = c->nw, nR = c->nR, nw2 = nw * nw, TN = kFourierTN, RC = kFourierRC;
+    const int nw = c->nw, nR = c->nR, TN = kFourierTN, RC = kFourierRC;
     FourierPlan &fp = c->fp;
     std::vector<int> elem;
     if (c->herm) { for (int m = 0; m < nw; ++m) for (int n = 0; n <= m; ++n) elem.push_back(n | (m << 16)); }
@@ -163,16 +170,6 @@ cudaError_t build_fourier_plan(mepb_ctx *c, const mepb_model *model, const std::
     fp.nRp = (nR + RC - 1) / RC * RC;
     fp.herm = c->herm ? 1 : 0;
     elem.resize((size_t)fp.ntiles * TN, elem[0]);
-    std::vector<double2> Hp((size_t)fp.ntiles * fp.nRp * TN, make_double2(0.0, 0.0));
-    for (int t = 0; t < fp.ntiles; ++t)
-        for (int R = 0; R < nR; ++R)
-            for (int j = 0; j < TN; ++j) {
-                const int el = t * TN + j;
-                if (el >= fp.nel) continue;
-                const int n = elem[el] & 0xffff, m = elem[el] >> 16;
-                const double *h = model->H + 2 * ((size_t)n + (size_t)nw * m + (size_t)nw2 * R);
-                Hp[((size_t)t * fp.nRp + R) * TN + j] = make_double2(h[0], h[1]);
-            }
     // distinct lattice coordinates per axis
     std::vector<double> uv[3];
     for (int a = 0; a < 3; ++a) {
@@ -207,11 +204,12 @@ cudaError_t build_fourier_plan(mepb_ctx *c, const mepb_model *model, const std::
     cudaError_t e;
     if ((e = up((void **)&c->d_ridx, ridx.data(), sizeof(int) * ridx.size())) != cudaSuccess) return e;
     if ((e = up((void **)&c->d_elem, elem.data(), sizeof(int) * elem.size())) != cudaSuccess) return e;
-    if ((e = up((void **)&c->d_Hp, Hp.data(), sizeof(double2) * Hp.size())) != cudaSuccess) return e;
     if ((e = up((void **)&c->d_Rfp, Rfp.data(), sizeof(double) * Rfp.size())) != cudaSuccess) return e;
     if ((e = up((void **)&c->d_cRp, cRp.data(), sizeof(double) * cRp.size())) != cudaSuccess) return e;
+    if (!c->d_Hp && (e = cudaMalloc((void **)&c->d_Hp, sizeof(double2) * (size_t)fp.ntiles * fp.nRp * TN)) != cudaSuccess) return e;
     fp.ridx = c->d_ridx; fp.elem = c->d_elem; fp.Hp = c->d_Hp; fp.Rf = c->d_Rfp; fp.cR = c->d_cRp;
-    return cudaSuccess;
+    if ((e = pack_fourier_operand(c, 0)) != cudaSuccess) return e;
+    return cudaDeviceSynchronize();
 }
 
 // Mesh-separable transform (SepPlan): index map of the R set on the product grid of its distinct coordinates, per-axis
@@ -406,6 +404,7 @@ const char *mepb_strerror(int code) {
         case MEPB_ERR_UNSUPPORTED: return "unsupported input (position operator / size limits)";
         case MEPB_ERR_EIG: return "eigensolver did not converge";
         case MEPB_ERR_STATE: return "invalid call order";
+        case MEPB_ERR_NCCL: return "NCCL unavailable or NCCL call failed";
         default: return "unknown error";
     }
 }
@@ -435,7 +434,7 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
     mepb_ctx *c = new mepb_ctx();
     c->device = device; c->sm_count = prop.multiProcessorCount;
     c->p = p; c->nw = model->nw; c->nR = model->nR; c->has_tau = (model->wf_centers != nullptr);
-    { std::string why; c->herm = hermitian_closed(model, &why); }
+    c->herm = hermitian_closed(model, &c->herm_why);
     c->large = want_large;
     { const char *es = getenv("MEPB_LARGE_EIG"); c->tri = c->large && !(es && std::string(es) == "jacobi"); }
     c->eig_thread = !c->large && eig_thread_supported(model->nw) && !getenv("MEPB_WARP_JACOBI");
@@ -581,6 +580,7 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
 
 void mepb_destroy(mepb_ctx *c) {
     if (!c) return;
+    mepb::comm_release(c);
     free_all(c);
     delete c;
 }
@@ -593,6 +593,7 @@ int mepb_reset(mepb_ctx *c) {
     CUDA_TRY(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->sb[0].st));
     for (auto &s : c->sb) CUDA_TRY(cudaStreamSynchronize(s.st));
     c->packed_from_host = false; c->have_data = false;
+    c->t_acc_ms = c->t_ar_ms = c->t_fin_ms = 0.0;
     return MEPB_OK;
 }
 
@@ -678,21 +679,16 @@ static int launch_wave(mepb_ctx *c, StreamBuf &s, long long k0, long long nk, co
     return MEPB_OK;
 }
 
-int mepb_accumulate(mepb_ctx *c, int64_t lin_begin, int64_t lin_end) {
-    if (!c) return fail(MEPB_ERR_ARG, "null ctx");
-    const mepb_params &p = c->p;
-    const long long nk_mesh = (long long)p.mp_grid[0] * p.mp_grid[1] * p.mp_grid[2];
-    if (lin_begin < 0 || lin_end > nk_mesh || lin_begin > lin_end) return fail(MEPB_ERR_ARG, "k range outside the mesh");
-    if (c->packed_from_host) return fail(MEPB_ERR_STATE, "accumulate after set_partials; call mepb_reset first");
+// Runs a list of waves [k0, k0 + nk) alternating over the two streams; returns when all of them are done.
+static int run_waves(mepb_ctx *c, const std::vector<std::pair<long long, long long>> &waves) {
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaEventRecord(c->ev0, c->sb[0].st));
     CUDA_TRY(cudaStreamWaitEvent(c->sb[1].st, c->ev0, 0));
     int which = 0;
-    for (long long k0 = lin_begin; k0 < lin_end; k0 += c->chunk) {       // waves alternate over the two streams
-        const long long nk = std::min<long long>(c->chunk, lin_end - k0);
+    for (const auto &w : waves) {
         StreamBuf &s = c->sb[which];
         if (!c->profiling) which ^= 1;
-        const int rc = launch_wave(c, s, k0, nk, nullptr, nullptr);
+        const int rc = launch_wave(c, s, w.first, w.second, nullptr, nullptr);
         if (rc) return rc;
     }
     CUDA_TRY(cudaEventRecord(c->sb[1].done, c->sb[1].st));
@@ -702,9 +698,53 @@ int mepb_accumulate(mepb_ctx *c, int64_t lin_begin, int64_t lin_end) {
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     c->last_ms = ms;
+    c->t_acc_ms += ms;
     c->have_data = true;
     if (c->profiling) prof_collect(c);
     return check_err_flag(c);
+}
+
+int mepb_accumulate(mepb_ctx *c, int64_t lin_begin, int64_t lin_end) {
+    return mepb_accumulate_strided(c, lin_begin, lin_end, 0, 0, 1);
+}
+
+// Rank `rank` of `nranks` takes the blocks j = rank, rank + nranks, ... of `block` consecutive k-points of [lin_begin, lin_end)
+// (block <= 0: one block = the whole range).  The reference deals single k-points round-robin (mpi_comm.f90:80-99), which
+// balances the load by construction; contiguous slabs do not (band-pair items per k-point vary over the zone), blocks dealt
+// round-robin do, and they keep the waves large.
+int mepb_accumulate_strided(mepb_ctx *c, int64_t lin_begin, int64_t lin_end, int64_t block, int rank, int nranks) {
+    if (!c) return fail(MEPB_ERR_ARG, "null ctx");
+    const mepb_params &p = c->p;
+    const long long nk_mesh = (long long)p.mp_grid[0] * p.mp_grid[1] * p.mp_grid[2];
+    if (lin_begin < 0 || lin_end > nk_mesh || lin_begin > lin_end) return fail(MEPB_ERR_ARG, "k range outside the mesh");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(MEPB_ERR_ARG, "bad rank / nranks");
+    if (c->packed_from_host) return fail(MEPB_ERR_STATE, "accumulate after set_partials; call mepb_reset first");
+    if (block <= 0) block = std::max<long long>(lin_end - lin_begin, 1);
+    std::vector<std::pair<long long, long long>> waves;
+    for (long long b0 = lin_begin + (long long)rank * block; b0 < lin_end; b0 += (long long)nranks * block) {
+        const long long b1 = std::min<long long>(lin_end, b0 + block);
+        for (long long k0 = b0; k0 < b1; k0 += c->chunk) waves.emplace_back(k0, std::min<long long>(c->chunk, b1 - k0));
+    }
+    return run_waves(c, waves);
+}
+
+int64_t mepb_chunk_size(const mepb_ctx *c) { return c ? c->chunk : 0; }
+
+// Block size for mepb_accumulate_strided that gives every rank the same number of (nearly) equal blocks, each at most one wave:
+// nblocks = nranks * ceil(nk / (nranks * chunk)), block = ceil(nk / nblocks).
+int64_t mepb_balanced_block(const mepb_ctx *c, int64_t nk, int nranks) {
+    if (!c || nk <= 0 || nranks < 1) return 0;
+    const long long per = (long long)nranks * c->chunk;
+    const long long nblocks = (long long)nranks * ((nk + per - 1) / per);
+    return (nk + nblocks - 1) / nblocks;
+}
+
+int mepb_get_timing(const mepb_ctx *c, double *accumulate_ms, double *allreduce_ms, double *finalize_ms) {
+    if (!c) return fail(MEPB_ERR_ARG, "null ctx");
+    if (accumulate_ms) *accumulate_ms = c->t_acc_ms;
+    if (allreduce_ms) *allreduce_ms = c->t_ar_ms;
+    if (finalize_ms) *finalize_ms = c->t_fin_ms;
+    return MEPB_OK;
 }
 
 // Band sums on caller-supplied eigenpairs (include/mepb.h).  Waves of at most `chunk` k-points through stream buffer 0.
@@ -781,6 +821,7 @@ int mepb_partials_device_ptr(mepb_ctx *c, double **dptr) {
 int mepb_finalize(mepb_ctx *c, mepb_result *out) {
     if (!c || !out) return fail(MEPB_ERR_ARG, "null argument");
     if (!c->have_data) return fail(MEPB_ERR_STATE, "finalize before accumulate / set_partials");
+    const auto t_fin0 = std::chrono::steady_clock::now();
     const mepb_params &p = c->p;
     std::vector<double> h((size_t)c->L.total);
     {
@@ -836,6 +877,7 @@ int mepb_finalize(mepb_ctx *c, mepb_result *out) {
         if (out->opt_a) for (long long q = 0; q < sl; ++q) out->opt_a[q] = 0.0;
         if (out->photo2) for (long long q = 0; q < 54LL * n_hw * n_ef; ++q) out->photo2[q] = h[L.photo + q] / norm;   // core.f90:515
     }
+    c->t_fin_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_fin0).count();
     return MEPB_OK;
 }
 
@@ -958,17 +1000,63 @@ int mepb_update_model(mepb_ctx *c, const mepb_model *model) {
     if ((model->wf_centers != nullptr) != c->has_tau) return fail(MEPB_ERR_ARG, "update_model: FT convention differs");
     if (model->r) return fail(MEPB_ERR_UNSUPPORTED, "position operator (r_tb) branch is not implemented");
     CUDA_TRY(cudaSetDevice(c->device));
-    { std::string why; c->herm = hermitian_closed(model, &why); }
+    {   // buffers, launch shapes and the pair-item format were sized at mepb_create for this closure flag: it must not flip
+        std::string why;
+        const bool herm = hermitian_closed(model, &why);
+        if (herm != c->herm)
+            return fail(MEPB_ERR_UNSUPPORTED, std::string("update_model: Hermitian closure of H(R) differs from the model the context was created "
+                                                          "with (") + (herm ? "now closed" : why) + "); create a new context");
+    }
     cudaStream_t st = c->sb[0].st;
     CUDA_TRY(cudaMemcpyAsync(c->d_H, model->H, sizeof(double) * 2 * (size_t)c->nw * c->nw * c->nR, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
     if (c->large) {
-        std::vector<double> cR(3 * (size_t)c->nR);
-        CUDA_TRY(cudaMemcpy(cR.data(), c->d_cR, sizeof(double) * cR.size(), cudaMemcpyDeviceToHost));
-        CUDA_TRY(build_fourier_plan(c, model, cR));
+        CUDA_TRY(pack_fourier_operand(c, st));     // element tiles repacked on the device, behind the copy on the same stream
+        c->launches += 1;
+        CUDA_TRY(cudaStreamSynchronize(st));       // the caller may reuse its host buffer
     } else {
+        CUDA_TRY(cudaStreamSynchronize(st));
         CUDA_TRY(build_sparse(c, model));
     }
+    return MEPB_OK;
+}
+
+// New frequency list / smearing / Fermi levels / temperature / tolerance for an existing context (the per-call input of a
+// scripts/probe_hw.py-style sweep).  Everything that sizes buffers must stay as it was at mepb_create.
+int mepb_update_params(mepb_ctx *c, const mepb_params *np) {
+    if (!c || !np) return fail(MEPB_ERR_ARG, "null argument");
+    const mepb_params &o = c->p;
+    const bool same = np->mp_grid[0] == o.mp_grid[0] && np->mp_grid[1] == o.mp_grid[1] && np->mp_grid[2] == o.mp_grid[2] &&
+                      np->do_gauge_trafo == o.do_gauge_trafo && np->use_cart_velo == o.use_cart_velo && np->do_mep == o.do_mep &&
+                      np->do_kubo == o.do_kubo && np->do_ahc == o.do_ahc && np->do_opt == o.do_opt &&
+                      np->do_write_mep_bands == o.do_write_mep_bands && np->n_hw == o.n_hw && np->n_eF == o.n_eF &&
+                      (np->valence_bands == o.valence_bands || !o.do_mep);
+    if (!same) return fail(MEPB_ERR_ARG, "update_params: mp_grid, job flags, n_hw, n_eF (and valence_bands with do_mep) are fixed per context");
+    if ((o.do_mep || o.do_kubo) && (np->valence_bands < 0 || np->valence_bands > c->nw)) return fail(MEPB_ERR_ARG, "valence_bands out of range");
+    CUDA_TRY(cudaSetDevice(c->device));
+    c->p = *np;
+    auto linspace = [](double lo, double hi, int n) {
+        std::vector<double> v(n);
+        if (n > 1) { const double d = (hi - lo) / (double)(n - 1); for (int i = 0; i < n; ++i) v[i] = lo + (double)i * d; }
+        else v[0] = lo;
+        return v;
+    };
+    c->ef_lst = linspace(np->eF_min, np->eF_max, np->n_eF);
+    c->hw_lst = linspace(np->hw_min, np->hw_max, np->n_hw);
+    CUDA_TRY(cudaMemcpyAsync(c->d_hw, c->hw_lst.data(), sizeof(double) * np->n_hw, cudaMemcpyHostToDevice, c->sb[0].st));
+    CUDA_TRY(cudaStreamSynchronize(c->sb[0].st));
+    return MEPB_OK;
+}
+
+// What mepb_create decided for this model: herm_closed (1: H(-R) = H(R)^dagger bit for bit -> compact 10-double pair items and
+// upper-triangle Fourier sums; 0: general 20-double items, twice the sweep work), sparse (1: only the non-zero H(R) entries are
+// summed), path (0: thread-per-k eigensolver + band-sum kernel, num_wann 4 / 8; 1: warp-per-k kernel, num_wann <= 16; 2: general
+// path, num_wann <= 64).  `why` (may be NULL) receives the reason when the closure test failed.
+int mepb_model_info(const mepb_ctx *c, int *herm_closed, int *sparse, int *path, char *why, int why_len) {
+    if (!c) return fail(MEPB_ERR_ARG, "null ctx");
+    if (herm_closed) *herm_closed = c->herm ? 1 : 0;
+    if (sparse) *sparse = c->sparse ? 1 : 0;
+    if (path) *path = c->large ? 2 : (c->use_sub ? 0 : 1);
+    if (why && why_len > 0) { std::strncpy(why, c->herm_why.c_str(), (size_t)why_len - 1); why[why_len - 1] = 0; }
     return MEPB_OK;
 }
 

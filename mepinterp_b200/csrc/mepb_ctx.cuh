@@ -59,6 +59,7 @@ struct mepb_ctx {
     int nw = 0, nR = 0;
     bool has_tau = false;
     bool herm = true;      // H(R) Hermitian-closed: V_a Hermitian -> compact items / 18-accumulator sweep
+    std::string herm_why;  // why the closure test failed (mepb_model_info)
     bool eig_thread = false;   // eigenpairs from the thread-per-k kernel (nw 4, 8)
     bool large = false;        // general path (mepb_large.cu)
     bool use_sub = false;      // NW-lanes-per-k band-sum kernel (mepb_sub.cu) in mesh mode
@@ -102,11 +103,16 @@ struct mepb_ctx {
     // list-mode scratch
     double *d_kpt = nullptr, *d_e = nullptr; double2 *d_V = nullptr, *d_Hk = nullptr, *d_Hka = nullptr;
     long long list_cap = 0;
+    // multi-GPU (mepb_comm.cu): NCCL communicator of this rank, stage times of the last step (ms; reset by mepb_reset)
+    void *nccl_comm = nullptr; int comm_rank = 0, comm_size = 1;
+    cudaEvent_t ar0 = nullptr, ar1 = nullptr;
+    double t_acc_ms = 0.0, t_ar_ms = 0.0, t_fin_ms = 0.0;
     // mepb_band_sums staging (supplied eigenpairs)
     double *d_bs_e = nullptr; double2 *d_bs_V = nullptr; long long bs_cap = 0;
 };
 
 
 namespace mepb {
-int pack_now(mepb_ctx *c);                       // compact accumulators of both streams -> d_packed (device), on stream 0
+int pack_now(mepb_ctx *c);
+void comm_release(mepb_ctx *c);                  // destroys the context's NCCL communicator, if any (mepb_comm.cu)                       // compact accumulators of both streams -> d_packed (device), on stream 0
 }  // namespace mepb

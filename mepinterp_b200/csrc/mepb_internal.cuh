@@ -319,6 +319,8 @@ cudaError_t launch_fourier_dense(const FourierPlan &fp, const DevModel &m, const
 cudaError_t launch_fourier_mesh(const FourierPlan &fp, SepPlan sp, const DevModel &m, const KSource &ks, double2 *Hk,
                                 double2 *Hka, cudaStream_t st);
 cudaError_t launch_phase_table(double2 *P, const double *u, int n, int N, cudaStream_t st);
+// packed element tiles Hp of a real-space operator (fp.elem must be on the device already)
+cudaError_t launch_pack_hp(const FourierPlan &fp, const double2 *src, int stride, int off, int nw, int nR, double2 *Hp, cudaStream_t st);
 cudaError_t launch_hka_to_user(const double2 *in, double2 *out, int nw2, long long nk, cudaStream_t st);
 int eig_large_grid(int sm_count, long long nk);
 cudaError_t launch_eig_rot_large(const DevModel &m, const KSource &ks, const Jobs &jobs, const InterpOut &out, int max_pairs,

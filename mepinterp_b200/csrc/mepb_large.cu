@@ -274,6 +274,25 @@ sep_stage_b_kernel(const FourierPlan fp, const SepPlan sp, const int N2) {
     }
 }
 
+// Packed element tiles of a real-space operator for the dense contraction: Hp[t][R][j] = X_R(n, m) for the element (n, m) =
+// elem[t TN + j] of tile t (zero padded in R and j), so that one CTA's (tile, RC R points) chunk is one contiguous TMA bulk copy.
+// src element (n, m, R) at off + stride (n + nw m + nw^2 R): H(R) has stride 1, the component a of r(R) (3, nw, nw, nR) stride 3, off a.
+__global__ void pack_hp_kernel(const double2 *__restrict__ src, int stride, int off, int nw, int nR, int nel, int nRp,
+                               const int *__restrict__ elem, double2 *__restrict__ Hp, long long total) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(i % F_TN);
+        const long long tr = i / F_TN;
+        const int R = (int)(tr % nRp), t = (int)(tr / nRp);
+        const int el = t * F_TN + j;
+        double2 v = make_double2(0.0, 0.0);
+        if (el < nel && R < nR) {
+            const int e = elem[el], n = e & 0xffff, mm = e >> 16;
+            v = src[(size_t)off + (size_t)stride * ((size_t)n + (size_t)nw * mm + (size_t)nw * nw * R)];
+        }
+        Hp[i] = v;
+    }
+}
+
 // (3, nw, nw, nk) user layout from the internal [k][a][idx] layout
 __global__ void hka_to_user_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, int nw2, long long nk) {
     const long long total = nk * 3 * nw2;
@@ -877,6 +896,13 @@ cudaError_t launch_fourier_dense(const FourierPlan &fp, const DevModel &m, const
     dim3 grid((unsigned)((ks.nk + F_TK - 1) / F_TK), (unsigned)fp.ntiles);
     SepPlan sp; sp.on = 0;
     fourier_dense_kernel<false><<<grid, F_THREADS, smem, st>>>(fp, sp, m, ks, Hk, Hka);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_hp(const FourierPlan &fp, const double2 *src, int stride, int off, int nw, int nR, double2 *Hp, cudaStream_t st) {
+    const long long total = (long long)fp.ntiles * fp.nRp * F_TN;
+    const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    pack_hp_kernel<<<grid, 256, 0, st>>>(src, stride, off, nw, nR, fp.nel, fp.nRp, fp.elem, Hp, total);
     return cudaGetLastError();
 }
 

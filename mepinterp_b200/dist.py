@@ -35,18 +35,39 @@ def allreduce_partials(buf, group=None):
     return buf
 
 
-def run_mesh_sharded(ctx, rank: int, world: int, group=None) -> dict:
-    """core_worker over a mesh sharded on `world` GPUs: accumulate my slab, all-reduce in place on the device, finalize."""
-    import torch
+def init_comm(ctx, rank: int, world: int, group=None):
+    """Give `ctx` an NCCL communicator over the `world` ranks of the torch.distributed job: rank 0 draws the 128-byte unique id
+    (mepb_comm_unique_id), torch.distributed only carries those bytes to the other ranks (the job an MPI_Bcast does for an MPI
+    host); the all-reduce itself then runs inside libmepb on its own stream."""
+    if world <= 1:
+        return
+    import torch.distributed as dist
+    from . import api
+    box = [api.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    ctx.comm_init_rank(world, rank, box[0])
+
+
+def run_mesh_sharded(ctx, rank: int, world: int, group=None, partition: str = "blocks") -> dict:
+    """core_worker over a mesh sharded on `world` GPUs: accumulate my share, all-reduce in place on the device, finalize.
+    partition = "blocks": round-robin blocks (load balanced like the reference's round-robin k ownership); "slabs": one
+    contiguous slab per rank.  The all-reduce runs inside the library when the context has a communicator (init_comm),
+    else through torch.distributed on a zero-copy view of the packed buffer."""
     nk = ctx.n_kpts
-    b0, b1 = slab(rank, world, nk)
     ctx.reset()
-    ctx.accumulate(b0, b1)
+    if partition == "blocks":
+        ctx.accumulate_strided(0, nk, ctx.balanced_block(nk, world), rank, world)
+    else:
+        ctx.accumulate(*slab(rank, world, nk))
     if world > 1:
-        ptr = ctx.partials_device_ptr()
-        t = torch.as_tensor(_DevView(ptr, ctx.partials_size()), device=torch.device("cuda", torch.cuda.current_device()))
-        allreduce_partials(t, group)
-        torch.cuda.current_stream().synchronize()
+        if ctx.comm_size == world:
+            ctx.allreduce_partials()
+        else:
+            import torch
+            ptr = ctx.partials_device_ptr()
+            t = torch.as_tensor(_DevView(ptr, ctx.partials_size()), device=torch.device("cuda", torch.cuda.current_device()))
+            allreduce_partials(t, group)
+            torch.cuda.current_stream().synchronize()
     return ctx.finalize()
 
 

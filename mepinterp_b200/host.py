@@ -206,3 +206,19 @@ def probe_phi(phis, params, device: int = 0) -> list:
     finally:
         ctx.close()
     return out
+
+
+def probe_hw(model, params, sweeps, device: int = 0) -> list:
+    """scripts/probe_hw.py:167-208 as a library call: the reference starts `mpirun mepInterp` in a fresh run directory per
+    (hw window, eta, E_F, T) setting; here ONE live context (model resident on the GPU) takes each setting through
+    mepb_update_params and reruns the mesh.  `sweeps`: iterable of dicts with any of hw_min, hw_max, eF_min, eF_max, T_kelvin,
+    eta, kubo_tol (atomic units).  Returns the result dict per setting."""
+    ctx = api.Context(model, params, device)
+    out = []
+    try:
+        for kw in sweeps:
+            ctx.update_params(**kw)
+            out.append(ctx.run_mesh())
+    finally:
+        ctx.close()
+    return out

@@ -440,18 +440,66 @@ def test_repeatability_bitwise(libmepb):
         assert np.array_equal(a[k], b[k]), k
 
 
-def test_nccl_sharded_if_multi_gpu(libmepb):
+def _n_gpus():
     import torch
-    if torch.cuda.device_count() < 2:
+    return torch.cuda.device_count()
+
+
+def test_nccl_sharded_if_multi_gpu(libmepb):
+    n = _n_gpus()
+    if n < 2:
         pytest.skip("needs >= 2 GPUs")
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(n, 8)), "--master-addr", "127.0.0.1",
            "--master-port", "29533", os.path.join(root, "tests", "nccl_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=root)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "NCCL_SHARDED_OK" in r.stdout
+
+
+def test_multi_context_all_devices(libmepb):
+    """mepb_create_multi / mepb_multi_run_mesh (one process, every GPU of the box; round-robin blocks, in-library NCCL all-reduce
+    when there is more than one device) against the oracle, and bit-identical to itself on a second run."""
+    n = max(1, min(_n_gpus(), 8))
+    m, p = load_case("femn_d0.900", mp_grid=(20, 18, 16), n_hw=9, do_mep=True, do_kubo=True)
+    ref, scale, sens = oracle_reference(m, p)
+    with chunk_log2(10):
+        mc = libmepb.MultiContext(m, p, list(range(n)))
+    out = mc.run_mesh()
+    out2 = mc.run_mesh()
+    tm = mc.timings()
+    mc.close()
+    assert_parity(out, ref, scale, sens, tol=TENS_TOL, label=f"multi x{n}")
+    for k in ("ahc_tens", "ahcVELO", "mep_bands"):
+        assert np.array_equal(out[k], out2[k]), k
+    assert len(tm) == n and all(t["accumulate_ms"] > 0.0 for t in tm)
+    if n > 1:
+        assert all(t["allreduce_ms"] > 0.0 for t in tm)
+
+
+def test_strided_blocks_equal_whole_mesh(libmepb):
+    """mepb_accumulate_strided: the round-robin blocks of 3 'ranks' (ragged last block, a rank with fewer blocks) sum to the
+    partials of the whole mesh (the reference's round-robin ownership, mpi_comm.f90:80-99, at block granularity)."""
+    m, p = load_case("femn_rashba", mp_grid=(13, 11, 9), n_hw=17)
+    nk = 13 * 11 * 9
+    with chunk_log2(10):
+        ctx = libmepb.Context(m, p)
+    assert ctx.chunk_size == 1024
+    ctx.reset(); ctx.accumulate(0, nk)
+    whole = ctx.get_partials().copy()
+    tot = np.zeros_like(whole)
+    for block in (ctx.balanced_block(nk, 3), 100):
+        tot[:] = 0.0
+        for r in range(3):
+            ctx.reset(); ctx.accumulate_strided(0, nk, block, r, 3)
+            tot += ctx.get_partials()
+        assert tot[0] == whole[0] == nk
+        assert np.abs(tot - whole).max() <= 1e-11 * np.abs(whole).max()
+    with pytest.raises(libmepb.MepbError):
+        ctx.accumulate_strided(0, nk, 10, 3, 3)
+    ctx.close()
 
 
 def _run_variant(tmp_path, tag, case, over, env):
@@ -594,3 +642,74 @@ def test_band_sums_on_oracle_eigenpairs(libmepb, name, capsys):
         print(f"\n[band_sums {name}] " + " ".join(f"{k}={w:.1e}" for k, w in worst.items()))
     for k, w in worst.items():
         assert w <= BAND_SUM_TOL, f"{name} {k}: {w:.3e} of sum|term| (scale {scale[k]:.3e})"
+
+
+def test_update_params_sweep_equals_fresh_contexts(libmepb):
+    """mepb_update_params (scripts/probe_hw.py as a library call): frequency window, smearing, Fermi level and temperature changed
+    in ONE live context give bit-identical tensors to a fresh context per setting; fixed quantities are refused."""
+    import copy
+    from mepinterp_b200 import host
+    m, p = load_case("femn_rashba", mp_grid=(8, 8, 8), n_hw=24, do_ahc=True, do_opt=True, do_kubo=True)
+    sweeps = [dict(hw_min=ev(0.05), hw_max=ev(3.0)), dict(eta=ev(0.05)), dict(eF_min=ev(0.2), eF_max=ev(0.2), T_kelvin=250.0),
+              dict(hw_min=ev(0.03), hw_max=ev(6.0), eta=ev(0.1), T_kelvin=0.0, kubo_tol=1e-6)]
+    got = host.probe_hw(m, p, sweeps)
+    q = copy.copy(p)
+    for kw, res in zip(sweeps, got):
+        for k, v in kw.items():
+            setattr(q, k, v)
+        ctx = libmepb.Context(m, copy.copy(q))
+        fresh = ctx.run_mesh()
+        ctx.close()
+        for k, v in fresh.items():
+            assert np.array_equal(np.asarray(v), np.asarray(res[k])), (kw, k)
+    ctx = libmepb.Context(m, p)
+    for bad in (dict(n_hw=25), dict(mp_grid=(8, 8, 9)), dict(do_mep=True), dict(n_eF=2)):
+        with pytest.raises(libmepb.MepbError) as ei:
+            ctx.update_params(**bad)
+        assert ei.value.code == libmepb.api.ERR_ARG
+    ctx.close()
+
+
+def test_update_model_keeps_the_closure_flag(libmepb):
+    """a model whose Hermitian closure differs from the one the context was sized for must be refused (the pair-item
+    format, launch shapes and Fourier plan depend on it), on both paths; mepb_model_info reports the flag and the reason."""
+    m, p = load_case("souza_phi0", mp_grid=(6, 6, 6), do_kubo=True)
+    for force in (None, "large"):
+        with force_path(force):
+            ctx = libmepb.Context(m, p)
+        info = ctx.model_info()
+        assert info["herm_closed"] and info["path"] == ("general" if force else "sub")
+        ref = ctx.run_mesh()
+        H2 = m.H.copy()
+        H2[0, 1, 0] += 1e-9                                  # one asymmetric last digit, as a 6-decimal _hr.dat can carry
+        with pytest.raises(libmepb.MepbError) as ei:
+            ctx.update_model(H2)
+        assert ei.value.code == libmepb.api.ERR_UNSUPPORTED
+        ctx.update_model(m.H)                                # the context is still usable and unchanged
+        again = ctx.run_mesh()
+        for k in ("ahc_tens", "mep_bands", "kubo_mep_ic"):
+            assert np.array_equal(ref[k], again[k]), k
+        ctx.close()
+    mr, pr = load_case("femn_rashba", mp_grid=(4, 4, 4))
+    ctx = libmepb.Context(mr, pr)
+    info = ctx.model_info()
+    ctx.close()
+    assert not info["herm_closed"] and info["why"]
+
+
+def test_general_path_update_model_on_device(libmepb):
+    """mepb_update_model on the general path repacks the element tiles of H(R) with a device kernel: a sweep through one live
+    context equals fresh contexts bit for bit (nw = 24, mesh-separable Fourier transform)."""
+    p = mo.Params(mp_grid=(6, 5, 4), do_ahc=True, do_mep=True, valence_bands=9, n_hw=3, hw_max=ev(2.0), eta=ev(0.1), T_kelvin=100.0)
+    models = [synthetic_model(24, 3, seed=s) for s in (1, 2, 3)]
+    ctx = libmepb.Context(models[0], p)
+    for i, m in enumerate(models):
+        if i:
+            ctx.update_model(m.H)
+        live = ctx.run_mesh()
+        c2 = libmepb.Context(m, p)
+        fresh = c2.run_mesh()
+        c2.close()
+        for k, v in fresh.items():
+            assert np.array_equal(np.asarray(v), np.asarray(live[k])), (i, k)
+    ctx.close()
