@@ -27,7 +27,7 @@ extern "C" {
 #define MEPB_OK                 0
 #define MEPB_ERR_ARG          (-1)   /* NULL / out-of-range argument                                         */
 #define MEPB_ERR_CUDA         (-2)   /* no device, or a CUDA call failed (mepb_last_error has the text)      */
-#define MEPB_ERR_UNSUPPORTED  (-4)   /* position-operator branch (r != NULL), or nw/nR outside kernel limits */
+#define MEPB_ERR_UNSUPPORTED  (-4)   /* nw/nR outside kernel limits, or a model update that would change buffer shapes */
 #define MEPB_ERR_EIG          (-5)   /* eigensolver did not converge for some k (reference: zheevd info/=0 -> stop,
                                         src/matrix_math.f90:224)                                              */
 #define MEPB_ERR_STATE        (-6)   /* call order (finalize before accumulate, ...)                         */
@@ -40,7 +40,10 @@ typedef struct {
     int32_t nR;               /* number of R points                                                           */
     const double *R;          /* (3,nR)   R_vect as stored: fractional                       file_io.f90:724   */
     const double *H;          /* (nw,nw,nR) complex, Hartree                                 file_io.f90:732-741 */
-    const double *r;          /* (3,nw,nw,nR) complex position operator or NULL; non-NULL -> MEPB_ERR_UNSUPPORTED */
+    const double *r;          /* (3,nw,nw,nR) complex position operator <0n|r|Rm> in Bohr (file_io.f90:782-790, 644-652), or NULL.
+                                 Non-NULL switches on the Berry connection / curvature branch: A_ka, Om_kab Fourier sums
+                                 (wann_interp.f90:288-375), their gauge transformation (:465-658), connection-corrected
+                                 velocities (:406-444), mep_*_CS, kubo_opt_tens                                   */
     const double *wf_centers; /* (3,nw) fractional or NULL: NULL selects the Wannier FT convention, non-NULL the
                                  tight-binding convention                                    wann_interp.f90:192 */
     double a_latt[9];         /* Fortran a_latt(3,3) column-major; a_latt(i,:) = a_i*a0      input_paras.f90:165-168 */
@@ -54,6 +57,14 @@ typedef struct {
     int32_t valence_bands, n_hw, n_eF;
     double  hw_min, hw_max, eF_min, eF_max;     /* Hartree  (driver converts from eV, input_paras.f90:171-178) */
     double  T_kelvin, eta /* Hartree */, kubo_tol;
+    int32_t do_gyro;          /* jobs%do_gyro: gyrotropic tensors C, D, D(w) (src/gyro.f90:74-268)                      */
+    int32_t posop_mode;       /* position-operator branch only.  0 = PRB 74 195118 eqs. 21-31 (default): A <- U^dagger A U,
+                                 curvature and velocity corrections built from that rotated connection.  1 = the deterministic
+                                 part of the reference's coded behaviour: curvature (wann_interp.f90:647-652) and velocity
+                                 (:427-436) corrections use A AFTER A += iD.  The coded connection rotation itself
+                                 ((U^dagger H_a U) U, :530-533) depends on the eigenvector phases LAPACK happens to return and
+                                 the coded V diagonal is stale memory (:427-436): neither is reproducible by any implementation,
+                                 both are replaced by the eq. 21 rotation and by Hbar(n,n) in either mode   */
 } mepb_params;
 
 /* Outputs of integrate_over_k_space (src/core.f90:419-561), laid out as the arrays save_npy writes
@@ -68,8 +79,10 @@ typedef struct {
     double *kubo_mep_ic, *kubo_mep_lc, *kubo_mep_cs;   /* (3,3)                                                 */
     double *ahc;                               /* (3,3)                       ahc_tens.npy                      */
     double *ahc_velo, *ohc_velo;               /* (3,3,n_hw) complex          ahcVELO.npy, ohcVELO.npy          */
-    double *opt_s, *opt_a;                     /* (3,3,n_hw) complex          zeros without position operator   */
+    double *opt_s, *opt_a;                     /* (3,3,n_hw) complex          opt_Ssymm.npy, opt_Asymm.npy (zeros without position operator, kubo.f90:225) */
     double *photo2;                            /* (3,3,3,n_hw,n_eF) complex   photoC_2nd.npy                    */
+    double *gyro_c, *gyro_d;                   /* (3,3,n_eF) complex          gyro_C.npy, gyro_D.npy (all E_F, core.f90:523-530) */
+    double *gyro_dw;                           /* (3,3,n_hw,n_eF) complex     gyro_Dw.npy                       */
 } mepb_result;
 
 typedef struct mepb_ctx mepb_ctx;

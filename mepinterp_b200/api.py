@@ -44,7 +44,7 @@ class CParams(C.Structure):
                 ("do_mep", C.c_int32), ("do_kubo", C.c_int32), ("do_ahc", C.c_int32), ("do_opt", C.c_int32),
                 ("do_write_mep_bands", C.c_int32), ("valence_bands", C.c_int32), ("n_hw", C.c_int32), ("n_eF", C.c_int32),
                 ("hw_min", C.c_double), ("hw_max", C.c_double), ("eF_min", C.c_double), ("eF_max", C.c_double),
-                ("T_kelvin", C.c_double), ("eta", C.c_double), ("kubo_tol", C.c_double)]
+                ("T_kelvin", C.c_double), ("eta", C.c_double), ("kubo_tol", C.c_double), ("do_gyro", C.c_int32), ("posop_mode", C.c_int32)]
 
 
 class CResult(C.Structure):
@@ -52,7 +52,8 @@ class CResult(C.Structure):
                 ("mep_ic", C.c_void_p), ("mep_lc", C.c_void_p), ("mep_cs", C.c_void_p), ("mep_bands", C.c_void_p),
                 ("kubo_mep_ic", C.c_void_p), ("kubo_mep_lc", C.c_void_p), ("kubo_mep_cs", C.c_void_p),
                 ("ahc", C.c_void_p), ("ahc_velo", C.c_void_p), ("ohc_velo", C.c_void_p),
-                ("opt_s", C.c_void_p), ("opt_a", C.c_void_p), ("photo2", C.c_void_p)]
+                ("opt_s", C.c_void_p), ("opt_a", C.c_void_p), ("photo2", C.c_void_p),
+                ("gyro_c", C.c_void_p), ("gyro_d", C.c_void_p), ("gyro_dw", C.c_void_p)]
 
 
 def lib():

@@ -316,12 +316,18 @@ __device__ __forceinline__ void rr_pair_rt(int ne, int r, int i, int &p, int &q)
 }
 
 struct LargeSmemLayout {
-    int ne, ld;
+    int ne, ld, lda;
     size_t oA, oU, oT, oRot, oEs, oFn, oPerm, oMep, oKub, oRed, oCnt, total;
     __host__ __device__ LargeSmemLayout(int nw) {
-        ne = nw + (nw & 1); ld = ne + 1;
+        ne = nw + (nw & 1); ld = ne + 1; lda = ld;
+        // tensor-core rotation (nw % 8 == 0): leading dimensions that make the DMMA fragment loads of zgemm_dmma bank-conflict free.
+        // Rows are 16 ld bytes apart; a quarter-warp of an LDS.128 reads 2 rows x 64 B (A operand, row stride must be 64 mod 128:
+        // ld = 4 mod 8) or 4 rows x 32 B (B / conjugate-transposed A operand, row stride 32 mod 128: ld = 2 mod 8).  ne + 1 (odd)
+        // made every such load a 2-way conflict (profiles/r02b: 30 % of the wavefronts).  Buffer A carries the A operand (d_aH),
+        // buffers U and T the other two.
+        if ((nw & 7) == 0) { ld = ne + 2; lda = ne + 4; }
         size_t o = 0;
-        oA = o; o += sizeof(double2) * ne * ld;
+        oA = o; o += sizeof(double2) * ne * lda;
         oU = o; o += sizeof(double2) * ne * ld;
         oT = o; o += sizeof(double2) * ne * ld;
         oRot = o; o += sizeof(double) * 8 * (ne / 2);          // c, sx, sy, new a, new d, bb, p, q
@@ -344,8 +350,8 @@ struct LargeSmemLayout {
 // CONJT: op(Am) = Am^dagger (element (n, p) = conj(Am[p LD + n])).  Output: Cs row-major in shared memory, or Cg column-major
 // (n + nw j) in global memory.
 template <bool CONJT>
-__device__ __forceinline__ void zgemm_dmma(const int nw, const int LD, const double2 *__restrict__ Am, const double2 *__restrict__ Bm,
-                                           double2 *__restrict__ Cs, double2 *__restrict__ Cg) {
+__device__ __forceinline__ void zgemm_dmma(const int nw, const int LDA, const int LD, const double2 *__restrict__ Am,
+                                           const double2 *__restrict__ Bm, double2 *__restrict__ Cs, double2 *__restrict__ Cg) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int kq = lane & 3, nq = lane >> 2;
     const int nt = nw >> 3, ngrp = (nt + 3) >> 2;
@@ -355,7 +361,7 @@ __device__ __forceinline__ void zgemm_dmma(const int nw, const int LD, const dou
 #pragma unroll
         for (int t = 0; t < 4; ++t) { cr[t][0] = cr[t][1] = ci[t][0] = ci[t][1] = 0.0; }
         for (int ks = 0; ks < (nw >> 2); ++ks) {
-            double2 a = CONJT ? Am[(4 * ks + kq) * LD + 8 * tr + nq] : Am[(8 * tr + nq) * LD + 4 * ks + kq];
+            double2 a = CONJT ? Am[(4 * ks + kq) * LDA + 8 * tr + nq] : Am[(8 * tr + nq) * LDA + 4 * ks + kq];
             if (CONJT) a.y = -a.y;
             const double nay = -a.y;
             double2 b[4];
@@ -390,7 +396,7 @@ eig_rot_large_kernel(const DevModel m, const KSource ks, const Jobs jb, const In
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int nw = m.nw, nw2 = nw * nw;
     const LargeSmemLayout L(nw);
-    const int NE = L.ne, LD = L.ld, NP = NE / 2;
+    const int NE = L.ne, LD = L.ld, LDA = L.lda, NP = NE / 2;     // LDA: buffer A; LD: buffers U, T
     double2 *A = reinterpret_cast<double2 *>(smem_raw + L.oA);
     double2 *U = reinterpret_cast<double2 *>(smem_raw + L.oU);
     double2 *T = reinterpret_cast<double2 *>(smem_raw + L.oT);
@@ -429,7 +435,7 @@ eig_rot_large_kernel(const DevModel m, const KSource ks, const Jobs jb, const In
         double2 *taus = reinterpret_cast<double2 *>(rot);
         for (int idx = tid; idx < (nw - 1) * nw; idx += E_THREADS) {
             const int s = idx / nw, i = idx % nw;
-            A[s * LD + i] = Vr[(size_t)s * NEt + i];
+            A[s * LDA + i] = Vr[(size_t)s * NEt + i];
         }
         if (tid < nw) {
             es[tid] = tb.E[(size_t)ik * NEt + tid];
@@ -452,7 +458,7 @@ eig_rot_large_kernel(const DevModel m, const KSource ks, const Jobs jb, const In
                 for (int rr = 0; rr < 8; ++rr) {
                     const int r = part + 8 * rr;
                     v[rr] = make_double2(0.0, 0.0);
-                    if (8 * rr + 7 > j && r < nw) { v[rr] = A[j * LD + r]; cfmac(w, v[rr], z[rr]); }
+                    if (8 * rr + 7 > j && r < nw) { v[rr] = A[j * LDA + r]; cfmac(w, v[rr], z[rr]); }
                 }
                 w.x += __shfl_xor_sync(0xffffffffu, w.x, 1); w.y += __shfl_xor_sync(0xffffffffu, w.y, 1);
                 w.x += __shfl_xor_sync(0xffffffffu, w.x, 2); w.y += __shfl_xor_sync(0xffffffffu, w.y, 2);
@@ -483,7 +489,7 @@ eig_rot_large_kernel(const DevModel m, const KSource ks, const Jobs jb, const In
                 else v = make_double2(Hk[r + nw * c].x, 0.0);
                 nrm_l += v.x * v.x + v.y * v.y;
             }
-            A[r * LD + c] = v;
+            A[r * LDA + c] = v;
             U[r * LD + c] = make_double2(r == c ? 1.0 : 0.0, 0.0);
         }
         nrm_l = warp_sum(nrm_l);
@@ -502,8 +508,8 @@ eig_rot_large_kernel(const DevModel m, const KSource ks, const Jobs jb, const In
                 for (int r = 0; r < NE - 1; ++r) {
                     if (tid < NP) {
                         int p, q; rr_pair_rt(NE, r, tid, p, q);
-                        const double a = A[p * LD + p].x, d = A[q * LD + q].x;
-                        const double2 b = A[p * LD + q];
+                        const double a = A[p * LDA + p].x, d = A[q * LDA + q].x;
+                        const double2 b = A[p * LDA + q];
                         const double bb = fma(b.x, b.x, b.y * b.y);
                         double c = 1.0, sx = 0.0, sy = 0.0, tb = 0.0;
                         if (bb > 1e-300) {
@@ -529,9 +535,9 @@ eig_rot_large_kernel(const DevModel m, const KSource ks, const Jobs jb, const In
                         const double c = ro[0], sx = ro[1], sy = ro[2];
                         const int p = reinterpret_cast<const int *>(ro + 6)[0], q = reinterpret_cast<const int *>(ro + 6)[1];
                         for (int row = warp; row < NE; row += E_WARPS) {
-                            const double2 x = A[row * LD + p], y = A[row * LD + q], ux = U[row * LD + p], uy = U[row * LD + q];
-                            A[row * LD + p] = make_double2(c * x.x - (sx * y.x + sy * y.y), c * x.y - (sx * y.y - sy * y.x));
-                            A[row * LD + q] = make_double2(sx * x.x - sy * x.y + c * y.x, sx * x.y + sy * x.x + c * y.y);
+                            const double2 x = A[row * LDA + p], y = A[row * LDA + q], ux = U[row * LD + p], uy = U[row * LD + q];
+                            A[row * LDA + p] = make_double2(c * x.x - (sx * y.x + sy * y.y), c * x.y - (sx * y.y - sy * y.x));
+                            A[row * LDA + q] = make_double2(sx * x.x - sy * x.y + c * y.x, sx * x.y + sy * x.x + c * y.y);
                             U[row * LD + p] = make_double2(c * ux.x - (sx * uy.x + sy * uy.y), c * ux.y - (sx * uy.y - sy * uy.x));
                             U[row * LD + q] = make_double2(sx * ux.x - sy * ux.y + c * uy.x, sx * ux.y + sy * ux.x + c * uy.y);
                         }
@@ -543,12 +549,12 @@ eig_rot_large_kernel(const DevModel m, const KSource ks, const Jobs jb, const In
                         const double c = ro[0], sx = ro[1], sy = ro[2];
                         const int p = reinterpret_cast<const int *>(ro + 6)[0], q = reinterpret_cast<const int *>(ro + 6)[1];
                         for (int col = lane; col < NE; col += 32) {
-                            const double2 x = A[p * LD + col], y = A[q * LD + col];
+                            const double2 x = A[p * LDA + col], y = A[q * LDA + col];
                             double2 op = make_double2(c * x.x - (sx * y.x - sy * y.y), c * x.y - (sx * y.y + sy * y.x));
                             double2 oq = make_double2(sx * x.x + sy * x.y + c * y.x, sx * x.y - sy * x.x + c * y.y);
                             if (col == p) { op = make_double2(ro[3], 0.0); oq = make_double2(0.0, 0.0); }
                             else if (col == q) { op = make_double2(0.0, 0.0); oq = make_double2(ro[4], 0.0); }
-                            A[p * LD + col] = op; A[q * LD + col] = oq;
+                            A[p * LDA + col] = op; A[q * LDA + col] = oq;
                         }
                     }
                     __syncthreads();
@@ -565,10 +571,10 @@ eig_rot_large_kernel(const DevModel m, const KSource ks, const Jobs jb, const In
         if (!ok && tid == 0) atomicExch(out.err_flag, 1);
         // ------------------------------------------------------------------ ascending order, occupations
         if (tid < nw) {
-            const double ej = A[tid * LD + tid].x;
+            const double ej = A[tid * LDA + tid].x;
             int rank = 0;
             for (int i = 0; i < nw; ++i) {
-                const double ei = A[i * LD + i].x;
+                const double ei = A[i * LDA + i].x;
                 rank += (ei < ej || (ei == ej && i < tid)) ? 1 : 0;
             }
             es[rank] = ej; perm[rank] = tid;
@@ -598,12 +604,17 @@ eig_rot_large_kernel(const DevModel m, const KSource ks, const Jobs jb, const In
             for (int a = 0; a < 3; ++a) {
                 const double2 *Ha = Hka_in + ((size_t)ik * 3 + a) * nw2;
                 if (jb.do_gauge) {
-                    for (int idx = tid; idx < nw2; idx += E_THREADS) { const int n = idx % nw, mm = idx / nw; A[n * LD + mm] = Ha[idx]; }
+                    if (jb.herm) {      // d_aH(k) Hermitian (mirrored exactly by the Fourier kernel): A(n, m) = conj Ha(m, n) makes the
+                        //                 transposing copy coalesced in global AND conflict-free in shared memory
+                        for (int idx = tid; idx < nw2; idx += E_THREADS) { const int mm = idx % nw, n = idx / nw; A[n * LDA + mm] = cconj(Ha[idx]); }
+                    } else {
+                        for (int idx = tid; idx < nw2; idx += E_THREADS) { const int n = idx % nw, mm = idx / nw; A[n * LDA + mm] = Ha[idx]; }
+                    }
                     __syncthreads();
                     if ((nw & 7) == 0) {                            // tensor-core path: U(buffer) <- Ha Us ; V <- Us^dagger U
-                        zgemm_dmma<false>(nw, LD, A, T, U, nullptr);
+                        zgemm_dmma<false>(nw, LDA, LD, A, T, U, nullptr);
                         __syncthreads();
-                        zgemm_dmma<true>(nw, LD, T, U, nullptr, Vg + a * nw2);
+                        zgemm_dmma<true>(nw, LD, LD, T, U, nullptr, Vg + a * nw2);
                         __syncthreads();
                         continue;
                     }
@@ -614,7 +625,7 @@ eig_rot_large_kernel(const DevModel m, const KSource ks, const Jobs jb, const In
                         const int p1 = min(p0 + 1, nw - 1), j1 = min(j0 + njb, nw - 1);
                         double2 s00 = make_double2(0, 0), s01 = s00, s10 = s00, s11 = s00;
                         for (int q = 0; q < nw; ++q) {
-                            const double2 h0 = A[p0 * LD + q], h1 = A[p1 * LD + q], u0 = T[q * LD + j0], u1 = T[q * LD + j1];
+                            const double2 h0 = A[p0 * LDA + q], h1 = A[p1 * LDA + q], u0 = T[q * LD + j0], u1 = T[q * LD + j1];
                             cfma(s00, h0, u0); cfma(s01, h0, u1); cfma(s10, h1, u0); cfma(s11, h1, u1);
                         }
                         U[p0 * LD + j0] = s00; U[p0 * LD + j1] = s01; U[p1 * LD + j0] = s10; U[p1 * LD + j1] = s11;

@@ -13,7 +13,13 @@
  *                                                      allocated per call like the reference; symbol scipy_zheevd_
  *                                                      from the OpenBLAS 0.3.30 inside the scipy wheel (dlopen)
  *   rotate_gauge       src/wann_interp.f90:502-550     two zgemm per direction (scipy_zgemm_), matrix_math.f90:636-655
- *   get_velo           src/wann_interp.f90:406-444     V = Hbar (no position operator)
+ *   get_velo           src/wann_interp.f90:406-444     V = Hbar; with a position operator V(n,m) = Hbar(n,m) - i (E_m - E_n) A(n,m)
+ *   ft_pos_R_to_k      src/wann_interp.f90:288-375     A_ka, Om_kab Fourier sums (W gauge), both FT conventions
+ *   gauge_pos          src/wann_interp.f90:465-658     rotate_gauge (A, Om), get_gauge_covar_deriv, conn/curv_gaugeTrafo
+ *   mep_niu_CS / kubo_mep_CS   src/mep_niu.f90:20-44, src/kubo_mep.f90:16-47
+ *   kubo_opt (herm, aherm)     src/kubo.f90:204-405
+ *   gyro C / D / Dw    src/gyro.f90:74-268, get_kubo_curv src/wann_interp.f90:113-147, fd_stat_deriv src/statistics.f90:161-197
+ *   (position-operator branch: which coded defects are and are not reproduced is stated in oracle/mep_oracle.py's header)
  *   fd_stat            src/statistics.f90:65-90
  *   kubo_ahc_tens      src/kubo.f90:37-78
  *   velo_ahc_tens      src/kubo.f90:86-140
@@ -34,6 +40,10 @@
  *   if do_kubo: kubo_mep_ic (3,3,n_eF), kubo_mep_lc (3,3,n_eF)
  *   if do_ahc : kubo_ahc (3,3,n_eF), velo_ahc (3,3,n_hw,n_eF) c16, kubo_ohc (3,3,n_hw,n_eF) c16
  *   if do_opt : photo2 (3,3,3,n_hw,n_eF) c16
+ *   with a position operator (model.r != NULL):
+ *     if do_mep : mep_cs (nval)  — the scalar cs(i,i,n0) per band         if do_kubo: kubo_mep_cs (n_eF)
+ *     if do_opt : opt_herm (3,3,n_hw,n_eF) c16, opt_aherm (3,3,n_hw,n_eF) c16
+ *   if do_gyro: gyro_C (3,3,n_eF) c16, gyro_D (3,3,n_eF) c16, gyro_Dw (3,3,n_hw,n_eF) c16
  */
 #include <complex.h>
 #include <dlfcn.h>
@@ -79,10 +89,10 @@ int cpu_ref_init(const char *openblas_path) {
 
 /* ------------------------------------------------------------------ layout of the packed partials */
 typedef struct {
-    int64_t total, ne, mep_ic, mep_lc, kmep_ic, kmep_lc, ahc, velo, ohc, photo;
+    int64_t total, ne, mep_ic, mep_lc, kmep_ic, kmep_lc, ahc, velo, ohc, photo, mep_cs, kmep_cs, opt_h, opt_ah, gyro_c, gyro_d, gyro_dw;
 } layout_t;
 
-static layout_t make_layout(const mepb_params *p) {
+static layout_t make_layout(const mepb_params *p, int posop) {
     layout_t L; memset(&L, 0, sizeof L);
     int64_t o = 2; L.ne = o; o += p->n_eF;
     L.mep_ic = L.mep_lc = L.kmep_ic = L.kmep_lc = L.ahc = L.velo = L.ohc = L.photo = -1;
@@ -91,10 +101,16 @@ static layout_t make_layout(const mepb_params *p) {
     if (p->do_ahc)  { L.ahc = o; o += 9 * p->n_eF; L.velo = o; o += 2 * 9 * (int64_t)p->n_hw * p->n_eF;
                       L.ohc = o; o += 2 * 9 * (int64_t)p->n_hw * p->n_eF; }
     if (p->do_opt)  { L.photo = o; o += 2 * 27 * (int64_t)p->n_hw * p->n_eF; }
+    L.mep_cs = L.kmep_cs = L.opt_h = L.opt_ah = L.gyro_c = L.gyro_d = L.gyro_dw = -1;
+    if (posop && p->do_mep)  { L.mep_cs = o; o += p->valence_bands; }
+    if (posop && p->do_kubo) { L.kmep_cs = o; o += p->n_eF; }
+    if (posop && p->do_opt)  { L.opt_h = o; o += 2 * 9 * (int64_t)p->n_hw * p->n_eF; L.opt_ah = o; o += 2 * 9 * (int64_t)p->n_hw * p->n_eF; }
+    if (p->do_gyro) { L.gyro_c = o; o += 2 * 9 * (int64_t)p->n_eF; L.gyro_d = o; o += 2 * 9 * (int64_t)p->n_eF;
+                      L.gyro_dw = o; o += 2 * 9 * (int64_t)p->n_hw * p->n_eF; }
     L.total = o;
     return L;
 }
-int64_t cpu_ref_partials_size(const mepb_params *p) { return make_layout(p).total; }
+int64_t cpu_ref_partials_size(const mepb_model *mo, const mepb_params *p) { return make_layout(p, mo->r != NULL).total; }
 
 static void get_linspace(double lo, double hi, int n, double *out) { /* matrix_math.f90:74-100 */
     if (n > 1) { double d = (hi - lo) / (double)(n - 1); for (int i = 0; i < n; ++i) out[i] = lo + (double)i * d; }
@@ -198,6 +214,97 @@ static int get_wann_interp(const mepb_model *mo, const mepb_params *p, const dou
         }
     }
     memcpy(V, H_ka, sizeof(zc) * 3 * nw * nw); /* get_velo :440 */
+    return 0;
+}
+
+/* wann_interp.f90:288-375: A (3,nw,nw), Om (3,3,nw,nw) in the W gauge */
+#define AA(a, n, m) A[(a) + 3 * ((n) + nw * (m))]
+#define OM(a, b, n, m) Om[(a) + 3 * ((b) + 3 * ((n) + nw * (m)))]
+static void ft_pos_R_to_k(const mepb_model *mo, int use_cart_velo, const double *kpt, zc *A, zc *Om) {
+    const int nw = mo->nw, nR = mo->nR;
+    const zc *r = (const zc *)mo->r;
+    const double two_pi = 2.0 * PI_DP;
+    memset(A, 0, sizeof(zc) * 3 * nw * nw);
+    memset(Om, 0, sizeof(zc) * 9 * nw * nw);
+    for (int sc = 0; sc < nR; ++sc) {
+        const double *Rv = mo->R + 3 * sc;
+        for (int m = 0; m < nw; ++m)
+            for (int n = 0; n < nw; ++n) {
+                double dR[3], dRc[3];
+                for (int i = 0; i < 3; ++i) dR[i] = Rv[i] + (mo->wf_centers ? mo->wf_centers[i + 3 * m] - mo->wf_centers[i + 3 * n] : 0.0);
+                const double ang = two_pi * (kpt[0] * dR[0] + kpt[1] * dR[1] + kpt[2] * dR[2]);       /* :306, :344 */
+                const zc ph = cos(ang) + I * sin(ang);
+                if (use_cart_velo) matvec3(mo->a_latt, dR, dRc); else for (int i = 0; i < 3; ++i) dRc[i] = two_pi * dR[i];
+                const zc *rr = r + 3 * ((int64_t)n + nw * ((int64_t)m + (int64_t)nw * sc));             /* r(a,n,m,sc) */
+                for (int a = 0; a < 3; ++a) {
+                    AA(a, n, m) += ph * rr[a];
+                    for (int b = 0; b < 3; ++b) {
+                        OM(a, b, n, m) += ph * I * dRc[a] * rr[b];
+                        OM(a, b, n, m) -= ph * I * dRc[b] * rr[a];
+                    }
+                }
+            }
+    }
+}
+
+/* X <- U^dagger X U for one nw x nw matrix held with element stride `st` (slices of the (3,..) / (3,3,..) arrays) */
+static void rotate_slice(int nw, const zc *U, const zc *U_dag, zc *X, int st, zc *t1, zc *t2) {
+    for (int i = 0; i < nw * nw; ++i) t1[i] = X[(int64_t)st * i];
+    blas_matmul(nw, t1, U, t2);
+    blas_matmul(nw, U_dag, t2, t1);
+    for (int i = 0; i < nw * nw; ++i) X[(int64_t)st * i] = t1[i];
+}
+static void comm_acc(int nw, zc coef, const zc *X, const zc *Y, zc *out, int st, zc *t1, zc *t2) { /* out += coef [X, Y] */
+    blas_matmul(nw, X, Y, t1);
+    blas_matmul(nw, Y, X, t2);
+    for (int i = 0; i < nw * nw; ++i) out[(int64_t)st * i] += coef * (t1[i] - t2[i]);
+}
+
+/* wann_interp.f90:56-108 with a position operator.  e_k(nw), V(3,nw,nw), A(3,nw,nw), Om(3,3,nw,nw) in the H gauge */
+static int get_wann_interp_pos(const mepb_model *mo, const mepb_params *p, const double *recip, const double *kpt, double *e_k,
+                               zc *V, zc *A, zc *Om, zc *U, zc *H_ka, zc *wk /* >= 12 nw^2 */) {
+    const int nw = mo->nw, nw2 = nw * nw;
+    zc *U_dag = wk, *t1 = wk + nw2, *t2 = wk + 2 * nw2, *D = wk + 3 * nw2 /* 3 nw2, [a][n + nw m] */, *Ax = wk + 6 * nw2 /* 3 nw2 */,
+       *Ah = wk + 9 * nw2 /* 3 nw2 */;
+    ft_R_to_k(mo, p->use_cart_velo, recip, kpt, U, H_ka);
+    ft_pos_R_to_k(mo, p->use_cart_velo, kpt, A, Om);
+    int info = zheevd_wrapper(nw, U, e_k);
+    if (info != 0) return info;
+    const zc *Av = A;                                             /* connection that enters get_velo */
+    if (p->do_gauge_trafo) {
+        for (int n = 0; n < nw; ++n) for (int m = 0; m < nw; ++m) U_dag[n + nw * m] = conj(U[m + nw * n]);
+        for (int a = 0; a < 3; ++a) {
+            rotate_slice(nw, U, U_dag, H_ka + a, 3, t1, t2);                       /* :517-528 */
+            rotate_slice(nw, U, U_dag, A + a, 3, t1, t2);                          /* eq. (21); the coded line :530-533 is Q1 */
+            for (int b = 0; b < 3; ++b) rotate_slice(nw, U, U_dag, Om + a + 3 * b, 9, t1, t2);   /* :536-542 */
+        }
+        for (int a = 0; a < 3; ++a)                                                 /* get_gauge_covar_deriv :565-617 */
+            for (int m = 0; m < nw; ++m) for (int n = 0; n < nw; ++n) {
+                const double dE = e_k[m] - e_k[n];
+                D[a * nw2 + n + nw * m] = (n != m && fabs(dE) > p->kubo_tol) ? H_ka[a + 3 * (n + nw * m)] / dE : 0.0;
+            }
+        for (int a = 0; a < 3; ++a) for (int i = 0; i < nw2; ++i) {
+            Ax[a * nw2 + i] = A[a + 3 * i];                                         /* rotated W-gauge connection */
+            A[a + 3 * i] += I * D[a * nw2 + i];                                     /* conn_gaugeTrafo :620-633 */
+            Ah[a * nw2 + i] = A[a + 3 * i];
+        }
+        const zc *Ac = (p->posop_mode == 1) ? Ah : Ax;                              /* Q4 coded / eq. (27) */
+        for (int b = 0; b < 3; ++b) for (int a = 0; a < 3; ++a) {                   /* curv_gaugeTrafo :636-658 */
+            comm_acc(nw, -1.0, D + a * nw2, Ac + b * nw2, Om + a + 3 * b, 9, t1, t2);
+            comm_acc(nw, 1.0, D + b * nw2, Ac + a * nw2, Om + a + 3 * b, 9, t1, t2);
+            comm_acc(nw, -I, D + a * nw2, D + b * nw2, Om + a + 3 * b, 9, t1, t2);
+        }
+        Av = (p->posop_mode == 1) ? Ah : Ax;                                        /* Q15 coded / eq. (31) */
+        for (int a = 0; a < 3; ++a) for (int m = 0; m < nw; ++m) for (int n = 0; n < nw; ++n) {   /* get_velo :424-437; diagonal = Hbar (Q2) */
+            const zc h = H_ka[a + 3 * (n + nw * m)];
+            V[a + 3 * (n + nw * m)] = (n == m) ? h : h - I * (e_k[m] - e_k[n]) * Av[a * nw2 + n + nw * m];
+        }
+    } else {
+        for (int a = 0; a < 3; ++a) for (int m = 0; m < nw; ++m) for (int n = 0; n < nw; ++n) {
+            const zc h = H_ka[a + 3 * (n + nw * m)];
+            V[a + 3 * (n + nw * m)] = (n == m) ? h : h - I * (e_k[m] - e_k[n]) * Av[a + 3 * (n + nw * m)];
+        }
+    }
     return 0;
 }
 
@@ -331,6 +438,81 @@ static void kubo_mep_IC(int nw, int n_ef, const double *en, const zc *V, const d
     }
 }
 
+/* convert_tens_to_vect, matrix_math.f90:511-529, on Om(:,:,n,n) */
+static void om_vect_nn(int nw, const zc *Om, int n, zc *v) {
+    for (int c = 0; c < 3; ++c) { v[c] = 0.0; for (int b = 0; b < 3; ++b) for (int a = 0; a < 3; ++a) v[c] += (double)levi(a, b, c) * OM(a, b, n, n); }
+}
+/* mep_niu.f90:20-44 / kubo_mep.f90:16-47: 0.5 Re dot_product(A(:,n0,n0), om_vect)  (dot_product conjugates its first argument) */
+static double cs_scalar(int nw, const zc *A, const zc *Om, int n0) {
+    zc v[3]; om_vect_nn(nw, Om, n0, v);
+    zc d = 0.0;
+    for (int c = 0; c < 3; ++c) d += conj(AA(c, n0, n0)) * v[c];
+    return 0.5 * creal(d);
+}
+/* kubo.f90:272-405: herm and aherm sums, (3,3,n_hw,n_ef) each */
+static void kubo_opt_sums(int nw, int n_ef, int n_hw, const double *en, const zc *A, const double *hw, const double *fd, zc i_eta,
+                          zc *herm, zc *aherm) {
+    for (int m = 0; m < nw; ++m) for (int n = 0; n < nw; ++n) {
+        if (n == m) continue;
+        const double dE = en[m] - en[n];
+        zc a_nm_mn[9];
+        for (int b = 0; b < 3; ++b) for (int i = 0; i < 3; ++i) a_nm_mn[i + 3 * b] = dE * (AA(i, n, m) * AA(b, m, n));
+        const zc dE_smr = PI_DP * (dE - i_eta);                                       /* delta_broad :248-269 */
+        for (int h = 0; h < n_hw; ++h) {
+            const double d_broad = cimag(1.0 / (dE_smr - PI_DP * hw[h]));
+            const double den = creal(dE - hw[h] - i_eta);                            /* :389 real(...) */
+            for (int ef = 0; ef < n_ef; ++ef) {
+                const double df = FD(ef, m) - FD(ef, n);
+                for (int q = 0; q < 9; ++q) {
+                    herm[q + 9 * (h + (int64_t)n_hw * ef)] -= PI_DP * (a_nm_mn[q] * d_broad) * df;
+                    aherm[q + 9 * (h + (int64_t)n_hw * ef)] += I * (a_nm_mn[q] / den) * df;
+                }
+            }
+        }
+    }
+}
+/* gyro.f90 with fd_deriv = 1 / (2 + 2 cosh(f)) AS CODED (d1_fd_stat_deriv evaluates cosh on the occupations, statistics.f90:186) */
+static void gyro_sums(int nw, int n_ef, int n_hw, double kubo_tol, const double *en, const zc *V, const zc *A, const zc *Om,
+                      const double *hw, const double *fd, zc *C, zc *Dt, zc *Dw) {
+    for (int n = 0; n < nw; ++n) {
+        zc om[3];
+        if (Om) om_vect_nn(nw, Om, n, om);
+        else {                                                                        /* get_kubo_curv, wann_interp.f90:113-147 */
+            double curv[9]; memset(curv, 0, sizeof curv);
+            for (int np = 0; np < nw; ++np) {
+                if (np == n) continue;
+                const double dEE = (en[np] - en[n]) * (en[np] - en[n]);
+                if (fabs(dEE) < kubo_tol) continue;
+                for (int j = 0; j < 3; ++j) for (int i = 0; i < 3; ++i) curv[i + 3 * j] += cimag(VA(i, n, np) * VA(j, np, n)) / dEE;
+            }
+            for (int c = 0; c < 3; ++c) { om[c] = 0.0; for (int b = 0; b < 3; ++b) for (int a = 0; a < 3; ++a) om[c] += (double)levi(a, b, c) * (-2.0 * curv[a + 3 * b]); }
+        }
+        for (int ef = 0; ef < n_ef; ++ef) {
+            const double fdd = 1.0 / (2.0 + 2.0 * cosh(FD(ef, n)));
+            for (int b = 0; b < 3; ++b) for (int a = 0; a < 3; ++a) {
+                C[a + 3 * b + 9 * ef] += VA(a, n, n) * VA(b, n, n) * fdd;            /* get_gyro_C :200-232 */
+                Dt[a + 3 * b + 9 * ef] -= VA(a, n, n) * om[b] * fdd;                 /* get_gyro_D :74-150 */
+            }
+        }
+        if (A) {                                                                      /* get_gyro_Dw :153-197, get_curvTilde_hw :235-268 */
+            for (int h = 0; h < n_hw; ++h) {
+                double omt[3] = {0.0, 0.0, 0.0};
+                for (int m = 0; m < nw; ++m) {
+                    if (m == n) continue;
+                    const double ww = (en[m] - en[n]) * (en[m] - en[n]);
+                    const zc a1[3] = {AA(0, n, m), AA(1, n, m), AA(2, n, m)}, a2[3] = {AA(0, m, n), AA(1, m, n), AA(2, m, n)};
+                    const double cr[3] = {cimag(a1[1] * a2[2] - a1[2] * a2[1]), cimag(a1[2] * a2[0] - a1[0] * a2[2]), cimag(a1[0] * a2[1] - a1[1] * a2[0])};
+                    for (int b = 0; b < 3; ++b) omt[b] -= cr[b] * ww / (ww - hw[h]);
+                }
+                for (int ef = 0; ef < n_ef; ++ef) {
+                    const double fdd = 1.0 / (2.0 + 2.0 * cosh(FD(ef, n)));
+                    for (int b = 0; b < 3; ++b) for (int a = 0; a < 3; ++a) Dw[a + 3 * b + 9 * (h + (int64_t)n_hw * ef)] -= VA(a, n, n) * omt[b] * fdd;
+                }
+            }
+        }
+    }
+}
+
 /* k_space.f90:351-375 with the loop order of core.f90:165-167 for a 0-based linear index */
 static void mesh_kpt(const int32_t *g, int64_t lin, double *kpt) {
     int64_t kix = lin % g[0] + 1, kiy = (lin / g[0]) % g[1] + 1, kiz = lin / ((int64_t)g[0] * g[1]) + 1;
@@ -342,7 +524,7 @@ static void mesh_kpt(const int32_t *g, int64_t lin, double *kpt) {
 /* The per-k response functions of core.f90:187-253 on one set of eigenpairs (en, V): occupations, MEP, Kubo-MEP, AHC,
  * optical sums, all += into the packed partials. */
 static void band_sums_k(const mepb_model *mo, const mepb_params *p, const layout_t *Lp, const double *ef_lst, const double *hw_lst,
-                        const double *en, const zc *V, double *fd, zc *scr, double *partials) {
+                        const double *en, const zc *V, const zc *A, const zc *Om, double *fd, zc *scr, double *partials) {
     const int nw = mo->nw, n_ef = p->n_eF, n_hw = p->n_hw;
     const layout_t L = *Lp;
     zc i_eta = I * p->eta;
@@ -365,15 +547,23 @@ static void band_sums_k(const mepb_model *mo, const mepb_params *p, const layout
         kubo_ohc_tens(nw, n_ef, n_hw, en, V, hw_lst, fd, i_eta, (zc *)(partials + L.ohc), scr);
     }
     if (p->do_opt) photo_2nd_cond(nw, n_ef, n_hw, en, V, hw_lst, fd, i_eta, (zc *)(partials + L.photo), scr);
+    if (A && Om) {                                                   /* position operator: Chern-Simons terms, kubo_opt_tens */
+        if (p->do_mep) for (int n0 = 0; n0 < p->valence_bands; ++n0) partials[L.mep_cs + n0] += cs_scalar(nw, A, Om, n0);
+        if (p->do_kubo) for (int n0 = 0; n0 < nw; ++n0) { const double c = cs_scalar(nw, A, Om, n0); for (int ef = 0; ef < n_ef; ++ef) partials[L.kmep_cs + ef] += c * FD(ef, n0); }
+        if (p->do_opt) kubo_opt_sums(nw, n_ef, n_hw, en, A, hw_lst, fd, i_eta, (zc *)(partials + L.opt_h), (zc *)(partials + L.opt_ah));
+    }
+    if (p->do_gyro) gyro_sums(nw, n_ef, n_hw, p->kubo_tol, en, V, A, Om, hw_lst, fd, (zc *)(partials + L.gyro_c), (zc *)(partials + L.gyro_d),
+                              (zc *)(partials + L.gyro_dw));
 }
 
 /* One "rank": k-points lin_begin + rank, + rank + nranks, ... < lin_end  (mpi_comm.f90:80-99 round-robin).  partials += */
 int cpu_ref_accumulate(const mepb_model *mo, const mepb_params *p, int64_t lin_begin, int64_t lin_end, int rank, int nranks,
                        double *partials) {
     if (!p_zheevd) return -1;
-    if (mo->r) return -4;
     const int nw = mo->nw, n_ef = p->n_eF, n_hw = p->n_hw;
-    layout_t L = make_layout(p);
+    zc *Ak = NULL, *Omk = NULL, *wk = NULL;
+    if (mo->r) { Ak = (zc *)malloc(sizeof(zc) * 3 * nw * nw); Omk = (zc *)malloc(sizeof(zc) * 9 * nw * nw); wk = (zc *)malloc(sizeof(zc) * 12 * nw * nw); }
+    layout_t L = make_layout(p, mo->r != NULL);
     double recip[9]; set_recip_latt(mo->a_latt, recip);
     double *ef_lst = (double *)malloc(sizeof(double) * n_ef), *hw_lst = (double *)malloc(sizeof(double) * n_hw);
     get_linspace(p->eF_min, p->eF_max, n_ef, ef_lst); /* core.f90:124-125 */
@@ -385,26 +575,31 @@ int cpu_ref_accumulate(const mepb_model *mo, const mepb_params *p, int64_t lin_b
     int rc = 0;
     for (int64_t lin = lin_begin + rank; lin < lin_end; lin += nranks) {
         double kpt[3]; mesh_kpt(p->mp_grid, lin, kpt);
-        int info = get_wann_interp(mo, p, recip, kpt, en, V, U, H_ka, tmp, M_in, U_dag);
+        int info = mo->r ? get_wann_interp_pos(mo, p, recip, kpt, en, V, Ak, Omk, U, H_ka, wk)
+                         : get_wann_interp(mo, p, recip, kpt, en, V, U, H_ka, tmp, M_in, U_dag);
         if (info != 0) { rc = -5; break; }
-        band_sums_k(mo, p, &L, ef_lst, hw_lst, en, V, fd, scr, partials);
+        band_sums_k(mo, p, &L, ef_lst, hw_lst, en, V, Ak, Omk, fd, scr, partials);
         partials[0] += 1.0;
     }
     free(ef_lst); free(hw_lst); free(en); free(fd); free(V); free(U); free(H_ka); free(tmp); free(M_in); free(U_dag); free(scr);
+    free(Ak); free(Omk); free(wk);
     return rc;
 }
 
 /* Band sums on supplied eigenpairs: e_k (nw,nk), V_ka (3,nw,nw,nk).  partials += (test helper mirroring mepb_band_sums) */
-int cpu_ref_band_sums(const mepb_model *mo, const mepb_params *p, int64_t nk, const double *e_k, const double *V_ka, double *partials) {
+int cpu_ref_band_sums(const mepb_model *mo, const mepb_params *p, int64_t nk, const double *e_k, const double *V_ka, const double *A_ka,
+                      const double *Om_kab, double *partials) {
     const int nw = mo->nw, n_ef = p->n_eF, n_hw = p->n_hw;
-    layout_t L = make_layout(p);
+    layout_t L = make_layout(p, mo->r != NULL);
     double *ef_lst = (double *)malloc(sizeof(double) * n_ef), *hw_lst = (double *)malloc(sizeof(double) * n_hw);
     get_linspace(p->eF_min, p->eF_max, n_ef, ef_lst);
     get_linspace(p->hw_min, p->hw_max, n_hw, hw_lst);
     double *fd = (double *)malloc(sizeof(double) * n_ef * nw);
     zc *scr = (zc *)malloc(sizeof(zc) * 27 * n_hw);
     for (int64_t ik = 0; ik < nk; ++ik) {
-        band_sums_k(mo, p, &L, ef_lst, hw_lst, e_k + (int64_t)nw * ik, (const zc *)V_ka + (int64_t)3 * nw * nw * ik, fd, scr, partials);
+        band_sums_k(mo, p, &L, ef_lst, hw_lst, e_k + (int64_t)nw * ik, (const zc *)V_ka + (int64_t)3 * nw * nw * ik,
+                    (mo->r && A_ka) ? (const zc *)A_ka + (int64_t)3 * nw * nw * ik : NULL,
+                    (mo->r && Om_kab) ? (const zc *)Om_kab + (int64_t)9 * nw * nw * ik : NULL, fd, scr, partials);
         partials[0] += 1.0;
     }
     free(ef_lst); free(hw_lst); free(fd); free(scr);
@@ -414,7 +609,7 @@ int cpu_ref_band_sums(const mepb_model *mo, const mepb_params *p, int64_t nk, co
 /* nthreads workers standing in for MPI ranks; private accumulators summed at the end like MPI_REDUCE (core.f90:467-526) */
 int cpu_ref_accumulate_mt(const mepb_model *mo, const mepb_params *p, int64_t lin_begin, int64_t lin_end, int nthreads,
                           double *partials) {
-    int64_t n = make_layout(p).total;
+    int64_t n = make_layout(p, mo->r != NULL).total;
     if (nthreads < 1) nthreads = 1;
     double *priv = (double *)calloc((size_t)n * nthreads, sizeof(double));
     int rc = 0;
@@ -435,7 +630,7 @@ int cpu_ref_accumulate_mt(const mepb_model *mo, const mepb_params *p, int64_t li
  * plain sums, so cpu_ref_finalize of this buffer gives the per-tensor magnitudes with the same eF_idx). */
 int cpu_ref_accumulate_abs(const mepb_model *mo, const mepb_params *p, int64_t lin_begin, int64_t lin_end, int nthreads,
                            double *partials_abs) {
-    int64_t n = make_layout(p).total;
+    int64_t n = make_layout(p, mo->r != NULL).total;
     if (nthreads < 1) nthreads = 1;
     double *priv = (double *)calloc((size_t)n * nthreads * 2, sizeof(double));
     int rc = 0;
@@ -458,7 +653,7 @@ int cpu_ref_accumulate_abs(const mepb_model *mo, const mepb_params *p, int64_t l
 
 /* core.f90:317-415 (first minimum, strict <), :419-603, k_space.f90:81-202 */
 int cpu_ref_finalize(const mepb_model *mo, const mepb_params *p, const double *partials, mepb_result *out) {
-    layout_t L = make_layout(p);
+    layout_t L = make_layout(p, mo->r != NULL);
     const int n_ef = p->n_eF, n_hw = p->n_hw, nval = p->valence_bands;
     double recip[9]; double vol = set_recip_latt(mo->a_latt, recip);
     double nk_mesh = (double)p->mp_grid[0] * (double)p->mp_grid[1] * (double)p->mp_grid[2];
@@ -474,15 +669,23 @@ int cpu_ref_finalize(const mepb_model *mo, const mepb_params *p, const double *p
             for (int n0 = 0; n0 < nval; ++n0) { ic += partials[L.mep_ic + q + 9 * n0]; lc += partials[L.mep_lc + q + 9 * n0]; }
             if (out->mep_ic) out->mep_ic[q] = ic / norm;
             if (out->mep_lc) out->mep_lc[q] = lc / norm;
-            if (out->mep_cs) out->mep_cs[q] = 0.0;
+            if (out->mep_cs) {                                       /* cs(i,i,n0) summed over n0 <= nval; 0 without A, Om (mep_niu.f90:29) */
+                double cs = 0.0;
+                if (L.mep_cs >= 0 && (q == 0 || q == 4 || q == 8)) for (int n0 = 0; n0 < nval; ++n0) cs += partials[L.mep_cs + n0];
+                out->mep_cs[q] = cs / norm;
+            }
         }
-        if (out->mep_bands && p->do_write_mep_bands)
-            for (int q = 0; q < 9 * nval; ++q) out->mep_bands[q] = (partials[L.mep_ic + q] + partials[L.mep_lc + q]) / norm;
+        if (out->mep_bands && p->do_write_mep_bands)                 /* core.f90:591-599: ic + lc + cs per band */
+            for (int q = 0; q < 9 * nval; ++q) {
+                const int e = q % 9;
+                const double cs = (L.mep_cs >= 0 && (e == 0 || e == 4 || e == 8)) ? partials[L.mep_cs + q / 9] : 0.0;
+                out->mep_bands[q] = (partials[L.mep_ic + q] + partials[L.mep_lc + q] + cs) / norm;
+            }
     }
     if (p->do_kubo) for (int q = 0; q < 9; ++q) {
         if (out->kubo_mep_ic) out->kubo_mep_ic[q] = partials[L.kmep_ic + q + 9 * opt] / norm;
         if (out->kubo_mep_lc) out->kubo_mep_lc[q] = partials[L.kmep_lc + q + 9 * opt] / norm;
-        if (out->kubo_mep_cs) out->kubo_mep_cs[q] = 0.0;
+        if (out->kubo_mep_cs) out->kubo_mep_cs[q] = (L.kmep_cs >= 0 && (q == 0 || q == 4 || q == 8)) ? partials[L.kmep_cs + opt] / norm : 0.0;
     }
     if (p->do_ahc) {
         if (out->ahc) for (int q = 0; q < 9; ++q) out->ahc[q] = partials[L.ahc + q + 9 * opt] / norm;
@@ -492,9 +695,20 @@ int cpu_ref_finalize(const mepb_model *mo, const mepb_params *p, const double *p
     }
     if (p->do_opt) {
         int64_t sl = 2 * 9 * (int64_t)n_hw;
-        if (out->opt_s) for (int64_t q = 0; q < sl; ++q) out->opt_s[q] = 0.0;
-        if (out->opt_a) for (int64_t q = 0; q < sl; ++q) out->opt_a[q] = 0.0;
+        /* kubo.f90:225-233: opt_symm = Re(herm) + i Im(aherm), opt_asymm = Re(aherm) + i Im(herm); sliced at eF_idx (core.f90:510-511) */
+        for (int64_t q = 0; q < sl; q += 2) {
+            double hr = 0, hi = 0, ar = 0, ai = 0;
+            if (L.opt_h >= 0) { hr = partials[L.opt_h + q + sl * opt]; hi = partials[L.opt_h + q + 1 + sl * opt];
+                                ar = partials[L.opt_ah + q + sl * opt]; ai = partials[L.opt_ah + q + 1 + sl * opt]; }
+            if (out->opt_s) { out->opt_s[q] = hr / norm; out->opt_s[q + 1] = ai / norm; }
+            if (out->opt_a) { out->opt_a[q] = ar / norm; out->opt_a[q + 1] = hi / norm; }
+        }
         if (out->photo2) for (int64_t q = 0; q < 2 * 27 * (int64_t)n_hw * n_ef; ++q) out->photo2[q] = partials[L.photo + q] / norm;
+    }
+    if (p->do_gyro) {                                                /* every trial E_F is written (core.f90:523-530) */
+        if (out->gyro_c) for (int64_t q = 0; q < 18 * (int64_t)n_ef; ++q) out->gyro_c[q] = partials[L.gyro_c + q] / norm;
+        if (out->gyro_d) for (int64_t q = 0; q < 18 * (int64_t)n_ef; ++q) out->gyro_d[q] = partials[L.gyro_d + q] / norm;
+        if (out->gyro_dw) for (int64_t q = 0; q < 18 * (int64_t)n_hw * n_ef; ++q) out->gyro_dw[q] = partials[L.gyro_dw + q] / norm;
     }
     return 0;
 }
@@ -529,6 +743,33 @@ int cpu_ref_interp(const mepb_model *mo, const mepb_params *p, int64_t nk, const
             }
         }
         free(V); free(U); free(H_ka); free(tmp); free(M_in); free(U_dag);
+    }
+    return rc;
+}
+
+/* explicit k list with a position operator: e_k (nw,nk), V_ka (3,nw,nw,nk), A_ka (3,nw,nw,nk), Om_kab (3,3,nw,nw,nk) in the H gauge
+ * (or, with do_gauge_trafo = 0, the W-gauge A / Om and the velocity get_velo builds from them) */
+int cpu_ref_interp_pos(const mepb_model *mo, const mepb_params *p, int64_t nk, const double *kpt, double *e_k, double *V_ka,
+                       double *A_ka, double *Om_kab) {
+    if (!p_zheevd) return -1;
+    if (!mo->r) return -4;
+    const int nw = mo->nw;
+    double recip[9]; set_recip_latt(mo->a_latt, recip);
+    int rc = 0;
+#ifdef _OPENMP
+#pragma omp parallel
+#endif
+    {
+        zc *U = (zc *)malloc(sizeof(zc) * nw * nw), *H_ka = (zc *)malloc(sizeof(zc) * 3 * nw * nw), *wk = (zc *)malloc(sizeof(zc) * 12 * nw * nw);
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 4)
+#endif
+        for (int64_t ik = 0; ik < nk; ++ik) {
+            int info = get_wann_interp_pos(mo, p, recip, kpt + 3 * ik, e_k + (int64_t)nw * ik, (zc *)V_ka + (int64_t)3 * nw * nw * ik,
+                                           (zc *)A_ka + (int64_t)3 * nw * nw * ik, (zc *)Om_kab + (int64_t)9 * nw * nw * ik, U, H_ka, wk);
+            if (info) rc = -5;
+        }
+        free(U); free(H_ka); free(wk);
     }
     return rc;
 }

@@ -27,9 +27,27 @@ It restates, function by function, the Fortran of the reference (paths relative 
     core_worker         src/core.f90:79-298 (k loop + accumulation), :317-415 (fermi_selector),
                         :419-603 (integrate_over_k_space, mep_sum_bands), k_space.f90:81-202 (normalize_k_int)
 
-The position-operator branch (A_ka, Om_kab; *_CS terms; kubo_opt_tens) is never reached by inputs that
-consist of a `_hr.dat` only (k_space.f90:229-233): CS terms and opt_s/opt_a are returned as zeros exactly as
-the reference does (mep_niu.f90:29, kubo_mep.f90:28, kubo.f90:225).
+    position operator   src/file_io.f90:555-658 (read_tb_file), :750-795 (read_r_file), :800-860 (read_tb_basis)
+                        src/wann_interp.f90:288-375 (A_ka, Om_kab Fourier sums), :465-550 (rotate_gauge), :565-658
+                        (get_gauge_covar_deriv, conn_gaugeTrafo, curv_gaugeTrafo), :406-444 (get_velo)
+    mep_niu_CS          src/mep_niu.f90:20-44        kubo_mep_CS   src/kubo_mep.f90:16-47
+    kubo_opt_tens       src/kubo.f90:204-405  (get_hermitian, get_anti_herm, delta_broad)
+    gyro C / D / Dw     src/gyro.f90:74-310, get_kubo_curv src/wann_interp.f90:113-147, fd_stat_deriv src/statistics.f90:161-197
+
+Without a position operator (inputs that consist of a `_hr.dat` only, k_space.f90:229-233) CS terms and opt_s/opt_a are zeros
+exactly as the reference returns them (mep_niu.f90:29, kubo_mep.f90:28, kubo.f90:225).
+
+POSITION-OPERATOR BRANCH — what is and is not matched (DESIGN.md 'position operator'):
+  The reference's coded branch carries defects that make its OUTPUT irreproducible: (Q1) rotate_gauge multiplies the stale
+  temporary, A_a <- (U^dagger H_a U) U instead of U^dagger A_a U (wann_interp.f90:530-533) — the result depends on the
+  arbitrary phases / signs zheevd gives the eigenvectors, i.e. on the LAPACK build; (Q2) V_ka(:,n,n) is never assigned when A
+  is present (stale memory of the previous k-point, :427-436).  Those two cannot be a parity target.  Two further coded
+  choices are deterministic: (Q4) the curvature transform uses A AFTER A += iD (:495-496,647-652; PRB 74 195118 eq. 27 uses
+  the rotated W-gauge connection), (Q15) get_velo uses that same updated A (:101,:427-436; eq. 31 uses the rotated W-gauge
+  connection, so the coded off-diagonal velocity counts Hbar twice).  posop_mode "paper" (default) follows PRB 74 195118
+  eqs. 21-31; posop_mode "coded" reproduces Q4 and Q15 on top of the corrected Q1/Q2 (diagonal of V = Hbar).  Q3 (the
+  `_r.dat` path is mangled, file_io.f90:838 vs :760) is fixed: `<seed>_r.dat` is read.  Q9: `_tb.dat` R vectors are taken as
+  the integer (fractional) triples the file holds.
 
 Parity pin status: the reference cannot be compiled here (no Fortran compiler, no MPI).  The oracle is
 pinned by (a) the reference's own golden AHC tensors config/FeMn_TB/delta*/ahc_tens.npy and
@@ -84,6 +102,7 @@ class Model:
     H: np.ndarray            # (nw, nw, nR) complex, Hartree
     a_latt: np.ndarray       # (3,3): a_latt[i,:] = a_i * a0  (rows!)  input_paras.f90:165-168
     wf_centers: Optional[np.ndarray] = None   # (3, nw) fractional, or None -> Wannier FT convention
+    r: Optional[np.ndarray] = None            # (3, nw, nw, nR) complex position operator in Bohr, or None  file_io.f90:782-790
 
 
 @dataclass
@@ -109,6 +128,8 @@ class Params:
     seed_name: str = "wf1"
     plot_bands: bool = False
     R_vect_float: bool = False
+    do_gyro: bool = False
+    posop_mode: str = "paper"   # "paper": PRB 74 195118 eqs. 21-31; "coded": Q4 + Q15 as the reference codes them (see header)
 
 
 def read_hr_file(path: str, use_R_float: bool = False):
@@ -141,6 +162,70 @@ def read_hr_file(path: str, use_R_float: bool = False):
                 H[m - 1, n - 1, sc] = complex(re, im)
     H = H / AU_TO_EV
     return R, H
+
+
+def read_r_file(path: str, R: np.ndarray, nw: int, use_R_float: bool = False) -> np.ndarray:
+    """file_io.f90:750-795: comment; num_wann; then nR*nw^2 rows `R1 R2 R3 m n x_re x_im y_re y_im z_re z_im` (Angstrom) in the R order
+    of the _hr.dat (checked, :772-776).  Returns r (3,nw,nw,nR) in Bohr."""
+    with open(path, "r") as fh:
+        fh.readline()
+        f_nw = int(fh.readline().split()[0])
+        if f_nw != nw:
+            raise ValueError("[read_tb_basis]: r_mat and H_mat have different basis")
+        nR = R.shape[1]
+        r = np.zeros((3, nw, nw, nR), dtype=np.complex128)
+        for sc in range(nR):
+            for _ in range(nw * nw):
+                tok = fh.readline().split()
+                r3 = np.array([float(t) for t in tok[0:3]])
+                if np.abs(r3 - R[:, sc]).max() > 1e-8:
+                    raise ValueError("[read_r_file]: different R_vect order in _hr.dat and _r.dat file")
+                m, n = int(tok[3]), int(tok[4])
+                v = [float(t) for t in tok[5:11]]
+                r[0, m - 1, n - 1, sc] = complex(v[0], v[1])
+                r[1, m - 1, n - 1, sc] = complex(v[2], v[3])
+                r[2, m - 1, n - 1, sc] = complex(v[4], v[5])
+    return r / AU_TO_ANGSTRM
+
+
+def read_tb_file(path: str, use_R_float: bool = False):
+    """file_io.f90:555-658, wannier90 `_tb.dat`: comment; 3 lattice rows (Angstrom, OVERRIDE a_latt, :575-580); num_wann; nrpts;
+    degeneracies (15 per line, skipped); per R: blank, `R1 R2 R3`, nw^2 rows `m n Re Im` (eV, |x| < 1e-7 -> 0); then per R: blank,
+    `R1 R2 R3`, nw^2 rows `m n x_re x_im y_re y_im z_re z_im` (Angstrom).  Returns (a_latt rows in Bohr, R (3,nR), H Hartree, r Bohr).
+    Q9: the reference stores unit_cell.R (Cartesian) in R_vect but uses it as fractional; here R stays the file's triple."""
+    with open(path, "r") as fh:
+        fh.readline()
+        cell = np.array([[float(t) for t in fh.readline().split()[:3]] for _ in range(3)]) / AU_TO_ANGSTRM
+        nw = int(fh.readline().split()[0])
+        nR = int(fh.readline().split()[0])
+        for _ in range(-(-nR // 15)):
+            fh.readline()
+        R = np.zeros((3, nR))
+        H = np.zeros((nw, nw, nR), dtype=np.complex128)
+        r = np.zeros((3, nw, nw, nR), dtype=np.complex128)
+        for sc in range(nR):
+            fh.readline()
+            R[:, sc] = [float(t) for t in fh.readline().split()[:3]]
+            for _ in range(nw * nw):
+                tok = fh.readline().split()
+                m, n, re, im = int(tok[0]), int(tok[1]), float(tok[2]), float(tok[3])
+                if abs(re) < 1e-7:
+                    re = 0.0
+                if abs(im) < 1e-7:
+                    im = 0.0
+                H[m - 1, n - 1, sc] = complex(re, im)
+        for sc in range(nR):
+            fh.readline()
+            r3 = np.array([float(t) for t in fh.readline().split()[:3]])
+            if np.abs(r3 - R[:, sc]).max() > 1e-8:
+                raise ValueError("[read_tb_basis]: rHopp has different sc order than tHopp")
+            for _ in range(nw * nw):
+                tok = fh.readline().split()
+                m, n = int(tok[0]), int(tok[1])
+                v = [float(t) for t in tok[2:8]]
+                for a in range(3):
+                    r[a, m - 1, n - 1, sc] = complex(v[2 * a], v[2 * a + 1])
+    return cell, R, H / AU_TO_EV, r / AU_TO_ANGSTRM
 
 
 def _cfg_logical(tok: str) -> bool:
@@ -219,18 +304,27 @@ def parse_input_cfg(path: str):
         seed_name=get("wannBase%seed_name", str, "wf1"),
         plot_bands=get("jobs%plot_bands", _cfg_logical, False),
         R_vect_float=get("jobs%R_vect_float", _cfg_logical, False),
+        do_gyro=get("jobs%do_gyro", _cfg_logical, False),
     )
     return p, a_latt, wf_centers
 
 
 def load_model(run_dir: str):
-    """input.cfg + w90files/<seed>_hr.dat -> (Model, Params)   (main.f90:24-45, core.f90:144)."""
+    """input.cfg + w90files/<seed>_tb.dat | <seed>_hr.dat (+ <seed>_r.dat) -> (Model, Params)
+    (main.f90:24-45, core.f90:144, read_tb_basis file_io.f90:800-860: `_tb.dat` wins; else `_hr.dat`, and `_r.dat` if present)."""
     p, a_latt, wfc = parse_input_cfg(os.path.join(run_dir, "input.cfg"))
-    R, H = read_hr_file(os.path.join(run_dir, "w90files", p.seed_name + "_hr.dat"), p.R_vect_float)
+    seed = os.path.join(run_dir, "w90files", p.seed_name)
+    r = None
+    if os.path.exists(seed + "_tb.dat"):
+        a_latt, R, H, r = read_tb_file(seed + "_tb.dat", p.R_vect_float)
+    else:
+        R, H = read_hr_file(seed + "_hr.dat", p.R_vect_float)
+        if os.path.exists(seed + "_r.dat"):
+            r = read_r_file(seed + "_r.dat", R, H.shape[0], p.R_vect_float)
     nw = H.shape[0]
     if wfc is not None and wfc.shape[1] != nw:
         raise ValueError("N_wf does not match num_wann of the _hr file")
-    return Model(nw=nw, nR=R.shape[1], R=R, H=H, a_latt=a_latt, wf_centers=wfc), p
+    return Model(nw=nw, nR=R.shape[1], R=R, H=H, a_latt=a_latt, wf_centers=wfc, r=r), p
 
 
 # --------------------------------------------------------------------------- k-space
@@ -309,6 +403,198 @@ def ft_R_to_k(model: Model, kpts: np.ndarray, use_cart_velo: bool = False):
             for a in range(3):
                 H_ka[:, a] += ph[:, None, None] * (1j * dR_cart[a]) * Hr[None]   # :274
     return H_k, H_ka
+
+
+def ft_pos_R_to_k(model: Model, kpts: np.ndarray, use_cart_velo: bool = False):
+    """wann_interp.f90:288-375: A_ka (K,3,nw,nw) = sum_R ph r_R(a) and Om_kab (K,3,3,nw,nw) = sum_R ph i [c_a r_R(b) - c_b r_R(a)]
+    in the W gauge.  TB convention (:297-334): phase ALWAYS 2 pi k.dR with dR = R + tau_m - tau_n (:306), c per flag (:310-314);
+    Wannier convention (:343-372): phase per R."""
+    K = kpts.shape[0]
+    nw, nR = model.nw, model.nR
+    two_pi = 2.0 * PI_DP
+    A = np.zeros((K, 3, nw, nw), dtype=np.complex128)
+    Om = np.zeros((K, 3, 3, nw, nw), dtype=np.complex128)
+    a_latt = model.a_latt
+    if model.wf_centers is not None:
+        tau = model.wf_centers
+        delta = tau[:, None, :] - tau[:, :, None]                    # delta_at(:,n,m) = tau_m - tau_n
+        for sc in range(nR):
+            dR = model.R[:, sc][:, None, None] + delta
+            ang = two_pi * np.einsum("ki,inm->knm", kpts, dR)        # :306
+            ph = np.cos(ang) + 1j * np.sin(ang)
+            dRc = np.einsum("ij,jnm->inm", a_latt, dR) if use_cart_velo else two_pi * dR     # :310-314
+            rr = model.r[:, :, :, sc]                                # (3,n,m)
+            A += ph[:, None] * rr[None]
+            for a in range(3):
+                for b in range(3):
+                    Om[:, a, b] += ph * (1j * dRc[a])[None] * rr[b][None] - ph * (1j * dRc[b])[None] * rr[a][None]
+    else:
+        for sc in range(nR):
+            ang = two_pi * (kpts @ model.R[:, sc])
+            ph = (np.cos(ang) + 1j * np.sin(ang))[:, None, None]
+            dRc = a_latt @ model.R[:, sc] if use_cart_velo else two_pi * model.R[:, sc]
+            rr = model.r[:, :, :, sc]
+            A += ph[:, None] * rr[None]
+            for a in range(3):
+                for b in range(3):
+                    Om[:, a, b] += ph * 1j * dRc[a] * rr[b][None] - ph * 1j * dRc[b] * rr[a][None]
+    return A, Om
+
+
+def _comm(X, Y):
+    return X @ Y - Y @ X                                             # matrix_comm, matrix_math.f90:555-574
+
+
+def get_wann_interp_pos(model: Model, kpts: np.ndarray, do_gauge_trafo=True, use_cart_velo=False, kubo_tol=1e-5,
+                        posop_mode="paper", q1_coded=False):
+    """wann_interp.f90:56-108 with a position operator: returns e (K,nw), V (K,3,nw,nw), A (K,3,nw,nw), Om (K,3,3,nw,nw), U.
+    posop_mode / q1_coded: see the module header."""
+    H_k, H_ka = ft_R_to_k(model, kpts, use_cart_velo)
+    A, Om = ft_pos_R_to_k(model, kpts, use_cart_velo)
+    nw = model.nw
+    iu = np.triu_indices(nw, 1)
+    Hh = H_k.copy()
+    Hh[:, iu[1], iu[0]] = np.conj(H_k[:, iu[0], iu[1]])
+    dg = np.arange(nw)
+    Hh[:, dg, dg] = Hh[:, dg, dg].real
+    e, U = np.linalg.eigh(Hh, UPLO="U")
+    dE = e[:, None, :] - e[:, :, None]                                # [k,n,m] = e_m - e_n
+    off = _offdiag_mask(nw)
+    if do_gauge_trafo:
+        Ud = np.conj(np.swapaxes(U, -1, -2))
+        Hbar = np.einsum("knp,kapq,kqm->kanm", Ud, H_ka, U, optimize=True)           # rotate_gauge :517-528
+        if q1_coded:                                                                  # :530-533 as coded: (U^dagger H_a U) U
+            Abar = np.einsum("kanp,kpm->kanm", Hbar, U, optimize=True)
+        else:                                                                         # eq. (21)
+            Abar = np.einsum("knp,kapq,kqm->kanm", Ud, A, U, optimize=True)
+        Ombar = np.einsum("knp,kabpq,kqm->kabnm", Ud, Om, U, optimize=True)           # :536-542
+        ok = (np.abs(dE) > kubo_tol) & off[None]                                      # get_gauge_covar_deriv :565-617
+        with np.errstate(divide="ignore", invalid="ignore"):
+            D = np.where(ok[:, None], Hbar / dE[:, None], 0.0)
+        A_H = Abar + 1j * D                                                           # conn_gaugeTrafo :620-633
+        Ax = A_H if posop_mode == "coded" else Abar                                   # Q4 / eq. (27)
+        Om_H = Ombar.copy()
+        for a in range(3):
+            for b in range(3):
+                Om_H[:, a, b] += -_comm(D[:, a], Ax[:, b]) + _comm(D[:, b], Ax[:, a]) - 1j * _comm(D[:, a], D[:, b])
+        Av = A_H if posop_mode == "coded" else Abar                                   # Q15 / eq. (31)
+        Hv = Hbar
+    else:
+        A_H, Om_H, Av, Hv = A, Om, A, H_ka                                            # W gauge handed to get_velo as it is
+    V = np.where(off[None, None], Hv - 1j * dE[:, None] * Av, Hv)                     # get_velo :424-437; diagonal = Hbar (Q2)
+    return e, V, A_H, Om_H, U
+
+
+def om_vect(Om_diag):
+    """convert_tens_to_vect (matrix_math.f90:511-529): v_c = sum_ab eps_abc T_ab.  Om_diag (...,3,3,n) -> (...,3,n)."""
+    lc = levi_civita()
+    return np.einsum("abc,...abn->...cn", lc, Om_diag)
+
+
+def mep_niu_CS(A, Om, valence_bands):
+    """mep_niu.f90:20-44 -> (K,3,3,nval): cs(i,i,n0) = 0.5 Re sum_c conj(A(c,n0,n0)) om_c(n0)."""
+    K = A.shape[0]
+    Ad = np.einsum("kcnn->kcn", A)
+    ov = om_vect(np.einsum("kabnn->kabn", Om))
+    sc = 0.5 * np.real(np.einsum("kcn,kcn->kn", np.conj(Ad), ov))[:, :valence_bands]
+    out = np.zeros((K, 3, 3, valence_bands))
+    for i in range(3):
+        out[:, i, i, :] = sc
+    return out
+
+
+def kubo_mep_CS(A, Om, fd):
+    """kubo_mep.f90:16-47 -> (K,3,3,n_eF): all bands, weight f_n0."""
+    K = A.shape[0]
+    Ad = np.einsum("kcnn->kcn", A)
+    ov = om_vect(np.einsum("kabnn->kabn", Om))
+    sc = 0.5 * np.real(np.einsum("kcn,kcn->kn", np.conj(Ad), ov))
+    se = np.einsum("kn,ken->ke", sc, fd)
+    out = np.zeros((K, 3, 3, fd.shape[1]))
+    for i in range(3):
+        out[:, i, i, :] = se
+    return out
+
+
+def kubo_opt_herm_aherm(e, A, hw, fd, eta):
+    """get_hermitian (kubo.f90:272-338) and get_anti_herm (:341-405) -> two (K,3,3,n_hw,n_eF) complex arrays.
+    herm  = -pi sum_{m,n/=m} (f_m - f_n) dE A(i,n,m) A(b,m,n) Im[1 / (pi (dE - i eta) - pi hw)]      (delta_broad :248-269)
+    aherm =  i  sum_{m,n/=m} (f_m - f_n) dE A(i,n,m) A(b,m,n) / real(dE - hw - i eta)                 (real part: eta drops out)"""
+    nw = e.shape[1]
+    dE = e[:, :, None] - e[:, None, :]                                # [k,m,n] = e_m - e_n
+    P = np.einsum("kinm,kbmn->kibmn", A, A) * dE[:, None, None]        # dE A(i,n,m) A(b,m,n)
+    df = fd[:, :, :, None] - fd[:, :, None, :]                        # [k,ef,m,n] = f_m - f_n
+    mask = _offdiag_mask(nw)
+    df = np.where(mask[None, None], df, 0.0)
+    K = e.shape[0]
+    herm = np.zeros((K, 3, 3, hw.size, fd.shape[1]), dtype=np.complex128)
+    aherm = np.zeros_like(herm)
+    for h in range(hw.size):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            d_broad = np.imag(1.0 / (PI_DP * (dE - 1j * eta) - PI_DP * hw[h]))
+            inv = 1.0 / (dE - hw[h])
+        d_broad = np.where(mask[None], d_broad, 0.0)
+        inv = np.where(mask[None], inv, 0.0)
+        herm[:, :, :, h, :] = -PI_DP * np.einsum("kibmn,kmn,kemn->kibe", P, d_broad, df)
+        aherm[:, :, :, h, :] = 1j * np.einsum("kibmn,kmn,kemn->kibe", P, inv, df)
+    return herm, aherm
+
+
+def kubo_opt_tens(herm, aherm):
+    """kubo.f90:225-233: opt_symm = Re(herm) + i Im(aherm) (12.14), opt_asymm = Re(aherm) + i Im(herm) (12.15).  Applied per k in
+    the reference; Re / Im are linear, so it is applied to the k-sums here."""
+    return herm.real + 1j * aherm.imag, aherm.real + 1j * herm.imag
+
+
+def fd_stat_deriv(fd):
+    """d1_fd_stat_deriv (statistics.f90:161-197) AS CODED: 1 / (2 + 2 cosh(f)) evaluated on the OCCUPATIONS f, not on
+    (E - E_F)/kT (the commented w90 formula); core.f90:248 calls this variant.  Reproduced literally."""
+    return 1.0 / (2.0 + 2.0 * np.cosh(fd))
+
+
+def get_kubo_curv(e, V, kubo_tol):
+    """wann_interp.f90:113-147: curv(i,j,n) = -2 sum_{np/=n} Im[V(i,n,np) V(j,np,n)] / (e_np - e_n)^2, terms with dE^2 < kubo_tol skipped."""
+    nw = e.shape[1]
+    dE2 = (e[:, None, :] - e[:, :, None]) ** 2                        # [k,n,np]
+    W = np.imag(np.einsum("kinp,kjpn->kijnp", V, V))
+    ok = ~(np.abs(dE2) < kubo_tol) & _offdiag_mask(nw)[None]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        T = np.where(ok[:, None, None], W / dE2[:, None, None], 0.0)
+    return (-2.0 * T.sum(axis=-1)).astype(np.complex128)              # (k,i,j,n)
+
+
+def gyro_C(V, fdd):
+    """gyro.f90:200-232 -> (K,3,3,n_eF) complex: C(a,b) = sum_n V(a,n,n) V(b,n,n) f'_n."""
+    Vd = np.einsum("kann->kan", V)
+    return np.einsum("kan,kbn,ken->kabe", Vd, Vd, fdd)
+
+
+def gyro_D(e, V, Om, fdd, kubo_tol):
+    """gyro.f90:74-150 -> (K,3,3,n_eF) complex: D(a,b) = - sum_n V(a,n,n) om_b(n) f'_n, om from Om_kab(:,:,n,n) or from the
+    Kubo curvature (get_kubo_curv) when no position operator is present."""
+    curv = np.einsum("kabnn->kabn", Om) if Om is not None else get_kubo_curv(e, V, kubo_tol)
+    ov = om_vect(curv)                                                # (k,3,n)
+    Vd = np.einsum("kann->kan", V)
+    return -np.einsum("kan,kbn,ken->kabe", Vd, ov, fdd)
+
+
+def gyro_Dw(e, V, A, hw, fdd):
+    """gyro.f90:153-197,235-268 -> (K,3,3,n_hw,n_eF) complex; zero without A.  om~(b,hw,n) = - sum_{m/=n} Im[A(:,n,m) x A(:,m,n)]_b
+    w_mn^2 / (w_mn^2 - hw) with w_mn^2 = (e_m - e_n)^2 (hw NOT squared, as coded :262)."""
+    K, nw = e.shape
+    out = np.zeros((K, 3, 3, hw.size, fdd.shape[1]), dtype=np.complex128)
+    if A is None:
+        return out
+    ww = (e[:, None, :] - e[:, :, None]) ** 2                         # [k,n,m]
+    cr = np.imag(np.cross(A, np.swapaxes(A, -1, -2), axis=1))         # Im[A(:,n,m) x A(:,m,n)] (k,3,n,m)
+    mask = _offdiag_mask(nw)
+    Vd = np.einsum("kann->kan", V)
+    for h in range(hw.size):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            w = np.where(mask[None], ww / (ww - hw[h]), 0.0)
+        om_t = -np.einsum("kbnm,knm->kbn", cr, w)
+        out[:, :, :, h, :] = -np.einsum("kan,kbn,ken->kabe", Vd, om_t, fdd)
+    return out
 
 
 def get_wann_interp(model: Model, kpts: np.ndarray, do_gauge_trafo=True, use_cart_velo=False):
@@ -517,9 +803,11 @@ class Partials:
         return self
 
 
-def band_sums(p: Params, e: np.ndarray, V: np.ndarray, part: Optional[Partials] = None, mag: bool = False) -> Partials:
-    """The per-k response functions of core.f90:187-253 on a batch of eigenpairs e (K,nw), V (K,3,nw,nw), summed over the
-    batch into `part`.  mag=True: every term replaced by its magnitude (test yardstick, see kubo_ahc_tens)."""
+def band_sums(p: Params, e: np.ndarray, V: np.ndarray, part: Optional[Partials] = None, mag: bool = False,
+              A: Optional[np.ndarray] = None, Om: Optional[np.ndarray] = None) -> Partials:
+    """The per-k response functions of core.f90:187-253 on a batch of eigenpairs e (K,nw), V (K,3,nw,nw) (and, with a position
+    operator, the H-gauge connection A (K,3,nw,nw) and curvature Om (K,3,3,nw,nw)), summed over the batch into `part`.
+    mag=True: every term replaced by its magnitude (test yardstick, see kubo_ahc_tens)."""
     ef_lst = get_linspace(p.eF_min, p.eF_max, p.n_eF)                # core.f90:124
     hw_lst = get_linspace(p.hw_min, p.hw_max, p.n_hw)                # :125
     if part is None:
@@ -533,19 +821,76 @@ def band_sums(p: Params, e: np.ndarray, V: np.ndarray, part: Optional[Partials] 
     fd = fd_stat(e, ef_lst, p.T_kelvin)                              # (K, n_eF, nw)
     part.Ne += fd.sum(axis=(0, 2))                                   # core.f90:187
     part.n_k += e.shape[0]
+    ab = np.abs if mag else (lambda x: x)
     if p.do_mep:                                                     # :198-202
         add("mep_bands_ic", mep_niu_IC(e, V, p.valence_bands, p.kubo_tol, mag))
         add("mep_bands_lc", mep_niu_LC(e, V, p.valence_bands, p.kubo_tol, mag))
+        if A is not None:
+            add("mep_bands_cs", mep_niu_CS(ab(A), ab(Om), p.valence_bands) if not mag else _cs_mag(A, Om, None)[..., :p.valence_bands])
     if p.do_kubo:                                                    # :207-216
         add("kubo_mep_ic", kubo_mep_IC(e, V, fd, mag))
         add("kubo_mep_lc", kubo_mep_LC(e, V, fd, mag))
+        if A is not None:
+            add("kubo_mep_cs", kubo_mep_CS(A, Om, fd) if not mag else _cs_mag(A, Om, fd))
     if p.do_ahc:                                                     # :221-230
         add("kubo_ahc", kubo_ahc_tens(e, V, fd, mag))
         add("velo_ahc", velo_ahc_tens(e, V, hw_lst, fd, p.eta, mag))
         add("kubo_ohc", kubo_ohc_tens(e, V, hw_lst, fd, p.eta, mag))
     if p.do_opt:                                                     # :235-242 (kubo_opt_tens == 0 without A_ka)
         add("photo2", photo_2nd_cond(e, V, hw_lst, fd, p.eta, mag))
+        if A is not None:
+            if mag:
+                hm, ah = _opt_mag(e, A, hw_lst, fd, p.eta)
+            else:
+                hm, ah = kubo_opt_herm_aherm(e, A, hw_lst, fd, p.eta)
+            add("opt_herm", hm); add("opt_aherm", ah)
+    if p.do_gyro:                                                    # :247-253
+        fdd = fd_stat_deriv(fd)
+        if mag:
+            Va = np.abs(V)
+            add("gyro_C", gyro_C(Va, fdd).astype(np.complex128))
+            curv = np.abs(np.einsum("kabnn->kabn", Om)) if Om is not None else np.abs(get_kubo_curv(e, V, p.kubo_tol))
+            Vd = np.einsum("kann->kan", Va)
+            add("gyro_D", np.einsum("kan,kbn,ken->kabe", Vd, np.einsum("abc,kabn->kcn", np.abs(levi_civita()), curv), fdd).astype(np.complex128))
+            add("gyro_Dw", np.abs(gyro_Dw(e, V, A, hw_lst, fdd)))
+        else:
+            add("gyro_C", gyro_C(V, fdd))
+            add("gyro_D", gyro_D(e, V, Om, fdd, p.kubo_tol))
+            add("gyro_Dw", gyro_Dw(e, V, A, hw_lst, fdd))
     return part
+
+
+def _cs_mag(A, Om, fd):
+    """sum |term| yardstick of the Chern-Simons sums: per band (fd None) (K,3,3,nw) or Fermi weighted (K,3,3,n_eF)."""
+    Ad = np.abs(np.einsum("kcnn->kcn", A))
+    ov = np.einsum("abc,kabn->kcn", np.abs(levi_civita()), np.abs(np.einsum("kabnn->kabn", Om)))
+    sc = 0.5 * np.einsum("kcn,kcn->kn", Ad, ov)
+    if fd is not None:
+        sc = np.einsum("kn,ken->ke", sc, fd)
+    out = np.zeros((A.shape[0], 3, 3, sc.shape[1]))
+    for i in range(3):
+        out[:, i, i, :] = sc
+    return out
+
+
+def _opt_mag(e, A, hw, fd, eta):
+    nw = e.shape[1]
+    dE = e[:, :, None] - e[:, None, :]
+    P = np.abs(np.einsum("kinm,kbmn->kibmn", A, A) * dE[:, None, None])
+    mask = _offdiag_mask(nw)
+    df = np.abs(np.where(mask[None, None], fd[:, :, :, None] - fd[:, :, None, :], 0.0))
+    K = e.shape[0]
+    hm = np.zeros((K, 3, 3, hw.size, fd.shape[1]), dtype=np.complex128)
+    ah = np.zeros_like(hm)
+    for h in range(hw.size):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            d_broad = np.abs(np.imag(1.0 / (PI_DP * (dE - 1j * eta) - PI_DP * hw[h])))
+            inv = np.abs(1.0 / (dE - hw[h]))
+        d_broad = np.where(mask[None], d_broad, 0.0)
+        inv = np.where(mask[None], inv, 0.0)
+        hm[:, :, :, h, :] = PI_DP * np.einsum("kibmn,kmn,kemn->kibe", P, d_broad, df)
+        ah[:, :, :, h, :] = np.einsum("kibmn,kmn,kemn->kibe", P, inv, df)
+    return hm, ah
 
 
 def accumulate(model: Model, p: Params, lin_begin: int, lin_end: int, batch: int = 2048) -> Partials:
@@ -554,20 +899,21 @@ def accumulate(model: Model, p: Params, lin_begin: int, lin_end: int, batch: int
     for b0 in range(lin_begin, lin_end, batch):
         b1 = min(lin_end, b0 + batch)
         kpts = mesh_kpts(p.mp_grid, b0, b1)
-        e, V, _ = get_wann_interp(model, kpts, p.do_gauge_trafo, p.use_cart_velo)
-        band_sums(p, e, V, part)
+        if model.r is not None:
+            e, V, A, Om, _ = get_wann_interp_pos(model, kpts, p.do_gauge_trafo, p.use_cart_velo, p.kubo_tol, p.posop_mode)
+            band_sums(p, e, V, part, A=A, Om=Om)
+        else:
+            e, V, _ = get_wann_interp(model, kpts, p.do_gauge_trafo, p.use_cart_velo)
+            band_sums(p, e, V, part)
     return part
 
 
 def pack_partials(p: Params, part: Partials, nw: int) -> np.ndarray:
-    """Partials -> the packed FP64 buffer of include/mepb.h / oracle/cpu_ref.c (same order; complex = re, im)."""
+    """Partials -> the packed FP64 buffer of include/mepb.h / oracle/cpu_ref.c (same order; complex = re, im).  The position-
+    operator blocks (Chern-Simons scalars per band / per E_F, opt herm / aherm) follow the photo block when present; the gyro
+    blocks come last."""
     a = part.arrays
     out = [np.array([float(part.n_k), 0.0]), np.asarray(part.Ne, dtype=np.float64)]
-
-    def put(x):
-        x = np.asarray(x)
-        x = np.asfortranarray(x)
-        out.append(x.view(np.float64).ravel(order="K") if np.iscomplexobj(x) else x.ravel(order="F"))
 
     def putc(x):                                                     # complex, Fortran order, interleaved
         x = np.asarray(x, dtype=np.complex128).ravel(order="F")
@@ -581,6 +927,14 @@ def pack_partials(p: Params, part: Partials, nw: int) -> np.ndarray:
         out.append(np.asarray(a["kubo_ahc"]).ravel(order="F")); putc(a["velo_ahc"]); putc(a["kubo_ohc"])
     if p.do_opt:
         putc(a["photo2"])
+    if "mep_bands_cs" in a:
+        out.append(np.asarray(a["mep_bands_cs"])[0, 0, :])           # the scalar per band (cs(i,i,n0), i = 1..3 identical)
+    if "kubo_mep_cs" in a:
+        out.append(np.asarray(a["kubo_mep_cs"])[0, 0, :])
+    if "opt_herm" in a:
+        putc(a["opt_herm"]); putc(a["opt_aherm"])
+    if p.do_gyro:
+        putc(a["gyro_C"]); putc(a["gyro_D"]); putc(a["gyro_Dw"])
     return np.concatenate(out)
 
 
@@ -610,23 +964,32 @@ def finalize(model: Model, p: Params, part: Partials) -> dict:
         ic, lc = a["mep_bands_ic"], a["mep_bands_lc"]                 # (3,3,nval)
         out["mep_ic"] = ic.sum(axis=-1) / norm
         out["mep_lc"] = lc.sum(axis=-1) / norm
-        out["mep_cs"] = np.zeros((3, 3))
+        out["mep_cs"] = a["mep_bands_cs"].sum(axis=-1) / norm if "mep_bands_cs" in a else np.zeros((3, 3))
         out["mep_tens"] = out["mep_ic"] + out["mep_lc"] + out["mep_cs"]     # file_io.f90 write_mep_tensors
         if p.do_write_mep_bands:
-            out["mep_bands"] = (ic + lc) / norm
+            out["mep_bands"] = (ic + lc + (a["mep_bands_cs"] if "mep_bands_cs" in a else 0.0)) / norm     # core.f90:591-599
     if p.do_kubo:
         out["kubo_mep_ic"] = a["kubo_mep_ic"][:, :, eF_idx] / norm
         out["kubo_mep_lc"] = a["kubo_mep_lc"][:, :, eF_idx] / norm
-        out["kubo_mep_cs"] = np.zeros((3, 3))
+        out["kubo_mep_cs"] = a["kubo_mep_cs"][:, :, eF_idx] / norm if "kubo_mep_cs" in a else np.zeros((3, 3))
         out["kubo_mep_tens"] = out["kubo_mep_ic"] + out["kubo_mep_lc"] + out["kubo_mep_cs"]
     if p.do_ahc:
         out["ahc_tens"] = a["kubo_ahc"][:, :, eF_idx] / norm
         out["ahcVELO"] = a["velo_ahc"][:, :, :, eF_idx] / norm
         out["ohcVELO"] = a["kubo_ohc"][:, :, :, eF_idx] / norm
     if p.do_opt:
-        out["opt_Ssymm"] = np.zeros((3, 3, p.n_hw), dtype=np.complex128)
-        out["opt_Asymm"] = np.zeros((3, 3, p.n_hw), dtype=np.complex128)
+        if "opt_herm" in a:
+            S, As = kubo_opt_tens(a["opt_herm"], a["opt_aherm"])
+            out["opt_Ssymm"] = S[:, :, :, eF_idx] / norm             # sliced at eF_idx (core.f90:510-511)
+            out["opt_Asymm"] = As[:, :, :, eF_idx] / norm
+        else:
+            out["opt_Ssymm"] = np.zeros((3, 3, p.n_hw), dtype=np.complex128)
+            out["opt_Asymm"] = np.zeros((3, 3, p.n_hw), dtype=np.complex128)
         out["photoC_2nd"] = a["photo2"] / norm                        # not sliced at eF_idx (core.f90:515)
+    if p.do_gyro:                                                     # all Fermi levels are written (core.f90:523-530)
+        out["gyro_C"] = a["gyro_C"] / norm
+        out["gyro_D"] = a["gyro_D"] / norm
+        out["gyro_Dw"] = a["gyro_Dw"] / norm
     return out
 
 

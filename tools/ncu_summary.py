@@ -57,7 +57,7 @@ def raw(rep, pat=None):
                 print(f"   {w:70s} {r[i]:>18s} {units[i]}")
 
 
-def lines(rep, sass, func, src, top=40, kernel=None):
+def lines(rep, sass, func, src, top=40, kernel=None, by="inst"):
     """kernel: regex on the (demangled) kernel name of the report; default = first captured launch"""
     top = int(top)
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
@@ -96,7 +96,8 @@ def lines(rep, sass, func, src, top=40, kernel=None):
     text = open(src).read().splitlines()
     base = src.split("/")[-1]
     print(f"# total warp instructions executed {tot}, stall samples {tots}")
-    for (f, l), v in sorted(agg.items(), key=lambda x: -x[1])[:top]:
+    order = sorted(agg.items(), key=lambda x: -x[1]) if by == "inst" else sorted(agg.items(), key=lambda x: -smp[x[0]])
+    for (f, l), v in order[:top]:
         code = text[l - 1].strip()[:90] if f and f.endswith(base) and l <= len(text) else (f or "?").split("/")[-1]
         print(f"{100 * v / tot:6.2f}% inst {100 * smp[(f, l)] / tots:6.2f}% samples  line {l:4d}  {code}")
 
