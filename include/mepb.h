@@ -146,6 +146,12 @@ void      mepb_multi_destroy(mepb_multi *mm);
  * V_ka is gauge dependent (eigenvector phases); compare only gauge-invariant combinations. */
 int mepb_interp(mepb_ctx *ctx, int64_t nk, const double *kpt, double *e_k, double *V_ka);
 
+/* get_wann_interp on a k list with the outputs of the position-operator branch (wann_interp.f90:56-108, 465-658): e_k (nw,nk);
+ * V_ka (3,nw,nw,nk) velocities including the connection term; A_ka (3,nw,nw,nk) Berry connection in the Hamiltonian gauge;
+ * Om_vec (3,nw,nk) the curvature pseudo-vector sum_ab eps_abc Om_ab(n,n) of every band (convert_tens_to_vect of the only part of
+ * Om_kab the response functions read, matrix_math.f90:511-529).  Any pointer may be NULL.  Needs model.r (or do_gyro). */
+int mepb_interp_pos(mepb_ctx *ctx, int64_t nk, const double *kpt, double *e_k, double *V_ka, double *A_ka, double *Om_vec);
+
 /* Fourier sums only (FT_R_to_k, wann_interp.f90:151-281): H_k (nw,nw,nk), H_ka (3,nw,nw,nk) complex, W gauge.
  * Gauge independent, so it is compared element-wise against the oracle. */
 int mepb_fourier(mepb_ctx *ctx, int64_t nk, const double *kpt, double *H_k, double *H_ka);
@@ -197,7 +203,8 @@ int mepb_timer_stop(mepb_ctx *ctx, double *ms);
 #define MEPB_PROF_TRIDIAG      7   /* Householder tridiagonalisation, general path                     */
 #define MEPB_PROF_TQL          8   /* thread-per-k implicit QL on the tridiagonal (rotation log)       */
 #define MEPB_PROF_ZROT         9   /* replay of the rotation log -> eigenvectors of the tridiagonal    */
-#define MEPB_PROF_KINDS        10
+#define MEPB_PROF_POSOP        10  /* position-operator branch: A / Om Fourier sums, gauge transformation, CS / opt / gyro sums */
+#define MEPB_PROF_KINDS        11
 int mepb_set_profiling(mepb_ctx *ctx, int on);
 int mepb_get_profile(const mepb_ctx *ctx, int kind, double *ms_total, int64_t *launches);
 /* (k, band pair) items the last packed run handed to the frequency sweep `kind` (MEPB_PROF_SWEEP_AHC / _PHOTO): the

@@ -24,7 +24,7 @@ EXPORTS = ["mepb_create", "mepb_destroy", "mepb_run_mesh", "mepb_reset", "mepb_a
            "mepb_allreduce_partials", "mepb_get_timing", "mepb_create_multi", "mepb_multi_run_mesh", "mepb_multi_update_model",
            "mepb_multi_size", "mepb_multi_ctx", "mepb_multi_destroy", "mepb_partials_size",
            "mepb_get_partials", "mepb_set_partials", "mepb_partials_device_ptr", "mepb_finalize", "mepb_interp",
-           "mepb_fourier", "mepb_fourier_mesh", "mepb_band_sums", "mepb_update_model", "mepb_update_params", "mepb_model_info", "mepb_timer_start", "mepb_timer_stop", "mepb_set_profiling",
+           "mepb_interp_pos", "mepb_fourier", "mepb_fourier_mesh", "mepb_band_sums", "mepb_update_model", "mepb_update_params", "mepb_model_info", "mepb_timer_start", "mepb_timer_stop", "mepb_set_profiling",
            "mepb_get_profile", "mepb_work_items", "mepb_last_kernel_ms", "mepb_kernel_launches", "mepb_strerror", "mepb_last_error", "mepb_version"]
 
 
@@ -96,6 +96,7 @@ def lib():
         L.mepb_partials_device_ptr.argtypes = [vp, C.POINTER(vp)]
         L.mepb_finalize.argtypes = [vp, C.POINTER(CResult)]
         L.mepb_interp.argtypes = [vp, C.c_int64, vp, vp, vp]
+        L.mepb_interp_pos.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp]
         L.mepb_fourier.argtypes = [vp, C.c_int64, vp, vp, vp]
         L.mepb_fourier_mesh.argtypes = [vp, C.c_int64, C.c_int64, vp, vp]
         L.mepb_band_sums.argtypes = [vp, C.c_int64, vp, vp]
@@ -134,16 +135,20 @@ def make_params(**kw) -> SimpleNamespace:
     """Parameter bundle with the reference's names (src/input_paras.f90:49-68), energies already in Hartree."""
     d = dict(mp_grid=(4, 4, 4), do_gauge_trafo=True, use_cart_velo=False, do_mep=False, do_kubo=False, do_ahc=False,
              do_opt=False, do_write_mep_bands=True, valence_bands=1, n_hw=1, n_eF=1, hw_min=0.0, hw_max=0.0,
-             eF_min=0.0, eF_max=0.0, T_kelvin=0.0, eta=0.0, kubo_tol=1e-5)
+             eF_min=0.0, eF_max=0.0, T_kelvin=0.0, eta=0.0, kubo_tol=1e-5, do_gyro=False, posop_mode="paper")
     d.update(kw)
     return SimpleNamespace(**d)
 
 
-def make_model(R, H, a_latt, wf_centers=None) -> SimpleNamespace:
-    """R (3,nR) fractional; H (nw,nw,nR) complex Hartree; a_latt (3,3) rows = a_i; wf_centers (3,nw) or None."""
+def make_model(R, H, a_latt, wf_centers=None, r=None) -> SimpleNamespace:
+    """R (3,nR) fractional; H (nw,nw,nR) complex Hartree; a_latt (3,3) rows = a_i; wf_centers (3,nw) or None;
+    r (3,nw,nw,nR) complex position operator in Bohr or None."""
     H = np.asarray(H)
     return SimpleNamespace(nw=H.shape[0], nR=H.shape[2], R=np.asarray(R, dtype=np.float64), H=H,
-                           a_latt=np.asarray(a_latt, dtype=np.float64), wf_centers=wf_centers)
+                           a_latt=np.asarray(a_latt, dtype=np.float64), wf_centers=wf_centers, r=r)
+
+
+POSOP_MODES = {"paper": 0, "coded": 1, 0: 0, 1: 1}
 
 
 def comm_unique_id() -> bytes:
@@ -163,7 +168,10 @@ class _Marshal:
         self._wfc = None if model.wf_centers is None else _f(model.wf_centers, np.float64)
         m = CModel()
         m.nw, m.nR = self.nw, self.nR
-        m.R, m.H, m.r = self._R.ctypes.data, self._H.ctypes.data, None
+        self._r = None if getattr(model, "r", None) is None else _f(model.r, np.complex128)
+        if self._r is not None and self._r.shape != (3, self.nw, self.nw, self.nR):
+            raise ValueError("position operator must be (3, nw, nw, nR)")
+        m.R, m.H, m.r = self._R.ctypes.data, self._H.ctypes.data, (None if self._r is None else self._r.ctypes.data)
         m.wf_centers = None if self._wfc is None else self._wfc.ctypes.data
         al = np.asarray(model.a_latt, dtype=np.float64)
         for j in range(3):
@@ -177,6 +185,8 @@ class _Marshal:
         p.valence_bands, p.n_hw, p.n_eF = int(params.valence_bands), int(params.n_hw), int(params.n_eF)
         for k in ("hw_min", "hw_max", "eF_min", "eF_max", "T_kelvin", "eta", "kubo_tol"):
             setattr(p, k, float(getattr(params, k)))
+        p.do_gyro = int(bool(getattr(params, "do_gyro", False)))
+        p.posop_mode = POSOP_MODES[getattr(params, "posop_mode", "paper")]
         self.cm, self.cp, self.params = m, p, params
 
     def _result(self, call) -> dict:
@@ -199,13 +209,17 @@ class _Marshal:
             bufs["opt_s"] = np.zeros((3, 3, n_hw), dtype=np.complex128, order="F")
             bufs["opt_a"] = np.zeros((3, 3, n_hw), dtype=np.complex128, order="F")
             bufs["photo2"] = np.zeros((3, 3, 3, n_hw, n_eF), dtype=np.complex128, order="F")
+        if getattr(P, "do_gyro", False):
+            bufs["gyro_c"] = np.zeros((3, 3, n_eF), dtype=np.complex128, order="F")
+            bufs["gyro_d"] = np.zeros((3, 3, n_eF), dtype=np.complex128, order="F")
+            bufs["gyro_dw"] = np.zeros((3, 3, n_hw, n_eF), dtype=np.complex128, order="F")
         res = CResult()
         for k, v in bufs.items():
             setattr(res, k, v.ctypes.data)
         _check(call(res))
         out = {"n_k": int(res.n_k), "eF_idx": int(res.eF_idx), "n_degenerate": int(res.n_degenerate), "Ne": bufs["Ne"]}
-        names = {"ahc": "ahc_tens", "ahc_velo": "ahcVELO", "ohc_velo": "ohcVELO", "opt_s": "opt_Ssymm",
-                 "opt_a": "opt_Asymm", "photo2": "photoC_2nd"}     # file names of file_io.f90:266-398
+        names = {"ahc": "ahc_tens", "ahc_velo": "ahcVELO", "ohc_velo": "ohcVELO", "opt_s": "opt_Ssymm", "opt_a": "opt_Asymm",
+                 "photo2": "photoC_2nd", "gyro_c": "gyro_C", "gyro_d": "gyro_D", "gyro_dw": "gyro_Dw"}     # file names of file_io.f90:266-398
         for k, v in bufs.items():
             if k != "Ne":
                 out[names.get(k, k)] = v
@@ -345,6 +359,18 @@ class Context(_Marshal):
         _check(lib().mepb_interp(self._h, nk, kp.ctypes.data, e.ctypes.data, None if V is None else V.ctypes.data))
         return e, V
 
+    def interp_pos(self, kpts):
+        """get_wann_interp with a position operator: e (nw,nk), V (3,nw,nw,nk) connection-corrected, A (3,nw,nw,nk) H gauge,
+        om (3,nw,nk) curvature pseudo-vector per band."""
+        kp = _f(np.asarray(kpts, dtype=np.float64).T, np.float64)
+        nk, nw = kp.shape[1], self.nw
+        e = np.zeros((nw, nk), order="F")
+        V = np.zeros((3, nw, nw, nk), dtype=np.complex128, order="F")
+        A = np.zeros((3, nw, nw, nk), dtype=np.complex128, order="F")
+        om = np.zeros((3, nw, nk), dtype=np.complex128, order="F")
+        _check(lib().mepb_interp_pos(self._h, nk, kp.ctypes.data, e.ctypes.data, V.ctypes.data, A.ctypes.data, om.ctypes.data))
+        return e, V, A, om
+
     def fourier(self, kpts):
         kp = _f(np.asarray(kpts, dtype=np.float64).T, np.float64)
         nk, nw = kp.shape[1], self.nw
@@ -368,11 +394,15 @@ class Context(_Marshal):
         assert e.shape[0] == self.nw and V.shape == (3, self.nw, self.nw, e.shape[1])
         _check(lib().mepb_band_sums(self._h, e.shape[1], e.ctypes.data, V.ctypes.data))
 
-    def update_model(self, H):
-        """Re-upload H(R) (nw,nw,nR complex, Hartree) from host memory; same R set and FT convention."""
+    def update_model(self, H, r=None):
+        """Re-upload H(R) (nw,nw,nR complex, Hartree) from host memory (and r(R) for a position-operator context; kept when None);
+        same R set and FT convention."""
         self._H = _f(H, np.complex128)
         assert self._H.shape == (self.nw, self.nw, self.nR)
         self.cm.H = self._H.ctypes.data
+        if r is not None:
+            self._r = _f(r, np.complex128)
+            self.cm.r = self._r.ctypes.data
         _check(lib().mepb_update_model(self._h, C.byref(self.cm)))
 
     def update_params(self, **kw):
@@ -391,6 +421,8 @@ class Context(_Marshal):
             p.mp_grid[i] = int(P.mp_grid[i])
         for k in ("do_gauge_trafo", "use_cart_velo", "do_mep", "do_kubo", "do_ahc", "do_opt", "do_write_mep_bands"):
             setattr(p, k, int(bool(getattr(P, k))))
+        p.do_gyro = int(bool(getattr(P, "do_gyro", False)))
+        p.posop_mode = POSOP_MODES[getattr(P, "posop_mode", "paper")]
         _check(lib().mepb_update_params(self._h, C.byref(p)))
         self.cp, self.params = p, P
 
@@ -409,7 +441,7 @@ class Context(_Marshal):
         _check(lib().mepb_timer_stop(self._h, C.byref(ms)))
         return float(ms.value)
 
-    PROF_KINDS = ("interp", "sweep_ahc", "sweep_photo", "reduce", "eig", "fourier", "eig_rot", "tridiag", "tql", "zrot")
+    PROF_KINDS = ("interp", "sweep_ahc", "sweep_photo", "reduce", "eig", "fourier", "eig_rot", "tridiag", "tql", "zrot", "posop")
 
     def set_profiling(self, on: bool):
         _check(lib().mepb_set_profiling(self._h, int(bool(on))))

@@ -89,6 +89,31 @@ __global__ void pack_kernel(const double *__restrict__ c0, const double *__restr
             packed[L.photo + i] = C(ief, cs.ns + cs.sweep + w * kPhotoAcc + 2 * q + ri);
         }
     }
+    // position-operator row of the compact block (mepb_posop.cu): [nval CS per band | CS kubo | n_hw x 36 opt | C 18 | D 18 | n_hw x 18 Dw]
+    const int po = cs.ns + cs.sweep + cs.photo;
+    if (L.mep_cs >= 0) for (int i = tid; i < nval; i += nth) packed[L.mep_cs + i] = C(0, po + i);
+    if (L.kmep_cs >= 0) for (int i = tid; i < n_eF; i += nth) packed[L.kmep_cs + i] = C(i, po + nval);
+    if (L.opt_h >= 0) {
+        const long long per = 18LL * n_hw;
+        for (long long i = tid; i < per * n_eF; i += nth) {
+            const int ief = (int)(i / per);
+            const long long r = i % per;                                  // (q + 9 w)*2 + ri
+            const int ri = (int)(r & 1), q = (int)((r >> 1) % 9), w = (int)((r >> 1) / 9);
+            packed[L.opt_h + i] = C(ief, po + nval + 1 + 36 * w + 2 * q + ri);
+            packed[L.opt_ah + i] = C(ief, po + nval + 1 + 36 * w + 18 + 2 * q + ri);
+        }
+    }
+    if (L.gyro_c >= 0) {
+        const int go = po + nval + 1 + 36 * n_hw;
+        for (int i = tid; i < 18 * n_eF; i += nth) { packed[L.gyro_c + i] = C(i / 18, go + i % 18); packed[L.gyro_d + i] = C(i / 18, go + 18 + i % 18); }
+        const long long per = 18LL * n_hw;
+        for (long long i = tid; i < per * n_eF; i += nth) {
+            const int ief = (int)(i / per);
+            const long long r = i % per;
+            const int ri = (int)(r & 1), q = (int)((r >> 1) % 9), w = (int)((r >> 1) / 9);
+            packed[L.gyro_dw + i] = C(ief, go + 36 + 18 * w + 2 * q + ri);
+        }
+    }
 }
 
 }  // namespace
@@ -149,6 +174,30 @@ bool hermitian_closed(const mepb_model *m, std::string *why) {
                     return false;
                 }
             }
+    }
+    return true;
+}
+
+// r(-R)(a,m,n) == conj r(R)(a,n,m) for every R?  (then A_a(k) is Hermitian in the W gauge and stays so in the H gauge)
+bool position_closed(const mepb_model *m) {
+    const int nw = m->nw, nR = m->nR;
+    double rmax = 0.0;
+    for (long long i = 0; i < 6LL * nw * nw * nR; ++i) rmax = std::max(rmax, std::fabs(m->r[i]));
+    const double tol = 4e-16 * std::max(rmax, 1e-300);
+    for (int r = 0; r < nR; ++r) {
+        int partner = -1;
+        for (int s = 0; s < nR; ++s)
+            if (std::fabs(m->R[3 * r] + m->R[3 * s]) < 1e-9 && std::fabs(m->R[3 * r + 1] + m->R[3 * s + 1]) < 1e-9 &&
+                std::fabs(m->R[3 * r + 2] + m->R[3 * s + 2]) < 1e-9) { partner = s; break; }
+        const double *a = m->r + 6LL * nw * nw * r;
+        for (int mm = 0; mm < nw; ++mm)
+            for (int n = 0; n < nw; ++n)
+                for (int x = 0; x < 3; ++x) {
+                    const double *p1 = a + 2 * (x + 3 * ((long long)n + (long long)nw * mm));
+                    if (partner < 0) { if (std::fabs(p1[0]) > tol || std::fabs(p1[1]) > tol) return false; continue; }
+                    const double *p2 = m->r + 6LL * nw * nw * partner + 2 * (x + 3 * ((long long)mm + (long long)nw * n));
+                    if (std::fabs(p1[0] - p2[0]) > tol || std::fabs(p1[1] + p2[1]) > tol) return false;
+                }
     }
     return true;
 }
@@ -345,10 +394,13 @@ void free_all(mepb_ctx *c) {
         cudaFree(s.tb.Vr); cudaFree(s.tb.tau); cudaFree(s.tb.d); cudaFree(s.tb.e); cudaFree(s.tb.E); cudaFree(s.tb.rank);
         cudaFree(s.tb.hdr); cudaFree(s.tb.nhdr); cudaFree(s.tb.log); cudaFree(s.tb.Z);
         cudaFree(s.G1); cudaFree(s.G2);
+        for (int a = 0; a < 3; ++a) { cudaFree(s.Aw[a]); cudaFree(s.dA[a]); }
+        cudaFree(s.pE); cudaFree(s.pU); cudaFree(s.pV); cudaFree(s.pAH); cudaFree(s.pOmV); cudaFree(s.pScr); cudaFree(s.prow);
         if (s.st) cudaStreamDestroy(s.st);
         if (s.done) cudaEventDestroy(s.done);
     }
     cudaFree(c->d_packed); cudaFree(c->d_err);
+    cudaFree(c->d_r); for (int a = 0; a < 3; ++a) cudaFree(c->d_Hp_r[a]);
     cudaFree(c->d_map3); cudaFree(c->d_ra); cudaFree(c->d_P1); cudaFree(c->d_P2); cudaFree(c->d_P3); cudaFree(c->d_cw4);
     cudaFree(c->d_ridx); cudaFree(c->d_elem); cudaFree(c->d_Hp); cudaFree(c->d_Rfp); cudaFree(c->d_cRp); cudaFree(c->d_Hka_int);
     cudaFree(c->d_kpt); cudaFree(c->d_e); cudaFree(c->d_V); cudaFree(c->d_Hk); cudaFree(c->d_Hka);
@@ -413,8 +465,8 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
     if (!model || !params || !out) return fail(MEPB_ERR_ARG, "null argument");
     *out = nullptr;
     if (model->nw < 1 || model->nR < 1 || !model->R || !model->H) return fail(MEPB_ERR_ARG, "bad model");
-    if (model->r) return fail(MEPB_ERR_UNSUPPORTED, "position operator (r_tb) branch is not implemented");
     const mepb_params &p = *params;
+    if (p.posop_mode != 0 && p.posop_mode != 1) return fail(MEPB_ERR_ARG, "posop_mode must be 0 (PRB 74 195118) or 1 (as coded)");
     if (p.mp_grid[0] < 1 || p.mp_grid[1] < 1 || p.mp_grid[2] < 1 || p.n_hw < 1 || p.n_eF < 1)
         return fail(MEPB_ERR_ARG, "bad mp_grid / n_hw / n_eF");
     if ((p.do_mep || p.do_kubo) && (p.valence_bands < 0 || p.valence_bands > model->nw))
@@ -427,7 +479,9 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail(MEPB_ERR_CUDA, "libmepb is built for sm_100a only");
     const char *force = getenv("MEPB_PATH");                  // testing knob: "large" forces the general path
-    const bool want_large = (force && std::string(force) == "large") || !small_supported(model->nw, model->nR);
+    // the Berry-connection branch (and the gyrotropic tensors, which need V and a curvature per band) run on the general path
+    const bool pipe2 = (model->r != nullptr) || p.do_gyro;
+    const bool want_large = pipe2 || (force && std::string(force) == "large") || !small_supported(model->nw, model->nR);
     if (want_large && !large_supported(model->nw))
         return fail(MEPB_ERR_UNSUPPORTED, "num_wann outside the limits of the compiled kernels (2..64)");
 
@@ -435,6 +489,8 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
     c->device = device; c->sm_count = prop.multiProcessorCount;
     c->p = p; c->nw = model->nw; c->nR = model->nR; c->has_tau = (model->wf_centers != nullptr);
     c->herm = hermitian_closed(model, &c->herm_why);
+    c->pos = (model->r != nullptr); c->pipe2 = pipe2;
+    if (c->pos && c->herm && !position_closed(model)) { c->herm = false; c->herm_why = "r(-R)(m,n) != conj(r(R)(n,m))"; }
     c->large = want_large;
     { const char *es = getenv("MEPB_LARGE_EIG"); c->tri = c->large && !(es && std::string(es) == "jacobi"); }
     c->eig_thread = !c->large && eig_thread_supported(model->nw) && !getenv("MEPB_WARP_JACOBI");
@@ -488,7 +544,16 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
     if (p.do_ahc) per_k += sizeof(double) * istr * c->max_pairs + sizeof(int);
     if (p.do_opt) per_k += sizeof(double) * kPhotoItem * c->max_photo + sizeof(int);
     if (c->large) per_k += sizeof(double2) * 4 * (size_t)nw * nw;
+    if (c->pipe2) per_k += sizeof(double2) * ((c->pos ? 12 : 0) + 7) * (size_t)nw * nw + sizeof(double2) * 3 * nw + sizeof(double) * nw;
     if (c->large) { CT(build_fourier_plan(c, model, cR)); CT(build_sep_plan(c, model)); }
+    if (c->pos) {      // r(R): uploaded once, element tiles of its three components packed like H(R)
+        CT(up((void **)&c->d_r, model->r, sizeof(double) * 6 * (size_t)nw * nw * nR));
+        for (int a = 0; a < 3; ++a) {
+            CT(cudaMalloc((void **)&c->d_Hp_r[a], sizeof(double2) * (size_t)c->fp.ntiles * c->fp.nRp * kFourierTN));
+            CT(launch_pack_hp(c->fp, c->d_r, 3, a, nw, nR, c->d_Hp_r[a], 0));
+        }
+        CT(cudaDeviceSynchronize());
+    }
     if (c->sp.on) per_k += sizeof(double2) * (size_t)c->fp.ntiles * c->sp.nrp * kFourierTN / p.mp_grid[0] +
                            sizeof(double2) * 2 * (size_t)c->sp.n1 * c->sp.n2 * c->sp.nelp / ((size_t)p.mp_grid[0] * p.mp_grid[1]);
     const int tne = tri_padded_size(nw);
@@ -515,8 +580,15 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
     c->grid_sweep = sweep_ahc_grid(c->sm_count, chunk, p.n_hw, &c->ns_sweep, c->herm, c->max_pairs);
     c->grid_photo = sweep_photo_grid(c->sm_count, chunk, p.n_hw, &c->ns_photo, c->max_photo);
     c->cs.ns = static_size(nw); c->cs.sweep = p.n_hw * kSweepAcc; c->cs.photo = p.n_hw * kPhotoAcc;
-    c->cs.per_ef = c->cs.ns + c->cs.sweep + c->cs.photo;
-    c->L = make_layout(p);
+    c->pos_row = c->pipe2 ? posop_row_len(p.valence_bands, p.n_hw) : 0;
+    c->cs.pos = c->pos_row;
+    c->cs.per_ef = c->cs.ns + c->cs.sweep + c->cs.photo + c->cs.pos;
+    c->L = make_layout(p, c->pos);
+    if (c->pipe2) {
+        c->grid_pg = posop_gauge_grid(c->sm_count, chunk); c->grid_ps = posop_sums_grid(c->sm_count, chunk);
+        const int hb = posop_hw_block(p.n_hw);
+        c->pos_tiles = (p.n_hw + hb - 1) / hb;
+    }
     for (auto &s : c->sb) {
         CT(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
         CT(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
@@ -558,6 +630,23 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
             CT(cudaMalloc((void **)&t.nhdr, sizeof(int) * 2 * ck));
             CT(cudaMalloc((void **)&t.log, sizeof(double2) * t.log_cap * ck));
             CT(cudaMalloc((void **)&t.Z, sizeof(double) * tne * tne * ck));
+        }
+        if (c->pipe2) {
+            const size_t ck = (size_t)chunk, n2 = (size_t)nw * nw;
+            if (c->pos)
+                for (int a = 0; a < 3; ++a) {
+                    CT(cudaMalloc((void **)&s.Aw[a], sizeof(double2) * n2 * ck));
+                    CT(cudaMalloc((void **)&s.dA[a], sizeof(double2) * 3 * n2 * ck));
+                }
+            CT(cudaMalloc((void **)&s.pE, sizeof(double) * nw * ck));
+            CT(cudaMalloc((void **)&s.pU, sizeof(double2) * n2 * ck));
+            CT(cudaMalloc((void **)&s.pV, sizeof(double2) * 3 * n2 * ck));
+            CT(cudaMalloc((void **)&s.pAH, sizeof(double2) * 3 * n2 * ck));
+            CT(cudaMemset(s.pAH, 0, sizeof(double2) * 3 * n2 * ck));
+            CT(cudaMalloc((void **)&s.pOmV, sizeof(double2) * 3 * nw * ck));
+            CT(cudaMemset(s.pOmV, 0, sizeof(double2) * 3 * nw * ck));
+            CT(cudaMalloc((void **)&s.pScr, sizeof(double2) * 6 * n2 * (size_t)c->grid_pg));
+            CT(cudaMalloc((void **)&s.prow, sizeof(double) * (size_t)c->pos_row * c->grid_ps * c->pos_tiles));
         }
         if (c->eig_thread) {
             CT(cudaMalloc((void **)&s.eig_E, sizeof(double) * nw * (size_t)chunk));
@@ -635,6 +724,25 @@ static int launch_wave(mepb_ctx *c, StreamBuf &s, long long k0, long long nk, co
                 { ProfScope ps(c, s.st, MEPB_PROF_ZROT); CUDA_TRY(launch_zrot(c->nw, nk, s.tb, c->sm_count, s.st)); }
                 c->launches += 3;
             }
+            if (c->pipe2 && !V_in) {
+                // position-operator pipeline: A / dA Fourier sums, eigenvectors to HBM, gauge transformation + velocity correction;
+                // the band sums below then run on (E, V) through the supplied-eigenpair mode of the same kernel
+                if (first_ef) {
+                    ProfScope ps(c, s.st, MEPB_PROF_POSOP);
+                    if (c->pos)
+                        for (int a = 0; a < 3; ++a) {
+                            FourierPlan fr = c->fp; fr.Hp = c->d_Hp_r[a];
+                            CUDA_TRY(launch_fourier_dense(fr, m, ks, s.Aw[a], s.dA[a], s.st));
+                        }
+                    InterpOut o2; std::memset(&o2, 0, sizeof(o2));
+                    o2.e_out = s.pE; o2.U_out = s.pU; o2.err_flag = c->d_err;
+                    CUDA_TRY(launch_eig_rot_large(m, ks, make_jobs(c, 0, false), o2, c->max_pairs, s.Hk, s.Hka, s.Vscr, s.tb, gi, s.st));
+                    CUDA_TRY(launch_posop_gauge(c->nw, nk, p.do_gauge_trafo, p.posop_mode, p.kubo_tol, c->pos, s.pE, s.pU, s.Hka, s.Aw, s.dA,
+                                                s.pV, s.pAH, s.pOmV, s.pScr, posop_gauge_grid(c->sm_count, nk), s.st));
+                    c->launches += 2 + (c->pos ? 3 : 0);
+                }
+                o.e_in = s.pE; o.V_in = s.pV;
+            }
             { ProfScope ps(c, s.st, MEPB_PROF_EIGROT);
               CUDA_TRY(launch_eig_rot_large(m, ks, jb, o, c->max_pairs, s.Hk, s.Hka, s.Vscr, s.tb, gi, s.st)); }
             c->launches += 1;
@@ -673,6 +781,17 @@ static int launch_wave(mepb_ctx *c, StreamBuf &s, long long k0, long long nk, co
             { ProfScope ps(c, s.st, MEPB_PROF_REDUCE);
               CUDA_TRY(launch_reduce_rows(s.block_photo, gs * (nsl / p.n_hw), p.n_hw * kPhotoAcc,
                                           s.compact + (size_t)ief * c->cs.per_ef + ns + c->cs.sweep, kPhotoAcc, kPhotoAcc, 0, s.st)); }
+            c->launches += 2;
+        }
+        if (c->pipe2 && !V_in) {      // sums that need A / Om / the per-band curvature: CS terms, kubo_opt_tens, gyro C / D / Dw
+            const int gp = posop_sums_grid(c->sm_count, nk);
+            const size_t nrows = (size_t)gp * c->pos_tiles;
+            CUDA_TRY(cudaMemsetAsync(s.prow, 0, sizeof(double) * nrows * c->pos_row, s.st));
+            { ProfScope ps(c, s.st, MEPB_PROF_POSOP);
+              CUDA_TRY(launch_posop_sums(c->nw, nk, jb, c->pos, p.do_gyro != 0, p.n_hw, c->d_hw, s.pE, s.pV, s.pAH, s.pOmV, s.prow, gp, s.st)); }
+            { ProfScope ps(c, s.st, MEPB_PROF_REDUCE);
+              CUDA_TRY(launch_reduce_rows(s.prow, (int)nrows, c->pos_row, s.compact + (size_t)ief * c->cs.per_ef + ns + c->cs.sweep + c->cs.photo,
+                                          c->pos_row, c->pos_row, 0, s.st)); }
             c->launches += 2;
         }
     }
@@ -854,16 +973,25 @@ int mepb_finalize(mepb_ctx *c, mepb_result *out) {
             for (int n0 = 0; n0 < nval; ++n0) { ic += h[L.mep_ic + q + 9 * n0]; lc += h[L.mep_lc + q + 9 * n0]; }
             if (out->mep_ic) out->mep_ic[q] = ic / norm;
             if (out->mep_lc) out->mep_lc[q] = lc / norm;
-            if (out->mep_cs) out->mep_cs[q] = 0.0;                      // no position operator: mep_niu.f90:29
+            if (out->mep_cs) {                                          // cs(i,i,n0) summed over n0 <= nval; 0 without A, Om (mep_niu.f90:29)
+                double cs = 0.0;
+                if (L.mep_cs >= 0 && (q == 0 || q == 4 || q == 8)) for (int n0 = 0; n0 < nval; ++n0) cs += h[L.mep_cs + n0];
+                out->mep_cs[q] = cs / norm;
+            }
         }
-        if (out->mep_bands && p.do_write_mep_bands)
-            for (int q = 0; q < 9 * nval; ++q) out->mep_bands[q] = (h[L.mep_ic + q] + h[L.mep_lc + q]) / norm;
+        if (out->mep_bands && p.do_write_mep_bands)                     // ic + lc + cs per band, core.f90:591-599
+            for (int q = 0; q < 9 * nval; ++q) {
+                const int e = q % 9;
+                const double cs = (L.mep_cs >= 0 && (e == 0 || e == 4 || e == 8)) ? h[L.mep_cs + q / 9] : 0.0;
+                out->mep_bands[q] = (h[L.mep_ic + q] + h[L.mep_lc + q] + cs) / norm;
+            }
     }
     if (p.do_kubo)
         for (int q = 0; q < 9; ++q) {
             if (out->kubo_mep_ic) out->kubo_mep_ic[q] = h[L.kmep_ic + q + 9 * opt] / norm;
             if (out->kubo_mep_lc) out->kubo_mep_lc[q] = h[L.kmep_lc + q + 9 * opt] / norm;
-            if (out->kubo_mep_cs) out->kubo_mep_cs[q] = 0.0;            // kubo_mep.f90:28
+            if (out->kubo_mep_cs)                                       // 0 without A, Om (kubo_mep.f90:28)
+                out->kubo_mep_cs[q] = (L.kmep_cs >= 0 && (q == 0 || q == 4 || q == 8)) ? h[L.kmep_cs + opt] / norm : 0.0;
         }
     if (p.do_ahc) {
         if (out->ahc) for (int q = 0; q < 9; ++q) out->ahc[q] = h[L.ahc + q + 9 * opt] / norm;
@@ -873,9 +1001,20 @@ int mepb_finalize(mepb_ctx *c, mepb_result *out) {
     }
     if (p.do_opt) {
         const long long sl = 18LL * n_hw;
-        if (out->opt_s) for (long long q = 0; q < sl; ++q) out->opt_s[q] = 0.0;    // kubo.f90:225 (A_ka not allocated)
-        if (out->opt_a) for (long long q = 0; q < sl; ++q) out->opt_a[q] = 0.0;
+        // kubo.f90:225-233: opt_symm = Re(herm) + i Im(aherm), opt_asymm = Re(aherm) + i Im(herm), sliced at eF_idx (core.f90:510-511);
+        // zeros when A_ka is not allocated (:225)
+        for (long long q = 0; q < sl; q += 2) {
+            double hr = 0, hi = 0, ar = 0, ai = 0;
+            if (L.opt_h >= 0) { hr = h[L.opt_h + q + sl * opt]; hi = h[L.opt_h + q + 1 + sl * opt]; ar = h[L.opt_ah + q + sl * opt]; ai = h[L.opt_ah + q + 1 + sl * opt]; }
+            if (out->opt_s) { out->opt_s[q] = hr / norm; out->opt_s[q + 1] = ai / norm; }
+            if (out->opt_a) { out->opt_a[q] = ar / norm; out->opt_a[q + 1] = hi / norm; }
+        }
         if (out->photo2) for (long long q = 0; q < 54LL * n_hw * n_ef; ++q) out->photo2[q] = h[L.photo + q] / norm;   // core.f90:515
+    }
+    if (p.do_gyro) {                                                    // every trial E_F is written (core.f90:523-530)
+        if (out->gyro_c) for (long long q = 0; q < 18LL * n_ef; ++q) out->gyro_c[q] = h[L.gyro_c + q] / norm;
+        if (out->gyro_d) for (long long q = 0; q < 18LL * n_ef; ++q) out->gyro_d[q] = h[L.gyro_d + q] / norm;
+        if (out->gyro_dw) for (long long q = 0; q < 18LL * n_hw * n_ef; ++q) out->gyro_dw[q] = h[L.gyro_dw + q] / norm;
     }
     c->t_fin_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_fin0).count();
     return MEPB_OK;
@@ -906,7 +1045,8 @@ static int ensure_list(mepb_ctx *c, long long cap) {
     return MEPB_OK;
 }
 
-static int list_run(mepb_ctx *c, int64_t nk, const double *kpt, double *e_k, double *V_ka, double *H_k, double *H_ka) {
+static int list_run(mepb_ctx *c, int64_t nk, const double *kpt, double *e_k, double *V_ka, double *H_k, double *H_ka,
+                    double *A_ka = nullptr, double *Om_vec = nullptr) {
     if (!c || !kpt || nk < 0) return fail(MEPB_ERR_ARG, "bad argument");
     CUDA_TRY(cudaSetDevice(c->device));
     const long long cap = std::min<long long>(std::min<long long>(std::max<long long>(nk, 1), 1 << 16), c->chunk);
@@ -923,7 +1063,8 @@ static int list_run(mepb_ctx *c, int64_t nk, const double *kpt, double *e_k, dou
         InterpOut o; std::memset(&o, 0, sizeof(o));
         o.e_out = e_k ? c->d_e : nullptr; o.V_out = V_ka ? c->d_V : nullptr;
         o.Hk_out = H_k ? c->d_Hk : nullptr; o.Hka_out = H_ka ? c->d_Hka : nullptr;
-        if (V_ka && !e_k) o.e_out = c->d_e;
+        if ((V_ka || A_ka || Om_vec) && !e_k) o.e_out = c->d_e;
+        const bool pos_list = c->pipe2 && (V_ka || A_ka || Om_vec);        // connection-corrected velocities / H-gauge A, Om
         o.err_flag = c->d_err;
         if (c->eig_thread && o.e_out) {
             CUDA_TRY(launch_eig_small(m, ks, c->sb[0].eig_E, c->sb[0].eig_U, c->d_err, c->sm_count, st));
@@ -934,6 +1075,7 @@ static int list_run(mepb_ctx *c, int64_t nk, const double *kpt, double *e_k, dou
             CUDA_TRY(launch_fourier_dense(c->fp, m, ks, c->d_Hk, c->d_Hka_int, st));
             if (H_ka) CUDA_TRY(launch_hka_to_user(c->d_Hka_int, c->d_Hka, c->nw * c->nw, n, st));
             InterpOut o2 = o; o2.Hk_out = nullptr; o2.Hka_out = nullptr;
+            if (pos_list) { o2.V_out = nullptr; o2.U_out = c->sb[0].pU; }
             if (o2.e_out) {
                 if (c->tri) {
                     CUDA_TRY(launch_tridiag(c->nw, n, c->d_Hk, c->sb[0].tb, c->sm_count, st));
@@ -945,6 +1087,31 @@ static int list_run(mepb_ctx *c, int64_t nk, const double *kpt, double *e_k, dou
                                               eig_large_grid(c->sm_count, n), st));
             }
             c->launches += 2;
+            if (pos_list) {
+                StreamBuf &s0 = c->sb[0];
+                if (c->pos)
+                    for (int a = 0; a < 3; ++a) {
+                        FourierPlan fr = c->fp; fr.Hp = c->d_Hp_r[a];
+                        CUDA_TRY(launch_fourier_dense(fr, m, ks, s0.Aw[a], s0.dA[a], st));
+                    }
+                CUDA_TRY(launch_posop_gauge(c->nw, n, c->p.do_gauge_trafo, c->p.posop_mode, c->p.kubo_tol, c->pos, c->d_e, s0.pU, c->d_Hka_int,
+                                            s0.Aw, s0.dA, c->d_V, s0.pAH, s0.pOmV, s0.pScr, posop_gauge_grid(c->sm_count, n), st));
+                c->launches += 1 + (c->pos ? 3 : 0);
+                if (A_ka) {
+                    CUDA_TRY(launch_hka_to_user(s0.pAH, c->d_Hka, c->nw * c->nw, n, st));
+                    CUDA_TRY(cudaMemcpyAsync(A_ka + 2 * 3 * nw * nw * k0, c->d_Hka, sizeof(double2) * 3 * nw * nw * n, cudaMemcpyDeviceToHost, st));
+                }
+                if (Om_vec) {      // internal [k][c][n] -> user (c, n, k)
+                    std::vector<double> tmp(2 * 3 * nw * (size_t)n);
+                    CUDA_TRY(cudaMemcpyAsync(tmp.data(), s0.pOmV, sizeof(double2) * 3 * nw * n, cudaMemcpyDeviceToHost, st));
+                    CUDA_TRY(cudaStreamSynchronize(st));
+                    for (long long k = 0; k < n; ++k)
+                        for (size_t cc = 0; cc < 3; ++cc)
+                            for (size_t b = 0; b < nw; ++b)
+                                for (int ri = 0; ri < 2; ++ri)
+                                    Om_vec[2 * (cc + 3 * (b + nw * (size_t)(k0 + k))) + ri] = tmp[2 * ((size_t)(k * 3 + cc) * nw + b) + ri];
+                }
+            }
         } else {
             CUDA_TRY(launch_interp_small(m, ks, jb, o, c->max_pairs, interp_small_grid(c->nw, c->nR, c->sm_count, n), st));
             c->launches += 1;
@@ -961,6 +1128,14 @@ static int list_run(mepb_ctx *c, int64_t nk, const double *kpt, double *e_k, dou
 int mepb_interp(mepb_ctx *c, int64_t nk, const double *kpt, double *e_k, double *V_ka) {
     if (!e_k && !V_ka) return fail(MEPB_ERR_ARG, "nothing requested");
     return list_run(c, nk, kpt, e_k, V_ka, nullptr, nullptr);
+}
+// get_wann_interp with the position-operator outputs (wann_interp.f90:56-108): e_k (nw,nk), V_ka (3,nw,nw,nk) connection-corrected,
+// A_ka (3,nw,nw,nk) H-gauge connection, Om_vec (3,nw,nk) = the curvature pseudo-vector of every band, sum_ab eps_abc Om_ab(n,n)
+int mepb_interp_pos(mepb_ctx *c, int64_t nk, const double *kpt, double *e_k, double *V_ka, double *A_ka, double *Om_vec) {
+    if (!c) return fail(MEPB_ERR_ARG, "null ctx");
+    if (!c->pipe2) return fail(MEPB_ERR_STATE, "mepb_interp_pos: the context has no position operator (model.r == NULL and do_gyro off)");
+    if (!e_k && !V_ka && !A_ka && !Om_vec) return fail(MEPB_ERR_ARG, "nothing requested");
+    return list_run(c, nk, kpt, e_k, V_ka, nullptr, nullptr, A_ka, Om_vec);
 }
 int mepb_fourier(mepb_ctx *c, int64_t nk, const double *kpt, double *H_k, double *H_ka) {
     if (!H_k && !H_ka) return fail(MEPB_ERR_ARG, "nothing requested");
@@ -998,17 +1173,23 @@ int mepb_update_model(mepb_ctx *c, const mepb_model *model) {
     if (!c || !model || !model->H || !model->R) return fail(MEPB_ERR_ARG, "null argument");
     if (model->nw != c->nw || model->nR != c->nR) return fail(MEPB_ERR_ARG, "update_model: nw / nR differ from the context's");
     if ((model->wf_centers != nullptr) != c->has_tau) return fail(MEPB_ERR_ARG, "update_model: FT convention differs");
-    if (model->r) return fail(MEPB_ERR_UNSUPPORTED, "position operator (r_tb) branch is not implemented");
+    if ((model->r != nullptr) != c->pos) return fail(MEPB_ERR_ARG, "update_model: position operator present in one model only");
     CUDA_TRY(cudaSetDevice(c->device));
     {   // buffers, launch shapes and the pair-item format were sized at mepb_create for this closure flag: it must not flip
         std::string why;
-        const bool herm = hermitian_closed(model, &why);
+        bool herm = hermitian_closed(model, &why);
+        if (herm && c->pos && !position_closed(model)) { herm = false; why = "r(-R)(m,n) != conj(r(R)(n,m))"; }
         if (herm != c->herm)
             return fail(MEPB_ERR_UNSUPPORTED, std::string("update_model: Hermitian closure of H(R) differs from the model the context was created "
                                                           "with (") + (herm ? "now closed" : why) + "); create a new context");
     }
     cudaStream_t st = c->sb[0].st;
     CUDA_TRY(cudaMemcpyAsync(c->d_H, model->H, sizeof(double) * 2 * (size_t)c->nw * c->nw * c->nR, cudaMemcpyHostToDevice, st));
+    if (c->pos) {
+        CUDA_TRY(cudaMemcpyAsync(c->d_r, model->r, sizeof(double) * 6 * (size_t)c->nw * c->nw * c->nR, cudaMemcpyHostToDevice, st));
+        for (int a = 0; a < 3; ++a) CUDA_TRY(launch_pack_hp(c->fp, c->d_r, 3, a, c->nw, c->nR, c->d_Hp_r[a], st));
+        c->launches += 3;
+    }
     if (c->large) {
         CUDA_TRY(pack_fourier_operand(c, st));     // element tiles repacked on the device, behind the copy on the same stream
         c->launches += 1;
@@ -1029,6 +1210,7 @@ int mepb_update_params(mepb_ctx *c, const mepb_params *np) {
                       np->do_gauge_trafo == o.do_gauge_trafo && np->use_cart_velo == o.use_cart_velo && np->do_mep == o.do_mep &&
                       np->do_kubo == o.do_kubo && np->do_ahc == o.do_ahc && np->do_opt == o.do_opt &&
                       np->do_write_mep_bands == o.do_write_mep_bands && np->n_hw == o.n_hw && np->n_eF == o.n_eF &&
+                      np->do_gyro == o.do_gyro && (np->posop_mode == 0 || np->posop_mode == 1) &&
                       (np->valence_bands == o.valence_bands || !o.do_mep);
     if (!same) return fail(MEPB_ERR_ARG, "update_params: mp_grid, job flags, n_hw, n_eF (and valence_bands with do_mep) are fixed per context");
     if ((o.do_mep || o.do_kubo) && (np->valence_bands < 0 || np->valence_bands > c->nw)) return fail(MEPB_ERR_ARG, "valence_bands out of range");

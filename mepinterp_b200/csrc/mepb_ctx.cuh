@@ -19,8 +19,9 @@ const std::string &last_error_text();
 
 struct PackedLayout {  // identical to oracle/cpu_ref.c make_layout (documented in include/mepb.h)
     long long total, ne, mep_ic, mep_lc, kmep_ic, kmep_lc, ahc, velo, ohc, photo;
+    long long mep_cs, kmep_cs, opt_h, opt_ah, gyro_c, gyro_d, gyro_dw;      // position-operator / gyro blocks (-1: absent)
 };
-inline PackedLayout make_layout(const mepb_params &p) {
+inline PackedLayout make_layout(const mepb_params &p, bool posop) {
     PackedLayout L;
     long long o = 2;
     L.ne = o; o += p.n_eF;
@@ -29,13 +30,18 @@ inline PackedLayout make_layout(const mepb_params &p) {
     if (p.do_kubo) { L.kmep_ic = o; o += 9LL * p.n_eF; L.kmep_lc = o; o += 9LL * p.n_eF; }
     if (p.do_ahc) { L.ahc = o; o += 9LL * p.n_eF; L.velo = o; o += 18LL * p.n_hw * p.n_eF; L.ohc = o; o += 18LL * p.n_hw * p.n_eF; }
     if (p.do_opt) { L.photo = o; o += 54LL * p.n_hw * p.n_eF; }
+    L.mep_cs = L.kmep_cs = L.opt_h = L.opt_ah = L.gyro_c = L.gyro_d = L.gyro_dw = -1;
+    if (posop && p.do_mep) { L.mep_cs = o; o += p.valence_bands; }            // the scalar cs(i,i,n0) per band
+    if (posop && p.do_kubo) { L.kmep_cs = o; o += p.n_eF; }
+    if (posop && p.do_opt) { L.opt_h = o; o += 18LL * p.n_hw * p.n_eF; L.opt_ah = o; o += 18LL * p.n_hw * p.n_eF; }
+    if (p.do_gyro) { L.gyro_c = o; o += 18LL * p.n_eF; L.gyro_d = o; o += 18LL * p.n_eF; L.gyro_dw = o; o += 18LL * p.n_hw * p.n_eF; }
     L.total = o;
     return L;
 }
 
-// compact per-eF accumulator block on the device: [static NS | sweep n_hw*18 | photo n_hw*54]
+// compact per-eF accumulator block on the device: [static NS | sweep n_hw*36 | photo n_hw*54 | position-operator row]
 struct CompactShape {
-    int ns, sweep, photo, per_ef;
+    int ns, sweep, photo, pos, per_ef;
 };
 
 struct StreamBuf {
@@ -49,6 +55,11 @@ struct StreamBuf {
     double2 *Hk = nullptr, *Hka = nullptr, *Vscr = nullptr;   // general path: [chunk][nw^2], [chunk][3][nw^2], [grid][3][nw^2]
     TriBuf tb{};                                                // general path: Householder + QL intermediates (mepb_tri.cu)
     double2 *G1 = nullptr, *G2 = nullptr;                       // general path, mesh mode: separable-transform tables
+    // position-operator pipeline (mepb_posop.cu): W-gauge A_a [k][nw^2] and dA_a(b) [k][3][nw^2] per operand r_a, eigenpairs,
+    // H-gauge V (user layout) / A [k][3][nw^2] / curvature pseudo-vectors [k][3][nw], scratch [grid][6][nw^2], block rows
+    double2 *Aw[3] = {nullptr, nullptr, nullptr}, *dA[3] = {nullptr, nullptr, nullptr};
+    double *pE = nullptr; double2 *pU = nullptr, *pV = nullptr, *pAH = nullptr, *pOmV = nullptr, *pScr = nullptr;
+    double *prow = nullptr;
 };
 
 }  // namespace mepb
@@ -64,6 +75,10 @@ struct mepb_ctx {
     bool large = false;        // general path (mepb_large.cu)
     bool use_sub = false;      // NW-lanes-per-k band-sum kernel (mepb_sub.cu) in mesh mode
     bool tri = false;          // general path: Householder + QL eigensolver (default) instead of the in-kernel Jacobi
+    bool pos = false;          // model carries a position operator r(R): Berry connection / curvature branch
+    bool pipe2 = false;        // position-operator pipeline in use (pos, or do_gyro which needs V and the Kubo curvature per band)
+    double2 *d_r = nullptr, *d_Hp_r[3] = {nullptr, nullptr, nullptr};   // r(R) (3,nw,nw,nR) and its packed element tiles per component
+    int grid_pg = 0, grid_ps = 0, pos_tiles = 1, pos_row = 0;
     mepb::FourierPlan fp{};
     int *d_ridx = nullptr, *d_elem = nullptr; double2 *d_Hp = nullptr; double *d_Rfp = nullptr, *d_cRp = nullptr;
     double2 *d_Hka_int = nullptr;

@@ -332,4 +332,16 @@ cudaError_t launch_tridiag(int nw, long long nk, const double2 *Hk, const TriBuf
 cudaError_t launch_tql(int nw, long long nk, const TriBuf &tb, int *err_flag, cudaStream_t st);
 cudaError_t launch_zrot(int nw, long long nk, const TriBuf &tb, int sm_count, cudaStream_t st);
 
+// position-operator branch (mepb_posop.cu)
+size_t posop_gauge_smem(int nw);
+int posop_gauge_grid(int sm_count, long long nk);
+cudaError_t launch_posop_gauge(int nw, long long nk, int do_gauge, int mode, double kubo_tol, bool has_pos, const double *E,
+                               const double2 *U, const double2 *Hka, const double2 *const Aw[3], const double2 *const dA[3], double2 *V,
+                               double2 *AH, double2 *OmV, double2 *scratch, int grid, cudaStream_t st);
+int posop_row_len(int nval, int n_hw);
+int posop_hw_block(int n_hw);
+int posop_sums_grid(int sm_count, long long nk);
+cudaError_t launch_posop_sums(int nw, long long nk, const Jobs &jb, bool has_pos, bool do_gyro, int n_hw, const double *hw, const double *E,
+                              const double2 *V, const double2 *AH, const double2 *OmV, double *rows, int grid, cudaStream_t st);
+
 }  // namespace mepb

@@ -123,16 +123,85 @@ def read_hr_dat(path: str):
     return R, H / AU_TO_EV
 
 
+AU_TO_ANGSTRM = 0.52917721092  # src/constants.f90:19
+
+
+def read_r_dat(path: str, R: np.ndarray, nw: int) -> np.ndarray:
+    """`<seed>_r.dat` as read_r_file reads it (src/file_io.f90:750-795): comment; num_wann; nR*nw^2 rows
+    `R1 R2 R3 m n x_re x_im y_re y_im z_re z_im` in Angstrom, R blocks in the order of the _hr.dat (checked, :772-776).
+    Returns r (3,nw,nw,nR) in Bohr.  (The reference appends `_r.dat` twice to the path, :838 vs :760, and can never open the
+    file; the file itself is well defined — scripts/tb_input_writer.py:75-97 writes it.)"""
+    with open(path) as fh:
+        fh.readline()
+        if int(fh.readline().split()[0]) != nw:
+            raise ValueError("[read_tb_basis]: r_mat and H_mat have different basis")
+        body = np.loadtxt(fh, dtype=np.float64, ndmin=2)
+    nR = R.shape[1]
+    if body.shape != (nR * nw * nw, 11):
+        raise ValueError(f"[read_r_file]: expected {nR * nw * nw} rows of 11 columns, found {body.shape}")
+    blocks = body.reshape(nR, nw * nw, 11)
+    if np.abs(blocks[:, :, 0:3] - R.T[:, None, :]).max() > 1e-8:
+        raise ValueError("[read_r_file]: different R_vect order in _hr.dat and _r.dat file")
+    m = blocks[:, :, 3].astype(np.int64) - 1
+    n = blocks[:, :, 4].astype(np.int64) - 1
+    sc = np.broadcast_to(np.arange(nR)[:, None], m.shape)
+    r = np.zeros((3, nw, nw, nR), dtype=np.complex128)
+    for a in range(3):
+        r[a][m, n, sc] = blocks[:, :, 5 + 2 * a] + 1j * blocks[:, :, 6 + 2 * a]
+    return r / AU_TO_ANGSTRM
+
+
+def read_tb_dat(path: str):
+    """wannier90 `<seed>_tb.dat` as read_tb_file reads it (src/file_io.f90:555-658): comment; three lattice rows in Angstrom (they
+    OVERRIDE a_latt, :575-580); num_wann; nrpts; degeneracies (skipped); per R a blank line, `R1 R2 R3`, nw^2 rows `m n Re Im` (eV,
+    |x| < 1e-7 -> 0); then per R a blank line, `R1 R2 R3`, nw^2 rows `m n x_re x_im y_re y_im z_re z_im` (Angstrom).
+    Returns (a_latt rows in Bohr, R (3,nR) — the integer triples of the file, SURVEY Q9 —, H Hartree, r Bohr)."""
+    with open(path) as fh:
+        lines = fh.read().splitlines()
+    cell = np.array([[float(t) for t in lines[1 + i].split()[:3]] for i in range(3)]) / AU_TO_ANGSTRM
+    nw, nR = int(lines[4].split()[0]), int(lines[5].split()[0])
+    pos = 6 + -(-nR // 15)
+    R = np.zeros((3, nR))
+    H = np.zeros((nw, nw, nR), dtype=np.complex128)
+    r = np.zeros((3, nw, nw, nR), dtype=np.complex128)
+    for sc in range(nR):
+        pos += 1                                                       # blank line
+        R[:, sc] = [float(t) for t in lines[pos].split()[:3]]
+        blk = np.array([ln.split() for ln in lines[pos + 1: pos + 1 + nw * nw]], dtype=np.float64)
+        re, im = blk[:, 2].copy(), blk[:, 3].copy()
+        re[np.abs(re) < 1e-7] = 0.0
+        im[np.abs(im) < 1e-7] = 0.0
+        H[blk[:, 0].astype(int) - 1, blk[:, 1].astype(int) - 1, sc] = re + 1j * im
+        pos += 1 + nw * nw
+    for sc in range(nR):
+        pos += 1
+        r3 = np.array([float(t) for t in lines[pos].split()[:3]])
+        if np.abs(r3 - R[:, sc]).max() > 1e-8:
+            raise ValueError("[read_tb_basis]: rHopp has different sc order than tHopp")
+        blk = np.array([ln.split() for ln in lines[pos + 1: pos + 1 + nw * nw]], dtype=np.float64)
+        for a in range(3):
+            r[a, blk[:, 0].astype(int) - 1, blk[:, 1].astype(int) - 1, sc] = blk[:, 2 + 2 * a] + 1j * blk[:, 3 + 2 * a]
+        pos += 1 + nw * nw
+    return cell, R, H / AU_TO_EV, r / AU_TO_ANGSTRM
+
+
 def load_run_dir(run_dir: str):
-    """(model, params, meta) of a reference run directory (main.f90:24-45, core.f90:144)."""
+    """(model, params, meta) of a reference run directory (main.f90:24-45, core.f90:144; read_tb_basis file_io.f90:800-860:
+    `<seed>_tb.dat` wins, else `<seed>_hr.dat` plus `<seed>_r.dat` when present — a position operator switches on the Berry
+    connection branch)."""
     p, a_latt, wfc, meta = read_input_cfg(os.path.join(run_dir, "input.cfg"))
-    R, H = read_hr_dat(os.path.join(run_dir, "w90files", meta["seed_name"] + "_hr.dat"))
+    seed = os.path.join(run_dir, "w90files", meta["seed_name"])
+    r = None
+    if os.path.exists(seed + "_tb.dat"):
+        a_latt, R, H, r = read_tb_dat(seed + "_tb.dat")
+    else:
+        R, H = read_hr_dat(seed + "_hr.dat")
+        if os.path.exists(seed + "_r.dat"):
+            r = read_r_dat(seed + "_r.dat", R, H.shape[0])
     if wfc is not None and wfc.shape[1] != H.shape[0]:
         raise ValueError("input.cfg: N_wf differs from num_wann of the _hr.dat")
-    for other in ("_tb.dat", "_r.dat"):
-        if os.path.exists(os.path.join(run_dir, "w90files", meta["seed_name"] + other)):
-            raise api.MepbError(api.ERR_UNSUPPORTED, "position-operator inputs (%s) are not supported by this path" % other)
-    return api.make_model(R, H, a_latt, wfc), p, meta
+    p.do_gyro = bool(meta["do_gyro"])
+    return api.make_model(R, H, a_latt, wfc, r), p, meta
 
 
 # ------------------------------------------------------------------------------------------------ outputs
@@ -154,7 +223,7 @@ def write_outputs(run_dir: str, params, res: dict):
     hw = hw_list(params)
     save("hw_lst", hw * AU_TO_EV if params.n_hw > 1 else hw)
     for k in ("mep_ic", "mep_lc", "mep_cs", "mep_tens", "mep_bands", "kubo_mep_ic", "kubo_mep_lc", "kubo_mep_cs",
-              "kubo_mep_tens", "ahc_tens", "ahcVELO", "ohcVELO", "opt_Ssymm", "opt_Asymm", "photoC_2nd"):
+              "kubo_mep_tens", "ahc_tens", "ahcVELO", "ohcVELO", "opt_Ssymm", "opt_Asymm", "photoC_2nd", "gyro_C", "gyro_D", "gyro_Dw"):
         if k in res:
             save(k, res[k])
     ef = params.eF_min + (np.arange(params.n_eF) * ((params.eF_max - params.eF_min) / (params.n_eF - 1)) if params.n_eF > 1 else 0.0)

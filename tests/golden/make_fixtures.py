@@ -8,6 +8,10 @@
   parameters of tests/test_FeMn_AHE.f90:127-217 (wf_centers :144-150, 64^3, n_hw=121 over 0-6 eV, eta=0.1 eV, T=0).
 * souza_phi0/   : scripts/souza_tb_model.py:get_souza_tb(0.0) written through scripts/tb_input_writer.py:write_hr_file
   (BASELINE config 1; Wannier FT convention, no position operator).
+* souza_phi03_r/: the same generator at phi = 0.3 WITH its position operator: get_souza_Pos through write_r_file
+  (scripts/tb_input_writer.py:75-97) -> wf1_r.dat (on-site positions of the eight orbitals); all jobs on, use_cart_velo = T.
+* souza_phi03_tb/: the same model as ONE wannier90-format wf1_tb.dat (lattice + H(R) + r(R); written here from the two files above —
+  the reference has a reader for the format, file_io.f90:555-658, but no writer).
 * femn_rashba/  : scripts/FeMn_WX_rashba.py run unchanged (theta=54.7 deg; BASELINE config 4), its wf1_hr.dat and the
   input.cfg it emits, with the jobs switched to do_opt/do_ahc as SURVEY.md 8(d) states.
 The generators are executed from the reference tree; nothing of their source is copied here — only their outputs.
@@ -104,6 +108,48 @@ def main():
     subprocess.check_call([sys.executable, "-W", "ignore", "-c", code], cwd=tmp, stdout=subprocess.DEVNULL)
     write_case("souza_phi0", os.path.join(tmp, "wf1_hr.dat"), "wf1", np.diag([2.0, 2.0, 2.0]), None,
                do_ahc="True", do_mep="True", mp=32, nval=2, n_hw=1, hw_min=0.0, hw_max=0.0)
+    # ---- Souza model with the position operator the generator provides (write_r_file), phi = 0.3
+    tmp3 = tempfile.mkdtemp()
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from souza_tb_model import get_souza_tb\nfrom tb_input_writer import write_hr_file, write_r_file\n"
+            "nWfs, nrpts, tHopp, rHopp, ax, ay, az, a0 = get_souza_tb(0.3)\nwrite_hr_file('wf1', nWfs, nrpts, tHopp)\n"
+            "write_r_file('wf1', nWfs, rHopp)\n" % os.path.join(REF, "scripts"))
+    subprocess.check_call([sys.executable, "-W", "ignore", "-c", code], cwd=tmp3, stdout=subprocess.DEVNULL)
+    pos_jobs = dict(do_ahc="True", do_mep="True", do_kubo="True", do_opt="True", mp=12, nval=2, n_hw=6, hw_min=0.05, hw_max=4.0)
+    d = write_case("souza_phi03_r", os.path.join(tmp3, "wf1_hr.dat"), "wf1", np.diag([2.0, 2.0, 2.0]), None, **pos_jobs)
+    shutil.copyfile(os.path.join(tmp3, "wf1_r.dat"), os.path.join(d, "w90files", "wf1_r.dat"))
+    for name in ("souza_phi03_r",):
+        cfg = os.path.join(HERE, name, "input.cfg")
+        txt = open(cfg).read().replace("use_cart_velo= False", "use_cart_velo= True").replace("do_gyro= False", "do_gyro= True")
+        txt = txt.replace("Tkelvin= 0.0", "Tkelvin= 300.0")
+        open(cfg, "w").write(txt)
+    # the same model in the wannier90 _tb.dat format (Angstrom lattice + hoppings in eV + positions in Angstrom)
+    d2 = os.path.join(HERE, "souza_phi03_tb")
+    os.makedirs(os.path.join(d2, "w90files"), exist_ok=True)
+    shutil.copyfile(os.path.join(d, "input.cfg"), os.path.join(d2, "input.cfg"))
+    hr = open(os.path.join(tmp3, "wf1_hr.dat")).read().splitlines()
+    rr = open(os.path.join(tmp3, "wf1_r.dat")).read().splitlines()
+    nw, nR = int(hr[1].split()[0]), int(hr[2].split()[0])
+    ndl = -(-nR // 15)
+    hrows = [ln.split() for ln in hr[3 + ndl:]]
+    rrows = [ln.split() for ln in rr[2:]]
+    with open(os.path.join(d2, "w90files", "wf1_tb.dat"), "w") as fh:
+        fh.write("# written by tests/golden/make_fixtures.py from the reference generator's hr/r output\n")
+        for row in np.diag([2.0, 2.0, 2.0]) * 0.52917721092:
+            fh.write("  %.12f  %.12f  %.12f\n" % tuple(row))
+        fh.write("%d\n%d\n" % (nw, nR))
+        for i in range(ndl):
+            fh.write(" ".join(["1"] * min(15, nR - 15 * i)) + "\n")
+        for sc in range(nR):
+            blk = hrows[sc * nw * nw:(sc + 1) * nw * nw]
+            fh.write("\n%s %s %s\n" % tuple(blk[0][0:3]))
+            for t in blk:
+                fh.write("%s %s %s %s\n" % (t[3], t[4], t[5], t[6]))
+        for sc in range(nR):
+            blk = rrows[sc * nw * nw:(sc + 1) * nw * nw]
+            fh.write("\n%s %s %s\n" % tuple(blk[0][0:3]))
+            for t in blk:
+                fh.write(" ".join([t[3], t[4]] + t[5:11]) + "\n")
     # ---- FeMn Rashba model: run the generator script unchanged
     tmp2 = tempfile.mkdtemp()
     env = dict(os.environ, PYTHONPATH=os.path.join(REF, "scripts"))

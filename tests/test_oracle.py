@@ -251,3 +251,102 @@ def test_degenerate_bands_propagate_nonfinite_like_reference():
     assert out["n_degenerate"] == 2 * 8
     assert not np.all(np.isfinite(out["ahc_tens"]))
     assert np.all(np.isfinite(out["ahcVELO"]))
+
+
+# ------------------------------------------------------------------------------------------------ position-operator branch
+def _diag_r_models(nw=6, seed=3):
+    """Same H(R): Wannier FT convention + on-site diagonal position operator  vs  tight-binding convention without one."""
+    from tests.cases import synthetic_model
+    base = synthetic_model(nw, 3, a_latt=np.diag([2.0, 2.0, 2.0]))
+    tau = np.random.default_rng(seed).uniform(size=(3, nw))
+    r = np.zeros((3, nw, nw, base.nR), dtype=np.complex128)
+    i0 = [i for i in range(base.nR) if not base.R[:, i].any()][0]
+    for a in range(3):
+        r[a, :, :, i0] = np.diag(2.0 * tau[a])
+    mW = mo.Model(nw=nw, nR=base.nR, R=base.R, H=base.H, a_latt=base.a_latt, wf_centers=None, r=r)
+    mT = mo.Model(nw=nw, nR=base.nR, R=base.R, H=base.H, a_latt=base.a_latt, wf_centers=tau, r=None)
+    return mW, mT
+
+
+def test_posop_velocity_correction_equals_tb_convention():
+    """PRB 74 195118 eq. 31 (wann_interp.f90:406-444 in its corrected form): with r_0(n,n) = a tau_n the connection term
+    -i (E_m - E_n) Abar(n,m) must reproduce exactly what the tight-binding FT convention puts into dH/dk — the path the reference's
+    FeMn goldens pin.  The coded form (A after A += iD) counts Hbar twice and fails this identity."""
+    mW, mT = _diag_r_models()
+    kp = np.random.default_rng(4).uniform(-0.5, 0.5, size=(9, 3))
+    e1, V1, A1, Om1, _ = mo.get_wann_interp_pos(mW, kp, True, True, 1e-5, "paper")
+    e2, V2, _ = mo.get_wann_interp(mT, kp, True, True)
+    assert np.abs(e1 - e2).max() < 1e-13
+    P1 = np.einsum("kanm,kbmn->kabnm", V1, V1)
+    P2 = np.einsum("kanm,kbmn->kabnm", V2, V2)
+    assert np.abs(P1 - P2).max() < 1e-12 * np.abs(P2).max()
+    _, V3, _, _, _ = mo.get_wann_interp_pos(mW, kp, True, True, 1e-5, "coded")
+    P3 = np.einsum("kanm,kbmn->kabnm", V3, V3)
+    assert np.abs(P3 - P2).max() > 1e-2 * np.abs(P2).max()
+
+
+def test_posop_curvature_equals_kubo_curvature():
+    """PRB 74 195118 eq. 27 on a complete tight-binding basis: the H-gauge curvature of every band equals the Kubo curvature
+    -2 Im sum_m V_a(n,m) V_b(m,n) / (E_m - E_n)^2 of the corrected velocities (the quantity get_kubo_curv substitutes when no
+    position operator is given, wann_interp.f90:113-147).  The coded transform (-3i [D_a, D_b] in effect, Q4) does not."""
+    mW, _ = _diag_r_models(nw=7, seed=5)
+    kp = np.random.default_rng(6).uniform(-0.5, 0.5, size=(7, 3))
+    e, V, A, Om, _ = mo.get_wann_interp_pos(mW, kp, True, True, 0.0, "paper")
+    curv = mo.get_kubo_curv(e, V, 0.0)
+    assert np.abs(np.einsum("kabnn->kabn", Om) - curv).max() < 1e-11 * np.abs(curv).max()
+    _, _, _, Om_c, _ = mo.get_wann_interp_pos(mW, kp, True, True, 0.0, "coded")
+    assert np.abs(np.einsum("kabnn->kabn", Om_c) - curv).max() > 1e-2 * np.abs(curv).max()
+
+
+def test_posop_coded_connection_rotation_is_gauge_dependent():
+    """Why Q1 (wann_interp.f90:530-533, A_a <- (U^dagger H_a U) U) is not a parity target: its gauge-'invariant' content changes when
+    the eigenvectors are multiplied by phases, which LAPACK is free to do; the eq. 21 rotation's does not."""
+    from tests.cases import synthetic_model
+    base = synthetic_model(5, 2)
+    r = np.random.default_rng(8).normal(size=(3, 5, 5, base.nR)) * 0.1 + 0j
+    m = mo.Model(nw=5, nR=base.nR, R=base.R, H=base.H, a_latt=base.a_latt, wf_centers=None, r=r)
+    kp = np.random.default_rng(9).uniform(-0.5, 0.5, size=(3, 3))
+    H_k, H_ka = mo.ft_R_to_k(m, kp)
+    A, _ = mo.ft_pos_R_to_k(m, kp)
+    e, U = np.linalg.eigh(H_k)
+    ph = np.exp(1j * np.random.default_rng(10).uniform(0, 2 * np.pi, size=(3, 1, 5)))
+    diag = {}
+    for tag, Ux in (("a", U), ("b", U * ph)):
+        Ud = np.conj(np.swapaxes(Ux, -1, -2))
+        Hbar = np.einsum("knp,kapq,kqm->kanm", Ud, H_ka, Ux)
+        diag[tag] = (np.einsum("kanp,kpm->kanm", Hbar, Ux), np.einsum("knp,kapq,kqm->kanm", Ud, A, Ux))
+    q1a, goodA = (np.einsum("kann->kan", x) for x in diag["a"])
+    q1b, goodB = (np.einsum("kann->kan", x) for x in diag["b"])
+    assert np.abs(goodA - goodB).max() < 1e-13
+    assert np.abs(q1a - q1b).max() > 1e-3
+
+
+def test_posop_restatements_agree_and_readers():
+    """C and numpy restatements of the whole branch (CS, opt, gyro included) agree to rounding on a random Hermitian-closed r in
+    both FT conventions and both posop modes; `_r.dat` and `_tb.dat` fixtures (written by the reference's generator / in the
+    wannier90 format) load to the same model."""
+    from tests.cases import ev, synthetic_model
+    m1, p1 = mo.load_model(os.path.join(GOLDEN, "souza_phi03_r"))
+    m2, _ = mo.load_model(os.path.join(GOLDEN, "souza_phi03_tb"))
+    assert m1.r is not None and np.abs(m1.r - m2.r).max() == 0.0 and np.abs(m1.H - m2.H).max() == 0.0
+    assert np.abs(m1.a_latt - m2.a_latt).max() < 1e-12 and p1.do_gyro and p1.use_cart_velo
+    assert np.count_nonzero(m1.r) == 12 and abs(np.abs(m1.r).max() - 1.0) < 1e-8        # on-site positions 0 or a/2 = 1 Bohr
+    rng = np.random.default_rng(5)
+    jobs = dict(do_mep=True, do_kubo=True, do_ahc=True, do_opt=True, do_gyro=True, n_hw=3, hw_min=ev(0.05), hw_max=ev(3.0), eta=ev(0.1))
+    for tb, mode in ((False, "paper"), (True, "coded")):
+        base = synthetic_model(5, 2, tb_centers=tb, a_latt=np.array([[3.0, 0.2, 0.0], [0.1, 3.5, 0.0], [0.0, 0.3, 4.0]]))
+        r = (rng.normal(size=(3, 5, 5, base.nR)) + 1j * rng.normal(size=(3, 5, 5, base.nR))) * 0.2
+        idx = {tuple(base.R[:, i]): i for i in range(base.nR)}
+        rs = np.zeros_like(r)
+        for i in range(base.nR):
+            rs[:, :, :, i] = 0.5 * (r[:, :, :, i] + np.conj(np.swapaxes(r[:, :, :, idx[tuple(-base.R[:, i])]], 1, 2)))
+        m = mo.Model(nw=5, nR=base.nR, R=base.R, H=base.H, a_latt=base.a_latt, wf_centers=base.wf_centers, r=rs)
+        p = mo.Params(mp_grid=(3, 2, 2), valence_bands=2, n_eF=2, eF_min=ev(-0.2), eF_max=ev(0.3), T_kelvin=200.0, use_cart_velo=tb,
+                      posop_mode=mode, **jobs)
+        a = cpu_ref.Handle(m, p).accumulate(0, 12, nthreads=2)
+        b = mo.pack_partials(p, mo.accumulate(m, p, 0, 12), 5)
+        assert a.shape == b.shape
+        assert np.abs(a - b).max() < 1e-11 * np.abs(a).max()
+        ra, rb = cpu_ref.Handle(m, p).finalize(a), mo.finalize(m, p, mo.accumulate(m, p, 0, 12))
+        for k in ("mep_cs", "kubo_mep_cs", "opt_Ssymm", "opt_Asymm", "gyro_C", "gyro_D", "gyro_Dw", "mep_bands"):
+            assert np.abs(ra[k] - rb[k]).max() <= 1e-10 * max(np.abs(rb[k]).max(), 1e-300), k
