@@ -1,10 +1,12 @@
 // mepInterp — C++ host driver of libmepb.so: the reference's response run without Fortran.
 //
-//   cd <run dir with input.cfg and w90files/<seed>_hr.dat> && mepInterp [--devices 0,1,..] [--check-input]
+//   cd <run dir with input.cfg and w90files/<seed>_hr.dat (+ <seed>_r.dat) or <seed>_tb.dat> && mepInterp [--devices 0,1,..] [--check-input]
 //
 // Mirrors main.f90:24-45 -> init_parameters (src/input_paras.f90:79-293) -> core_worker (src/core.f90:79-298):
 // parses ./input.cfg (INI dialect of thirdparty/config_fortran/m_config.f90:226-311), reads the wannier90 _hr.dat as
-// read_hr_file does (src/file_io.f90:663-746: degeneracies read and ignored, |x| < 1e-7 eV zeroed, eV -> Hartree),
+// read_hr_file does (src/file_io.f90:663-746: degeneracies read and ignored, |x| < 1e-7 eV zeroed, eV -> Hartree), or — like
+// read_tb_basis (src/file_io.f90:800-860) — prefers <seed>_tb.dat and otherwise adds <seed>_r.dat when present (the position
+// operator switches on the Berry connection / curvature branch),
 // runs the whole Monkhorst-Pack mesh through the C ABI (include/mepb.h) and writes out/*.npy + out/occ.dat with the
 // names / shapes / Fortran order / units of write_*_tensors (src/file_io.f90:186-398) — NPY v1.0, little endian.
 // All physics happens in the CUDA kernels behind mepb_*; there is no CPU compute path in this file.
@@ -29,6 +31,7 @@
 namespace {
 
 const double aUtoEv = 27.211385;   // src/constants.f90:18
+const double aUtoAngstrm = 0.52917721092;   // src/constants.f90:19
 
 struct Config {
     std::map<std::string, std::vector<std::string>> kv;   // "section%key" -> tokens
@@ -101,6 +104,7 @@ struct Inputs {
     bool plot_bands = false, do_write_velo = false;
     int nw = 0, nR = 0;
     std::vector<double> R, H;               // (3,nR), (nw,nw,nR) complex interleaved, Hartree
+    std::vector<double> r;                  // (3,nw,nw,nR) complex interleaved, Bohr; empty without a position operator
 };
 
 void read_inputs_cfg(const std::string &path, Inputs &I) {
@@ -137,6 +141,9 @@ void read_inputs_cfg(const std::string &path, Inputs &I) {
     p.T_kelvin = c.real("Fermi%Tkelvin", 0.0);
     p.eta = c.real("Fermi%eta_smearing", 0.0) / aUtoEv;
     p.kubo_tol = c.real("Fermi%kuboTol", 1e-5);
+    p.do_gyro = c.logical("jobs%do_gyro", false);
+    p.posop_mode = 0;                                                          // PRB 74 195118 form; MEPB_POSOP_MODE=coded selects 1
+    if (const char *e = std::getenv("MEPB_POSOP_MODE")) p.posop_mode = (std::string(e) == "coded" || std::string(e) == "1") ? 1 : 0;
 }
 
 void read_hr(const std::string &path, Inputs &I) {
@@ -164,6 +171,79 @@ void read_hr(const std::string &path, Inputs &I) {
             I.H[idx] = re / aUtoEv; I.H[idx + 1] = im / aUtoEv;
         }
 }
+
+// <seed>_r.dat, file_io.f90:750-795: comment; num_wann; nR*nw^2 rows "R1 R2 R3 m n x_re x_im y_re y_im z_re z_im" (Angstrom), R
+// blocks in the order of the _hr.dat (checked :772-776).  (The reference mangles the path, :838 vs :760; the format is the one
+// scripts/tb_input_writer.py:75-97 writes.)
+void read_r(const std::string &path, Inputs &I) {
+    std::ifstream in(path);
+    if (!in) throw std::runtime_error("[read_r_file]: cannot open " + path);
+    std::string line;
+    std::getline(in, line);
+    int f_nw = 0;
+    in >> f_nw;
+    if (!in || f_nw != I.nw) throw std::runtime_error("[read_tb_basis]: r_mat and H_mat have different basis");
+    const size_t nw2 = (size_t)I.nw * I.nw;
+    I.r.assign(6 * nw2 * I.nR, 0.0);
+    for (int sc = 0; sc < I.nR; ++sc)
+        for (size_t it = 0; it < nw2; ++it) {
+            double r3[3], v[6]; int m, n;
+            in >> r3[0] >> r3[1] >> r3[2] >> m >> n >> v[0] >> v[1] >> v[2] >> v[3] >> v[4] >> v[5];
+            if (!in) throw std::runtime_error("[read_r_file]: file ends early");
+            for (int i = 0; i < 3; ++i)
+                if (std::fabs(r3[i] - I.R[3 * sc + i]) > 1e-8) throw std::runtime_error("[read_r_file]: different R_vect order in _hr.dat and _r.dat file");
+            if (m < 1 || n < 1 || m > I.nw || n > I.nw) throw std::runtime_error("[read_r_file]: orbital index out of range");
+            for (int a = 0; a < 3; ++a) {
+                const size_t idx = 2 * ((size_t)a + 3 * ((size_t)(m - 1) + (size_t)I.nw * (n - 1) + nw2 * sc));
+                I.r[idx] = v[2 * a] / aUtoAngstrm; I.r[idx + 1] = v[2 * a + 1] / aUtoAngstrm;
+            }
+        }
+}
+
+// wannier90 <seed>_tb.dat, file_io.f90:555-658: comment; lattice (Angstrom, OVERRIDES a_latt :575-580); num_wann; nrpts; degeneracies
+// (skipped); per R: "R1 R2 R3", nw^2 rows "m n Re Im" (eV); then per R: "R1 R2 R3", nw^2 rows "m n x_re x_im y_re y_im z_re z_im"
+// (Angstrom).  R kept as the file's integer triples.
+void read_tb(const std::string &path, Inputs &I) {
+    std::ifstream in(path);
+    if (!in) throw std::runtime_error("[read_tb_file]: cannot open " + path);
+    std::string line;
+    std::getline(in, line);
+    for (int i = 0; i < 3; ++i) { double v[3]; in >> v[0] >> v[1] >> v[2]; for (int j = 0; j < 3; ++j) I.a_latt[i + 3 * j] = v[j] / aUtoAngstrm; }
+    in >> I.nw >> I.nR;
+    if (!in || I.nw < 1 || I.nR < 1) throw std::runtime_error("[read_tb_file]: bad header");
+    for (int i = 0; i < I.nR; ++i) { int deg; in >> deg; }
+    const size_t nw2 = (size_t)I.nw * I.nw;
+    I.R.assign(3 * (size_t)I.nR, 0.0); I.H.assign(2 * nw2 * I.nR, 0.0); I.r.assign(6 * nw2 * I.nR, 0.0);
+    for (int sc = 0; sc < I.nR; ++sc) {
+        in >> I.R[3 * sc] >> I.R[3 * sc + 1] >> I.R[3 * sc + 2];
+        for (size_t it = 0; it < nw2; ++it) {
+            int m, n; double re, im;
+            in >> m >> n >> re >> im;
+            if (!in || m < 1 || n < 1 || m > I.nw || n > I.nw) throw std::runtime_error("[read_tb_file]: bad hopping row");
+            if (std::fabs(re) < 1e-7) re = 0.0;
+            if (std::fabs(im) < 1e-7) im = 0.0;
+            const size_t idx = 2 * ((size_t)(m - 1) + (size_t)I.nw * (n - 1) + nw2 * sc);
+            I.H[idx] = re / aUtoEv; I.H[idx + 1] = im / aUtoEv;
+        }
+    }
+    for (int sc = 0; sc < I.nR; ++sc) {
+        double r3[3];
+        in >> r3[0] >> r3[1] >> r3[2];
+        for (int i = 0; i < 3; ++i)
+            if (std::fabs(r3[i] - I.R[3 * sc + i]) > 1e-8) throw std::runtime_error("[read_tb_basis]: rHopp has different sc order than tHopp");
+        for (size_t it = 0; it < nw2; ++it) {
+            int m, n; double v[6];
+            in >> m >> n >> v[0] >> v[1] >> v[2] >> v[3] >> v[4] >> v[5];
+            if (!in || m < 1 || n < 1 || m > I.nw || n > I.nw) throw std::runtime_error("[read_tb_file]: bad position row");
+            for (int a = 0; a < 3; ++a) {
+                const size_t idx = 2 * ((size_t)a + 3 * ((size_t)(m - 1) + (size_t)I.nw * (n - 1) + nw2 * sc));
+                I.r[idx] = v[2 * a] / aUtoAngstrm; I.r[idx + 1] = v[2 * a + 1] / aUtoAngstrm;
+            }
+        }
+    }
+}
+
+bool file_exists(const std::string &p) { struct stat st; return stat(p.c_str(), &st) == 0; }
 
 // NPY v1.0, little endian, fortran_order True (what numpy.load needs to give back the Fortran array of save_npy)
 void save_npy(const std::string &path, const double *data, const std::vector<long> &shape, bool cplx) {
@@ -272,11 +352,21 @@ int main(int argc, char **argv) {
     try {
         Inputs I;
         read_inputs_cfg(dir + "/input.cfg", I);
-        read_hr(dir + "/w90files/" + I.seed + "_hr.dat", I);
+        const std::string seed = dir + "/w90files/" + I.seed;                   // read_tb_basis, file_io.f90:800-860
+        if (file_exists(seed + "_tb.dat")) read_tb(seed + "_tb.dat", I);
+        else {
+            read_hr(seed + "_hr.dat", I);
+            if (file_exists(seed + "_r.dat")) read_r(seed + "_r.dat", I);
+        }
         if (!I.wf_centers.empty() && (int)(I.wf_centers.size() / 3) != I.nw) throw std::runtime_error("N_wf differs from num_wann");
         const mepb_params &p = I.p;
         if (check_only) {   // machine-readable echo of what was parsed (tests compare it with the oracle's reader)
             std::printf("nw %d nR %d seed %s plot_bands %d\n", I.nw, I.nR, I.seed.c_str(), (int)I.plot_bands);
+            {
+                double rs = 0.0, ra = 0.0;
+                for (size_t i = 0; i < I.r.size(); ++i) { rs += I.r[i] * (double)(i % 11 + 1); ra += std::fabs(I.r[i]); }
+                std::printf("posop %d do_gyro %d checksums_r %.17g %.17g\n", (int)!I.r.empty(), p.do_gyro, rs, ra);
+            }
             std::printf("mp_grid %d %d %d jobs %d %d %d %d gauge %d cart %d nval %d n_hw %d n_eF %d wmb %d\n", p.mp_grid[0], p.mp_grid[1],
                         p.mp_grid[2], p.do_mep, p.do_kubo, p.do_ahc, p.do_opt, p.do_gauge_trafo, p.use_cart_velo, p.valence_bands, p.n_hw,
                         p.n_eF, p.do_write_mep_bands);
@@ -290,7 +380,7 @@ int main(int argc, char **argv) {
             return 0;
         }
         mepb_model M{};
-        M.nw = I.nw; M.nR = I.nR; M.R = I.R.data(); M.H = I.H.data(); M.r = nullptr;
+        M.nw = I.nw; M.nR = I.nR; M.R = I.R.data(); M.H = I.H.data(); M.r = I.r.empty() ? nullptr : I.r.data();
         M.wf_centers = I.wf_centers.empty() ? nullptr : I.wf_centers.data();
         std::memcpy(M.a_latt, I.a_latt, sizeof(M.a_latt));
         if (I.plot_bands) return band_mode(dir, I, M, devices[0]);            // main.f90:32-36
@@ -303,13 +393,15 @@ int main(int argc, char **argv) {
         // outputs
         const int n_hw = p.n_hw, n_eF = p.n_eF, nval = p.valence_bands;
         std::vector<double> Ne(n_eF), mep_ic(9), mep_lc(9), mep_cs(9), mep_bands(9 * (size_t)std::max(nval, 1)), k_ic(9), k_lc(9), k_cs(9), ahc(9),
-            velo(18 * (size_t)n_hw), ohc(18 * (size_t)n_hw), opt_s(18 * (size_t)n_hw), opt_a(18 * (size_t)n_hw), photo(54 * (size_t)n_hw * n_eF);
+            velo(18 * (size_t)n_hw), ohc(18 * (size_t)n_hw), opt_s(18 * (size_t)n_hw), opt_a(18 * (size_t)n_hw), photo(54 * (size_t)n_hw * n_eF),
+            gyro_c(18 * (size_t)n_eF), gyro_d(18 * (size_t)n_eF), gyro_dw(18 * (size_t)n_hw * n_eF);
         mepb_result r{};
         r.Ne = Ne.data();
         if (p.do_mep) { r.mep_ic = mep_ic.data(); r.mep_lc = mep_lc.data(); r.mep_cs = mep_cs.data(); if (p.do_write_mep_bands) r.mep_bands = mep_bands.data(); }
         if (p.do_kubo) { r.kubo_mep_ic = k_ic.data(); r.kubo_mep_lc = k_lc.data(); r.kubo_mep_cs = k_cs.data(); }
         if (p.do_ahc) { r.ahc = ahc.data(); r.ahc_velo = velo.data(); r.ohc_velo = ohc.data(); }
         if (p.do_opt) { r.opt_s = opt_s.data(); r.opt_a = opt_a.data(); r.photo2 = photo.data(); }
+        if (p.do_gyro) { r.gyro_c = gyro_c.data(); r.gyro_d = gyro_d.data(); r.gyro_dw = gyro_dw.data(); }
         check(mepb_multi_run_mesh(mm, &r), "mepb_multi_run_mesh");
         const std::string out = dir + "/out";
         mkdir(out.c_str(), 0755);
@@ -342,6 +434,11 @@ int main(int argc, char **argv) {
             save_npy(out + "/opt_Ssymm.npy", opt_s.data(), {3, 3, n_hw}, true);
             save_npy(out + "/opt_Asymm.npy", opt_a.data(), {3, 3, n_hw}, true);
             save_npy(out + "/photoC_2nd.npy", photo.data(), {3, 3, 3, n_hw, n_eF}, true);
+        }
+        if (p.do_gyro) {                                                       // write_gyro_tensors, file_io.f90:382-397
+            save_npy(out + "/gyro_C.npy", gyro_c.data(), {3, 3, n_eF}, true);
+            save_npy(out + "/gyro_D.npy", gyro_d.data(), {3, 3, n_eF}, true);
+            save_npy(out + "/gyro_Dw.npy", gyro_dw.data(), {3, 3, n_hw, n_eF}, true);
         }
         {   // out/occ.dat, core.f90:378: '(f16.8,a,f16.8)' with a tab
             FILE *f = std::fopen((out + "/occ.dat").c_str(), "w");

@@ -118,7 +118,7 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
         }
         double2 u[NW];                                             // column g of U (eigenvector of band g)
         {
-            if (!vin) {
+            if (!vin && NW != 8) {                                  // (NW = 8: the tensor-core rotation below loads its own fragments)
                 const double2 *Uk = out.U_in + (size_t)ik * NW2 + (size_t)NW * g;   // element r + NW*c: 128 contiguous bytes per lane
 #pragma unroll
                 for (int q = 0; q < NW; ++q) u[q] = __ldg(Uk + q);
@@ -195,7 +195,46 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
         // ------------------------------------------------------------------ 4. gauge rotation V_a = U^dagger (d_a H) U
         // lane g: column g of T = H_a U from its own u (registers), written over H_a; then ROW g of V_a = U^dagger T,
         // again from its own u — U never goes through shared memory.
-        if (jb.do_gauge && !vin) {
+        if (NW == 8 && jb.do_gauge && !vin) {
+            // Tensor-core rotation (mma.sync.m8n8k4.f64 -> SASS DMMA): the warp takes its four k-points one after the other, all 32
+            // lanes on one 8 x 8 complex problem.  With the contraction index ordered p = 2 j + ks (j = lane & 3, ks = k-step) the
+            // SAME two U elements per lane, U(2j + ks, lane >> 2), are the A fragment of both products
+            //     T^T = U^T (d_aH)^T          (B fragment: two consecutive elements of a row of d_aH in shared memory)
+            //     V   = conj(U)^T T           (B fragment: the accumulator registers of the first product, no shuffle)
+            // so per k-point and direction the shared-memory traffic is 2 LDS.128 + 2 STS.128 per lane instead of 128 + 16 for the
+            // FMA formulation below, whose LDS stream co-limited the FP64 pipe (ncu r02b: pipe 43 %, stalls short_scoreboard 21 %).
+            const int j = lane & 3, rq = lane >> 2;
+#pragma unroll 1
+            for (int gq = 0; gq < NGRP; ++gq) {
+                long long ikq = first - grp + gq + it * gstride;
+                if (ikq >= ks.nk) ikq = ks.nk - 1;
+                const double2 *Uk = out.U_in + (size_t)ikq * NW2 + (size_t)NW * rq + 2 * j;     // U(2j + ks, rq): 32 contiguous bytes
+                const double2 u0 = __ldg(Uk), u1 = __ldg(Uk + 1);
+                double2 *Hq = reinterpret_cast<double2 *>(smem_raw + ((size_t)warp * NGRP + gq) * grp_bytes + L::oHa);
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    double2 *Hrow = Hq + a * NW * LD;
+                    const double2 h0 = Hrow[rq * LD + 2 * j], h1 = Hrow[rq * LD + 2 * j + 1];      // d_aH(p = rq, q = 2j + ks)
+                    double tr[2] = {0.0, 0.0}, ti[2] = {0.0, 0.0};
+#define MEPB_DMMA(c0, c1, av, bv) asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(av), "d"(bv))
+                    MEPB_DMMA(tr[0], tr[1], u0.x, h0.x); MEPB_DMMA(ti[0], ti[1], u0.x, h0.y);
+                    MEPB_DMMA(tr[0], tr[1], -u0.y, h0.y); MEPB_DMMA(ti[0], ti[1], u0.y, h0.x);
+                    MEPB_DMMA(tr[0], tr[1], u1.x, h1.x); MEPB_DMMA(ti[0], ti[1], u1.x, h1.y);
+                    MEPB_DMMA(tr[0], tr[1], -u1.y, h1.y); MEPB_DMMA(ti[0], ti[1], u1.y, h1.x);
+                    // lane holds T(p = 2j + e, m = rq), e = 0, 1: the B fragment of the second product for k-step e
+                    double vr[2] = {0.0, 0.0}, vi[2] = {0.0, 0.0};
+                    MEPB_DMMA(vr[0], vr[1], u0.x, tr[0]); MEPB_DMMA(vi[0], vi[1], u0.x, ti[0]);
+                    MEPB_DMMA(vr[0], vr[1], u0.y, ti[0]); MEPB_DMMA(vi[0], vi[1], -u0.y, tr[0]);
+                    MEPB_DMMA(vr[0], vr[1], u1.x, tr[1]); MEPB_DMMA(vi[0], vi[1], u1.x, ti[1]);
+                    MEPB_DMMA(vr[0], vr[1], u1.y, ti[1]); MEPB_DMMA(vi[0], vi[1], -u1.y, tr[1]);
+#undef MEPB_DMMA
+                    __syncwarp();                                    // every lane has its d_aH operands: V_a may overwrite them
+                    Hrow[rq * LD + 2 * j] = make_double2(vr[0], vi[0]);                          // V_a(n = rq, m = 2j), (n, 2j + 1)
+                    Hrow[rq * LD + 2 * j + 1] = make_double2(vr[1], vi[1]);
+                }
+            }
+            __syncwarp();
+        } else if (jb.do_gauge && !vin) {
 #pragma unroll 1
             for (int a = 0; a < 3; ++a) {
                 double2 *Hrow = Ha + a * NW * LD;

@@ -69,8 +69,26 @@ def test_driver_errors_are_loud(driver, tmp_path):
     assert r.returncode == 1 and "read_hr_file" in r.stderr
 
 
+@pytest.mark.parametrize("name", ["souza_phi03_r", "souza_phi03_tb"])
+def test_driver_reads_position_operator_inputs(driver, name):
+    """read_tb_basis (file_io.f90:800-860): `<seed>_tb.dat` wins, else `_hr.dat` + `_r.dat`; the driver's C++ readers give the arrays
+    the Python host reader and the oracle's reader give (checksums of r in Bohr), and jobs%do_gyro is honoured, not ignored."""
+    from mepinterp_b200 import host
+    run = os.path.join(GOLDEN, name)
+    r = subprocess.run([driver, "--dir", run, "--check-input"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("posop")][0].split()
+    assert line[1] == "1" and line[3] == "1"
+    model, params, _ = host.load_run_dir(run)
+    z = np.asarray(model.r).ravel(order="F")                                 # Fortran order (3,nw,nw,nR), complex interleaved
+    flat = np.stack([z.real, z.imag], axis=1).ravel()
+    w = (np.arange(flat.size) % 11 + 1).astype(np.float64)
+    assert abs(float(line[5]) - float((flat * w).sum())) < 1e-9 and abs(float(line[6]) - float(np.abs(flat).sum())) < 1e-9
+    assert params.do_gyro
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,mesh", [("femn_d0.900", 12), ("souza_phi0", 10), ("femn_rashba", 6)])
+@pytest.mark.parametrize("name,mesh", [("femn_d0.900", 12), ("souza_phi0", 10), ("femn_rashba", 6), ("souza_phi03_r", 8), ("souza_phi03_tb", 6)])
 def test_driver_end_to_end_files(driver, tmp_path, name, mesh):
     run = tmp_path / "run"
     shutil.copytree(os.path.join(GOLDEN, name), run)
