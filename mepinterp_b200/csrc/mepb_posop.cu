@@ -36,7 +36,7 @@ struct GaugeSmem {
         oU = o; o += sizeof(double2) * nw * ld;
         oX = o; o += sizeof(double2) * nw * ld;
         oT = o; o += sizeof(double2) * nw * ld;
-        oE = o; o += sizeof(double) * nw;
+        oE = o; o += sizeof(double) * (nw + (nw & 1));       // keeps the double2 array behind it 16-byte aligned
         oOm = o; o += sizeof(double2) * 3 * nw;
         total = (o + 15) / 16 * 16;
     }

@@ -395,13 +395,8 @@ def test_call_order_and_argument_errors(libmepb):
     ctx.reset(); ctx.accumulate(0, 8)
     assert ctx.finalize()["n_k"] == 8
     ctx.close()
-    # position operator branch is not implemented: loud error, not silent zeros
     cm = ctx.cm
-    dummy = np.zeros(8)
-    cm.r = dummy.ctypes.data
     h = C.c_void_p()
-    assert libmepb.lib().mepb_create(C.byref(cm), C.byref(ctx.cp), 0, C.byref(h)) == libmepb.api.ERR_UNSUPPORTED
-    cm.r = None
     assert libmepb.lib().mepb_create(C.byref(cm), C.byref(ctx.cp), 99, C.byref(h)) == libmepb.api.ERR_ARG
     bad = mo.Params(mp_grid=(2, 2, 0))
     with pytest.raises(libmepb.MepbError):
