@@ -128,7 +128,8 @@ def test_wannier_plus_diagonal_r_equals_tb_convention(libmepb):
         outs.append(ctx.run_mesh())
         ctx.close()
     a, b = outs
-    for k in ("ahc_tens", "ahcVELO", "ohcVELO", "photoC_2nd", "mep_bands", "kubo_mep_ic", "kubo_mep_lc"):
+    # (mep_bands is left out: with a position operator it also carries the Chern-Simons term of each band, core.f90:591-599)
+    for k in ("ahc_tens", "ahcVELO", "ohcVELO", "photoC_2nd", "mep_ic", "mep_lc", "kubo_mep_ic", "kubo_mep_lc"):
         s = max(float(np.abs(b[k]).max()), 1e-300)
         assert np.abs(a[k] - b[k]).max() <= 1e-7 * s, k
 
