@@ -161,7 +161,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
@@ -179,7 +179,7 @@ class ClockSampler:
         sm, smax, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ts, r in list(self.rows):
-            if len(r) < 9 or (t0 is not None and ts < t0) or (t1 is not None and ts > t1 + 0.15):
+            if len(r) < 9 or (t0 is not None and ts < t0) or (t1 is not None and ts > t1 + 0.05):
                 continue
             try:
                 sm.append(float(r[1])); smax.append(float(r[2])); pw.append(float(r[3]))
@@ -432,15 +432,27 @@ def measure(env: Env, workload: str, steps: int, warmup: int, scaling: str, mesh
 
 
 def eigensolver_yardstick(nw: int, batch: int):
-    """cuSOLVER heevjBatched on the batch shape of the workload (tools/heevj_compare, comparison only: libmepb never links cuSOLVER)."""
+    """cuSOLVER heevjBatched on the batch shape of the workload (tools/heevj_compare, comparison only: libmepb never links cuSOLVER).
+    A batch cuSOLVER refuses is halved (down to batch / 64) and the batch actually timed is reported."""
     exe = os.path.join(ROOT, "tools", "heevj_compare")
     if not os.path.exists(exe):
         return {"unavailable": "tools/heevj_compare not built"}
-    try:
-        r = subprocess.run([exe, str(nw), str(batch), "2"], capture_output=True, text=True, timeout=240)
-        return json.loads(r.stdout.strip().splitlines()[-1])
-    except Exception as e:                                   # noqa: BLE001 — the yardstick must never break the bench line
-        return {"unavailable": f"{type(e).__name__}: {e}"}
+    last = ""
+    b = batch
+    while b >= max(1, batch // 64):
+        try:
+            r = subprocess.run([exe, str(nw), str(b), "2"], capture_output=True, text=True, timeout=240)
+            lines = r.stdout.strip().splitlines()
+            if r.returncode == 0 and lines:
+                out = json.loads(lines[-1])
+                if b != batch:
+                    out["note"] = f"batch {batch} refused ({last.strip()[:120]}); timed on {b}"
+                return out
+            last = r.stderr or f"exit {r.returncode}"
+        except Exception as e:                               # noqa: BLE001 — the yardstick must never break the bench line
+            last = f"{type(e).__name__}: {e}"
+        b //= 2
+    return {"unavailable": last.strip()[:300]}
 
 
 def main():
