@@ -31,6 +31,24 @@ def _free_port():
     return p
 
 
+def blocks(rank: int, world: int, nk: int, block: int):
+    """[begin, end) ranges rank owns under round-robin blocks (what mepb_accumulate_strided schedules)."""
+    out, b0 = [], rank * block
+    while b0 < nk:
+        out.append((b0, min(nk, b0 + block)))
+        b0 += world * block
+    return out
+
+
+def test_round_robin_blocks_cover_mesh_exactly():
+    for nk in (1, 7, 210, 4096, 128 ** 3):
+        for world in (1, 2, 3, 8):
+            for block in (1, 5, 1024, max(1, -(-nk // world))):
+                seen = sorted(r for rank in range(world) for r in blocks(rank, world, nk, block))
+                assert seen[0][0] == 0 and seen[-1][1] == nk
+                assert all(a[1] == b[0] for a, b in zip(seen[:-1], seen[1:]))
+
+
 def _worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
@@ -44,11 +62,16 @@ def _worker(rank, world, port, q):
                          eF_min=ev(-0.4), eF_max=ev(0.4), T_kelvin=50.0)
         h = cpu_ref.Handle(m, p)
         nk = 6 * 5 * 7
-        b0, b1 = mdist.slab(rank, world, nk)
-        part = h.accumulate(b0, b1)
+        part = h.accumulate(*mdist.slab(rank, world, nk))
+        part_blocks = np.zeros_like(part)                      # the same share dealt as round-robin blocks of 16 k-points
+        for b0, b1 in blocks(rank, world, nk, 16):
+            h.accumulate(b0, b1, partials=part_blocks)
+        tb = torch.from_numpy(part_blocks)
+        mdist.allreduce_partials(tb)
         t = torch.from_numpy(part)
         mdist.allreduce_partials(t)
         out = h.finalize(t.numpy())
+        out["__blocks_vs_slabs"] = float(np.abs(tb.numpy() - t.numpy()).max() / np.abs(t.numpy()).max())
         q.put((rank, {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in out.items()}))
     finally:
         dist.destroy_process_group()
@@ -76,6 +99,7 @@ def test_gloo_sharded_equals_single(world):
     ref, scale, sens = oracle_reference(m, p, nthreads=1)
     for r in range(world):
         out = res[r]
+        assert out.pop("__blocks_vs_slabs") < 1e-9          # any partition of the mesh gives the same sums (up to reassociation)
         assert out["n_k"] == 210
         assert_parity(out, ref, scale, sens, tol=1e-12)
     # every rank holds the identical reduced result (no root + broadcast needed)
