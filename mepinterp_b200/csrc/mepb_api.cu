@@ -143,6 +143,7 @@ Jobs make_jobs(const mepb_ctx *c, int ief, bool response) {
     j.eF = c->ef_lst[ief];
     j.inv_kT = j.zero_T ? 0.0 : 1.0 / (kBoltzEhK * p.T_kelvin);
     j.eta = p.eta; j.kubo_tol = p.kubo_tol;
+    j.hka_upper = 0;
     return j;
 }
 
@@ -218,6 +219,7 @@ cudaError_t build_fourier_plan(mepb_ctx *c, const mepb_model *model, const std::
     fp.ntiles = (fp.nel + TN - 1) / TN;
     fp.nRp = (nR + RC - 1) / RC * RC;
     fp.herm = c->herm ? 1 : 0;
+    fp.upper_only = 0;
     elem.resize((size_t)fp.ntiles * TN, elem[0]);
     // distinct lattice coordinates per axis
     std::vector<double> uv[3];
@@ -695,8 +697,13 @@ static int launch_wave(mepb_ctx *c, StreamBuf &s, long long k0, long long nk, co
     const DevModel m = dev_model(c);
     const int ns = c->cs.ns;
     for (int ief = 0; ief < p.n_eF; ++ief) {
-        const Jobs jb = make_jobs(c, ief, true);
+        Jobs jb = make_jobs(c, ief, true);
         const bool first_ef = (ief == 0);
+        // general path, mesh mode, Hermitian-closed model, tensor-core rotation: the Fourier kernel stores the upper triangles of
+        // H(k), d_aH(k) only and the consumers (tridiag reads the upper triangle anyway; eig_rot mirrors on load) complete them
+        const bool upper = c->large && c->sp.on && c->herm && p.do_gauge_trafo && !c->pipe2 && c->tri && (c->nw % 8 == 0) && !V_in &&
+                           !getenv("MEPB_FOURIER_MIRROR");
+        jb.hka_upper = upper ? 1 : 0;
         KSource ks; ks.list = nullptr; ks.lin_begin = k0; ks.nk = nk; ks.N1 = p.mp_grid[0]; ks.N2 = p.mp_grid[1]; ks.N3 = p.mp_grid[2];
         InterpOut o; std::memset(&o, 0, sizeof(o));
         o.items_ahc = jb.do_ahc ? s.items_ahc : nullptr; o.cnt_ahc = s.cnt_ahc;
@@ -711,8 +718,9 @@ static int launch_wave(mepb_ctx *c, StreamBuf &s, long long k0, long long nk, co
             if (V_in || !first_ef) {
             } else if (c->sp.on) {
                 SepPlan sp = c->sp; sp.G1 = s.G1; sp.G2 = s.G2;
+                FourierPlan fpu = c->fp; fpu.upper_only = upper ? 1 : 0;
                 ProfScope ps(c, s.st, MEPB_PROF_FOURIER);
-                CUDA_TRY(launch_fourier_mesh(c->fp, sp, m, ks, s.Hk, s.Hka, s.st));
+                CUDA_TRY(launch_fourier_mesh(fpu, sp, m, ks, s.Hk, s.Hka, s.st));
                 c->launches += 3;
             } else {
                 ProfScope ps(c, s.st, MEPB_PROF_FOURIER); CUDA_TRY(launch_fourier_dense(c->fp, m, ks, s.Hk, s.Hka, s.st));

@@ -82,6 +82,7 @@ struct Jobs {
     int nval;
     int herm;             // H(R) Hermitian-closed -> Hermitian items (10 doubles) else general items (20)
     int zero_T;           // T_kelvin <= min_temp -> step function                            statistics.f90:74-87
+    int hka_upper;        // general path: d_aH(k) in HBM holds the upper triangle only (Hermitian; mirrored on load)
     double eF, inv_kT, eta, kubo_tol;
 };
 
@@ -119,6 +120,7 @@ constexpr int kFourierMaxU = 96;  // distinct lattice coordinates over the three
 struct FourierPlan {
     int nel, ntiles, nRp;         // computed elements (upper triangle if herm, else nw^2), tiles of kFourierTN, nR padded to kFourierRC
     int herm;                     // mirror (m,n) = conj(n,m)
+    int upper_only;               // herm: store the computed upper triangle only (consumers that mirror on load); 0 = full matrices
     int direct;                   // 1: phases by sincospi per (k,R); 0: product of three per-axis table entries
     int u1, u2, u3, utot;         // distinct coordinates per axis
     double uval[kFourierMaxU];    // the distinct coordinates, axis 1 first

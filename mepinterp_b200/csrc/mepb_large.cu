@@ -15,6 +15,8 @@
 //     matrix_math.f90:220), ascending sort, V_a = U^dagger (d_a H) U (wann_interp.f90:517-528), occupations, static AHC,
 //     MEP (Niu + Kubo) sums, and the pair / photo items for the frequency-sweep kernels — same outputs as the
 //     warp-per-k kernel in mepb_small.cu, so everything downstream (mepb_sweep.cu, packing, finalize) is shared.
+#include <cstdlib>
+
 #include "mepb_internal.cuh"
 
 namespace mepb {
@@ -36,8 +38,9 @@ constexpr int F_TN = kFourierTN;     // matrix elements per CTA
 constexpr int F_RC = kFourierRC;     // R points per pipeline stage
 constexpr int F_THREADS = 256;
 
-struct FourierSmem {                 // fixed part; the axis tables (Utot x F_TK complex) follow
-    double2 ph[2][F_RC][F_TK];       // 2 x 16 KB
+template <int TK>
+struct FourierSmem {                 // fixed part; the axis tables (Utot x TK complex) follow
+    double2 ph[2][F_RC][TK];         // 2 x 16 KB at TK = 64
     double2 h[2][F_RC][F_TN];        // 2 x  8 KB   (TMA destination)
     double cw[2][F_RC][4];           // c_a(R) = (M.R)_a ; [3] = weight of the row in H itself (line mode)
     uint64_t bar[2];
@@ -46,13 +49,19 @@ struct FourierSmem {                 // fixed part; the axis tables (Utot x F_TK
 // LINE = false: explicit k list or mesh points, all nR terms per k-point (phases from per-axis tables or sincospi).
 // LINE = true : stage C of the mesh-separable transform — one CTA works on 64 k-points of ONE mesh line (q2, q3) and
 //               contracts that line's table G2 (sp.nrp rows) with the axis-1 phases.
-template <bool LINE>
-__global__ void __launch_bounds__(F_THREADS, 1)
+// KJ = k-points per thread: 4 (CTA tile of 64 k-points, 128 accumulator registers, one CTA per SM: the long nR-term contraction) or
+//      2 (32 k-points, two CTAs per SM).  Stage C contracts only 3 n1 rows (three pipeline chunks at n1 = 15): a CTA is mostly
+//      prologue (phase lookups) and epilogue (131 KB of stores per 64 k-points), which a second resident CTA overlaps with the
+//      first one's multiply-adds (ncu r03c: one CTA per SM left the FP64 pipe at 39 %, 11 % of the warp slots in use); the smaller
+//      tile also wastes less of the last tile of a mesh line (N1 = 100: 3 % instead of 22 %).
+template <bool LINE, int KJ>
+__global__ void __launch_bounds__(F_THREADS, KJ == 2 ? 2 : 1)
 fourier_dense_kernel(const FourierPlan fp, const SepPlan sp, const DevModel m, const KSource ks, double2 *__restrict__ Hk_out,
                      double2 *__restrict__ Hka_out) {
+    constexpr int F_TK = 16 * KJ;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    FourierSmem &S = *reinterpret_cast<FourierSmem *>(smem_raw);
-    double2 *tab = reinterpret_cast<double2 *>(smem_raw + sizeof(FourierSmem));      // [Utot][F_TK]
+    FourierSmem<F_TK> &S = *reinterpret_cast<FourierSmem<F_TK> *>(smem_raw);
+    double2 *tab = reinterpret_cast<double2 *>(smem_raw + sizeof(FourierSmem<F_TK>));      // [Utot][F_TK]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lk = lane & 7, ln = lane >> 3, wk = warp & 1, wn = warp >> 1;
     const int tile = blockIdx.y;
@@ -128,9 +137,9 @@ fourier_dense_kernel(const FourierPlan fp, const SepPlan sp, const DevModel m, c
         else if (tid < F_RC * 3) { const int r = tid / 3, a = tid % 3; S.cw[b][r][a] = fp.cR[3 * (c * F_RC + r) + a]; }
     };
 
-    double2 hk[4][2], g[3][4][2];
+    double2 hk[KJ][2], g[3][KJ][2];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < KJ; ++j)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             hk[j][e] = make_double2(0.0, 0.0);
@@ -148,13 +157,13 @@ fourier_dense_kernel(const FourierPlan fp, const SepPlan sp, const DevModel m, c
         for (int r = 0; r < F_RC; ++r) {
             const double c0 = S.cw[b][r][0], c1 = S.cw[b][r][1], c2 = S.cw[b][r][2];
             const double ch = LINE ? S.cw[b][r][3] : 1.0;
-            double2 p[4], h[2];
+            double2 p[KJ], h[2];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) p[j] = S.ph[b][r][wk * 32 + lk + 8 * j];
+            for (int j = 0; j < KJ; ++j) p[j] = S.ph[b][r][wk * (8 * KJ) + lk + 8 * j];
 #pragma unroll
             for (int e = 0; e < 2; ++e) h[e] = S.h[b][r][wn * 8 + ln + 4 * e];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < KJ; ++j)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const double tx = fma(p[j].x, h[e].x, -(p[j].y * h[e].y));
@@ -187,8 +196,8 @@ fourier_dense_kernel(const FourierPlan fp, const SepPlan sp, const DevModel m, c
         const int packed = fp.elem[el];
         const int n = packed & 0xffff, mm = packed >> 16;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int kk = wk * 32 + lk + 8 * j;
+        for (int j = 0; j < KJ; ++j) {
+            const int kk = wk * (8 * KJ) + lk + 8 * j;
             if (!kvalid(kk)) continue;
             const long long ik = kbase + kk;
             double2 h0 = hk[j][e];
@@ -208,7 +217,9 @@ fourier_dense_kernel(const FourierPlan fp, const SepPlan sp, const DevModel m, c
             Hk_out[(size_t)ik * nw2 + n + nw * mm] = h0;
 #pragma unroll
             for (int a = 0; a < 3; ++a) Hka_out[((size_t)ik * 3 + a) * nw2 + n + nw * mm] = ga[a];
-            if (fp.herm && n != mm) {
+            // mirrored element: a 16-byte store with stride nw -> half-written 32-byte sectors, read-modify-write in L2/DRAM
+            // (ncu r03c: 718 KB of DRAM traffic per k-point for 256 KB of output); skipped when the consumers mirror on load
+            if (fp.herm && n != mm && !fp.upper_only) {
                 Hk_out[(size_t)ik * nw2 + mm + nw * n] = cconj(h0);
 #pragma unroll
                 for (int a = 0; a < 3; ++a) Hka_out[((size_t)ik * 3 + a) * nw2 + mm + nw * n] = cconj(ga[a]);
@@ -604,7 +615,16 @@ eig_rot_large_kernel(const DevModel m, const KSource ks, const Jobs jb, const In
             for (int a = 0; a < 3; ++a) {
                 const double2 *Ha = Hka_in + ((size_t)ik * 3 + a) * nw2;
                 if (jb.do_gauge) {
-                    if (jb.herm) {      // d_aH(k) Hermitian (mirrored exactly by the Fourier kernel): A(n, m) = conj Ha(m, n) makes the
+                    if (jb.herm && jb.hka_upper) {      // only the upper triangle (row <= column) of the Hermitian d_aH(k) is in HBM
+                        for (int idx = tid; idx < nw2; idx += E_THREADS) {             // lower triangle + diagonal of A: coalesced, conflict-free
+                            const int mm = idx % nw, n = idx / nw;
+                            if (mm <= n) A[n * LDA + mm] = cconj(Ha[idx]);
+                        }
+                        for (int idx = tid; idx < nw2; idx += E_THREADS) {             // strict upper triangle: coalesced reads, strided stores
+                            const int n = idx % nw, mm = idx / nw;
+                            if (n < mm) A[n * LDA + mm] = Ha[idx];
+                        }
+                    } else if (jb.herm) {      // d_aH(k) Hermitian (mirrored exactly by the Fourier kernel): A(n, m) = conj Ha(m, n) makes the
                         //                 transposing copy coalesced in global AND conflict-free in shared memory
                         for (int idx = tid; idx < nw2; idx += E_THREADS) { const int mm = idx % nw, n = idx / nw; A[n * LDA + mm] = cconj(Ha[idx]); }
                     } else {
@@ -893,20 +913,22 @@ eig_rot_large_kernel(const DevModel m, const KSource ks, const Jobs jb, const In
 }  // namespace
 
 // ================================================================================================= launchers
-size_t fourier_dense_smem(const FourierPlan &fp, int nw, bool has_tau) {
-    size_t s = sizeof(FourierSmem) + sizeof(double2) * (size_t)(fp.direct ? 0 : fp.utot) * F_TK;
-    const size_t epi = has_tau ? sizeof(double2) * (size_t)F_TK * nw : 0;      // d_n(k) table of the epilogue reuses the buffers
+template <int TK>
+static size_t fourier_smem_t(const FourierPlan &fp, int nw, bool has_tau) {
+    size_t s = sizeof(FourierSmem<TK>) + sizeof(double2) * (size_t)(fp.direct ? 0 : fp.utot) * TK;
+    const size_t epi = has_tau ? sizeof(double2) * (size_t)TK * nw : 0;        // d_n(k) table of the epilogue reuses the buffers
     return s > epi ? s : epi;
 }
+size_t fourier_dense_smem(const FourierPlan &fp, int nw, bool has_tau) { return fourier_smem_t<F_TK>(fp, nw, has_tau); }
 
 cudaError_t launch_fourier_dense(const FourierPlan &fp, const DevModel &m, const KSource &ks, double2 *Hk, double2 *Hka,
                                  cudaStream_t st) {
     const size_t smem = fourier_dense_smem(fp, m.nw, m.tau != nullptr);
-    cudaError_t e = cudaFuncSetAttribute(fourier_dense_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(fourier_dense_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((unsigned)((ks.nk + F_TK - 1) / F_TK), (unsigned)fp.ntiles);
     SepPlan sp; sp.on = 0;
-    fourier_dense_kernel<false><<<grid, F_THREADS, smem, st>>>(fp, sp, m, ks, Hk, Hka);
+    fourier_dense_kernel<false, 4><<<grid, F_THREADS, smem, st>>>(fp, sp, m, ks, Hk, Hka);
     return cudaGetLastError();
 }
 
@@ -941,12 +963,22 @@ cudaError_t launch_fourier_mesh(const FourierPlan &fp, SepPlan sp, const DevMode
         sep_stage_b_kernel<<<grid, 256, 0, st>>>(fp, sp, ks.N2);
     }
     FourierPlan f0 = fp; f0.direct = 1; f0.utot = 0;        // no per-axis tables in shared memory
-    const size_t smem = fourier_dense_smem(f0, m.nw, m.tau != nullptr);
-    cudaError_t e = cudaFuncSetAttribute(fourier_dense_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static const bool wide = getenv("MEPB_STAGEC_TK64") != nullptr;      // testing knob: the 64-k-point tile of round 1
+    if (wide) {
+        const size_t smem = fourier_smem_t<64>(f0, m.nw, m.tau != nullptr);
+        cudaError_t e = cudaFuncSetAttribute(fourier_dense_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        const int ktl = (ks.N1 + 63) / 64;
+        dim3 grid((unsigned)(ktl * sp.nlines), (unsigned)fp.ntiles);
+        fourier_dense_kernel<true, 4><<<grid, F_THREADS, smem, st>>>(fp, sp, m, ks, Hk, Hka);
+        return cudaGetLastError();
+    }
+    const size_t smem = fourier_smem_t<32>(f0, m.nw, m.tau != nullptr);
+    cudaError_t e = cudaFuncSetAttribute(fourier_dense_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const int ktl = (ks.N1 + F_TK - 1) / F_TK;
+    const int ktl = (ks.N1 + 31) / 32;
     dim3 grid((unsigned)(ktl * sp.nlines), (unsigned)fp.ntiles);
-    fourier_dense_kernel<true><<<grid, F_THREADS, smem, st>>>(fp, sp, m, ks, Hk, Hka);
+    fourier_dense_kernel<true, 2><<<grid, F_THREADS, smem, st>>>(fp, sp, m, ks, Hk, Hka);
     return cudaGetLastError();
 }
 
