@@ -80,61 +80,72 @@ tridiag_kernel(const int nw, const long long nk, const double2 *__restrict__ Hk_
                 }
                 if (s == nw - 1) break;
                 __syncthreads();                                                            // (1) x visible
-                const double2 alpha = xs[buf][s + 1];
-                double pn = 0.0;
+                // Warps whose rows are all finished (i <= s) have nothing to add: reflector entry 0, p = 0, no update.  They only keep
+                // the barriers (and a zero partial of p^H v); the issue slots they leave go to the co-resident CTA.  Half of the
+                // warps are in that state on average — the trailing matrix shrinks, the CTA does not.
+                const bool idle = (warp * (32 / PARTS) + (32 / PARTS) - 1) <= s;
+                double2 tau = make_double2(0.0, 0.0), scale = tau, vi = tau, p = tau;
+                if (!idle) {
+                    const double2 alpha = xs[buf][s + 1];
+                    double pn = 0.0;
 #pragma unroll
-                for (int r = lane; r < NE; r += 32)
-                    if (r > s + 1) { const double2 x = xs[buf][r]; pn = fma(x.x, x.x, fma(x.y, x.y, pn)); }
-                const double xnorm2 = warp_sum(pn);
-                double2 tau, scale;
-                double beta;
-                if (xnorm2 == 0.0 && alpha.y == 0.0) {                                      // zlarfg: H = 1
-                    tau = make_double2(0.0, 0.0); scale = make_double2(0.0, 0.0); beta = alpha.x;
-                } else {
-                    beta = -copysign(sqrt(fma(alpha.x, alpha.x, fma(alpha.y, alpha.y, xnorm2))), alpha.x);
-                    const double rb = 1.0 / beta;
-                    tau = make_double2((beta - alpha.x) * rb, -alpha.y * rb);
-                    scale = crcp(make_double2(alpha.x - beta, alpha.y));
-                }
-                // own row's reflector entry
-                const double2 vi = (i <= s) ? make_double2(0.0, 0.0) : (i == s + 1) ? make_double2(1.0, 0.0) : cmul(xs[buf][i], scale);
-                // p = tau A v  (rows <= s are finished: p = 0 there)
-                double2 p1 = make_double2(0.0, 0.0), p2 = make_double2(0.0, 0.0);
+                    for (int r = lane; r < NE; r += 32)
+                        if (r > s + 1) { const double2 x = xs[buf][r]; pn = fma(x.x, x.x, fma(x.y, x.y, pn)); }
+                    const double xnorm2 = warp_sum(pn);
+                    double beta;
+                    if (xnorm2 == 0.0 && alpha.y == 0.0) {                                      // zlarfg: H = 1
+                        tau = make_double2(0.0, 0.0); scale = make_double2(0.0, 0.0); beta = alpha.x;
+                    } else {
+                        beta = -copysign(sqrt(fma(alpha.x, alpha.x, fma(alpha.y, alpha.y, xnorm2))), alpha.x);
+                        const double rb = 1.0 / beta;
+                        tau = make_double2((beta - alpha.x) * rb, -alpha.y * rb);
+                        scale = crcp(make_double2(alpha.x - beta, alpha.y));
+                    }
+                    // own row's reflector entry
+                    vi = (i <= s) ? make_double2(0.0, 0.0) : (i == s + 1) ? make_double2(1.0, 0.0) : cmul(xs[buf][i], scale);
+                    // p = tau A v  (rows <= s are finished: p = 0 there)
+                    double2 p1 = make_double2(0.0, 0.0), p2 = make_double2(0.0, 0.0);
 #pragma unroll
-                for (int jj = 0; jj < JJ; ++jj) {
-                    const int j = part + PARTS * jj;
-                    if (j > s + 1) cfma(p1, a[jj], xs[buf][j]);
-                    else if (j == s + 1) p2 = a[jj];
-                }
-                double2 p = cadd(cmul(scale, p1), p2);
+                    for (int jj = 0; jj < JJ; ++jj) {
+                        const int j = part + PARTS * jj;
+                        if (j > s + 1) cfma(p1, a[jj], xs[buf][j]);
+                        else if (j == s + 1) p2 = a[jj];
+                    }
+                    p = cadd(cmul(scale, p1), p2);
 #pragma unroll
-                for (int o = 1; o < PARTS; o <<= 1) p = cadd(p, shfl_xor2(p, o));
-                p = cmul(tau, p);
-                if (i <= s) p = make_double2(0.0, 0.0);
-                // p^H v
-                double2 dt = (part == 0) ? cmulc(vi, p) : make_double2(0.0, 0.0);
+                    for (int o = 1; o < PARTS; o <<= 1) p = cadd(p, shfl_xor2(p, o));
+                    p = cmul(tau, p);
+                    if (i <= s) p = make_double2(0.0, 0.0);
+                    // p^H v
+                    double2 dt = (part == 0) ? cmulc(vi, p) : make_double2(0.0, 0.0);
 #pragma unroll
-                for (int o = PARTS; o < 32; o <<= 1) dt = cadd(dt, shfl_xor2(dt, o));
-                if (lane == 0) red[warp] = dt;
-                if (part == 0) Vr[(size_t)s * NE + i] = vi;
-                if (tid == 0) { tau_o[s] = tau; e_o[s] = beta; }
+                    for (int o = PARTS; o < 32; o <<= 1) dt = cadd(dt, shfl_xor2(dt, o));
+                    if (lane == 0) red[warp] = dt;
+                    if (part == 0) Vr[(size_t)s * NE + i] = vi;      // (rows of idle warps keep the 0 the buffer was initialised with)
+                    if (i == s + 1 && part == 0) { tau_o[s] = tau; e_o[s] = beta; }
+                } else if (lane == 0) red[warp] = make_double2(0.0, 0.0);
                 __syncthreads();                                                            // (2)
-                double2 dot = make_double2(0.0, 0.0);
+                double2 wi = make_double2(0.0, 0.0);
+                if (!idle) {
+                    double2 dot = make_double2(0.0, 0.0);
 #pragma unroll
-                for (int w = 0; w < NWARP; ++w) dot = cadd(dot, red[w]);
-                const double2 alc = cscale(-0.5, cmul(tau, dot));
-                double2 wi = p;
-                cfma(wi, alc, vi);
-                if (part == 0) ws[i] = wi;
+                    for (int w = 0; w < NWARP; ++w) dot = cadd(dot, red[w]);
+                    const double2 alc = cscale(-0.5, cmul(tau, dot));
+                    wi = p;
+                    cfma(wi, alc, vi);
+                    if (part == 0) ws[i] = wi;
+                }
                 __syncthreads();                                                            // (3)
-                const double2 wis = cmulc(wi, scale);                                       // w_i conj(scale)
+                if (!idle) {
+                    const double2 wis = cmulc(wi, scale);                                   // w_i conj(scale)
 #pragma unroll
-                for (int jj = 0; jj < JJ; ++jj) {
-                    const int j = part + PARTS * jj;
-                    if (j > s) {
-                        const double2 u1 = cmulc(vi, ws[j]);
-                        const double2 u2 = (j == s + 1) ? wi : cmulc(wis, xs[buf][j]);
-                        a[jj].x -= u1.x + u2.x; a[jj].y -= u1.y + u2.y;
+                    for (int jj = 0; jj < JJ; ++jj) {
+                        const int j = part + PARTS * jj;
+                        if (j > s) {
+                            const double2 u1 = cmulc(vi, ws[j]);
+                            const double2 u2 = (j == s + 1) ? wi : cmulc(wis, xs[buf][j]);
+                            a[jj].x -= u1.x + u2.x; a[jj].y -= u1.y + u2.y;
+                        }
                     }
                 }
             }
