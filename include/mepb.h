@@ -211,6 +211,12 @@ int mepb_get_profile(const mepb_ctx *ctx, int kind, double *ms_total, int64_t *l
  * unit count behind the sweeps' algorithmic flop figures (valid after mepb_get_partials / mepb_finalize). */
 int64_t mepb_work_items(const mepb_ctx *ctx, int kind);
 
+/* Accuracy harness for the device reciprocals that stand in for IEEE division in the sweeps and eigensolvers (a MUFU seed refined
+ * by Newton / cubic steps: <= 1 ulp-level error on normal inputs; x = 0 or subnormal x give NaN / flushed results where IEEE
+ * division gives +-inf — reached only by an exactly resonant denominator with eta = 0, where the reference's inf is as
+ * meaningless).  Evaluates them on n caller-supplied values. */
+int mepb_selftest_math(mepb_ctx *ctx, int n, const double *x, double *rcp_newton2, double *rcp_cubic, double *rsqrt_cubic);
+
 /* timing of the last mepb_accumulate / mepb_run_mesh on the device (CUDA events), and kernel launches issued */
 double  mepb_last_kernel_ms(const mepb_ctx *ctx);
 int64_t mepb_kernel_launches(const mepb_ctx *ctx);

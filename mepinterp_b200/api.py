@@ -24,7 +24,7 @@ EXPORTS = ["mepb_create", "mepb_destroy", "mepb_run_mesh", "mepb_reset", "mepb_a
            "mepb_allreduce_partials", "mepb_get_timing", "mepb_create_multi", "mepb_multi_run_mesh", "mepb_multi_update_model",
            "mepb_multi_size", "mepb_multi_ctx", "mepb_multi_destroy", "mepb_partials_size",
            "mepb_get_partials", "mepb_set_partials", "mepb_partials_device_ptr", "mepb_finalize", "mepb_interp",
-           "mepb_interp_pos", "mepb_fourier", "mepb_fourier_mesh", "mepb_band_sums", "mepb_update_model", "mepb_update_params", "mepb_model_info", "mepb_timer_start", "mepb_timer_stop", "mepb_set_profiling",
+           "mepb_interp_pos", "mepb_fourier", "mepb_fourier_mesh", "mepb_band_sums", "mepb_update_model", "mepb_update_params", "mepb_model_info", "mepb_selftest_math", "mepb_timer_start", "mepb_timer_stop", "mepb_set_profiling",
            "mepb_get_profile", "mepb_work_items", "mepb_last_kernel_ms", "mepb_kernel_launches", "mepb_strerror", "mepb_last_error", "mepb_version"]
 
 
@@ -102,6 +102,7 @@ def lib():
         L.mepb_band_sums.argtypes = [vp, C.c_int64, vp, vp]
         L.mepb_update_model.argtypes = [vp, C.POINTER(CModel)]
         L.mepb_update_params.argtypes = [vp, C.POINTER(CParams)]
+        L.mepb_selftest_math.argtypes = [vp, C.c_int, vp, vp, vp, vp]
         L.mepb_model_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p, C.c_int]
         L.mepb_timer_start.argtypes = [vp]
         L.mepb_timer_stop.argtypes = [vp, C.POINTER(C.c_double)]
@@ -432,6 +433,13 @@ class Context(_Marshal):
         _check(lib().mepb_model_info(self._h, C.byref(h), C.byref(s), C.byref(pth), why, 256))
         return {"herm_closed": bool(h.value), "sparse": bool(s.value), "path": ("sub", "warp", "general")[pth.value],
                 "why": why.value.decode()}
+
+    def selftest_math(self, x):
+        """(1/x by two Newton steps, 1/x by one cubic step, 1/sqrt(x) by one cubic step) as the kernels compute them."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        a, b, c = np.zeros_like(x), np.zeros_like(x), np.zeros_like(x)
+        _check(lib().mepb_selftest_math(self._h, x.size, x.ctypes.data, a.ctypes.data, b.ctypes.data, c.ctypes.data))
+        return a, b, c
 
     def timer_start(self):
         _check(lib().mepb_timer_start(self._h))

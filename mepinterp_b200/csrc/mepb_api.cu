@@ -26,6 +26,16 @@ const std::string &last_error_text() { return g_last_error; }
 
 namespace {
 
+// device math helpers evaluated on caller-supplied inputs (mepb_selftest_math)
+__global__ void selftest_math_kernel(const double *__restrict__ x, double *__restrict__ rcp2, double *__restrict__ rcp3,
+                                     double *__restrict__ rsq3, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    rcp2[i] = fast_rcp(x[i]);
+    rcp3[i] = fast_rcp3(x[i]);
+    rsq3[i] = (x[i] > 0.0) ? fast_rsqrt3(x[i]) : 0.0;
+}
+
 __global__ void pack_kernel(const double *__restrict__ c0, const double *__restrict__ c1, CompactShape cs, int nw, int nval,
                             int n_hw, int n_eF, int do_mep, int do_kubo, int do_ahc, int do_opt, PackedLayout L,
                             double *__restrict__ packed) {
@@ -1276,6 +1286,27 @@ int mepb_get_profile(const mepb_ctx *c, int kind, double *ms_total, int64_t *lau
     if (!c || kind < 0 || kind >= MEPB_PROF_KINDS) return fail(MEPB_ERR_ARG, "bad argument");
     if (ms_total) *ms_total = c->prof_ms[kind];
     if (launches) *launches = c->prof_n[kind];
+    return MEPB_OK;
+}
+
+// The MUFU-seeded reciprocals the frequency sweeps / eigensolvers use in place of IEEE division (mepb_internal.cuh), evaluated
+// on n host-supplied values: 1/x with two Newton steps, 1/x with one cubic step, 1/sqrt(x) with one cubic step (0 for x <= 0).
+int mepb_selftest_math(mepb_ctx *c, int n, const double *x, double *rcp_newton2, double *rcp_cubic, double *rsqrt_cubic) {
+    if (!c || n < 0 || !x || !rcp_newton2 || !rcp_cubic || !rsqrt_cubic) return fail(MEPB_ERR_ARG, "bad argument");
+    if (n == 0) return MEPB_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    double *d = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&d, sizeof(double) * 4 * (size_t)n));
+    cudaStream_t st = c->sb[0].st;
+    cudaError_t e = cudaMemcpyAsync(d, x, sizeof(double) * n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) { selftest_math_kernel<<<(n + 255) / 256, 256, 0, st>>>(d, d + n, d + 2 * (size_t)n, d + 3 * (size_t)n, n); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(rcp_newton2, d + n, sizeof(double) * n, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(rcp_cubic, d + 2 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(rsqrt_cubic, d + 3 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(MEPB_ERR_CUDA, std::string("selftest_math: ") + cudaGetErrorString(e));
+    c->launches += 1;
     return MEPB_OK;
 }
 

@@ -1,20 +1,28 @@
 // mepb_large.cu — the general path for num_wann up to 64 (BASELINE config 5: nw = 64, nR ~ 2000).
 //
-// Two kernels per k-batch, intermediates (H(k), dH/dk_a(k): 4 nw^2 complex per k) staged through HBM/L2:
+// Kernels per wave of k-points, intermediates (H(k), dH/dk_a(k): upper triangles, 4 x 64 KB per k at nw = 64) staged through HBM/L2:
 //
 //  fourier_dense_kernel   FT_R_to_k (wann_interp.f90:151-281) as a dense contraction
-//        [64 k-points x nR] (phases, generated on chip)  x  [nR x 32 matrix elements] (H(R), streamed by TMA bulk copies)
-//     * the phase tile e^{2 pi i k.R} is built in shared memory from three per-axis tables (one sincospi per k and per
-//       distinct lattice coordinate, then two complex multiplies per (k,R)) — the separable form of the phase;
-//     * the four sums H, d_x H, d_y H, d_z H share the product t = phase * H(R): 12 FP64 instructions per (k, element, R)
-//       on the FMA pipe instead of the 16 a four-output complex GEMM on DMMA would need (DMMA peak == DFMA peak on B200,
-//       profiles/r01_fp64_peaks.json), accumulators (4 k x 2 elements x 4 sums, complex) live in registers;
-//     * for Hermitian-closed H(R) only the upper triangle n <= m is computed and mirrored (H(k), d_a H(k) are Hermitian);
-//     * the tight-binding convention (wf_centers) is the diagonal-phase epilogue of SURVEY.md A.1.
-//  eig_rot_large_kernel   one CTA per k-point: cyclic two-sided Jacobi on H(k) in shared memory (replaces zheevd,
-//     matrix_math.f90:220), ascending sort, V_a = U^dagger (d_a H) U (wann_interp.f90:517-528), occupations, static AHC,
-//     MEP (Niu + Kubo) sums, and the pair / photo items for the frequency-sweep kernels — same outputs as the
-//     warp-per-k kernel in mepb_small.cu, so everything downstream (mepb_sweep.cu, packing, finalize) is shared.
+//        [k-points x rows] (phases, generated on chip)  x  [rows x 32 matrix elements] (streamed by TMA bulk copies)
+//     * LINE = false (explicit k lists): rows = the nR lattice vectors; the phase tile e^{2 pi i k.R} is built in shared memory
+//       from three per-axis tables (one sincospi per k and per distinct lattice coordinate, two complex multiplies per (k,R));
+//     * LINE = true (Monkhorst-Pack meshes): stage C of the mesh-separable transform — rows = the 3 n1 entries of the mesh line's
+//       table G2 built by sep_stage_a/b_kernel (15 instead of 2007 terms per k-point and output at nw = 64, nR = 2007);
+//     * the four sums H, d_x H, d_y H, d_z H share the product t = phase * X: 12 FP64 instructions per (k, element, row) on the FMA
+//       pipe instead of the 16 a four-output complex GEMM on DMMA would need (DMMA peak == DFMA peak on B200); accumulators live
+//       in registers (KJ k-points x 2 elements x 4 sums per thread);
+//     * for Hermitian-closed H(R) only the upper triangle n <= m is computed; it is mirrored for callers that want full matrices
+//       and left as it is (fp.upper_only) for the mesh pipeline, whose consumers mirror on load — the mirrored 16-byte stores with
+//       stride nw were the kernel's bound (half-written sectors: 718 KB of DRAM traffic per k-point for 256 KB of output);
+//     * the tight-binding convention (wf_centers) is the diagonal-phase epilogue of SURVEY.md A.1;
+//     * run on the operands r_x, r_y, r_z it yields the W-gauge Berry connection A_a and dA_a(b) (wann_interp.f90:288-375).
+//  eig_rot_large_kernel   one CTA per k-point: eigenvectors U = Q Z from the Householder + QL pipeline of mepb_tri.cu (reflectors
+//     applied to the eigenvectors of the tridiagonal matrix; replaces zheevd, matrix_math.f90:220) — or, with MEPB_LARGE_EIG=jacobi,
+//     a cyclic two-sided Jacobi in shared memory kept as the independent cross-check —, V_a = U^dagger (d_a H) U as DMMA zgemms
+//     (wann_interp.f90:517-528), occupations, static AHC, MEP (Niu + Kubo) sums, and the pair / photo items for the frequency-sweep
+//     kernels: same outputs as the small-num_wann kernels, so everything downstream (sweeps, packing, finalize) is shared.  The same
+//     kernel runs its band-sum sections on supplied eigenpairs (out.V_in: mepb_band_sums, position-operator pipeline) and can hand
+//     the eigenvectors to HBM (out.U_out).
 #include <cstdlib>
 
 #include "mepb_internal.cuh"

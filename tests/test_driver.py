@@ -145,3 +145,28 @@ def test_driver_band_mode_files(driver, tmp_path):
         assert np.all(blk[:, 0] == ki + 1) and np.allclose(blk[:, 1:4], k, atol=5e-9) and np.allclose(blk[:, 4], e_ref, atol=5e-9)
     velo = (run / "out" / "velo" / "velo_Vka.0000001").read_text().splitlines()
     assert len([ln for ln in velo if not ln.lstrip().startswith("#")]) == 3 * m.nw * m.nw
+
+
+@pytest.mark.gpu
+def test_driver_devices_all_gpus(driver, tmp_path):
+    """`mepInterp --devices 0,1,..` (mepb_create_multi: round-robin blocks per device, NCCL all-reduce inside the library) on every
+    GPU of the box against the oracle; on a one-GPU box it degenerates to --devices 0."""
+    import ctypes
+    n = ctypes.c_int(0)
+    ctypes.CDLL("libcudart.so.12").cudaGetDeviceCount(ctypes.byref(n))
+    devs = ",".join(str(i) for i in range(max(1, min(n.value, 8))))
+    run = tmp_path / "run"
+    shutil.copytree(os.path.join(GOLDEN, "femn_d0.900"), run)
+    cfg = (run / "input.cfg").read_text().splitlines()
+    cfg = [("    mp_grid= 14 13 12") if ln.strip().startswith("mp_grid") else ln for ln in cfg]
+    cfg = [("    N_hw= 9") if ln.strip().startswith("N_hw") else ln for ln in cfg]
+    (run / "input.cfg").write_text("\n".join(cfg) + "\n")
+    r = subprocess.run([driver, "--dir", str(run), "--devices", devs], capture_output=True, text=True, env=dict(os.environ, MEPB_CHUNK_LOG2="10"))
+    assert r.returncode == 0, r.stdout + r.stderr
+    m, p = mo.load_model(str(run))
+    ref, scale, sens = oracle_reference(m, p)
+    out = {"n_k": ref["n_k"], "eF_idx": ref["eF_idx"], "n_degenerate": ref["n_degenerate"], "Ne": ref["Ne"]}
+    for k, v in ref.items():
+        if isinstance(v, np.ndarray) and k != "Ne":
+            out[k] = np.load(run / "out" / (k + ".npy"))
+    assert_parity(out, ref, scale, sens, tol=1e-8, label="driver --devices " + devs)

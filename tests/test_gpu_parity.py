@@ -708,3 +708,19 @@ def test_general_path_update_model_on_device(libmepb):
         for k, v in fresh.items():
             assert np.array_equal(np.asarray(v), np.asarray(live[k])), (i, k)
     ctx.close()
+
+
+def test_device_reciprocals_accuracy(libmepb):
+    """fast_rcp / fast_rcp3 / fast_rsqrt3 (mepb_internal.cuh: MUFU seed + Newton / cubic refinement, used instead of IEEE division in
+    the sweeps, the MEP loops and the eigensolvers) on 10^6 values over 600 decades, both signs: relative error <= 2^-51."""
+    m, p = load_case("souza_phi0", mp_grid=(2, 2, 2))
+    ctx = libmepb.Context(m, p)
+    rng = np.random.default_rng(12)
+    x = rng.uniform(1.0, 2.0, size=1_000_000) * 10.0 ** rng.uniform(-300, 300, size=1_000_000) * rng.choice([-1.0, 1.0], size=1_000_000)
+    r2, r3, rs = ctx.selftest_math(x)
+    ctx.close()
+    ulp = 2.0 ** -52
+    assert np.abs(r2 * x - 1.0).max() <= 2 * ulp
+    assert np.abs(r3 * x - 1.0).max() <= 2 * ulp
+    pos = x > 0
+    assert np.abs(rs[pos] * rs[pos] * x[pos] - 1.0).max() <= 4 * ulp
