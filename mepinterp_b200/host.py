@@ -291,3 +291,20 @@ def probe_hw(model, params, sweeps, device: int = 0) -> list:
     finally:
         ctx.close()
     return out
+
+
+def probe_spiral(thetas, params, device: int = 0, **model_kw) -> list:
+    """scripts/FeMn_WX_rashba.py:loop_spiral as a library call: the FeMn spin-spiral model regenerated in memory per canting angle
+    (models.femn_rashba_tb) and re-uploaded into ONE live context (mepb_update_model); returns the result dict per angle."""
+    from . import models
+    thetas = [float(x) for x in thetas]
+    ctx = api.Context(models.femn_rashba_tb(thetas[0], **model_kw), params, device)
+    out = []
+    try:
+        for i, th in enumerate(thetas):
+            if i:
+                ctx.update_model(models.femn_rashba_tb(th, **model_kw).H)
+            out.append(ctx.run_mesh())
+    finally:
+        ctx.close()
+    return out

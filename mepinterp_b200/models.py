@@ -88,3 +88,105 @@ def souza_tb(phi: float = 0.0, as_file: bool = True):
         H = re + 1j * im
     H = H / AU_TO_EV
     return make_model(R, H, np.diag([2.0, 2.0, 2.0]), None)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# FeMn 3q / spin-spiral tight-binding model with an in-plane Rashba term, as the reference's generator parametrises it
+# (scripts/FeMn_WX_rashba.py:76-428 write_3q_HR, scripts/FeMn_latt_OPT.py, scripts/FeMn_get_spin_config.py:60-78; SURVEY.md 8(d) C4,
+# 8(f) row 3).  Restated, not copied: four Fe/Mn sites of the fcc cell in the rhombohedral setting, two spin blocks (orbital index =
+# 4 spin + site), nearest-neighbour hopping within (111) planes (t) and between them (t / strain^2), local exchange -J m_i.sigma,
+# Rashba-like complex hopping on the bonds the generator's index test selects (its `i <= natoms` / `j > natoms` comparisons are
+# 0-based against natoms = 4, so only the orbital pairs (4, 5..7) and (5..7, 4) receive it — reproduced literally), lattice strained
+# along (111) at constant cell volume (the same bounded scalar minimisation the reference runs, scipy.optimize.minimize_scalar).
+_FEMN_LATT0 = ((5.60092859, 0.00000000, 3.96045459), (-2.80046430, 4.85054644, 3.96045459), (-2.80046430, -4.85054644, 3.96045459))
+_FEMN_SITES = ((0.0, 0.0, 0.0), (0.5, 0.5, 0.0), (0.5, 0.0, 0.5), (0.0, 0.5, 0.5))
+_FEMN_PHI_DEG = (45.0, -135.0, 135.0, -45.0)
+
+
+def femn_strained_lattice(strain: float) -> np.ndarray:
+    """Rows a_1, a_2, a_3 (Bohr) of the rhombohedral cell stretched by `strain` along (111) at the volume of the unstrained cell."""
+    from scipy.optimize import minimize_scalar
+    latt0 = np.array(_FEMN_LATT0)
+    vol0 = np.dot(latt0[0, :], np.cross(latt0[1, :], latt0[2, :]))
+    z1 = latt0[0, 2] * strain
+
+    def cell(x):
+        return np.array([[2.0 * x, 0.0, z1], [-x, x * np.sqrt(3), z1], [-x, -x * np.sqrt(3), z1]])
+
+    def miss(x):
+        c = cell(x)
+        return np.abs(np.dot(c[0, :], np.cross(c[1, :], c[2, :])) - vol0)
+
+    opt = minimize_scalar(miss, bounds=(0, 6.8597), method="bounded", tol=None, options={"xatol": 1e-7, "maxiter": 5000, "disp": 0})
+    return cell(opt.x)
+
+
+def femn_rashba_tb(theta_deg: float = 54.7, t: float = -1.2, strain: float = 1.2, J_ex: float = -3.0, tso: float = -0.3,
+                   as_file: bool = True):
+    """In-memory FeMn spin-spiral + Rashba model for the canting angle `theta_deg` (the knob scripts/FeMn_WX_rashba.py:loop_spiral
+    sweeps); defaults = BASELINE config 4.  as_file=True reproduces what the reference pipeline hands to core_worker bit for bit:
+    the generator's eV values rounded to the 6 decimals of its `{:12.6f}` writer, the reader's |x| < 1e-7 eV -> 0 rule and its
+    division by 27.211385 (file_io.f90:732-741).  Tight-binding FT convention (wf_centers = the site positions, twice)."""
+    sx, sy, sz = np.array([[0, 1], [1, 0]]), np.array([[0, -1j], [1j, 0]]), np.array([[1, 0], [0, -1]])
+    nat, norb = 4, 8
+    t_intra, t_inter = t, t / float(strain) ** 2
+    nns = 2 if abs(strain - 1.0) > 1e-3 else 1
+    latt = femn_strained_lattice(strain)
+    sites = np.array(_FEMN_SITES)
+    sites_cart = sites @ latt
+    th = np.pi / 180.0 * theta_deg
+    theta = np.array([th, th, np.pi - th, np.pi - th])
+    phi = np.pi / 180.0 * np.array(_FEMN_PHI_DEG)
+    mag = np.stack([np.sin(theta) * np.cos(phi), np.sin(theta) * np.sin(phi), np.cos(theta)], axis=1)
+    # neighbour shells: distances from the four sites to every site of the 3 x 3 x 3 block, distinct values in ascending order
+    cells = [(x, y, z) for x in (-1, 0, 1) for y in (-1, 0, 1) for z in (-1, 0, 1)]
+    block = np.array([x * latt[0] + y * latt[1] + z * latt[2] + sites_cart[i] for (x, y, z) in cells for i in range(nat)])
+    dist = np.unique(np.array([np.linalg.norm(sites_cart[i] - block[j]) for i in range(nat) for j in range(len(block))]))
+    shells = [d for d in dist if abs(d) > 1e-3]
+    for i in range(len(shells)):
+        if shells[i] > 0:
+            for j in range(i + 1, len(shells)):
+                if abs(shells[j] - shells[i]) < 1e-5:
+                    shells[j] = 0
+    shells = [d for d in shells if abs(d) > 1e-3]
+    cutoff = shells[nns + 1]
+    # exchange term: -J sum_i (m_i . sigma) (x) |i><i|
+    H1 = np.zeros((norb, norb), dtype=np.complex128)
+    for i in range(nat):
+        proj = np.zeros((nat, nat))
+        proj[i, i] = 1
+        H1 = H1 + np.kron(mag[i, 0] * sx + mag[i, 1] * sy + mag[i, 2] * sz, proj)
+    H1 = -J_ex * H1
+    R = np.array(cells, dtype=np.float64).T
+    H = np.zeros((norb, norb, len(cells)), dtype=np.complex128)
+    for ir, (x, y, z) in enumerate(cells):
+        Rf = np.array([x, y, z], dtype=np.float64)
+        Rc = x * latt[0] + y * latt[1] + z * latt[2]
+        for i in range(norb):
+            for j in range(norb):
+                hh = 0
+                ii, jj = i % nat, j % nat
+                if ii != jj and ((i < nat) == (j < nat)):
+                    d_frac = Rf - sites[jj] - sites[ii]
+                    d_cart = Rc + sites_cart[jj] - sites_cart[ii]
+                    if np.linalg.norm(d_cart) < cutoff:
+                        if abs(d_cart[2]) < 1e-5:
+                            hh = t_intra
+                            if i <= nat and j > nat:
+                                hh = hh + 1j * tso * (d_frac[1] + 1j * d_frac[0])
+                            elif i > nat and j <= nat:
+                                hh = hh + 1j * tso * (d_frac[1] - 1j * d_frac[0])
+                        else:
+                            hh = t_inter
+                if x == 0 and y == 0 and z == 0:
+                    hh = hh + H1[i, j]
+                H[i, j, ir] = hh
+    if as_file:
+        re = np.vectorize(lambda v: float("{:.6f}".format(v)))(H.real)
+        im = np.vectorize(lambda v: float("{:.6f}".format(v)))(H.imag)
+        re[np.abs(re) < 1e-7] = 0.0
+        im[np.abs(im) < 1e-7] = 0.0
+        H = re + 1j * im
+    H = H / AU_TO_EV
+    wfc = np.ascontiguousarray(np.vstack([sites, sites]).T)
+    return make_model(R, H, latt, wfc)

@@ -724,3 +724,18 @@ def test_device_reciprocals_accuracy(libmepb):
     assert np.abs(r3 * x - 1.0).max() <= 2 * ulp
     pos = x > 0
     assert np.abs(rs[pos] * rs[pos] * x[pos] - 1.0).max() <= 4 * ulp
+
+
+def test_probe_spiral_live_context_equals_fixture_run(libmepb):
+    """scripts/FeMn_WX_rashba.py:loop_spiral as a library call: the in-memory generator at theta = 54.7 deg in a
+    live context gives the tensors of the reference-generated fixture run directory bit for bit (same H(R); the lattice agrees to the
+    8 decimals of the fixture's .latt copy), and other canting angles go through mepb_update_model."""
+    from mepinterp_b200 import host
+    m, p = load_case("femn_rashba", mp_grid=(8, 8, 8), n_hw=12)
+    res = host.probe_spiral([20.0, 54.7], p)
+    ctx = libmepb.Context(m, p)
+    fix = ctx.run_mesh()
+    ctx.close()
+    for k in ("ahc_tens", "ahcVELO", "photoC_2nd"):
+        assert np.abs(res[1][k] - fix[k]).max() <= 1e-7 * np.abs(fix[k]).max(), k
+    assert np.abs(res[0]["ahcVELO"] - res[1]["ahcVELO"]).max() > 1e-3 * np.abs(fix["ahcVELO"]).max()

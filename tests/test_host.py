@@ -10,7 +10,7 @@ from mepinterp_b200 import host
 from oracle import mep_oracle as mo
 from tests.cases import GOLDEN
 
-RUNS = ["femn_d0.900", "femn_d1.000", "femn_d1.100", "femn_rashba", "souza_phi0"]
+RUNS = ["femn_d0.900", "femn_d1.000", "femn_d1.100", "femn_rashba", "souza_phi0", "souza_phi03_r", "souza_phi03_tb"]
 
 
 @pytest.mark.parametrize("name", RUNS)
@@ -30,6 +30,11 @@ def test_readers_match_oracle(name):
               "valence_bands", "n_hw", "n_eF", "hw_min", "hw_max", "eF_min", "eF_max", "T_kelvin", "eta", "kubo_tol"):
         assert getattr(params, k) == getattr(op, k), k
     assert meta["seed_name"] == op.seed_name
+    if om.r is None:
+        assert model.r is None
+    else:                                                        # position operator: `_r.dat` / `_tb.dat` readers, Bohr
+        np.testing.assert_array_equal(model.r, om.r)
+        assert bool(params.do_gyro) == bool(op.do_gyro)
 
 
 def test_cfg_dialect(tmp_path):
@@ -89,3 +94,24 @@ def test_souza_generator_equals_the_reference_generated_fixture():
     Hh = np.asarray(other.H)
     for r, rm in ((0, 6), (1, 5), (2, 4), (3, 3)):                  # Hermitian closure H(-R) = H(R)^dagger
         assert np.array_equal(Hh[:, :, r], Hh[:, :, rm].conj().T)
+
+
+def test_femn_rashba_generator_equals_the_reference_generated_fixture():
+    """mepinterp_b200.models.femn_rashba_tb (BASELINE config 4) against tests/golden/femn_rashba, which
+    make_fixtures.py produced by running the reference's scripts/FeMn_WX_rashba.py unchanged: bit-identical H(R), R, centres; the
+    strained lattice bit-identical to the full-precision values the reference generator wrote into its own input.cfg
+    (input.cfg.as_generated; the fixture's input.cfg carries the 8-decimal copy of the generator's .latt file)."""
+    from mepinterp_b200 import models
+    ref, _, _ = host.load_run_dir(os.path.join(GOLDEN, "femn_rashba"))
+    gen = models.femn_rashba_tb()
+    assert gen.nw == ref.nw == 8 and gen.nR == ref.nR == 27
+    assert np.array_equal(np.asarray(gen.R), np.asarray(ref.R))
+    assert np.array_equal(np.asarray(gen.H), np.asarray(ref.H))
+    assert np.array_equal(np.asarray(gen.wf_centers), np.asarray(ref.wf_centers))
+    assert np.abs(np.asarray(gen.a_latt) - np.asarray(ref.a_latt)).max() < 1e-8
+    rows = [ln for ln in open(os.path.join(GOLDEN, "femn_rashba", "input.cfg.as_generated")) if ln.strip().startswith(("a1=", "a2=", "a3="))]
+    full = np.array([[float(x) for x in ln.split("=")[1].split()] for ln in rows])
+    assert np.array_equal(np.asarray(gen.a_latt), full)
+    other = models.femn_rashba_tb(theta_deg=20.0)                  # the canting angle only enters the on-site exchange block
+    changed = {int(r) for _, _, r in np.argwhere(np.asarray(other.H) != np.asarray(gen.H))}
+    assert changed == {13}                                          # R = (0, 0, 0) is the 14th of the 27 cells
