@@ -28,14 +28,19 @@ constexpr double kMinTemp = 1e-2;
 //       Re Asym = Im Sym = 0:  [0] c, [1..3] fdm Im Asym, [4..9] (fdm/dE) Re Sym
 //   Sweep accumulators per frequency (36 doubles): X1 = sum fdm ReAsym g (3 complex), X2 = sum fdm ImAsym g (3 complex),
 //       Y1 = sum (fdm/dE) ReSym z g (6 complex), Y2 = sum (fdm/dE) ImSym z g (6 complex); the Hermitian kernel fills X2, Y1.
-//   PHOTO item (56 doubles) for an ordered pair (n,l), l != n, df = f_l - f_n:
+//   PHOTO item (58 doubles) for an ordered pair (n,l), l != n, df = f_l - f_n:
 //     [0..53] T(a,b,c) = df V(a,n,l) sum_m V(b,l,m) V(c,m,n) / (E_n - E_m - i eta)   complex, index a+3b+9c
-//     [54] xr = E_n - E_l     [55] pad
+//     [54] xr = E_n - E_l     [55..57] zero pad — 29 double2 per item.  The tensor-core sweep reads four contraction units (pairs
+//     of items) at once, one per lane quad; at 28 double2 their 896-byte stride put all four on the same shared-memory banks (ncu
+//     r02k: 75 % of the wavefronts were conflicts), at 29 the stride is 32 mod 128 bytes and the fragment loads are conflict free
+//     (sweep 65.1 -> 57.4 ms on C4, r03q).  The producers WRITE the pad: items start on 16-byte, not 32-byte, boundaries now and
+//     a sector left partly unwritten costs a read-modify-write in L2 (r03q: producer 22.9 -> 28.0 ms without the pad store).
+//     (Padding only the shared-memory copy — one 896-byte bulk copy per pair — was slower than either: 70.7 ms, r03r.)
 //   photo2(a,b,c,w) = sum T(abc) (1/w^2) sum_{s=+-1} 1/(xr + s w - 2 i eta)          (photo.f90:44-81)
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kAhcItemH = 10;   // Hermitian item
 constexpr int kAhcItemG = 20;   // general item
-constexpr int kPhotoItem = 56;
+constexpr int kPhotoItem = 58;
 constexpr int kSweepAcc = 36;   // per frequency: X1(3c) X2(3c) Y1(6c) Y2(6c)
 constexpr int kSweepAccH = 18;  // Hermitian kernel: X2, Y1 (contiguous at offset 6 of the 36)
 constexpr int kPhotoAcc = 54;   // per frequency: 27 complex

@@ -626,6 +626,7 @@ interp_small_kernel(const DevModel m, const KSource ks, const Jobs jb, const Int
                         for (int q = 0; q < 9; ++q) dst[a + 3 * q] = cmul(va, W[q]);
                     }
                     dst[27] = make_double2(es[n] - es[l], 0.0);
+                    dst[28] = make_double2(0.0, 0.0);                           // pad, written: keeps every 32-byte sector whole
                 }
                 n_before += __popc(bal);
             }

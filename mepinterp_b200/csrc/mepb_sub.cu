@@ -117,8 +117,9 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
             dn[g] = make_double2(c, s);
         }
         double2 u[NW];                                             // column g of U (eigenvector of band g)
+        constexpr bool kDmmaRot = (NW == 8) && (MEP || !PH) && !VIN;   // tensor-core rotation (section 4)
         {
-            if (!vin && !(NW == 8 && (MEP || !PH))) {                // (tensor-core rotation below loads its own fragments)
+            if (!vin && !kDmmaRot) {                                 // (the tensor-core rotation has its own fragments)
                 const double2 *Uk = out.U_in + (size_t)ik * NW2 + (size_t)NW * g;   // element r + NW*c: 128 contiguous bytes per lane
 #pragma unroll
                 for (int q = 0; q < NW; ++q) u[q] = __ldg(Uk + q);
@@ -195,7 +196,7 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
         // ------------------------------------------------------------------ 4. gauge rotation V_a = U^dagger (d_a H) U
         // lane g: column g of T = H_a U from its own u (registers), written over H_a; then ROW g of V_a = U^dagger T,
         // again from its own u — U never goes through shared memory.
-        if (NW == 8 && (MEP || !PH) && jb.do_gauge && !vin) {      // (photo-only build: store bound, the FMA form below is faster there)
+        if (kDmmaRot && jb.do_gauge) {      // (photo-only build: store bound, the FMA form below is faster there)
             // Tensor-core rotation (mma.sync.m8n8k4.f64 -> SASS DMMA): the warp takes its four k-points one after the other, all 32
             // lanes on one 8 x 8 complex problem.  With the contraction index ordered p = 2 j + ks (j = lane & 3, ks = k-step) the
             // SAME two U elements per lane, U(2j + ks, lane >> 2), are the A fragment of both products
@@ -206,10 +207,11 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
             const int j = lane & 3, rq = lane >> 2;
 #pragma unroll 1
             for (int gq = 0; gq < NGRP; ++gq) {
+                // (fetching these fragments ahead of the Fourier sums, to hide their latency, was measured slower: r03q, 5.23 vs 5.06 ms)
                 long long ikq = first - grp + gq + it * gstride;
                 if (ikq >= ks.nk) ikq = ks.nk - 1;
-                const double2 *Uk = out.U_in + (size_t)ikq * NW2 + (size_t)NW * rq + 2 * j;     // U(2j + ks, rq): 32 contiguous bytes
-                const double2 u0 = __ldg(Uk), u1 = __ldg(Uk + 1);
+                const double2 *Uq = out.U_in + (size_t)ikq * NW2 + (size_t)NW * rq + 2 * j;     // U(2j + ks, rq): 32 contiguous bytes
+                const double2 u0 = __ldg(Uq), u1 = __ldg(Uq + 1);
                 double2 *Hq = reinterpret_cast<double2 *>(smem_raw + ((size_t)warp * NGRP + gq) * grp_bytes + L::oHa);
 #pragma unroll
                 for (int a = 0; a < 3; ++a) {
@@ -475,6 +477,7 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
 #pragma unroll
                         for (int a = 0; a < 3; ++a) dst[a + 3 * q] = cmul(va[a], W[q]);     // fill whole 32-byte sectors
                     dst[27] = make_double2(es[n] - es[l], 0.0);
+                    dst[28] = make_double2(0.0, 0.0);                           // pad, written: keeps every 32-byte sector whole
                 }
             }
             if (valid && g == 0) { out.cnt_photo[ik] = 2 * n_pairs; acc_nph += (double)(2 * n_pairs); }
