@@ -246,6 +246,10 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// one 256-bit global store (sm_100: STG.E.256) of two double2 to a 32-byte aligned address
+__device__ __forceinline__ void st_global_256(double2 *p, const double2 a, const double2 b) {
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
         "{\n"

@@ -468,16 +468,23 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
                             for (int c = 0; c < 3; ++c) cfma(W[b + 3 * c], vb, qc[c]);
                         }
                     }
-                    double2 *dst = reinterpret_cast<double2 *>(out.items_photo + ((size_t)ik * NORD + 2 * idx + dir) * kPhotoItem);
+                    // The two items of a pair are one 928-byte run that starts on a 32-byte boundary: 29 256-bit stores (STG.256),
+                    // each a whole sector.  Lanes write to 32 different lines per instruction whatever the width, so half the
+                    // instructions is half the LSU time of this store-bound section (r03s: 58 128-bit stores per pair).
+                    double2 *run = reinterpret_cast<double2 *>(out.items_photo + ((size_t)ik * NORD + 2 * idx) * kPhotoItem);
                     double2 va[3];
 #pragma unroll
                     for (int a = 0; a < 3; ++a) va[a] = cscale(df, Vs[a * NW * LD + n * LD + l]);
+                    const double2 xr = make_double2(es[n] - es[l], 0.0), zero = make_double2(0.0, 0.0);
+                    auto elem = [&](int e) { return e < 27 ? cmul(va[e % 3], W[e / 3]) : (e == 27 ? xr : zero); };   // e: compile time
+                    if (dir == 0) {
 #pragma unroll
-                    for (int q = 0; q < 9; ++q)                                 // ascending addresses: consecutive 16-byte stores
+                        for (int k = 0; k < 14; ++k) st_global_256(run + 2 * k, elem(2 * k), elem(2 * k + 1));
+                    } else {
+                        st_global_256(run + 28, zero, elem(0));                 // pad of the first item | head of the second
 #pragma unroll
-                        for (int a = 0; a < 3; ++a) dst[a + 3 * q] = cmul(va[a], W[q]);     // fill whole 32-byte sectors
-                    dst[27] = make_double2(es[n] - es[l], 0.0);
-                    dst[28] = make_double2(0.0, 0.0);                           // pad, written: keeps every 32-byte sector whole
+                        for (int k = 0; k < 14; ++k) st_global_256(run + 30 + 2 * k, elem(2 * k + 1), elem(2 * k + 2));
+                    }
                 }
             }
             if (valid && g == 0) { out.cnt_photo[ik] = 2 * n_pairs; acc_nph += (double)(2 * n_pairs); }
