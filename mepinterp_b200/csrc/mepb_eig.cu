@@ -545,7 +545,8 @@ eig_small_hq_kernel(const DevModel m, const KSource ks, double *__restrict__ E_o
 #pragma unroll
             for (int t = 0; t < 2; ++t)
 #pragma unroll
-                for (int r = 0; r < NW; ++r) Uo[r + NW * rank[t]] = make_double2(xr[t][r], xi[t][r]);
+                for (int r = 0; r < NW; r += 2)                                      // 256-bit stores: half the LSU time of 128-bit ones
+                    st_global_256(Uo + r + NW * rank[t], make_double2(xr[t][r], xi[t][r]), make_double2(xr[t][r + 1], xi[t][r + 1]));
         }
     }
 }

@@ -38,7 +38,7 @@ constexpr double kMinTemp = 1e-2;
 //     (Padding only the shared-memory copy — one 896-byte bulk copy per pair — was slower than either: 70.7 ms, r03r.)
 //   photo2(a,b,c,w) = sum T(abc) (1/w^2) sum_{s=+-1} 1/(xr + s w - 2 i eta)          (photo.f90:44-81)
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kAhcItemH = 10;   // Hermitian item
+constexpr int kAhcItemH = 10;   // Hermitian item (padding it to 12 for 256-bit stores gained nothing in the producer and cost the sweep 2 %: r03u)
 constexpr int kAhcItemG = 20;   // general item
 constexpr int kPhotoItem = 58;
 constexpr int kSweepAcc = 36;   // per frequency: X1(3c) X2(3c) Y1(6c) Y2(6c)
@@ -249,6 +249,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 // one 256-bit global store (sm_100: STG.E.256) of two double2 to a 32-byte aligned address
 __device__ __forceinline__ void st_global_256(double2 *p, const double2 a, const double2 b) {
     asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
+}
+// AHC item -> its slot in HBM: 5 128-bit stores (Hermitian, 80 bytes) or 5 256-bit stores (general, 160 bytes = whole sectors)
+__device__ __forceinline__ void store_ahc_item(double *dst, const double *item, const bool herm) {
+    double2 *d2 = reinterpret_cast<double2 *>(dst);
+    if (herm) {
+#pragma unroll
+        for (int j = 0; j < kAhcItemH / 2; ++j) d2[j] = make_double2(item[2 * j], item[2 * j + 1]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < kAhcItemG / 4; ++j)
+            st_global_256(d2 + 2 * j, make_double2(item[4 * j], item[4 * j + 1]), make_double2(item[4 * j + 2], item[4 * j + 3]));
+    }
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(

@@ -755,9 +755,7 @@ eig_rot_large_kernel(const DevModel m, const KSource ks, const Jobs jb, const In
                 for (int w = 0; w < E_WARPS; ++w) { const int cw = cnt[w]; if (w < warp) before += cw; total += cw; }
                 if (emit) {
                     const int slot = before + __popc(bal & ((1u << lane) - 1u));
-                    double2 *dst = reinterpret_cast<double2 *>(out.items_ahc + ((size_t)ik * max_pairs + slot) * istride);
-                    const int nd2 = istride / 2;
-                    for (int j = 0; j < nd2; ++j) dst[j] = make_double2(item[2 * j], item[2 * j + 1]);
+                    store_ahc_item(out.items_ahc + ((size_t)ik * max_pairs + slot) * istride, item, jb.herm);
                 }
                 n_items_before += total;
                 __syncthreads();

@@ -471,14 +471,7 @@ interp_small_kernel(const DevModel m, const KSource ks, const Jobs jb, const Int
                 const unsigned bal = __ballot_sync(0xffffffffu, emit);
                 if (emit) {
                     const int slot = n_items_before + __popc(bal & ((1u << lane) - 1u));
-                    double2 *dst = reinterpret_cast<double2 *>(out.items_ahc + ((size_t)ik * max_pairs + slot) * istride);
-                    if (jb.herm) {
-#pragma unroll
-                        for (int j = 0; j < kAhcItemH / 2; ++j) dst[j] = make_double2(item[2 * j], item[2 * j + 1]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < kAhcItemG / 2; ++j) dst[j] = make_double2(item[2 * j], item[2 * j + 1]);
-                    }
+                    store_ahc_item(out.items_ahc + ((size_t)ik * max_pairs + slot) * istride, item, jb.herm);
                 }
                 n_items_before += __popc(bal);
             }
