@@ -250,6 +250,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 __device__ __forceinline__ void st_global_256(double2 *p, const double2 a, const double2 b) {
     asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
 }
+// one 256-bit read-only global load (LDG.E.256) of two double2 from a 32-byte aligned address
+__device__ __forceinline__ void ld_global_nc_256(const double2 *p, double2 &a, double2 &b) {
+    asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
+}
 // AHC item -> its slot in HBM: 5 128-bit stores (Hermitian, 80 bytes) or 5 256-bit stores (general, 160 bytes = whole sectors)
 __device__ __forceinline__ void store_ahc_item(double *dst, const double *item, const bool herm) {
     double2 *d2 = reinterpret_cast<double2 *>(dst);

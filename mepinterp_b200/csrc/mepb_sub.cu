@@ -122,7 +122,7 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
             if (!vin && !kDmmaRot) {                                 // (the tensor-core rotation has its own fragments)
                 const double2 *Uk = out.U_in + (size_t)ik * NW2 + (size_t)NW * g;   // element r + NW*c: 128 contiguous bytes per lane
 #pragma unroll
-                for (int q = 0; q < NW; ++q) u[q] = __ldg(Uk + q);
+                for (int q = 0; q < NW; q += 2) ld_global_nc_256(Uk + q, u[q], u[q + 1]);
             }
             const double e = out.e_in[(size_t)ik * NW + g];
             const double f = fermi(e, jb);
@@ -211,7 +211,8 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
                 long long ikq = first - grp + gq + it * gstride;
                 if (ikq >= ks.nk) ikq = ks.nk - 1;
                 const double2 *Uq = out.U_in + (size_t)ikq * NW2 + (size_t)NW * rq + 2 * j;     // U(2j + ks, rq): 32 contiguous bytes
-                const double2 u0 = __ldg(Uq), u1 = __ldg(Uq + 1);
+                double2 u0, u1;
+                ld_global_nc_256(Uq, u0, u1);
                 double2 *Hq = reinterpret_cast<double2 *>(smem_raw + ((size_t)warp * NGRP + gq) * grp_bytes + L::oHa);
 #pragma unroll
                 for (int a = 0; a < 3; ++a) {
