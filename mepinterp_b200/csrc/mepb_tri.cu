@@ -280,7 +280,22 @@ zrot_kernel(const int n, const long long nk, const TriBuf tb) {
             const int p_hi = pos0 + (m - 1);          // rotation of plane i sits at log position p_hi - i
 #pragma unroll
             for (int blk = NE / 8 - 1; blk >= 0; --blk) {
-                if (8 * blk < m && 8 * blk + 7 >= l) {
+                if (8 * blk + 7 <= NE - 2 && 8 * blk >= l && 8 * blk + 7 < m) {
+                    // block entirely inside the chase (the common case of the long early chases): no clamps, no predicates —
+                    // the replay is issue-bound (ncu r03v: issue 66 %, FP64 pipe 27 %), the index arithmetic is what costs
+                    const unsigned r7 = ring0 + (unsigned)(p_hi - (8 * blk + 7));       // ring position of plane 8 blk + 7
+                    double2 csb[8];
+#pragma unroll
+                    for (int ii = 0; ii < 8; ++ii) csb[ii] = ring[(r7 + (unsigned)(7 - ii)) % RING];
+#pragma unroll
+                    for (int ii = 7; ii >= 0; --ii) {
+                        const int i = 8 * blk + ii;
+                        const double2 cs = csb[ii];
+                        const double f = z[i + 1 <= NE - 1 ? i + 1 : NE - 1], zi = z[i];
+                        z[i + 1 <= NE - 1 ? i + 1 : NE - 1] = fma(cs.y, zi, cs.x * f);
+                        z[i] = fma(-cs.y, f, cs.x * zi);                                // one dependent FMA per plane on the chain through f
+                    }
+                } else if (8 * blk < m && 8 * blk + 7 >= l) {
                     double2 csb[8];
 #pragma unroll
                     for (int ii = 0; ii < 8; ++ii) {
@@ -297,7 +312,7 @@ zrot_kernel(const int n, const long long nk, const TriBuf tb) {
                                 const double f = z[i + 1 <= NE - 1 ? i + 1 : NE - 1];
                                 const double zi = z[i];
                                 z[i + 1 <= NE - 1 ? i + 1 : NE - 1] = fma(cs.y, zi, cs.x * f);
-                                z[i] = fma(cs.x, zi, -(cs.y * f));
+                                z[i] = fma(-cs.y, f, cs.x * zi);
                             }
                         }
                     }
