@@ -99,7 +99,7 @@ tridiag_kernel(const int nw, const long long nk, const double2 *__restrict__ Hk_
                         beta = -copysign(sqrt(fma(alpha.x, alpha.x, fma(alpha.y, alpha.y, xnorm2))), alpha.x);
                         const double rb = 1.0 / beta;
                         tau = make_double2((beta - alpha.x) * rb, -alpha.y * rb);
-                        scale = crcp(make_double2(alpha.x - beta, alpha.y));
+                        scale = crcp(make_double2(alpha.x - beta, alpha.y));       // (MUFU-seeded forms of this chain: no gain, r03y)
                     }
                     // own row's reflector entry
                     vi = (i <= s) ? make_double2(0.0, 0.0) : (i == s + 1) ? make_double2(1.0, 0.0) : cmul(xs[buf][i], scale);
@@ -190,10 +190,14 @@ tql_kernel(const int n, const long long nk, const TriBuf tb, int *__restrict__ e
             for (; i >= l; --i) {
                 const double ei = E(i);
                 const double f = s * ei, b = c * ei;
-                r = sqrt(fma(f, f, g * g));
+                // r = sqrt(f^2 + g^2) and 1/r from ONE MUFU-seeded reciprocal square root (the IEEE sqrt + division they replace were
+                // two thirds of the dependent chain of a plane, and this kernel is nothing but that chain: ncu r03v, 55 % `wait`)
+                const double h2 = fma(f, f, g * g);
+                double rr;
+                if (h2 > 1e-280) { rr = fast_rsqrt3(h2); r = h2 * rr; }
+                else { r = sqrt(h2); rr = (r == 0.0) ? 0.0 : 1.0 / r; }
                 E(i + 1) = r;
                 if (r == 0.0) { D(i + 1) -= p; E(m) = 0.0; break; }
-                const double rr = 1.0 / r;
                 s = f * rr; c = g * rr;
                 g = D(i + 1) - p;
                 r = (D(i) - g) * s + 2.0 * c * b;
