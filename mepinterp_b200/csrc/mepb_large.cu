@@ -408,12 +408,15 @@ __device__ __forceinline__ void zgemm_dmma(const int nw, const int LDA, const in
     }
 }
 
+// NWT: num_wann as a compile-time constant (0: run-time m.nw).  With it the leading dimensions, buffer offsets and trip counts
+// fold into immediates: the run-time form spends a fifth of its instructions on address arithmetic and spill reloads (ncu r03v).
+template <int NWT>
 __global__ void __launch_bounds__(E_THREADS, 1)
 eig_rot_large_kernel(const DevModel m, const KSource ks, const Jobs jb, const InterpOut out, const int max_pairs,
                      const double2 *__restrict__ Hk_in, const double2 *__restrict__ Hka_in, double2 *__restrict__ Vscr,
                      const TriBuf tb) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int nw = m.nw, nw2 = nw * nw;
+    const int nw = NWT > 0 ? NWT : m.nw, nw2 = nw * nw;
     const LargeSmemLayout L(nw);
     const int NE = L.ne, LD = L.ld, LDA = L.lda, NP = NE / 2;     // LDA: buffer A; LD: buffers U, T
     double2 *A = reinterpret_cast<double2 *>(smem_raw + L.oA);
@@ -1005,9 +1008,17 @@ int eig_large_grid(int sm_count, long long nk) { return (int)(nk < sm_count ? (n
 cudaError_t launch_eig_rot_large(const DevModel &m, const KSource &ks, const Jobs &jobs, const InterpOut &out, int max_pairs,
                                  const double2 *Hk, const double2 *Hka, double2 *Vscr, const TriBuf &tb, int grid, cudaStream_t st) {
     const size_t smem = LargeSmemLayout(m.nw).total;
-    cudaError_t e = cudaFuncSetAttribute(eig_rot_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    eig_rot_large_kernel<<<grid, E_THREADS, smem, st>>>(m, ks, jobs, out, max_pairs, Hk, Hka, Vscr, tb);
+    static const bool generic_only = getenv("MEPB_EIGROT_GENERIC") != nullptr;       // A/B knob: run-time num_wann build for every size
+    cudaError_t e;
+    if (m.nw == 64 && !generic_only) {
+        e = cudaFuncSetAttribute(eig_rot_large_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        eig_rot_large_kernel<64><<<grid, E_THREADS, smem, st>>>(m, ks, jobs, out, max_pairs, Hk, Hka, Vscr, tb);
+    } else {
+        e = cudaFuncSetAttribute(eig_rot_large_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        eig_rot_large_kernel<0><<<grid, E_THREADS, smem, st>>>(m, ks, jobs, out, max_pairs, Hk, Hka, Vscr, tb);
+    }
     return cudaGetLastError();
 }
 
