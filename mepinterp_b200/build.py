@@ -7,7 +7,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["mepb_small.cu", "mepb_sub.cu", "mepb_eig.cu", "mepb_sweep.cu", "mepb_sweep_mma.cu", "mepb_large.cu", "mepb_tri.cu", "mepb_posop.cu", "mepb_api.cu", "mepb_comm.cu"]
+SOURCES = ["mepb_small.cu", "mepb_sub.cu", "mepb_mep.cu", "mepb_eig.cu", "mepb_sweep.cu", "mepb_sweep_mma.cu", "mepb_large.cu", "mepb_tri.cu", "mepb_posop.cu", "mepb_api.cu", "mepb_comm.cu"]
 LIB = os.path.join(HERE, "libmepb.so")
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3"]

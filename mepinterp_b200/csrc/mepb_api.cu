@@ -402,7 +402,7 @@ void free_all(mepb_ctx *c) {
     for (auto &s : c->sb) {
         cudaFree(s.items_ahc); cudaFree(s.cnt_ahc); cudaFree(s.items_photo); cudaFree(s.cnt_photo);
         cudaFree(s.block_static); cudaFree(s.block_sweep); cudaFree(s.block_photo); cudaFree(s.compact);
-        cudaFree(s.eig_E); cudaFree(s.eig_U); cudaFree(s.Hk); cudaFree(s.Hka); cudaFree(s.Vscr);
+        cudaFree(s.eig_E); cudaFree(s.eig_U); cudaFree(s.Hk); cudaFree(s.Hka); cudaFree(s.Vscr); cudaFree(s.V_pad);
         cudaFree(s.tb.Vr); cudaFree(s.tb.tau); cudaFree(s.tb.d); cudaFree(s.tb.e); cudaFree(s.tb.E); cudaFree(s.tb.rank);
         cudaFree(s.tb.hdr); cudaFree(s.tb.nhdr); cudaFree(s.tb.log); cudaFree(s.tb.Z);
         cudaFree(s.G1); cudaFree(s.G2);
@@ -556,6 +556,7 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
     if (p.do_ahc) per_k += sizeof(double) * istr * c->max_pairs + sizeof(int);
     if (p.do_opt) per_k += sizeof(double) * kPhotoItem * c->max_photo + sizeof(int);
     if (c->large) per_k += sizeof(double2) * 4 * (size_t)nw * nw;
+    if (c->use_sub && (p.do_mep || p.do_kubo)) per_k += sizeof(double2) * mep_vpad_elems(nw);     // velocities for mep_sums_kernel
     if (c->pipe2) per_k += sizeof(double2) * ((c->pos ? 12 : 0) + 7) * (size_t)nw * nw + sizeof(double2) * 3 * nw + sizeof(double) * nw;
     if (c->large) { CT(build_fourier_plan(c, model, cR)); CT(build_sep_plan(c, model)); }
     if (c->pos) {      // r(R): uploaded once, element tiles of its three components packed like H(R)
@@ -586,9 +587,9 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
     c->chunk = chunk;
     if (!c->large) CT(build_sparse(c, model));
     c->grid_interp = c->large ? eig_large_grid(c->sm_count, chunk) : interp_small_grid(nw, nR, c->sm_count, chunk);
-    if (c->use_sub)      // block_static holds grid_interp rows: the largest grid any variant of the band-sum kernel is launched with
-        c->grid_interp = std::max(c->grid_interp, std::max(bands_sub_grid(nw, nR, c->sm_count, chunk, c->sparse ? c->sp_nnz : 0, true),
-                                                           bands_sub_grid(nw, nR, c->sm_count, chunk, c->sparse ? c->sp_nnz : 0, false)));
+    if (c->use_sub)      // block_static holds grid_interp rows: the largest grid the band-sum kernel is launched with ...
+        c->grid_interp = std::max(c->grid_interp, bands_sub_grid(nw, nR, c->sm_count, chunk, c->sparse ? c->sp_nnz : 0));
+    c->grid_mep = (c->use_sub && (p.do_mep || p.do_kubo)) ? mep_sums_grid(nw, c->sm_count, chunk) : 0;    // ... plus the rows of mep_sums_kernel
     c->grid_sweep = sweep_ahc_grid(c->sm_count, chunk, p.n_hw, &c->ns_sweep, c->herm, c->max_pairs);
     c->grid_photo = sweep_photo_grid(c->sm_count, chunk, p.n_hw, &c->ns_photo, c->max_photo);
     c->cs.ns = static_size(nw); c->cs.sweep = p.n_hw * kSweepAcc; c->cs.photo = p.n_hw * kPhotoAcc;
@@ -664,7 +665,8 @@ int mepb_create(const mepb_model *model, const mepb_params *params, int device, 
             CT(cudaMalloc((void **)&s.eig_E, sizeof(double) * nw * (size_t)chunk));
             CT(cudaMalloc((void **)&s.eig_U, sizeof(double2) * nw * nw * (size_t)chunk));
         }
-        CT(cudaMalloc((void **)&s.block_static, sizeof(double) * (size_t)c->cs.ns * c->grid_interp));
+        CT(cudaMalloc((void **)&s.block_static, sizeof(double) * (size_t)c->cs.ns * (c->grid_interp + c->grid_mep)));
+        if (c->grid_mep) CT(cudaMalloc((void **)&s.V_pad, sizeof(double2) * mep_vpad_elems(nw) * (size_t)chunk));
         CT(cudaMalloc((void **)&s.compact, sizeof(double) * (size_t)c->cs.per_ef * p.n_eF));
         CT(cudaMemset(s.compact, 0, sizeof(double) * (size_t)c->cs.per_ef * p.n_eF));
     }
@@ -721,9 +723,10 @@ static int launch_wave(mepb_ctx *c, StreamBuf &s, long long k0, long long nk, co
         o.block_static = s.block_static; o.err_flag = c->d_err;
         o.e_in = e_in; o.V_in = V_in;
         int gi = c->large ? eig_large_grid(c->sm_count, nk)
-                 : c->use_sub ? bands_sub_grid(c->nw, c->nR, c->sm_count, nk, c->sparse ? c->sp_nnz : 0, V_in ? true : (jb.do_mep || jb.do_kubo))
+                 : c->use_sub ? bands_sub_grid(c->nw, c->nR, c->sm_count, nk, c->sparse ? c->sp_nnz : 0)
                               : interp_small_grid(c->nw, c->nR, c->sm_count, nk);
-        gi = std::min(gi, c->grid_interp);                          // block_static holds grid_interp rows
+        gi = std::min(gi, c->grid_interp);                          // block_static holds grid_interp (+ grid_mep) rows
+        int gm = 0;                                                 // rows written by mep_sums_kernel
         if (c->large) {
             if (V_in || !first_ef) {
             } else if (c->sp.on) {
@@ -775,12 +778,22 @@ static int launch_wave(mepb_ctx *c, StreamBuf &s, long long k0, long long nk, co
         }
         if (!c->large) {
             ProfScope ps(c, s.st, MEPB_PROF_INTERP);
-            if (c->use_sub) CUDA_TRY(launch_bands_sub(m, ks, jb, o, c->max_pairs, gi, s.st));
-            else CUDA_TRY(launch_interp_small(m, ks, jb, o, c->max_pairs, gi, s.st));
+            if (c->use_sub) {
+                // MEP jobs: the band-sum kernel leaves the H-gauge velocities in HBM and mep_sums_kernel adds its rows of static sums
+                // behind the gi rows of the band-sum kernel (every other slot of them zero): one reduction over gi + gm rows
+                const bool mep = (jb.do_mep || jb.do_kubo) && c->grid_mep > 0;
+                o.V_pad = mep ? s.V_pad : nullptr;
+                CUDA_TRY(launch_bands_sub(m, ks, jb, o, c->max_pairs, gi, s.st));
+                if (mep) {
+                    gm = std::min(mep_sums_grid(c->nw, c->sm_count, nk), c->grid_mep);
+                    CUDA_TRY(launch_mep_sums(c->nw, nk, jb, o.e_in, s.V_pad, s.block_static + (size_t)gi * ns, gm, s.st));
+                    c->launches += 1;
+                }
+            } else CUDA_TRY(launch_interp_small(m, ks, jb, o, c->max_pairs, gi, s.st));
             c->launches += 1;
         }
         { ProfScope ps(c, s.st, MEPB_PROF_REDUCE);
-          CUDA_TRY(launch_reduce_rows(s.block_static, gi, ns, s.compact + (size_t)ief * c->cs.per_ef, ns, 0, 0, s.st)); }
+          CUDA_TRY(launch_reduce_rows(s.block_static, gi + gm, ns, s.compact + (size_t)ief * c->cs.per_ef, ns, 0, 0, s.st)); }
         c->launches += 1;
         if (jb.do_ahc) {
             int nsl; const int gs = sweep_ahc_grid(c->sm_count, nk, p.n_hw, &nsl, c->herm, c->max_pairs);

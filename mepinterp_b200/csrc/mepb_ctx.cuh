@@ -52,6 +52,7 @@ struct StreamBuf {
     double *block_static = nullptr, *block_sweep = nullptr, *block_photo = nullptr;
     double *compact = nullptr;   // [n_eF][per_ef]
     double *eig_E = nullptr; double2 *eig_U = nullptr;   // [chunk][nw], [chunk][nw*nw] from the thread-per-k eigensolver
+    double2 *V_pad = nullptr;                             // [chunk][3 nw (nw + 1)] H-gauge velocities, bands_sub_kernel -> mep_sums_kernel
     double2 *Hk = nullptr, *Hka = nullptr, *Vscr = nullptr;   // general path: [chunk][nw^2], [chunk][3][nw^2], [grid][3][nw^2]
     TriBuf tb{};                                                // general path: Householder + QL intermediates (mepb_tri.cu)
     double2 *G1 = nullptr, *G2 = nullptr;                       // general path, mesh mode: separable-transform tables
@@ -96,7 +97,7 @@ struct mepb_ctx {
     // schedule
     long long chunk = 0;
     int max_pairs = 0, max_photo = 0;
-    int grid_interp = 0, grid_sweep = 0, ns_sweep = 0, grid_photo = 0, ns_photo = 0;
+    int grid_interp = 0, grid_mep = 0, grid_sweep = 0, ns_sweep = 0, grid_photo = 0, ns_photo = 0;
     mepb::CompactShape cs{};
     mepb::PackedLayout L{};
     mepb::StreamBuf sb[2];

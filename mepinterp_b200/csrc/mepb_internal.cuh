@@ -112,6 +112,8 @@ struct InterpOut {
     // user layout a + 3 (n + nw m) per k-point, with e_in the energies; the kernels then skip Fourier sums, eigensolve
     // and rotation and run only their band-sum sections
     const double2 *V_in;  // (3, nw, nw, nk) or nullptr
+    // bands_sub_kernel -> mep_sums_kernel: H-gauge velocities in the padded shared-memory layout, 3 nw (nw + 1) double2 per k-point
+    double2 *V_pad;       // or nullptr (no MEP job)
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -309,7 +311,13 @@ int interp_small_grid(int nw, int nR, int sm_count, long long nk);
 bool eig_thread_supported(int nw);
 // NW-lanes-per-k band-sum kernel (mepb_sub.cu): response mode, num_wann 4 / 8, eigenpairs from launch_eig_small
 bool sub_supported(int nw, int nR);
-int bands_sub_grid(int nw, int nR, int sm_count, long long nk, int nnz, bool mep);   // nnz: staged sparse records (0: dense)
+int bands_sub_grid(int nw, int nR, int sm_count, long long nk, int nnz);   // nnz: staged sparse records (0: dense)
+// MEP (Niu + Kubo) band sums of the num_wann 4 / 8 path from the velocities bands_sub_kernel left in HBM (mepb_mep.cu); `rows`:
+// grid rows of static_size(nw) doubles in the block_static layout (only the MEP slots are non-zero)
+size_t mep_vpad_elems(int nw);
+int mep_sums_grid(int nw, int sm_count, long long nk);
+cudaError_t launch_mep_sums(int nw, long long nk, const Jobs &jobs, const double *e_in, const double2 *V_pad, double *rows, int grid,
+                            cudaStream_t st);
 cudaError_t launch_bands_sub(const DevModel &m, const KSource &ks, const Jobs &jobs, const InterpOut &out, int max_pairs, int grid,
                              cudaStream_t st);
 cudaError_t launch_eig_small(const DevModel &m, const KSource &ks, double *E_out, double2 *U_out, int *err_flag, int sm_count,

@@ -2,15 +2,16 @@
 //
 // Successor of the warp-per-k kernel of mepb_small.cu for the hot configurations (that one stays for num_wann = 16, for
 // explicit k lists and as the fallback).  A warp carries 32/NW k-points at once; lane g of a group owns row g in the
-// Fourier sums, column g in the gauge rotation, band n0 = g in the MEP sums, and a strided share of the band pairs.
+// Fourier sums, column g in the gauge rotation, and a strided share of the band pairs.
 // Everything the groups do is the same instruction stream, so the per-k instruction count drops ~3x against one warp
 // per k (profiles/r01c: 2.1 k warp instructions per k, 20 % of the FP64 roofline).  Per k-point:
 //   1. phases e^{2 pi i k.R} (sincospi) and tight-binding diagonal phases                (wann_interp.f90:215-223,259-260)
 //   2. Fourier sums of d_a H(k) from the sparse or dense H(R)                             (wann_interp.f90:206-279)
 //   3. eigenpairs from the thread-per-k solver (mepb_eig.cu)                              (matrix_math.f90:192-226)
 //   4. V_a = U^dagger (d_a H) U                                                          (wann_interp.f90:517-528)
-//   5. occupations, static AHC, pair items, MEP (Niu + Kubo) sums, photo items           (kubo.f90, mep_niu.f90, kubo_mep.f90,
-//                                                                                         photo.f90:44-81)
+//   5. occupations, static AHC, pair items, photo items                                  (kubo.f90, photo.f90:44-81)
+//   6. with the MEP jobs: the H-gauge velocities of every k-point go to HBM in the padded layout of the shared-memory buffer
+//      (out.V_pad) for mep_sums_kernel (mepb_mep.cu) — fused in here those sums cost this kernel a third of its occupancy
 // Output formats (block_static rows, item buffers) are those of mepb_small.cu, so the sweeps and the packing are shared.
 #include "mepb_internal.cuh"
 
@@ -32,17 +33,15 @@ struct SubL {  // shared-memory layout per GROUP (one k-point), bytes
     static constexpr size_t oDn = oFn + sizeof(double) * NW;
     static constexpr size_t oPh = oDn + sizeof(double2) * NW;
     // group stride = 16 mod 128 bytes, so that the same element of the 32/NW groups of a warp falls into different banks
-    // MEP builds append a table of reciprocals 1/(E_n0 - E_n), NW rows of NW + 1 doubles (conflict-free), after the nR phases
-    static size_t bytes(int nR, bool mep) {
-        size_t b = oPh + sizeof(double2) * nR + (mep ? sizeof(double) * NW * (NW + 1) : 0);
+    static size_t bytes(int nR) {
+        size_t b = oPh + sizeof(double2) * nR;
         return (b + 127) / 128 * 128 + 16;
     }
 };
 
-// MEP: build with the MEP sums (two CTAs per SM, 255 registers; otherwise three CTAs, 168); PH: build with the photo items
-// VIN: band sums on supplied eigenpairs (out.e_in, out.V_in) — Fourier sums and rotation compiled out
-template <int NW, bool MEP, bool PH, bool VIN>
-__global__ void __launch_bounds__(kSubWarps * 32, MEP ? 2 : 3)      // 36 more accumulators with the MEP jobs: 3 CTAs would spill 1.1 KB
+// PH: build with the photo items;  VIN: band sums on supplied eigenpairs (out.e_in, out.V_in) — Fourier sums and rotation compiled out
+template <int NW, bool PH, bool VIN>
+__global__ void __launch_bounds__(kSubWarps * 32, 3)                // 168 registers
 bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const InterpOut out, const int max_pairs, const size_t grp_bytes,
                  const int rec_cap) {
     using L = SubL<NW>;
@@ -77,12 +76,8 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
 
     // per-lane accumulators over all k-points of this thread's groups
     double acc_nk = 0.0, acc_ndeg = 0.0, acc_ne = 0.0, acc_nit = 0.0, acc_nph = 0.0, acc_ahc[9];
-    constexpr int NM = MEP ? 9 : 1;
-    double niu_ic[NM], niu_lc[NM], kub_ic[NM], kub_lc[NM];        // band n0 = g (only with the MEP jobs)
 #pragma unroll
     for (int q = 0; q < 9; ++q) acc_ahc[q] = 0.0;
-#pragma unroll
-    for (int q = 0; q < NM; ++q) { niu_ic[q] = 0.0; niu_lc[q] = 0.0; kub_ic[q] = 0.0; kub_lc[q] = 0.0; }
 
     const long long gstride = (long long)gridDim.x * kSubWarps * NGRP;
     const long long first = ((long long)blockIdx.x * kSubWarps + warp) * NGRP + grp;
@@ -117,7 +112,7 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
             dn[g] = make_double2(c, s);
         }
         double2 u[NW];                                             // column g of U (eigenvector of band g)
-        constexpr bool kDmmaRot = (NW == 8) && (MEP || !PH) && !VIN;   // tensor-core rotation (section 4)
+        constexpr bool kDmmaRot = (NW == 8) && !PH && !VIN;            // tensor-core rotation (section 4)
         {
             if (!vin && !kDmmaRot) {                                 // (the tensor-core rotation has its own fragments)
                 const double2 *Uk = out.U_in + (size_t)ik * NW2 + (size_t)NW * g;   // element r + NW*c: 128 contiguous bytes per lane
@@ -268,6 +263,22 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
         }
         const double2 *Vs = Ha;                                     // Vs[a*NW*LD + n*LD + m] = V_ka(a,n,m)
         if (valid && g == 0) acc_nk += 1.0;
+        // ------------------------------------------------------------------ 6. velocities for mep_sums_kernel (MEP jobs only)
+        // The padded buffers of the warp's k-points leave as they are: 3 NW (NW + 1) double2 each, coalesced 128-bit stores
+        // (32 lanes x 16 contiguous bytes per instruction).  (The rotation ended with a __syncwarp: every buffer is complete.)
+        if (out.V_pad) {
+            constexpr int VSZ = 3 * NW * LD;
+#pragma unroll 1
+            for (int gq = 0; gq < NGRP; ++gq) {
+                const long long ikq = first - grp + gq + it * gstride;
+                if (ikq < ks.nk) {
+                    const double2 *src = reinterpret_cast<const double2 *>(smem_raw + ((size_t)warp * NGRP + gq) * grp_bytes + L::oHa);
+                    double2 *dst = out.V_pad + (size_t)ikq * VSZ;
+#pragma unroll
+                    for (int idx = lane; idx < VSZ; idx += 32) dst[idx] = src[idx];
+                }
+            }
+        }
         // ------------------------------------------------------------------ 5. pair sums + AHC items
         {
             const int istride = jb.herm ? kAhcItemH : kAhcItemG;
@@ -336,82 +347,6 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
                 n_items_before += __popc(bal);
             }
             if (valid && out.cnt_ahc && g == 0) { out.cnt_ahc[ik] = n_items_before; acc_nit += (double)n_items_before; }
-        }
-        // ------------------------------------------------------------------ MEP sums, band n0 = g (mep_niu.f90, kubo_mep.f90)
-        if (MEP && (jb.do_mep || jb.do_kubo) && valid) {               // idle groups (past the end of the launch) contribute nothing
-            const int n0 = g;
-            const double e0 = es[n0];
-            // reciprocals 1/(E_n0 - E_n): one division per band and lane (row n0 of the table) instead of one per (n, m) term
-            double *rt = reinterpret_cast<double *>(base + L::oPh + sizeof(double2) * nR) + n0 * (NW + 1);
-#pragma unroll
-            for (int n = 0; n < NW; ++n) rt[n] = 1.0 / (e0 - es[n]);          // entry n0 is inf and never used
-            // the per-k terms go straight into the launch-long accumulators with their weights (1 for band n0 <= nval of
-            // mep_niu, f_n0 for kubo_mep): 36 fewer live doubles in a kernel that spills at 255 registers
-            const double w_niu = (jb.do_mep && n0 < jb.nval) ? 1.0 : 0.0;
-            const double w_kub = jb.do_kubo ? fn[n0] : 0.0;
-            double2 v00[3];
-#pragma unroll
-            for (int a = 0; a < 3; ++a) v00[a] = Vs[a * NW * LD + n0 * LD + n0];
-#pragma unroll 1
-            for (int n = 0; n < NW; ++n) {
-                if (n == n0) continue;
-                const double d0n = e0 - es[n];
-                double2 v0n[3], vn0[3];
-#pragma unroll
-                for (int a = 0; a < 3; ++a) { v0n[a] = Vs[a * NW * LD + n0 * LD + n]; vn0[a] = Vs[a * NW * LD + n * LD + n0]; }
-                const double rn = rt[n], rn2 = rn * rn;
-                {   // local term: sum_kl eps_jkl Re[V(i,n0,n) V(k,n,n0) V(l,n0,n0)] / (E_n0-E_n)^3
-                    const double den = d0n * d0n * d0n;
-                    const bool pass = fabs(den) > jb.kubo_tol;
-                    const double inv = rn2 * rn;
-                    auto re = [](double2 x, double2 y) { return x.x * y.x - x.y * y.y; };
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        double2 Q[3];
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) Q[k] = cmul(v0n[i], vn0[k]);
-                        const double c0 = re(Q[1], v00[2]) - re(Q[2], v00[1]);
-                        const double c1 = re(Q[2], v00[0]) - re(Q[0], v00[2]);
-                        const double c2 = re(Q[0], v00[1]) - re(Q[1], v00[0]);
-                        const double iu = inv * w_kub, ig = pass ? inv * w_niu : 0.0;
-                        kub_lc[i] = fma(c0, iu, kub_lc[i]); kub_lc[i + 3] = fma(c1, iu, kub_lc[i + 3]); kub_lc[i + 6] = fma(c2, iu, kub_lc[i + 6]);
-                        niu_lc[i] = fma(c0, ig, niu_lc[i]); niu_lc[i + 3] = fma(c1, ig, niu_lc[i + 3]); niu_lc[i + 6] = fma(c2, ig, niu_lc[i + 6]);
-                    }
-                }
-                {   // itinerant term: - sum_{m != n0} eps_jkl Re[V(i,n0,n) V(k,n,m) V(l,m,n0)] / ((E_n0-E_n)^2 (E_n0-E_m))
-                    double2 Zg[3], Zu[3];
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) { Zg[j] = make_double2(0, 0); Zu[j] = make_double2(0, 0); }
-                    const double d2 = d0n * d0n;
-#pragma unroll 2
-                    for (int mm = 0; mm < NW; ++mm) {
-                        if (mm == n0) continue;
-                        const double den = d2 * (e0 - es[mm]);
-                        const double inv = rn2 * rt[mm];
-                        const bool pass = fabs(den) > jb.kubo_tol;
-                        double2 a_[3], b_[3];
-#pragma unroll
-                        for (int a = 0; a < 3; ++a) { a_[a] = Vs[a * NW * LD + n * LD + mm]; b_[a] = Vs[a * NW * LD + mm * LD + n0]; }
-                        double2 X[3];
-                        X[0] = csub(cmul(a_[1], b_[2]), cmul(a_[2], b_[1]));
-                        X[1] = csub(cmul(a_[2], b_[0]), cmul(a_[0], b_[2]));
-                        X[2] = csub(cmul(a_[0], b_[1]), cmul(a_[1], b_[0]));
-                        const double wg = pass ? inv : 0.0;                    // guarded weight: one select instead of six predicated FMAs
-#pragma unroll
-                        for (int j = 0; j < 3; ++j) {
-                            Zu[j].x = fma(X[j].x, inv, Zu[j].x); Zu[j].y = fma(X[j].y, inv, Zu[j].y);
-                            Zg[j].x = fma(X[j].x, wg, Zg[j].x); Zg[j].y = fma(X[j].y, wg, Zg[j].y);
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 3; ++j)
-#pragma unroll
-                        for (int i = 0; i < 3; ++i) {
-                            kub_ic[i + 3 * j] -= w_kub * (v0n[i].x * Zu[j].x - v0n[i].y * Zu[j].y);
-                            niu_ic[i + 3 * j] -= w_niu * (v0n[i].x * Zg[j].x - v0n[i].y * Zg[j].y);
-                        }
-                }
-            }
         }
         // ------------------------------------------------------------------ photo items (photo.f90:44-81)
         // PAIRED ORDER: the items of the ordered band pairs (n, l) and (l, n) go into two consecutive slots (2p, 2p + 1).
@@ -494,40 +429,13 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
         const double nit = warp_sum(acc_nit), nph = warp_sum(acc_nph);
 #pragma unroll
         for (int q = 0; q < 9; ++q) acc_ahc[q] = warp_sum(acc_ahc[q]);
-        // band-resolved sums: add the lanes with the same g across the groups of the warp
-#pragma unroll
-        for (int q = 0; q < NM; ++q) {
-#pragma unroll
-            for (int o = NW; o < 32; o <<= 1) {
-                niu_ic[q] += __shfl_xor_sync(0xffffffffu, niu_ic[q], o);
-                niu_lc[q] += __shfl_xor_sync(0xffffffffu, niu_lc[q], o);
-                kub_ic[q] += __shfl_xor_sync(0xffffffffu, kub_ic[q], o);
-                kub_lc[q] += __shfl_xor_sync(0xffffffffu, kub_lc[q], o);
-            }
-        }
-        // kubo sums run over all bands: reduce over g as well
-        double kic[9], klc[9];
-#pragma unroll
-        for (int q = 0; q < 9; ++q) {
-            kic[q] = MEP ? kub_ic[q % NM] : 0.0; klc[q] = MEP ? kub_lc[q % NM] : 0.0;
-#pragma unroll
-            for (int o = NW / 2; o > 0; o >>= 1) {
-                kic[q] += __shfl_xor_sync(0xffffffffu, kic[q], o);
-                klc[q] += __shfl_xor_sync(0xffffffffu, klc[q], o);
-            }
-        }
         double *wv = stage + (size_t)warp * NS;
         if (lane == 0) {
             wv[S_NK] = nk; wv[S_NDEG] = nd; wv[S_NE] = ne; wv[S_NIT] = nit; wv[S_NPH] = nph;
 #pragma unroll
-            for (int q = 0; q < 9; ++q) { wv[S_AHC + q] = acc_ahc[q]; wv[S_KIC + q] = kic[q]; wv[S_KLC + q] = klc[q]; }
+            for (int q = 0; q < 9; ++q) { wv[S_AHC + q] = acc_ahc[q]; wv[S_KIC + q] = 0.0; wv[S_KLC + q] = 0.0; }   // MEP slots:
         }
-        if (lane < NW) {
-#pragma unroll
-            for (int q = 0; q < 9; ++q) {
-                wv[S_NIU + 9 * lane + q] = MEP ? niu_ic[q % NM] : 0.0; wv[S_NIU + 9 * NW + 9 * lane + q] = MEP ? niu_lc[q % NM] : 0.0;
-            }
-        }
+        for (int i = lane; i < 18 * NW; i += 32) wv[S_NIU + i] = 0.0;                                                  // mep_sums_kernel
     }
     __syncthreads();
     for (int i = threadIdx.x; i < NS; i += blockDim.x) {
@@ -540,8 +448,8 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
 inline int sub_rec_cap(int nnz) { return (nnz > 0 && nnz <= kSubMaxNnz) ? (nnz + 7) / 8 * 8 : 8; }   // staged sparse records
 
 template <int NW>
-size_t sub_smem(int nR, int nnz = kSubMaxNnz, bool mep = true) {
-    const size_t groups = (size_t)kSubWarps * (32 / NW) * SubL<NW>::bytes(nR, mep) + sizeof(SpRec) * sub_rec_cap(nnz) + sizeof(int) * (NW * NW + 4);
+size_t sub_smem(int nR, int nnz = kSubMaxNnz) {
+    const size_t groups = (size_t)kSubWarps * (32 / NW) * SubL<NW>::bytes(nR) + sizeof(SpRec) * sub_rec_cap(nnz) + sizeof(int) * (NW * NW + 4);
     const size_t stage = sizeof(double) * kSubWarps * (S_NIU + 18 * NW);
     return groups > stage ? groups : stage;
 }
@@ -550,24 +458,18 @@ template <int NW>
 cudaError_t launch_sub_t(const DevModel &m, const KSource &ks, const Jobs &jobs, const InterpOut &out, int max_pairs, int grid,
                          cudaStream_t st) {
     const int rec_cap = sub_rec_cap(m.sp_ptr ? m.sp_nnz : 0);
-    const bool mep = jobs.do_mep || jobs.do_kubo, ph = jobs.do_opt != 0;
-    const size_t smem = sub_smem<NW>(m.nR, m.sp_ptr ? m.sp_nnz : 0, mep);
+    const bool ph = jobs.do_opt != 0;
+    const size_t smem = sub_smem<NW>(m.nR, m.sp_ptr ? m.sp_nnz : 0);
     cudaError_t e;
-#define MEPB_LAUNCH_SUB(M, P, V)                                                                                               \
+#define MEPB_LAUNCH_SUB(P, V)                                                                                                  \
     do {                                                                                                                        \
-        e = cudaFuncSetAttribute(bands_sub_kernel<NW, M, P, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+        e = cudaFuncSetAttribute(bands_sub_kernel<NW, P, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
         if (e != cudaSuccess) return e;                                                                                         \
-        bands_sub_kernel<NW, M, P, V><<<grid, kSubWarps * 32, smem, st>>>(m, ks, jobs, out, max_pairs, SubL<NW>::bytes(m.nR, M), rec_cap); \
+        bands_sub_kernel<NW, P, V><<<grid, kSubWarps * 32, smem, st>>>(m, ks, jobs, out, max_pairs, SubL<NW>::bytes(m.nR), rec_cap); \
     } while (0)
-    if (out.V_in) {                                        // supplied eigenpairs: one build with every job compiled in
-        const size_t smem_v = sub_smem<NW>(m.nR, m.sp_ptr ? m.sp_nnz : 0, true);
-        e = cudaFuncSetAttribute(bands_sub_kernel<NW, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v);
-        if (e != cudaSuccess) return e;
-        bands_sub_kernel<NW, true, true, true><<<grid, kSubWarps * 32, smem_v, st>>>(m, ks, jobs, out, max_pairs, SubL<NW>::bytes(m.nR, true), rec_cap);
-    }
-    else if (mep) MEPB_LAUNCH_SUB(true, true, false);
-    else if (ph) MEPB_LAUNCH_SUB(false, true, false);
-    else MEPB_LAUNCH_SUB(false, false, false);
+    if (out.V_in) MEPB_LAUNCH_SUB(true, true);             // supplied eigenpairs: one build with every job compiled in
+    else if (ph) MEPB_LAUNCH_SUB(true, false);
+    else MEPB_LAUNCH_SUB(false, false);
 #undef MEPB_LAUNCH_SUB
     return cudaGetLastError();
 }
@@ -580,10 +482,10 @@ bool sub_supported(int nw, int nR) {
     return false;
 }
 
-int bands_sub_grid(int nw, int nR, int sm_count, long long nk, int nnz, bool mep) {
-    const size_t smem = (nw == 4 ? sub_smem<4>(nR, nnz, mep) : sub_smem<8>(nR, nnz, mep)) + 1024;
+int bands_sub_grid(int nw, int nR, int sm_count, long long nk, int nnz) {
+    const size_t smem = (nw == 4 ? sub_smem<4>(nR, nnz) : sub_smem<8>(nR, nnz)) + 1024;
     int per_sm = (int)((227 * 1024) / smem);
-    if (per_sm > (mep ? 2 : 3)) per_sm = mep ? 2 : 3;  // __launch_bounds__(128, MEP ? 2 : 3)
+    if (per_sm > 3) per_sm = 3;                        // __launch_bounds__(128, 3)
     if (per_sm < 1) per_sm = 1;
     const int kpb = kSubWarps * (32 / nw);
     long long need = (nk + kpb - 1) / kpb;
