@@ -79,24 +79,34 @@ mep_sums_kernel(const long long nk, const Jobs jb, const double *__restrict__ e_
             }
         }
         const long long ik = first + grp + it * gstride;
-        const bool valid = ik < nk;
-        const int n0 = g;
-        const double e0 = valid ? e_in[(size_t)ik * NW + g] : 0.0;
-        const double f0 = fermi(e0, jb);
-        es[g] = e0;
+        const bool valid = ik < nk;                                // idle groups (past the end of the launch) contribute nothing
+        const double e_own = valid ? e_in[(size_t)ik * NW + g] : 0.0;
+        es[g] = e_own;
+        // Roles.  A band has work when one of its weights is non-zero: 1 for n0 <= valence_bands of mep_niu, f(E_n0) for kubo_mep.
+        // At T = 0 that is half of the bands or fewer (the reference's MEP runs: insulators, FeMn at E_F = 0 with valence_bands = 4 —
+        // bands 5..8 never contribute), so lane g is paired with lane g ^ NW/2: when exactly one of the two bands has work, both
+        // lanes take half of its n loop.  The mep_niu sums stay band-resolved: a lane that helps is one whose own band has no
+        // mep_niu weight ever (its band index is above valence_bands), so its registers only ever hold its partner's band.
+        constexpr int P = NW / 2;
+        const bool own = valid && ((jb.do_mep && g < jb.nval) || (jb.do_kubo && fermi(e_own, jb) != 0.0));
+        const unsigned owners = __ballot_sync(0xffffffffu, own);
+        const bool partner_own = (owners >> (lane ^ P)) & 1u;
+        const int n0 = own ? g : (g ^ P);
+        const int n_lo = own ? 0 : P, n_hi = (own && !partner_own) ? P : NW;
         __syncwarp();
-        if (valid) {                                               // idle groups (past the end of the launch) contribute nothing
-            // reciprocals 1/(E_n0 - E_n): one division per band and lane (row n0 of the table) instead of one per (n, m) term
+        if (own || partner_own) {
+            const double e0 = es[n0];
+            // reciprocals 1/(E_n0 - E_n): one division per band and lane (row g of the table; a helper fills its own idle row with its
+            // partner's values) instead of one per (n, m) term
 #pragma unroll
             for (int n = 0; n < NW; ++n) rt[n] = 1.0 / (e0 - es[n]);          // entry n0 is inf and never used
-            // weights: 1 for band n0 <= valence_bands of mep_niu, f(E_n0) for kubo_mep
             const double w_niu = (jb.do_mep && n0 < jb.nval) ? 1.0 : 0.0;
-            const double w_kub = jb.do_kubo ? f0 : 0.0;
+            const double w_kub = jb.do_kubo ? fermi(e0, jb) : 0.0;
             double2 v00[3];
 #pragma unroll
             for (int a = 0; a < 3; ++a) v00[a] = Vs[a * NW * LD + n0 * LD + n0];
 #pragma unroll 1
-            for (int n = 0; n < NW; ++n) {
+            for (int n = n_lo; n < n_hi; ++n) {
                 if (n == n0) continue;
                 const double d0n = e0 - es[n];
                 double2 v0n[3], vn0[3];
@@ -169,6 +179,17 @@ mep_sums_kernel(const long long nk, const Jobs jb, const double *__restrict__ e_
     constexpr int NS = S_NIU + 18 * NW;
     double *stage = reinterpret_cast<double *>(smem_raw);          // [kMepWarps][NS]  (group buffers are dead now)
     {
+        // mep_niu: what the partner lane gathered as a helper belongs to this band (a partner with an index above valence_bands never
+        // has a mep_niu weight of its own); lanes above valence_bands own nothing
+        {
+            const bool take = (g < jb.nval) && ((g ^ (NW / 2)) >= jb.nval);
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+                const double ti = __shfl_xor_sync(0xffffffffu, niu_ic[q], NW / 2), tl = __shfl_xor_sync(0xffffffffu, niu_lc[q], NW / 2);
+                niu_ic[q] = (g < jb.nval) ? niu_ic[q] + (take ? ti : 0.0) : 0.0;
+                niu_lc[q] = (g < jb.nval) ? niu_lc[q] + (take ? tl : 0.0) : 0.0;
+            }
+        }
         // band-resolved sums: add the lanes with the same band across the groups of the warp
 #pragma unroll
         for (int q = 0; q < 9; ++q) {
