@@ -120,9 +120,17 @@ def flops_model(model, params):
         interp += 48.0 * nw ** 3                                      # U^dagger (d_a H) U, a = 1..3
     if params.do_ahc:
         interp += 60.0 * nw * nw
+    # MEP sums (mep_niu IC + LC and kubo_mep IC + LC share every product).  Per band n0 and intermediate band n:
+    # (nw - 1) x [complex cross product 42 + 12 accumulate FMAs 24 + weights 4] + local term 105 + epilogue 84 = 99 per (n0, n, m) triple.  mep_sums_kernel (nw 4 / 8) skips the bands whose weights are zero — at T = 0 only max(valence_bands, occupied) bands
+    # per k-point are worked on (measure() takes the occupied count from the run's own N_el); the other paths do all nw bands,
+    # with the guard and the weights applied per term (130 per triple)
+    mep_per_band = 0.0
     if params.do_mep or params.do_kubo:
-        interp += 130.0 * nw * (nw - 1) ** 2
-    out = {"interp_per_k": interp, "sparse": sparse, "nnz": nnz, "herm": herm,
+        if split:
+            mep_per_band = 99.0 * (nw - 1) ** 2
+        else:
+            interp += 130.0 * nw * (nw - 1) ** 2
+    out = {"interp_per_k": interp, "mep_per_band": mep_per_band, "sparse": sparse, "nnz": nnz, "herm": herm,
            # context only (LAPACK-convention count of a Hermitian eigensolve with vectors); not used for a roofline fraction
            "eig_lapack_per_k": (8.0 * (nnz_up if sparse else nR * (nw * (nw + 1) // 2)) + 36.0 * nw ** 3) if split else 0.0,
            "sweep_ahc_per_item_hw": 56.0 if herm else 92.0,          # 1 complex reciprocal + 18 (36) accumulate FMAs
@@ -367,6 +375,14 @@ def measure(env: Env, workload: str, steps: int, warmup: int, scaling: str, mesh
     ctx.set_profiling(False)
     info = ctx.model_info()
     fm = flops_model(model, params)
+    if fm["mep_per_band"]:
+        # bands mep_sums_kernel works on per k-point, a lower bound: the union of {n0 <= valence_bands} (mep_niu) and, for kubo_mep,
+        # the bands with f(E) != 0 — all of them at T > 0, the occupied ones at T = 0 (N_el of this rank's share / its k-points)
+        zero_T = not (params.T_kelvin > 1e-2)
+        occ = (float(part[2]) / max(nk_loc, 1)) if zero_T else float(model.nw)
+        bands = max(float(params.valence_bands) if params.do_mep else 0.0, occ if params.do_kubo else 0.0)
+        fm["interp_per_k"] += fm["mep_per_band"] * min(bands, float(model.nw))
+        fm["mep_bands_per_k"] = bands
     work = {"interp": fm["interp_per_k"] * nk_loc, "fourier": fm["fourier_per_k"] * nk_loc, "eig_rot": fm["eig_rot_per_k"] * nk_loc,
             "sweep_ahc": fm["sweep_ahc_per_item_hw"] * items["sweep_ahc"] * params.n_hw,
             "sweep_photo": fm["sweep_photo_per_item_hw"] * items["sweep_photo"] * params.n_hw}

@@ -112,7 +112,7 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
             dn[g] = make_double2(c, s);
         }
         double2 u[NW];                                             // column g of U (eigenvector of band g)
-        constexpr bool kDmmaRot = (NW == 8) && !PH && !VIN;            // tensor-core rotation (section 4)
+        constexpr bool kDmmaRot = (NW == 8) && !VIN;                   // tensor-core rotation (section 4)
         {
             if (!vin && !kDmmaRot) {                                 // (the tensor-core rotation has its own fragments)
                 const double2 *Uk = out.U_in + (size_t)ik * NW2 + (size_t)NW * g;   // element r + NW*c: 128 contiguous bytes per lane
@@ -191,7 +191,7 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
         // ------------------------------------------------------------------ 4. gauge rotation V_a = U^dagger (d_a H) U
         // lane g: column g of T = H_a U from its own u (registers), written over H_a; then ROW g of V_a = U^dagger T,
         // again from its own u — U never goes through shared memory.
-        if (kDmmaRot && jb.do_gauge) {      // (photo-only build: store bound, the FMA form below is faster there)
+        if (kDmmaRot && jb.do_gauge) {      // (every NW = 8 build; the FMA form below serves NW = 4)
             // Tensor-core rotation (mma.sync.m8n8k4.f64 -> SASS DMMA): the warp takes its four k-points one after the other, all 32
             // lanes on one 8 x 8 complex problem.  With the contraction index ordered p = 2 j + ks (j = lane & 3, ks = k-step) the
             // SAME two U elements per lane, U(2j + ks, lane >> 2), are the A fragment of both products
