@@ -41,6 +41,8 @@ def _cases_small():
     for nw in (4, 16):
         yield f"syn_nw{nw}_wannier_T200", (synthetic_model(nw, 3), mo.Params(mp_grid=(8, 8, 8), valence_bands=nw // 2, T_kelvin=200.0,
                                                                               **dict(all_jobs, n_hw=5)))
+    yield "syn_nw8_nval6_T0_all_jobs", (sm, mo.Params(mp_grid=(7, 7, 6), valence_bands=6, **all_jobs))       # mep_sums_kernel helper lanes
+    yield "syn_nw4_nval1_T0_all_jobs", (synthetic_model(4, 3), mo.Params(mp_grid=(9, 8, 7), valence_bands=1, **dict(all_jobs, n_hw=5)))
     yield "syn_nw16_tb_neF2", (synthetic_model(16, 2, tb_centers=True),
                                mo.Params(mp_grid=(5, 5, 5), valence_bands=7, n_eF=2, eF_min=ev(-0.3), eF_max=ev(0.2), **all_jobs))
 
@@ -602,6 +604,17 @@ def _band_sum_cases():
     yield "syn_nw64_T300_no_photo", (synthetic_model(64, 4), mo.Params(mp_grid=(3, 3, 2), valence_bands=30, T_kelvin=300.0,
                                                                       **dict(jobs, n_hw=16, do_opt=False))), None
     yield "femn_general_path", load_case("femn_d0.900", mp_grid=(8, 8, 8), valence_bands=4, **jobs), "large"
+    # mep_sums_kernel (mepb_mep.cu): lanes whose band has no weight help their partner band (g ^ NW/2).  valence_bands above, at and
+    # below NW/2, T = 0 (occupied set varies over the mesh: kubo-only owners above valence_bands) and T > 0 (nobody helps), one job only
+    mj = dict(do_mep=True, do_kubo=True, do_ahc=False, do_opt=False, n_hw=1, hw_max=0.0)
+    s8, s4 = synthetic_model(8, 3, tb_centers=True), synthetic_model(4, 3)
+    yield "mep_nw8_nval6_T0", (s8, mo.Params(mp_grid=(7, 6, 5), valence_bands=6, **mj)), None
+    yield "mep_nw8_nval2_T0_neF2", (s8, mo.Params(mp_grid=(6, 5, 7), valence_bands=2, n_eF=2, eF_min=ev(-0.8), eF_max=ev(0.6), **mj)), None
+    yield "mep_nw8_nval5_T150", (s8, mo.Params(mp_grid=(5, 5, 5), valence_bands=5, T_kelvin=150.0, **mj)), None
+    yield "mep_nw8_niu_only_nval3", (s8, mo.Params(mp_grid=(6, 6, 5), valence_bands=3, **dict(mj, do_kubo=False))), None
+    yield "mep_nw8_kubo_only_T0", (s8, mo.Params(mp_grid=(6, 6, 5), valence_bands=4, **dict(mj, do_mep=False))), None
+    yield "mep_nw4_nval1_T0", (s4, mo.Params(mp_grid=(8, 7, 6), valence_bands=1, **mj)), None
+    yield "mep_nw4_nval3_T0", (s4, mo.Params(mp_grid=(8, 7, 6), valence_bands=3, **mj)), None
 
 
 BS_CASES = {n: (c, f) for n, c, f in _band_sum_cases()}
