@@ -113,6 +113,18 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
         }
         double2 u[NW];                                             // column g of U (eigenvector of band g)
         constexpr bool kDmmaRot = (NW == 8) && !VIN;                   // tensor-core rotation (section 4)
+        // its U fragments, U(2j + ks, lane >> 2) of one k-point at a time, are fetched one k-point ahead: the first here, behind the
+        // Fourier sums, the next ones behind the multiply-adds of their predecessor (ncu r03v: 14 % of the kernel's stall samples sat
+        // on the first DMMA of a k-point, waiting for this load; fetching all four up front costs 32 registers and was slower).
+        // Not in the photo build: there it cost 16 % (r04n), the fragments are fetched where they are used.
+        constexpr bool kPipeU = kDmmaRot && !PH;
+        double2 un0 = make_double2(0.0, 0.0), un1 = un0;
+        auto fetch_u = [&](int gq) {
+            long long ikq = first - grp + gq + it * gstride;
+            if (ikq >= ks.nk) ikq = ks.nk - 1;
+            ld_global_nc_256(out.U_in + (size_t)ikq * NW2 + (size_t)NW * (lane >> 2) + 2 * (lane & 3), un0, un1);   // 32 contiguous bytes
+        };
+        if (kPipeU && jb.do_gauge) fetch_u(0);
         {
             if (!vin && !kDmmaRot) {                                 // (the tensor-core rotation has its own fragments)
                 const double2 *Uk = out.U_in + (size_t)ik * NW2 + (size_t)NW * g;   // element r + NW*c: 128 contiguous bytes per lane
@@ -202,12 +214,9 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
             const int j = lane & 3, rq = lane >> 2;
 #pragma unroll 1
             for (int gq = 0; gq < NGRP; ++gq) {
-                // (fetching these fragments ahead of the Fourier sums, to hide their latency, was measured slower: r03q, 5.23 vs 5.06 ms)
-                long long ikq = first - grp + gq + it * gstride;
-                if (ikq >= ks.nk) ikq = ks.nk - 1;
-                const double2 *Uq = out.U_in + (size_t)ikq * NW2 + (size_t)NW * rq + 2 * j;     // U(2j + ks, rq): 32 contiguous bytes
-                double2 u0, u1;
-                ld_global_nc_256(Uq, u0, u1);
+                if (!kPipeU) fetch_u(gq);
+                const double2 u0 = un0, u1 = un1;
+                if (kPipeU && gq + 1 < NGRP) fetch_u(gq + 1);
                 double2 *Hq = reinterpret_cast<double2 *>(smem_raw + ((size_t)warp * NGRP + gq) * grp_bytes + L::oHa);
 #pragma unroll
                 for (int a = 0; a < 3; ++a) {
