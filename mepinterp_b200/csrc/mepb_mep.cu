@@ -78,6 +78,15 @@ mep_sums_kernel(const long long nk, const Jobs jb, const double *__restrict__ e_
                 for (int idx = lane; idx < VSZ; idx += 32) dst[idx] = __ldg(src + idx);
             }
         }
+        // next iteration's records towards L2 while this one computes (the warp's 32 / NW records are contiguous: one bulk prefetch;
+        // ncu r04p: 23 % of the stall samples were these loads, with no room in shared memory for a second buffer)
+        {
+            const long long ikn = first + (it + 1) * gstride;
+            if (lane == 0 && ikn < nk) {
+                const unsigned cnt = (unsigned)((nk - ikn < NGRP) ? (nk - ikn) : NGRP);
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(V_pad + (size_t)ikn * VSZ), "r"(cnt * (unsigned)(sizeof(double2) * VSZ)) : "memory");
+            }
+        }
         const long long ik = first + grp + it * gstride;
         const bool valid = ik < nk;                                // idle groups (past the end of the launch) contribute nothing
         const double e_own = valid ? e_in[(size_t)ik * NW + g] : 0.0;
