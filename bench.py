@@ -115,7 +115,9 @@ def flops_model(model, params):
     large = nw not in (4, 8, 16)
     # band-sum kernel: Fourier sums of the three d_aH — per entry one complex multiply (6), the H accumulate (2) and three
     # real x complex multiply-adds (12) = 20 flops (dense: per (R, element))
-    interp = 20.0 * (nnz if sparse else nR * nw * nw) + (0.0 if split else 36.0 * nw ** 3)
+    # (Hermitian-closed sparse models on the nw 4 / 8 path: the kernel sums the upper triangle only and mirrors it)
+    up_only = sparse and split and herm and nnz <= 256                # mepb_api.cu build_sparse / kSubMaxNnz
+    interp = 20.0 * ((nnz_up if up_only else nnz) if sparse else nR * nw * nw) + (0.0 if split else 36.0 * nw ** 3)
     if params.do_gauge_trafo:
         interp += 48.0 * nw ** 3                                      # U^dagger (d_a H) U, a = 1..3
     if params.do_ahc:

@@ -135,6 +135,7 @@ DevModel dev_model(const mepb_ctx *c) {
     m.nw = c->nw; m.nR = c->nR; m.H = c->d_H; m.Rf = c->d_Rf; m.cR = c->d_cR;
     m.tau = c->has_tau ? c->d_tau : nullptr; m.tM = c->d_tM;
     m.sp_ptr = c->sparse ? c->d_sp_ptr : nullptr; m.sp_R = c->d_sp_R; m.sp_val = c->d_sp_val; m.sp_nnz = c->sp_nnz;
+    m.sp_up = c->sparse ? c->sp_up : 0;
     m.ell_n = c->ell_n; m.ell_nR = c->ell_nR;
     m.ell_R = (c->sparse && c->ell_n > 0) ? c->d_ell_R : nullptr; m.ell_val = c->d_ell_val; m.ell_x = c->d_ell_x;
     return m;
@@ -345,7 +346,32 @@ cudaError_t build_sparse(mepb_ctx *c, const mepb_model *model) {
     }
     c->sparse = !getenv("MEPB_DENSE_FOURIER") && (2 * col.size() < (size_t)nw2 * nR);
     c->sp_nnz = (int)col.size();
+    c->sp_up = 0;
     if (!c->sparse) return cudaSuccess;
+    // Hermitian-closed model: H(k) and d_aH(k) are Hermitian, so the band-sum kernel (mepb_sub.cu) sums the upper triangle only
+    // and mirrors it.  Its NW lanes share the nw (nw + 1) / 2 elements by non-zero count (longest first onto the least loaded lane);
+    // the schedule rides behind the CSR pointers: [nw^2 + 1] = 1, then nw + 1 lane offsets, then the elements n | m << 8.
+    if (c->herm && (c->nw == 4 || c->nw == 8) && !getenv("MEPB_FOURIER_ROWS")) {
+        const int nw = c->nw, nel = nw * (nw + 1) / 2;
+        std::vector<std::pair<int, int>> el;                      // (cost, n | m << 8)
+        for (int mm = 0; mm < nw; ++mm)
+            for (int n = 0; n <= mm; ++n) { const int idx = n + nw * mm; el.push_back({2 * (ptr[idx + 1] - ptr[idx]) + 3, n | (mm << 8)}); }
+        std::stable_sort(el.begin(), el.end(), [](const std::pair<int, int> &a, const std::pair<int, int> &b) { return a.first > b.first; });
+        std::vector<std::vector<int>> lanes(nw);
+        std::vector<int> load(nw, 0);
+        for (const auto &e : el) {
+            int best = 0;
+            for (int l = 1; l < nw; ++l) if (load[l] < load[best]) best = l;
+            lanes[best].push_back(e.second); load[best] += e.first;
+        }
+        ptr.push_back(1);
+        int off = 0;
+        for (int l = 0; l < nw; ++l) { ptr.push_back(off); off += (int)lanes[l].size(); }
+        ptr.push_back(off);
+        for (int l = 0; l < nw; ++l) for (int code : lanes[l]) ptr.push_back(code);
+        (void)nel;
+        c->sp_up = 1;
+    }
     cudaFree(c->d_sp_ptr); cudaFree(c->d_sp_R); cudaFree(c->d_sp_val);
     c->d_sp_ptr = c->d_sp_R = nullptr; c->d_sp_val = nullptr;
     cudaError_t e;

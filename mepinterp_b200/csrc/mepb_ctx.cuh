@@ -88,6 +88,7 @@ struct mepb_ctx {
     double Mmat[9];            // c_a(R) = sum_j Mmat[a + 3 j] R_j
     int *d_sp_ptr = nullptr, *d_sp_R = nullptr; double2 *d_sp_val = nullptr;   // sparse H(R) (warp-per-k Fourier sums)
     bool sparse = false; int sp_nnz = 0;
+    int sp_up = 0;             // Hermitian-closed model: upper-triangle lane schedule appended to d_sp_ptr (mepb_api.cu build_sparse)
     int *d_ell_R = nullptr; double2 *d_ell_val = nullptr; double *d_ell_x = nullptr; int ell_n = 0, ell_nR = 0;   // mepb_eig.cu
     std::vector<double> h_Rf, h_tau;   // host copies (fractional R, centres) for rebuilding the sparse forms in update_model
     double a_latt[9];

@@ -65,6 +65,7 @@ struct DevModel {
     const int *sp_R;     // [nnz] R index
     const double2 *sp_val;   // [nnz]
     int sp_nnz;
+    int sp_up;           // 1: behind sp_ptr[nw*nw] follow {1, nw + 1 lane offsets, nw (nw + 1) / 2 elements n | m << 8}: upper-triangle schedule
     // padded (ELL) form of the UPPER triangle for the thread-per-k eigensolver (mepb_eig.cu): every element p <= q, in the
     // order q-major / p-minor, has ell_n slots (R index into the compact list of R points that carry any entry, value);
     // empty slots are (0, 0+0i).  ell_x = coordinates whose phases a thread needs: the ell_nR used R points, then

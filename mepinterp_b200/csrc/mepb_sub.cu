@@ -70,8 +70,11 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
             SpRec r; r.val = m.sp_val[t]; r.c0 = m.cR[3 * R]; r.c1 = m.cR[3 * R + 1]; r.c2 = m.cR[3 * R + 2]; r.R = R; r.pad = 0;
             rec[t] = r;
         }
-        for (int i = threadIdx.x; i <= NW2; i += blockDim.x) sptr[i] = m.sp_ptr[i];
+        const int n_ptr = NW2 + 1 + (m.sp_up ? 1 + (NW + 1) + NW * (NW + 1) / 2 : 0);     // + the upper-triangle lane schedule
+        for (int i = threadIdx.x; i < n_ptr; i += blockDim.x) sptr[i] = m.sp_ptr[i];
     }
+    const bool up_sched = sp_smem && m.sp_up;                     // Hermitian-closed model: upper triangle + mirror (section 2)
+    const int *up_off = sptr + NW2 + 2, *up_el = sptr + NW2 + 2 + (NW + 1);
     __syncthreads();
 
     // per-lane accumulators over all k-points of this thread's groups
@@ -145,9 +148,13 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
                 Ha[a * NW * LD + n * LD + mm] = __ldg(Vk + idx);
             }
         } else {
-            const int n = g;
+            // rows: lane g sums row n = g (NW elements).  Hermitian-closed sparse models: the lanes share the upper triangle by
+            // non-zero count (host schedule) and mirror each element — half the records, evenly spread
+            const int e0 = up_sched ? up_off[g] : 0, e1 = up_sched ? up_off[g + 1] : NW;
 #pragma unroll 1
-            for (int mm = 0; mm < NW; ++mm) {
+            for (int e = e0; e < e1; ++e) {
+                const int code = up_sched ? up_el[e] : 0;
+                const int n = up_sched ? (code & 0xff) : g, mm = up_sched ? (code >> 8) : e;
                 const int idx = n + NW * mm;
                 double2 hk = make_double2(0, 0), gs[3] = {make_double2(0, 0), make_double2(0, 0), make_double2(0, 0)};
                 if (sp_smem) {
@@ -197,6 +204,10 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
                 }
 #pragma unroll
                 for (int a = 0; a < 3; ++a) Ha[a * NW * LD + n * LD + mm] = ga[a];
+                if (up_sched && n != mm) {
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) Ha[a * NW * LD + mm * LD + n] = cconj(ga[a]);
+                }
             }
         }
         __syncwarp();
@@ -458,7 +469,7 @@ inline int sub_rec_cap(int nnz) { return (nnz > 0 && nnz <= kSubMaxNnz) ? (nnz +
 
 template <int NW>
 size_t sub_smem(int nR, int nnz = kSubMaxNnz) {
-    const size_t groups = (size_t)kSubWarps * (32 / NW) * SubL<NW>::bytes(nR) + sizeof(SpRec) * sub_rec_cap(nnz) + sizeof(int) * (NW * NW + 4);
+    const size_t groups = (size_t)kSubWarps * (32 / NW) * SubL<NW>::bytes(nR) + sizeof(SpRec) * sub_rec_cap(nnz) + sizeof(int) * (2 * NW * NW + 8);
     const size_t stage = sizeof(double) * kSubWarps * (S_NIU + 18 * NW);
     return groups > stage ? groups : stage;
 }
