@@ -309,9 +309,9 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
                 bool emit = false;
                 double item[kAhcItemG];
                 if (pidx < NPAIR) {
-                    int mm = 1, rem = pidx;
-                    while (rem >= mm) { rem -= mm; ++mm; }
-                    const int n = rem;
+                    // pair index -> (n < mm), pidx = mm (mm - 1) / 2 + n: closed form (single precision is exact far beyond NPAIR)
+                    const int mm = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)pidx)) * 0.5f);
+                    const int n = pidx - ((mm * (mm - 1)) >> 1);
                     const double dE = es[mm] - es[n];
                     const double f_n = fn[n], f_m = fn[mm], fdm = f_m - f_n;
                     if (dE == 0.0 && valid) acc_ndeg += 1.0;
@@ -384,9 +384,8 @@ bands_sub_kernel(const DevModel m, const KSource ks, const Jobs jb, const Interp
                 bool emit = false;
                 int n0 = 0, l0 = 0;
                 if (pidx < NPAIR) {
-                    int mm = 1, rem = pidx;
-                    while (rem >= mm) { rem -= mm; ++mm; }
-                    n0 = rem; l0 = mm;                                          // n0 < l0
+                    l0 = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)pidx)) * 0.5f);
+                    n0 = pidx - ((l0 * (l0 - 1)) >> 1);                         // n0 < l0
                     emit = valid && (fn[l0] - fn[n0] != 0.0);
                 }
                 const unsigned bal = (__ballot_sync(0xffffffffu, emit) >> gshift) & gbits;
