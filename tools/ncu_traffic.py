@@ -4,7 +4,7 @@ Per kernel class (the names bench.py uses) the DRAM bytes (dram__bytes_read.sum 
 averaged over the captured launches of that class.  bench.py copies the dominant kernel's figure into roofline.traffic."""
 import collections, csv, io, json, os, re, subprocess, sys
 
-CLASSES = [("eig_small", "eig"), ("bands_sub|interp_small", "interp"), ("sweep_ahc", "sweep_ahc"), ("sweep_photo", "sweep_photo"),
+CLASSES = [("eig_small", "eig"), ("bands_sub|interp_small", "interp"), ("mep_sums", "mep_sums"), ("sweep_ahc", "sweep_ahc"), ("sweep_photo", "sweep_photo"),
            ("fourier|stage_[abc]|sep_", "fourier"), ("tridiag", "tridiag"), ("tql", "tql"), ("zrot", "zrot"), ("eig_rot_large", "eig_rot")]
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 
