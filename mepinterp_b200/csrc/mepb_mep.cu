@@ -67,17 +67,21 @@ mep_sums_kernel(const long long nk, const Jobs jb, const double *__restrict__ e_
     const long long n_iter = (nk + gstride - 1) / gstride;        // same trip count for every warp: __syncwarp stays uniform
     for (long long it = 0; it < n_iter; ++it) {
         // ------------------------------------------------------------------ the warp's 32 / NW k-points: V into shared memory
-        // (coalesced 128-bit loads: 32 lanes x 16 bytes of one k-point's contiguous 16 VSZ bytes per instruction)
+        // (coalesced 16-byte copies: 32 lanes x 16 bytes of one k-point's contiguous 16 VSZ bytes per instruction)
 #pragma unroll
         for (int gq = 0; gq < NGRP; ++gq) {
             const long long ikq = first + gq + it * gstride;
             if (ikq < nk) {
                 const double2 *src = V_pad + (size_t)ikq * VSZ;
                 double2 *dst = reinterpret_cast<double2 *>(smem_raw + ((size_t)warp * NGRP + gq) * L::bytes + L::oV);
+                // cp.async: global -> shared without a register stage, so all 4 x 7 copies of a lane are in flight together (through
+                // registers the compiler issued them in batches of one k-point: four L2 round trips per iteration instead of one)
 #pragma unroll
-                for (int idx = lane; idx < VSZ; idx += 32) dst[idx] = __ldg(src + idx);
+                for (int idx = lane; idx < VSZ; idx += 32)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + idx)), "l"(src + idx) : "memory");
             }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
         // next iteration's records towards L2 while this one computes (the warp's 32 / NW records are contiguous: one bulk prefetch;
         // ncu r04p: 23 % of the stall samples were these loads, with no room in shared memory for a second buffer)
         {
@@ -102,6 +106,7 @@ mep_sums_kernel(const long long nk, const Jobs jb, const double *__restrict__ e_
         const bool partner_own = (owners >> (lane ^ P)) & 1u;
         const int n0 = own ? g : (g ^ P);
         const int n_lo = own ? 0 : P, n_hi = (own && !partner_own) ? P : NW;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
         if (own || partner_own) {
             const double e0 = es[n0];
