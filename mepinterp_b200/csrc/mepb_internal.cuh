@@ -249,6 +249,12 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// 16-byte asynchronous copy global -> shared (LDGSTS, no register stage), its group commit and the wait for every group of the thread
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 // one 256-bit global store (sm_100: STG.E.256) of two double2 to a 32-byte aligned address
 __device__ __forceinline__ void st_global_256(double2 *p, const double2 a, const double2 b) {
     asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");

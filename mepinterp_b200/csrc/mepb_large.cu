@@ -368,7 +368,9 @@ struct LargeSmemLayout {
 // shared-memory pipe (20 TF); here it is one LDS.128 per 2.5 DMMA = 640 FMA.
 // CONJT: op(Am) = Am^dagger (element (n, p) = conj(Am[p LD + n])).  Output: Cs row-major in shared memory, or Cg column-major
 // (n + nw j) in global memory.
-template <bool CONJT>
+// LOWCONJ (with CONJT = false): Am holds a Hermitian matrix as its upper triangle copied raw to (p, q) AND (q, p): the strictly
+// lower elements are conjugated as they are loaded.
+template <bool CONJT, bool LOWCONJ = false>
 __device__ __forceinline__ void zgemm_dmma(const int nw, const int LDA, const int LD, const double2 *__restrict__ Am,
                                            const double2 *__restrict__ Bm, double2 *__restrict__ Cs, double2 *__restrict__ Cg) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -382,6 +384,7 @@ __device__ __forceinline__ void zgemm_dmma(const int nw, const int LDA, const in
         for (int ks = 0; ks < (nw >> 2); ++ks) {
             double2 a = CONJT ? Am[(4 * ks + kq) * LDA + 8 * tr + nq] : Am[(8 * tr + nq) * LDA + 4 * ks + kq];
             if (CONJT) a.y = -a.y;
+            if (LOWCONJ && (8 * tr + nq) > (4 * ks + kq)) a.y = -a.y;
             const double nay = -a.y;
             double2 b[4];
 #pragma unroll
@@ -623,7 +626,35 @@ eig_rot_large_kernel(const DevModel m, const KSource ks, const Jobs jb, const In
             __syncthreads();
         } else if (want_V) {
             // -------------------------------------------------------------- V_a = Us^dagger (d_a H) Us   (Us = T)
-            for (int a = 0; a < 3; ++a) {
+            // Fast path (Hermitian d_aH(k) stored as its upper triangle, tensor-core rotation): the operand buffer A is filled by
+            // asynchronous copies — element (p <= q) raw to A(p, q) and A(q, p), the first product conjugates the lower half on load —
+            // and the copy of direction a + 1 runs under the second product of direction a, which does not touch A
+            // (ncu r04c: 15 % of this kernel's stall samples were these loads, nothing overlapping them).
+            const bool async_A = jb.do_gauge && jb.herm && jb.hka_upper && (nw & 7) == 0;
+            auto fill_A_async = [&](int a) {
+                const double2 *Ha = Hka_in + ((size_t)ik * 3 + a) * nw2;
+                for (int idx = tid; idx < nw2; idx += E_THREADS) {
+                    const int p = idx % nw, q = idx / nw;                 // column-major source: row p, column q
+                    if (p <= q) {
+                        cp_async16(&A[p * LDA + q], Ha + idx);
+                        if (p < q) cp_async16(&A[q * LDA + p], Ha + idx);
+                    }
+                }
+                cp_async_commit();
+            };
+            if (async_A) {
+                fill_A_async(0);
+                for (int a = 0; a < 3; ++a) {
+                    cp_async_wait_all();
+                    __syncthreads();
+                    zgemm_dmma<false, true>(nw, LDA, LD, A, T, U, nullptr);          // U(buffer) <- d_aH Us
+                    __syncthreads();
+                    if (a < 2) fill_A_async(a + 1);
+                    zgemm_dmma<true>(nw, LD, LD, T, U, nullptr, Vg + a * nw2);       // V_a <- Us^dagger U
+                    __syncthreads();
+                }
+            }
+            for (int a = 0; a < 3 && !async_A; ++a) {
                 const double2 *Ha = Hka_in + ((size_t)ik * 3 + a) * nw2;
                 if (jb.do_gauge) {
                     if (jb.herm && jb.hka_upper) {      // only the upper triangle (row <= column) of the Hermitian d_aH(k) is in HBM

@@ -78,10 +78,10 @@ mep_sums_kernel(const long long nk, const Jobs jb, const double *__restrict__ e_
                 // registers the compiler issued them in batches of one k-point: four L2 round trips per iteration instead of one)
 #pragma unroll
                 for (int idx = lane; idx < VSZ; idx += 32)
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + idx)), "l"(src + idx) : "memory");
+                    cp_async16(dst + idx, src + idx);
             }
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        cp_async_commit();
         // next iteration's records towards L2 while this one computes (the warp's 32 / NW records are contiguous: one bulk prefetch;
         // ncu r04p: 23 % of the stall samples were these loads, with no room in shared memory for a second buffer)
         {
@@ -106,7 +106,7 @@ mep_sums_kernel(const long long nk, const Jobs jb, const double *__restrict__ e_
         const bool partner_own = (owners >> (lane ^ P)) & 1u;
         const int n0 = own ? g : (g ^ P);
         const int n_lo = own ? 0 : P, n_hi = (own && !partner_own) ? P : NW;
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        cp_async_wait_all();
         __syncwarp();
         if (own || partner_own) {
             const double e0 = es[n0];
