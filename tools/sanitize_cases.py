@@ -22,7 +22,7 @@ def run(model, params, tag):
 m, p, _ = host.load_run_dir(os.path.join(G, "femn_d0.900"))
 p.mp_grid, p.n_hw, p.do_mep, p.do_kubo, p.do_opt = (5, 4, 3), 40, True, True, True
 p.hw_min = 0.002
-run(m, p, "femn all jobs (eig_hq, bands_sub MEP, DMMA sweeps)")
+run(m, p, "femn all jobs (eig_hq, bands_sub, mep_sums, DMMA sweeps)")
 m, p, _ = host.load_run_dir(os.path.join(G, "femn_rashba"))
 p.mp_grid, p.n_hw = (4, 3, 3), 24
 run(m, p, "rashba general items + photo")
