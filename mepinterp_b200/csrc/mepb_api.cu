@@ -11,6 +11,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -188,6 +190,62 @@ bool hermitian_closed(const mepb_model *m, std::string *why) {
             }
     }
     return true;
+}
+
+// The same test for the large models mepb_update_model sees every step (nw = 64, nR = 2007: 131 MB of H(R)): partners through a
+// hash of the lattice vectors, every (R, -R) pair compared once, the R range split over a few host threads.  It answers only yes /
+// no — the largest closure violation against the same tolerance — and hermitian_closed() above is re-run for the reason on a no.
+bool hermitian_closed_fast(const mepb_model *m) {
+    const int nw = m->nw, nR = m->nR;
+    const size_t blk = 2 * (size_t)nw * nw;
+    std::vector<int> partner(nR, -1);
+    {
+        auto key = [](const double *R) {
+            const long long a = std::llround(R[0] * 1e6), b = std::llround(R[1] * 1e6), c = std::llround(R[2] * 1e6);
+            return (unsigned long long)(a * 73856093LL) ^ (unsigned long long)(b * 19349663LL) ^ (unsigned long long)(c * 83492791LL);
+        };
+        std::unordered_multimap<unsigned long long, int> idx;
+        idx.reserve((size_t)nR * 2);
+        for (int r = 0; r < nR; ++r) idx.emplace(key(&m->R[3 * r]), r);
+        for (int r = 0; r < nR; ++r) {
+            const double neg[3] = {-m->R[3 * r], -m->R[3 * r + 1], -m->R[3 * r + 2]};
+            int best = -1;
+            auto range = idx.equal_range(key(neg));
+            for (auto it = range.first; it != range.second; ++it) {           // the first index that matches, like the linear search
+                const int s = it->second;
+                if (std::fabs(m->R[3 * r] + m->R[3 * s]) < 1e-9 && std::fabs(m->R[3 * r + 1] + m->R[3 * s + 1]) < 1e-9 &&
+                    std::fabs(m->R[3 * r + 2] + m->R[3 * s + 2]) < 1e-9 && (best < 0 || s < best)) best = s;
+            }
+            partner[r] = best;
+        }
+    }
+    const int nt = (int)std::max(1u, std::min(8u, std::min(std::thread::hardware_concurrency(), (unsigned)((nR + 63) / 64))));
+    std::vector<double> hmax(nt, 0.0), viol(nt, 0.0);
+    auto work = [&](int t) {
+        double hm = 0.0, vm = 0.0;
+        for (int r = t; r < nR; r += nt) {
+            const double *Hr = m->H + blk * r;
+            for (size_t i = 0; i < blk; ++i) hm = std::max(hm, std::fabs(Hr[i]));
+            const int s = partner[r];
+            if (s < 0) { for (size_t i = 0; i < blk; ++i) vm = std::max(vm, std::fabs(Hr[i])); continue; }
+            if (s < r) continue;                                               // the pair was compared from its other member
+            const double *Hs = m->H + blk * s;
+            for (int a = 0; a < nw; ++a)
+                for (int b = 0; b < nw; ++b) {
+                    const double re1 = Hr[2 * (a + nw * b)], im1 = Hr[2 * (a + nw * b) + 1];
+                    const double re2 = Hs[2 * (b + nw * a)], im2 = Hs[2 * (b + nw * a) + 1];
+                    vm = std::max(vm, std::max(std::fabs(re1 - re2), std::fabs(im1 + im2)));
+                }
+        }
+        hmax[t] = hm; viol[t] = vm;
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+    double hm = 0.0, vm = 0.0;
+    for (int t = 0; t < nt; ++t) { hm = std::max(hm, hmax[t]); vm = std::max(vm, viol[t]); }
+    return !(vm > 4e-16 * std::max(hm, 1e-300));
 }
 
 // r(-R)(a,m,n) == conj r(R)(a,n,m) for every R?  (then A_a(k) is Hermitian in the W gauge and stays so in the H gauge)
@@ -1234,7 +1292,8 @@ int mepb_update_model(mepb_ctx *c, const mepb_model *model) {
     CUDA_TRY(cudaSetDevice(c->device));
     {   // buffers, launch shapes and the pair-item format were sized at mepb_create for this closure flag: it must not flip
         std::string why;
-        bool herm = hermitian_closed(model, &why);
+        bool herm = hermitian_closed_fast(model);
+        if (!herm) herm = hermitian_closed(model, &why);        // (the reason; agrees with the fast test by construction)
         if (herm && c->pos && !position_closed(model)) { herm = false; why = "r(-R)(m,n) != conj(r(R)(n,m))"; }
         if (herm != c->herm)
             return fail(MEPB_ERR_UNSUPPORTED, std::string("update_model: Hermitian closure of H(R) differs from the model the context was created "
