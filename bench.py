@@ -11,7 +11,7 @@ the library when N > 1, finalize (Fermi selection + normalisation) with the resp
 Headline (the one JSON line's `value`) = BASELINE.json configs[1] (C2): FeMn 3q TB model, anomalous Hall conductivity (static +
 121-point hw sweep), 128^3 k-mesh; for N > 1 the mesh grows with N (128 x 128 x 128N): "scaling": "weak".  The other four BASELINE
 configs are measured in the same process after the headline and reported under `configs` at their BASELINE meshes with FIXED total
-work ("scaling": "strong"): C1 32^3, C3 256^3, C4 128^3 (n_hw = 200), C5 100^3 (BASELINE 200^3 = 8 M k-points takes 17 s per step on
+work ("scaling": "strong"): C1 32^3, C3 256^3, C4 128^3 (n_hw = 200), C5 100^3 (BASELINE 200^3 = 8 M k-points takes 14 s per step on
 one GPU; `--workload C5 --mesh 200` runs it).  `--no-configs` skips them.
 
 Keys beyond the base contract: `roofline` (FP64-pipe roofline of the dominant kernel + `step_frac` for the whole step; per-kernel
